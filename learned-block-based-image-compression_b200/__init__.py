@@ -1,0 +1,8 @@
+"""B200-native closed-loop encode/decode of the block-based masked-convolution codec (v9).
+
+Drop-in for the reference's compress/decompress path (graphs/models/BlockBasedImgCompLossy_net.py:
+319-452 behind agents/blkbsdimgcomp_agent.py:560-641).  Host code is Python/PyTorch; all compute is
+hand-written sm_100a CUDA behind the C ABI declared in include/lbic.h.  There is no CPU fallback.
+"""
+from . import weights  # noqa: F401
+from .config import load_config  # noqa: F401
