@@ -1,0 +1,154 @@
+/*
+ * lbic.h -- C ABI of the B200-native closed-loop block codec (liblbic_b200.so).
+ *
+ * The reference (kamisli-icpl/Learned-block-based-image-compression) has no FFI of its own on
+ * this path; its only foreign-function edge is pybind11 into CompressAI.  Each entry point below
+ * therefore names the reference *Python* interface it stands behind (paths relative to the
+ * reference root; NET = graphs/models/BlockBasedImgCompLossy_net.py,
+ * ENT = graphs/layers/entropy_layers_cai.py, AGENT = agents/blkbsdimgcomp_agent.py).
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a negative lbic_status;
+ * the message of the last failure on the calling thread is lbic_last_error(); nothing throws or
+ * aborts.  All work is enqueued on the caller's CUDA stream (pass the cudaStream_t as void*;
+ * NULL = legacy default stream).  "device pointer" arguments must be device-accessible memory on
+ * the model's device; the *_host entry points take ordinary host memory and perform the
+ * host<->device copies themselves.  One lbic_model per device; calls on one model are not
+ * re-entrant.  Requires an sm_100a GPU: there is no CPU fallback.
+ */
+#ifndef LBIC_H_
+#define LBIC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lbic_model lbic_model;
+
+typedef enum {
+    LBIC_OK = 0,
+    LBIC_ERR_INVALID = -1,     /* bad argument / unsupported configuration            */
+    LBIC_ERR_CUDA = -2,        /* a CUDA runtime or driver call failed                */
+    LBIC_ERR_STATE = -3,       /* weights or tables missing (reference: ValueError, ENT:185-204) */
+    LBIC_ERR_NOMEM = -4,
+    LBIC_ERR_NO_DEVICE = -5,   /* no sm_100 device: the product path refuses to run   */
+    LBIC_ERR_OVERFLOW = -6     /* a caller-provided stream buffer was too small       */
+} lbic_status;
+
+/* Model hyper-parameters: the four keys the reference model reads from its config JSON
+ * (NET:262-302: config.block_size, config.KS, config.N, config.M). */
+typedef struct {
+    int block_size;            /* B                                  */
+    int ks[4];                 /* KS, [3,1,1,1] or [3,3,1,1]         */
+    int n;                     /* N                                  */
+    int m;                     /* M                                  */
+} lbic_config;
+
+/* One state_dict entry (name as in the reference state_dict).
+ * data may be a host or a device pointer (fp32, C-contiguous). */
+typedef struct {
+    const char *name;
+    const float *data;
+    int ndim;
+    int64_t shape[4];
+} lbic_tensor_desc;
+
+/* GEMM core selection (lbic_set_option LBIC_OPT_GEMM_CORE):
+ *   0 = tcgen05/TMEM/TMA tensor-core tiles, bf16 hi/lo split, 3 MMAs per product (product path)
+ *   1 = fp32 SIMT evaluation of the same split operands (bring-up / cross-check twin)      */
+#define LBIC_OPT_GEMM_CORE 1
+#define LBIC_OPT_USE_GRAPH 2   /* 1 = replay the per-(n,Hb,Wb) step sequence as a CUDA graph */
+
+const char *lbic_last_error(void);
+const char *lbic_version(void);
+
+/* Model(config) -- NET:259-317.  device = CUDA ordinal. */
+int lbic_create(const lbic_config *cfg, int device, lbic_model **out);
+void lbic_destroy(lbic_model *m);
+int lbic_set_option(lbic_model *m, int option, int value);
+
+/* model.load_state_dict(sd) -- agents/base.py:95-96.  Consumes every `*.weight/bias/mask`,
+ * `*.beta/gamma` and GDN reparam buffer of Appendix A.7; folds the masks (NET:381), applies the
+ * non-negative reparametrisation (utils/parametrizers.py:45-48) and packs bf16 hi/lo planes on
+ * the device.  The library keeps no reference to the caller's memory. */
+int lbic_load_weights(lbic_model *m, const lbic_tensor_desc *tensors, int n_tensors, void *stream);
+
+/* model.update(force=True) -- NET:121-125 -> ENT:579-613 (+ compressai._CXX.pmf_to_quantized_cdf).
+ * scale_table: host pointer to the n_levels scale values (NET:13-18); tail_mass as ENT:528.
+ * Builds quantized_cdf / cdf_length / offset on the GPU. */
+int lbic_build_tables(lbic_model *m, const float *scale_table, int n_levels, double tail_mass, void *stream);
+/* Install tables produced elsewhere (e.g. `conditional_gaussian_model._quantized_cdf` buffers
+ * found in a reference checkpoint).  Host pointers. */
+int lbic_set_tables(lbic_model *m, const float *scale_table, int n_levels, const int32_t *cdf,
+                    int cdf_stride, const int32_t *cdf_length, const int32_t *offset);
+/* Read the tables back (host pointers; cdf must hold n_levels*cdf_stride ints).  Queries with
+ * NULL outputs just return the sizes. */
+int lbic_get_tables(lbic_model *m, int *n_levels, int *cdf_stride, int32_t *cdf, int32_t *cdf_length,
+                    int32_t *offset);
+
+/* model.compress(x, LRU, chlat) -- NET:319-361, batched over n_img images of identical size.
+ *   x          device, (n_img, 3B^2, Hb, Wb) fp32 in [-0.5,0.5]: the layout eval_model passes
+ *              (AGENT:588-592)
+ *   zhat_out   device, same shape: the encoder-side reconstruction (second return value)
+ *   sym_out    device or NULL, (n_img, Hb, Wb, M) int32 quantised latent symbols (NET:353)
+ *   idx_out    device or NULL, (n_img, Hb, Wb, M) uint8 CDF indexes (NET:354)
+ *   stream_out device, n_img * stream_cap bytes; image i's bitstream starts at i*stream_cap
+ *   stream_len device, n_img uint32 byte counts
+ *   lanes      1 = the reference container: one rANS64 stream per image, raw words, no header
+ *              (NET:359-360);  0 = one lane per block row (container extension)
+ * stream_cap >= lbic_stream_bound(...).  stream_out == NULL skips entropy coding. */
+int lbic_encode(lbic_model *m, const float *x, int n_img, int Hb, int Wb, float *zhat_out,
+                int32_t *sym_out, uint8_t *idx_out, uint8_t *stream_out, size_t stream_cap,
+                uint32_t *stream_len, int lanes, void *stream);
+
+/* model.decompress(bitstream, LRU, xshape, chlat, devc) -- NET:400-452, batched.
+ *   streams / stream_len / stream_cap as produced by lbic_encode (device pointers)
+ *   zhat_out   device, (n_img, 3B^2, Hb, Wb) fp32
+ *   sym_out    device or NULL: the decoded symbols */
+int lbic_decode(lbic_model *m, const uint8_t *streams, const uint32_t *stream_len, size_t stream_cap,
+                int n_img, int Hb, int Wb, float *zhat_out, int32_t *sym_out, int lanes, void *stream);
+
+/* Same two calls with HOST buffers (pageable or pinned): the copies are part of the call and the
+ * call returns after the results are in host memory.  This is what a reference-side binding
+ *  calls from eval_model (AGENT:591-599). */
+int lbic_encode_host(lbic_model *m, const float *x, int n_img, int Hb, int Wb, float *zhat_out,
+                     uint8_t *stream_out, size_t stream_cap, uint32_t *stream_len, int lanes);
+int lbic_decode_host(lbic_model *m, const uint8_t *streams, const uint32_t *stream_len,
+                     size_t stream_cap, int n_img, int Hb, int Wb, float *zhat_out, int lanes);
+
+/* Upper bound on one image's bitstream size in bytes for the given grid. */
+size_t lbic_stream_bound(const lbic_model *m, int Hb, int Wb, int lanes);
+
+/* arrange_block_pixels_to_channel_dim / arrange_channel_dim_to_block_pixels -- AGENT:853-873.
+ * img: (n, C, Hb*B, Wb*B); blk: (n, C*B*B, Hb, Wb), channel (v*B+h)*C + c.  Device pointers. */
+int lbic_space_to_depth(const float *img, float *blk, int n, int C, int Hb, int Wb, int B, void *stream);
+int lbic_depth_to_space(const float *blk, float *img, int n, int C, int Hb, int Wb, int B, void *stream);
+
+/* The entropy coder on its own: compressai.ans.BufferedRansEncoder.encode_with_indexes + flush
+ * (NET:359-360) and RansDecoder.set_stream + decode_stream (NET:409-410,439) for n_streams
+ * independent streams of n_sym symbols each.  Device pointers; symbols int32, indexes uint8. */
+int lbic_rans_encode(lbic_model *m, const int32_t *symbols, const uint8_t *indexes, int n_streams,
+                     int64_t n_sym, uint8_t *stream_out, size_t stream_cap, uint32_t *stream_len,
+                     void *stream);
+int lbic_rans_decode(lbic_model *m, const uint8_t *streams, const uint32_t *stream_len, size_t stream_cap,
+                     const uint8_t *indexes, int n_streams, int64_t n_sym, int32_t *symbols_out,
+                     void *stream);
+
+/* Bring-up / test hook: D[R,cout] = A[R,K] * W[cout,K]^T with fp32 host-visible results, through
+ * the selected GEMM core (A, W, D device fp32; the split into bf16 hi/lo planes happens inside). */
+int lbic_debug_gemm(lbic_model *m, const float *A, const float *W, float *D, int R, int K, int cout,
+                    void *stream);
+
+/* Number of kernels this library has launched on behalf of `m` since creation. */
+int64_t lbic_launch_count(const lbic_model *m);
+/* Per-kernel-family launch counts and (if timing is enabled) accumulated device milliseconds for
+ * the GEMM family; used by bench.py for the roofline line. */
+int lbic_set_profiling(lbic_model *m, int enabled);
+int lbic_get_profile(lbic_model *m, int64_t *gemm_launches, double *gemm_ms, double *gemm_flops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBIC_H_ */

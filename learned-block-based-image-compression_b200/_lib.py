@@ -1,0 +1,80 @@
+"""ctypes binding of liblbic_b200.so (the C ABI in include/lbic.h).
+
+The product path has no fallback: if the shared library is missing (run `python
+__graft_entry__.py build` or `build.py`) or no sm_100 GPU is present, calls raise."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "liblbic_b200.so")
+_lib = None
+
+
+class LbicConfig(ctypes.Structure):
+    _fields_ = [("block_size", ctypes.c_int), ("ks", ctypes.c_int * 4), ("n", ctypes.c_int), ("m", ctypes.c_int)]
+
+
+class LbicTensorDesc(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char_p), ("data", ctypes.c_void_p), ("ndim", ctypes.c_int),
+                ("shape", ctypes.c_int64 * 4)]
+
+
+LBIC_OPT_GEMM_CORE = 1
+LBIC_OPT_USE_GRAPH = 2
+
+# every symbol include/lbic.h declares: (restype, argtypes)
+_vp, _i, _sz, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_int64
+PROTOTYPES = {
+    "lbic_last_error": (ctypes.c_char_p, []),
+    "lbic_version": (ctypes.c_char_p, []),
+    "lbic_create": (_i, [ctypes.POINTER(LbicConfig), _i, ctypes.POINTER(_vp)]),
+    "lbic_destroy": (None, [_vp]),
+    "lbic_set_option": (_i, [_vp, _i, _i]),
+    "lbic_load_weights": (_i, [_vp, ctypes.POINTER(LbicTensorDesc), _i, _vp]),
+    "lbic_build_tables": (_i, [_vp, _vp, _i, ctypes.c_double, _vp]),
+    "lbic_set_tables": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
+    "lbic_get_tables": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i), _vp, _vp, _vp]),
+    "lbic_encode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp, _i, _vp]),
+    "lbic_decode": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "lbic_encode_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp, _i]),
+    "lbic_decode_host": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _vp, _i]),
+    "lbic_stream_bound": (_sz, [_vp, _i, _i, _i]),
+    "lbic_space_to_depth": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "lbic_depth_to_space": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "lbic_rans_encode": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _sz, _vp, _vp]),
+    "lbic_rans_decode": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _i64, _vp, _vp]),
+    "lbic_debug_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "lbic_launch_count": (_i64, [_vp]),
+    "lbic_set_profiling": (_i, [_vp, _i]),
+    "lbic_get_profile": (_i, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_double),
+                              ctypes.POINTER(ctypes.c_double)]),
+}
+
+
+def lib():
+    """Loads liblbic_b200.so; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(
+                f"{SO_PATH} not found: build the CUDA extension first (python __graft_entry__.py build). "
+                "lbic_b200 has no CPU fallback.")
+        L = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    """Maps a negative lbic_status to a Python exception (STATE -> ValueError like the reference's
+    _check_cdf_size, entropy_layers_cai.py:185-204; everything else RuntimeError)."""
+    if rc == 0:
+        return
+    msg = lib().lbic_last_error().decode(errors="replace")
+    if rc == -3:
+        raise ValueError(msg)
+    raise RuntimeError(f"lbic error {rc}: {msg}")

@@ -1,0 +1,882 @@
+// C ABI (include/lbic.h): model management, weight packing, workspace, and the wavefront drivers for
+// encode (NET:319-361) and decode (NET:400-452).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "lbic_internal.h"
+
+// ------------------------------------------------------------------------------------------------
+// errors, launch accounting
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+thread_local int64_t *g_launch_counter = nullptr;
+
+int lbic_fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+void count_launch(int family) {
+    if (g_launch_counter) g_launch_counter[family]++;
+}
+
+extern "C" const char *lbic_last_error(void) { return g_err; }
+extern "C" const char *lbic_version(void) { return "lbic_b200 0.1 (sm_100a; tcgen05 bf16x3 + SIMT twin)"; }
+
+// ------------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+enum LayerId {
+    L_E0, L_E1, L_E2, L_E3,                       // entropy-parameter net (get_meanscale.{0,2,4,6})
+    L_F0, L_G0, L_F1, L_G1, L_F2, L_G2, L_F3,     // encoder: prtr_forward1+2, prtr_forward3.{0..5}
+    L_D0, L_IG0, L_D1, L_IG1, L_D2, L_IG2, L_D3,  // decoder: prtr_inverse1+2, prtr_inverse3.{0..5}
+    L_COUNT
+};
+
+struct PackedSeg {
+    int K = 0;
+    bf16 *hi = nullptr, *lo = nullptr;
+    CUtensorMap tm_hi, tm_lo;
+};
+
+struct PackedLayer {
+    int cout = 0, bn = 0, nseg = 0;
+    PackedSeg seg[2];
+    float *bias = nullptr;
+};
+
+struct ActBuf {
+    bf16 *hi = nullptr, *lo = nullptr;
+    int ld = 0;
+};
+
+struct ActView {   // an activation buffer seen as a GEMM A operand of logical width K
+    const ActBuf *buf = nullptr;
+    int K = 0;
+    CUtensorMap tm_hi, tm_lo;
+};
+
+struct Workspace {
+    int n_img = 0, Hb = 0, Wb = 0, R_cap = 0;
+    float *x_cl = nullptr, *zhat_cl = nullptr;
+    ActBuf X, T, YQ, H1, H2, H3, S, U;
+    float *A32 = nullptr, *KSI = nullptr;
+    int ldA32 = 0, ldKSI = 0;
+    ActView vX, vT, vYQ, vH1, vH2, vH3, vS[3], vU[3];
+    int32_t *sym = nullptr;
+    uint8_t *idx = nullptr;
+    uint32_t *rans_scratch = nullptr;
+    size_t rans_scratch_words = 0;   // total words allocated
+    RansStreamState *dec_states = nullptr;
+    const uint8_t **lane_ptr = nullptr;
+    std::vector<void *> allocs;
+};
+
+struct ProfRec {
+    cudaEvent_t a, b;
+    double flops;
+};
+
+}  // namespace
+
+struct lbic_model {
+    lbic_config cfg;
+    int device = 0;
+    int Cin = 0, N = 0, C2 = 0, C3 = 0, M = 0, E1 = 0, E2 = 0, E3 = 0, EO = 0, k1 = 1;
+    PackedLayer L[L_COUNT];
+    bool weights_loaded = false;
+    std::vector<void *> weight_allocs;
+    Tables tables;
+    Workspace ws;
+    int gemm_core = 0;
+    int use_graph = 0;
+    int64_t launches[2] = {0, 0};
+    int *err_flag = nullptr;
+    // host-call staging
+    void *io_dev = nullptr;
+    size_t io_bytes = 0;
+    // profiling
+    int profiling = 0;
+    std::vector<ProfRec> prof;
+};
+
+namespace {
+
+struct Active {   // routes launch counting to the model for the duration of an API call
+    explicit Active(lbic_model *m) {
+        g_launch_counter = m ? m->launches : nullptr;
+        if (m) cudaSetDevice(m->device);
+    }
+    ~Active() { g_launch_counter = nullptr; }
+};
+
+int dev_alloc(std::vector<void *> &list, void **p, size_t bytes, bool zero = false) {
+    *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) return lbic_fail(LBIC_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    list.push_back(*p);
+    if (zero) LBIC_CUDA(cudaMemset(*p, 0, bytes));
+    return 0;
+}
+
+void free_all(std::vector<void *> &list) {
+    for (void *p : list) cudaFree(p);
+    list.clear();
+}
+
+int pick_bn(int cout) {
+    const int ntiles = (cout + 255) / 256;
+    int bn = (cout + ntiles - 1) / ntiles;
+    bn = (bn + 15) / 16 * 16;
+    return bn;
+}
+
+// ---- weight loading ---------------------------------------------------------------------------
+struct SdView {
+    std::map<std::string, const lbic_tensor_desc *> by_name;
+    const lbic_tensor_desc *find(const std::string &k) const {
+        auto it = by_name.find(k);
+        return it == by_name.end() ? nullptr : it->second;
+    }
+};
+
+int64_t numel(const lbic_tensor_desc *t) {
+    int64_t n = 1;
+    for (int i = 0; i < t->ndim; ++i) n *= t->shape[i];
+    return n;
+}
+
+// copies a state_dict tensor to a temporary device buffer (host or device source)
+int stage(const SdView &sd, const std::string &name, int64_t expect, std::vector<void *> &tmp, float **out,
+          cudaStream_t st) {
+    const lbic_tensor_desc *t = sd.find(name);
+    if (!t) return lbic_fail(LBIC_ERR_STATE, "state_dict is missing key '%s'", name.c_str());
+    if (numel(t) != expect)
+        return lbic_fail(LBIC_ERR_INVALID, "state_dict['%s'] has %lld elements, expected %lld", name.c_str(),
+                         (long long)numel(t), (long long)expect);
+    LBIC_TRY(dev_alloc(tmp, (void **)out, sizeof(float) * (size_t)expect));
+    LBIC_CUDA(cudaMemcpyAsync(*out, t->data, sizeof(float) * (size_t)expect, cudaMemcpyDefault, st));
+    return 0;
+}
+
+int scalar(const SdView &sd, const std::string &name, float fallback, float *out) {
+    const lbic_tensor_desc *t = sd.find(name);
+    *out = fallback;
+    if (t && numel(t) == 1) LBIC_CUDA(cudaMemcpy(out, t->data, sizeof(float), cudaMemcpyDefault));
+    return 0;
+}
+
+const int TAPS_A[8] = {0, 0, 0, 1, 0, 2, 1, 0};            // 3x3 mask 'A' live taps (kh,kw)  MC:12-17
+const int TAPS_B[10] = {0, 0, 0, 1, 0, 2, 1, 0, 1, 1};     // 3x3 mask 'B' adds the centre
+const int TAPS_1[2] = {0, 0};
+
+int pack_conv_seg(lbic_model *m, const SdView &sd, const std::string &prefix, int cout, int cin, int k,
+                  const int *taps, int ntaps, int bn, PackedSeg &seg, float **bias_tmp, std::vector<void *> &tmp,
+                  cudaStream_t st) {
+    float *w = nullptr, *mask = nullptr;
+    const int64_t nw = (int64_t)cout * cin * k * k;
+    LBIC_TRY(stage(sd, prefix + ".weight", nw, tmp, &w, st));
+    if (sd.find(prefix + ".mask")) LBIC_TRY(stage(sd, prefix + ".mask", nw, tmp, &mask, st));
+    LBIC_TRY(stage(sd, prefix + ".bias", cout, tmp, bias_tmp, st));
+    seg.K = ntaps * cin;
+    LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&seg.hi, sizeof(bf16) * (size_t)cout * seg.K));
+    LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&seg.lo, sizeof(bf16) * (size_t)cout * seg.K));
+    LBIC_TRY(launch_pack_conv(w, mask, cout, cin, k, k, taps, ntaps, seg.hi, seg.lo, seg.K, st));
+    LBIC_TRY(make_tmap_2d(&seg.tm_hi, seg.hi, seg.K, cout, seg.K, 64, bn));
+    LBIC_TRY(make_tmap_2d(&seg.tm_lo, seg.lo, seg.K, cout, seg.K, 64, bn));
+    return 0;
+}
+
+int pack_linear(lbic_model *m, const SdView &sd, int id, const std::string &prefix, int cout, int cin, int k,
+                const int *taps, int ntaps, std::vector<void *> &tmp, cudaStream_t st) {
+    PackedLayer &L = m->L[id];
+    L.cout = cout;
+    L.bn = pick_bn(cout);
+    L.nseg = 1;
+    float *b = nullptr;
+    LBIC_TRY(pack_conv_seg(m, sd, prefix, cout, cin, k, taps, ntaps, L.bn, L.seg[0], &b, tmp, st));
+    LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&L.bias, sizeof(float) * cout));
+    LBIC_TRY(launch_add_vec(b, nullptr, L.bias, cout, st));
+    return 0;
+}
+
+// first layer of the encoder / decoder nets: 1x1 conv on x (or y_qnt) plus masked 3x3 conv on zhat, summed
+int pack_dual(lbic_model *m, const SdView &sd, int id, const std::string &p1, int cin1, const std::string &p2,
+              int cout, std::vector<void *> &tmp, cudaStream_t st) {
+    PackedLayer &L = m->L[id];
+    L.cout = cout;
+    L.bn = pick_bn(cout);
+    L.nseg = 2;
+    float *b1 = nullptr, *b2 = nullptr;
+    LBIC_TRY(pack_conv_seg(m, sd, p1, cout, cin1, 1, TAPS_1, 1, L.bn, L.seg[0], &b1, tmp, st));
+    LBIC_TRY(pack_conv_seg(m, sd, p2, cout, m->Cin, 3, TAPS_A, 4, L.bn, L.seg[1], &b2, tmp, st));
+    LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&L.bias, sizeof(float) * cout));
+    LBIC_TRY(launch_add_vec(b1, b2, L.bias, cout, st));
+    return 0;
+}
+
+int pack_gdn(lbic_model *m, const SdView &sd, int id, const std::string &prefix, int C, std::vector<void *> &tmp,
+             cudaStream_t st) {
+    PackedLayer &L = m->L[id];
+    L.cout = C;
+    L.bn = pick_bn(C);
+    L.nseg = 1;
+    float *g = nullptr, *b = nullptr;
+    LBIC_TRY(stage(sd, prefix + ".gamma", (int64_t)C * C, tmp, &g, st));
+    LBIC_TRY(stage(sd, prefix + ".beta", C, tmp, &b, st));
+    // defaults = NonNegativeParametrizer constants (utils/parametrizers.py:33-40, GDNF:55-61)
+    const float ped = (float)pow(2.0, -36.0);
+    float gped, gbound, bped, bbound;
+    LBIC_TRY(scalar(sd, prefix + ".gamma_reparam.pedestal", ped, &gped));
+    LBIC_TRY(scalar(sd, prefix + ".gamma_reparam.lower_bound.bound", (float)sqrt(0.0 + pow(2.0, -36.0)), &gbound));
+    LBIC_TRY(scalar(sd, prefix + ".beta_reparam.pedestal", ped, &bped));
+    LBIC_TRY(scalar(sd, prefix + ".beta_reparam.lower_bound.bound", (float)sqrt(1e-6 + pow(2.0, -36.0)), &bbound));
+    PackedSeg &seg = L.seg[0];
+    seg.K = C;
+    LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&seg.hi, sizeof(bf16) * (size_t)C * C));
+    LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&seg.lo, sizeof(bf16) * (size_t)C * C));
+    LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&L.bias, sizeof(float) * C));
+    LBIC_TRY(launch_pack_gdn(g, b, C, gbound, gped, bbound, bped, seg.hi, seg.lo, C, L.bias, st));
+    LBIC_TRY(make_tmap_2d(&seg.tm_hi, seg.hi, C, C, C, 64, L.bn));
+    LBIC_TRY(make_tmap_2d(&seg.tm_lo, seg.lo, C, C, C, 64, L.bn));
+    return 0;
+}
+
+// ---- workspace ----------------------------------------------------------------------------------
+int alloc_act(Workspace &ws, ActBuf &b, int ld) {
+    b.ld = ld;
+    LBIC_TRY(dev_alloc(ws.allocs, (void **)&b.hi, sizeof(bf16) * (size_t)ws.R_cap * ld, true));
+    LBIC_TRY(dev_alloc(ws.allocs, (void **)&b.lo, sizeof(bf16) * (size_t)ws.R_cap * ld, true));
+    return 0;
+}
+
+int make_view(Workspace &ws, ActView &v, const ActBuf &b, int K) {
+    v.buf = &b;
+    v.K = K;
+    LBIC_TRY(make_tmap_2d(&v.tm_hi, b.hi, K, ws.R_cap, b.ld, 64, 128));
+    LBIC_TRY(make_tmap_2d(&v.tm_lo, b.lo, K, ws.R_cap, b.ld, 64, 128));
+    return 0;
+}
+
+int ensure_workspace(lbic_model *m, int n_img, int Hb, int Wb) {
+    Workspace &ws = m->ws;
+    if (ws.n_img >= n_img && ws.Hb == Hb && ws.Wb == Wb) return 0;
+    LBIC_CUDA(cudaDeviceSynchronize());
+    free_all(ws.allocs);
+    ws = Workspace();
+    ws.n_img = n_img; ws.Hb = Hb; ws.Wb = Wb;
+    const int max_nv = Hb < (Wb + 1) / 2 ? Hb : (Wb + 1) / 2;
+    ws.R_cap = ((n_img * max_nv) + 127) / 128 * 128;
+    const size_t nblk = (size_t)n_img * Hb * Wb;
+    LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.x_cl, sizeof(float) * nblk * m->Cin));
+    LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.zhat_cl, sizeof(float) * nblk * m->Cin));
+    LBIC_TRY(alloc_act(ws, ws.X, m->Cin));
+    LBIC_TRY(alloc_act(ws, ws.T, 4 * m->Cin));
+    LBIC_TRY(alloc_act(ws, ws.YQ, m->M));
+    LBIC_TRY(alloc_act(ws, ws.H1, m->E1));
+    LBIC_TRY(alloc_act(ws, ws.H2, m->E2));
+    LBIC_TRY(alloc_act(ws, ws.H3, m->E3));
+    LBIC_TRY(alloc_act(ws, ws.S, m->N));
+    LBIC_TRY(alloc_act(ws, ws.U, m->N));
+    ws.ldA32 = m->N; ws.ldKSI = m->EO;
+    LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.A32, sizeof(float) * (size_t)ws.R_cap * ws.ldA32, true));
+    LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.KSI, sizeof(float) * (size_t)ws.R_cap * ws.ldKSI, true));
+    LBIC_TRY(make_view(ws, ws.vX, ws.X, m->Cin));
+    LBIC_TRY(make_view(ws, ws.vT, ws.T, 4 * m->Cin));
+    LBIC_TRY(make_view(ws, ws.vYQ, ws.YQ, m->M));
+    LBIC_TRY(make_view(ws, ws.vH1, ws.H1, m->E1));
+    LBIC_TRY(make_view(ws, ws.vH2, ws.H2, m->E2));
+    LBIC_TRY(make_view(ws, ws.vH3, ws.H3, m->E3));
+    const int wd[3] = {m->N, m->C2, m->C3};
+    for (int i = 0; i < 3; ++i) {
+        LBIC_TRY(make_view(ws, ws.vS[i], ws.S, wd[i]));
+        LBIC_TRY(make_view(ws, ws.vU[i], ws.U, wd[i]));
+    }
+    LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.sym, sizeof(int32_t) * nblk * m->M));
+    LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.idx, nblk * m->M));
+    LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.dec_states, sizeof(RansStreamState) * (size_t)n_img * Hb));
+    LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.lane_ptr, sizeof(void *) * (size_t)n_img * Hb));
+    return 0;
+}
+
+int ensure_rans_scratch(lbic_model *m, size_t words) {
+    Workspace &ws = m->ws;
+    if (ws.rans_scratch_words >= words) return 0;
+    // (old block stays in ws.allocs until the workspace is rebuilt; growth is rare)
+    LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.rans_scratch, sizeof(uint32_t) * words));
+    ws.rans_scratch_words = words;
+    return 0;
+}
+
+// ---- GEMM dispatch --------------------------------------------------------------------------------
+int run_gemm(lbic_model *m, int id, int R, const ActView *a0, const ActView *a1, EpiParams ep, cudaStream_t st) {
+    const PackedLayer &L = m->L[id];
+    GemmCall g;
+    g.R = R; g.cout = L.cout; g.bn = L.bn; g.nseg = L.nseg;
+    const ActView *av[2] = {a0, a1};
+    double flops = 0;
+    for (int s = 0; s < L.nseg; ++s) {
+        if (!av[s] || av[s]->K != L.seg[s].K)
+            return lbic_fail(LBIC_ERR_INVALID, "internal: layer %d segment %d K mismatch", id, s);
+        g.K[s] = L.seg[s].K;
+        g.A[s].hi = av[s]->buf->hi; g.A[s].lo = av[s]->buf->lo; g.A[s].ld = av[s]->buf->ld;
+        g.A[s].tm_hi = &av[s]->tm_hi; g.A[s].tm_lo = &av[s]->tm_lo;
+        g.W[s].hi = L.seg[s].hi; g.W[s].lo = L.seg[s].lo; g.W[s].ld = L.seg[s].K;
+        g.W[s].tm_hi = &L.seg[s].tm_hi; g.W[s].tm_lo = &L.seg[s].tm_lo;
+        flops += 2.0 * R * (double)L.seg[s].K * L.cout;
+    }
+    ep.R = R; ep.cout = L.cout; ep.bias = L.bias;
+    ep.scale_tab = m->tables.d_scale_table;
+    g.ep = ep;
+    ProfRec rec;
+    if (m->profiling) {
+        cudaEventCreate(&rec.a); cudaEventCreate(&rec.b);
+        rec.flops = flops;
+        cudaEventRecord(rec.a, st);
+    }
+    const int rc = m->gemm_core == 1 ? gemm_simt_launch(g, st) : gemm_tc_launch(g, st);
+    if (m->profiling) {
+        cudaEventRecord(rec.b, st);
+        m->prof.push_back(rec);
+    }
+    return rc;
+}
+
+EpiParams epi(int mode, const StepDesc &sd) {
+    EpiParams e;
+    memset(&e, 0, sizeof(e));
+    e.mode = mode;
+    e.step = sd;
+    return e;
+}
+
+EpiParams epi_hilo(int mode, const StepDesc &sd, const ActBuf &out) {
+    EpiParams e = epi(mode, sd);
+    e.out_hi = out.hi; e.out_lo = out.lo; e.ld_out = out.ld;
+    return e;
+}
+
+// entropy-parameter net: T -> ksi   (get_meanscale_fast, NET:389-398; KS[1] == 1)
+int run_ent(lbic_model *m, const StepDesc &sd, int R, cudaStream_t st) {
+    Workspace &ws = m->ws;
+    LBIC_TRY(run_gemm(m, L_E0, R, &ws.vT, nullptr, epi_hilo(EPI_LRELU, sd, ws.H1), st));
+    LBIC_TRY(run_gemm(m, L_E1, R, &ws.vH1, nullptr, epi_hilo(EPI_LRELU, sd, ws.H2), st));
+    LBIC_TRY(run_gemm(m, L_E2, R, &ws.vH2, nullptr, epi_hilo(EPI_LRELU, sd, ws.H3), st));
+    EpiParams e = epi(EPI_KSI, sd);
+    e.out_f32 = ws.KSI; e.ld_f32 = ws.ldKSI;
+    LBIC_TRY(run_gemm(m, L_E3, R, &ws.vH3, nullptr, e, st));
+    return 0;
+}
+
+// GDN / IGDN stage i (widths N, C2, C3): S (squares) -> U
+int run_gdn(lbic_model *m, int id, int i, bool inverse, const StepDesc &sd, int R, cudaStream_t st) {
+    Workspace &ws = m->ws;
+    EpiParams e = epi_hilo(inverse ? EPI_IGDN : EPI_GDN, sd, ws.U);
+    e.aux = ws.A32; e.ld_aux = ws.ldA32;
+    return run_gemm(m, id, R, &ws.vS[i], nullptr, e, st);
+}
+
+EpiParams epi_pregdn(lbic_model *m, const StepDesc &sd) {
+    Workspace &ws = m->ws;
+    EpiParams e = epi_hilo(EPI_PREGDN, sd, ws.S);
+    e.out_f32 = ws.A32; e.ld_f32 = ws.ldA32;
+    return e;
+}
+
+// encoder net + quantisation: X, T, ksi -> symbols, indexes, y_qnt   (forward_prtr_fast NET:379-382, NET:371-374)
+int run_enc(lbic_model *m, const StepDesc &sd, int R, int32_t *sym, uint8_t *idx, cudaStream_t st) {
+    Workspace &ws = m->ws;
+    LBIC_TRY(run_gemm(m, L_F0, R, &ws.vX, &ws.vT, epi_pregdn(m, sd), st));
+    LBIC_TRY(run_gdn(m, L_G0, 0, false, sd, R, st));
+    LBIC_TRY(run_gemm(m, L_F1, R, &ws.vU[0], nullptr, epi_pregdn(m, sd), st));
+    LBIC_TRY(run_gdn(m, L_G1, 1, false, sd, R, st));
+    LBIC_TRY(run_gemm(m, L_F2, R, &ws.vU[1], nullptr, epi_pregdn(m, sd), st));
+    LBIC_TRY(run_gdn(m, L_G2, 2, false, sd, R, st));
+    EpiParams e = epi_hilo(EPI_QUANT, sd, ws.YQ);
+    e.aux = ws.KSI; e.ld_aux = ws.ldKSI; e.M = m->M;
+    e.sym = sym; e.idx = idx;
+    LBIC_TRY(run_gemm(m, L_F3, R, &ws.vU[2], nullptr, e, st));
+    return 0;
+}
+
+// decoder net: y_qnt, T -> zhat block, clamped   (inverse_prtr_fast NET:384-387, NET:357)
+int run_dec(lbic_model *m, const StepDesc &sd, int R, cudaStream_t st) {
+    Workspace &ws = m->ws;
+    LBIC_TRY(run_gemm(m, L_D0, R, &ws.vYQ, &ws.vT, epi_pregdn(m, sd), st));
+    LBIC_TRY(run_gdn(m, L_IG0, 0, true, sd, R, st));
+    LBIC_TRY(run_gemm(m, L_D1, R, &ws.vU[0], nullptr, epi_pregdn(m, sd), st));
+    LBIC_TRY(run_gdn(m, L_IG1, 1, true, sd, R, st));
+    LBIC_TRY(run_gemm(m, L_D2, R, &ws.vU[1], nullptr, epi_pregdn(m, sd), st));
+    LBIC_TRY(run_gdn(m, L_IG2, 2, true, sd, R, st));
+    EpiParams e = epi(EPI_RECON, sd);
+    e.zhat = ws.zhat_cl;
+    LBIC_TRY(run_gemm(m, L_D3, R, &ws.vU[2], nullptr, e, st));
+    return 0;
+}
+
+bool wave_step(int t, int n_img, int Hb, int Wb, StepDesc &sd) {
+    int vmin = t - (Wb - 1) <= 0 ? 0 : (t - (Wb - 1) + 1) / 2;
+    int vmax = t / 2 < Hb - 1 ? t / 2 : Hb - 1;
+    if (vmax < vmin) return false;
+    sd.n_img = n_img; sd.nv = vmax - vmin + 1; sd.vmin = vmin; sd.t = t; sd.Hb = Hb; sd.Wb = Wb;
+    return true;
+}
+
+int check_ready(lbic_model *m, bool need_tables) {
+    if (!m) return lbic_fail(LBIC_ERR_INVALID, "null model");
+    if (!m->weights_loaded) return lbic_fail(LBIC_ERR_STATE, "weights not loaded: call lbic_load_weights first");
+    if (need_tables && !m->tables.cdf) return lbic_fail(LBIC_ERR_STATE, "Uninitialized CDFs. Run update() first");
+    if (!m->tables.d_scale_table) return lbic_fail(LBIC_ERR_STATE, "Uninitialized scale table. Run update() first");
+    return 0;
+}
+
+size_t stream_bound(const lbic_model *m, int Hb, int Wb, int lanes) {
+    if (lanes == 1) return 4 * ((size_t)Hb * Wb * m->M) + 64;
+    return 8 + 4 * (size_t)Hb + (size_t)Hb * (4 * ((size_t)Wb * m->M) + 64);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int lbic_create(const lbic_config *cfg, int device, lbic_model **out) {
+    if (!cfg || !out) return lbic_fail(LBIC_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return lbic_fail(LBIC_ERR_NO_DEVICE, "no CUDA device: liblbic_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return lbic_fail(LBIC_ERR_INVALID, "device %d out of range", device);
+    cudaDeviceProp prop;
+    LBIC_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return lbic_fail(LBIC_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                         prop.major, prop.minor);
+    if (cfg->ks[0] != 3 || (cfg->ks[1] != 1 && cfg->ks[1] != 3) || cfg->ks[2] != 1 || cfg->ks[3] != 1)
+        return lbic_fail(LBIC_ERR_INVALID, "unsupported KS [%d,%d,%d,%d]", cfg->ks[0], cfg->ks[1], cfg->ks[2], cfg->ks[3]);
+    if (cfg->ks[1] == 3)
+        return lbic_fail(LBIC_ERR_INVALID, "KS[1]=3 (5-tap entropy layer) is not implemented yet in this build");
+    if (cfg->block_size < 1 || cfg->n % 8 || cfg->n < 16 || cfg->m % 16 || cfg->m < 16 || cfg->m > 256 ||
+        (3 * cfg->block_size * cfg->block_size) % 16)
+        return lbic_fail(LBIC_ERR_INVALID, "unsupported sizes B=%d N=%d M=%d (need 3B^2, M multiples of 16)",
+                         cfg->block_size, cfg->n, cfg->m);
+    LBIC_CUDA(cudaSetDevice(device));
+    lbic_model *m = new lbic_model();
+    m->cfg = *cfg;
+    m->device = device;
+    m->Cin = 3 * cfg->block_size * cfg->block_size;
+    m->N = cfg->n; m->C2 = cfg->n / 8 * 7; m->C3 = cfg->n / 8 * 6; m->M = cfg->m;
+    m->E1 = cfg->n / 8 * 12; m->E2 = cfg->n / 8 * 10; m->E3 = cfg->n / 8 * 8; m->EO = 2 * cfg->m;
+    m->k1 = cfg->ks[1];
+    const int dims[] = {m->N, m->C2, m->C3, m->E1, m->E2, m->E3};
+    for (int d : dims)
+        if (d % 16) {
+            delete m;
+            return lbic_fail(LBIC_ERR_INVALID, "channel width %d is not a multiple of 16", d);
+        }
+    if (cudaMalloc(&m->err_flag, sizeof(int)) != cudaSuccess) {
+        delete m;
+        return lbic_fail(LBIC_ERR_NOMEM, "cudaMalloc failed");
+    }
+    cudaMemset(m->err_flag, 0, sizeof(int));
+    const char *core = getenv("LBIC_GEMM_CORE");
+    if (core && !strcmp(core, "simt")) m->gemm_core = 1;
+    *out = m;
+    return 0;
+}
+
+extern "C" void lbic_destroy(lbic_model *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    free_all(m->ws.allocs);
+    free_all(m->weight_allocs);
+    if (m->tables.cdf) { cudaFree(m->tables.cdf); cudaFree(m->tables.cdf_length); cudaFree(m->tables.offset); }
+    if (m->tables.d_scale_table) cudaFree(m->tables.d_scale_table);
+    if (m->err_flag) cudaFree(m->err_flag);
+    if (m->io_dev) cudaFree(m->io_dev);
+    for (auto &r : m->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    delete m;
+}
+
+extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
+    if (!m) return lbic_fail(LBIC_ERR_INVALID, "null model");
+    switch (option) {
+    case LBIC_OPT_GEMM_CORE:
+        if (value != 0 && value != 1) return lbic_fail(LBIC_ERR_INVALID, "gemm core must be 0 or 1");
+        m->gemm_core = value;
+        return 0;
+    case LBIC_OPT_USE_GRAPH:
+        m->use_graph = value ? 1 : 0;
+        return 0;
+    default:
+        return lbic_fail(LBIC_ERR_INVALID, "unknown option %d", option);
+    }
+}
+
+extern "C" int lbic_load_weights(lbic_model *m, const lbic_tensor_desc *tensors, int n_tensors, void *stream) {
+    if (!m || !tensors) return lbic_fail(LBIC_ERR_INVALID, "null argument");
+    Active act(m);
+    cudaStream_t st = (cudaStream_t)stream;
+    LBIC_TRY(gemm_tc_init());
+    SdView sd;
+    for (int i = 0; i < n_tensors; ++i)
+        if (tensors[i].name && tensors[i].data) sd.by_name[tensors[i].name] = &tensors[i];
+    LBIC_CUDA(cudaDeviceSynchronize());
+    free_all(m->weight_allocs);
+    m->weights_loaded = false;
+    std::vector<void *> tmp;
+    int rc = 0;
+    do {
+        const int Cin = m->Cin, N = m->N, C2 = m->C2, C3 = m->C3, M = m->M;
+#define P(call) if ((rc = (call)) != 0) break
+        P(pack_linear(m, sd, L_E0, "get_meanscale.0", m->E1, Cin, 3, TAPS_A, 4, tmp, st));
+        P(pack_linear(m, sd, L_E1, "get_meanscale.2", m->E2, m->E1, 1, TAPS_1, 1, tmp, st));
+        P(pack_linear(m, sd, L_E2, "get_meanscale.4", m->E3, m->E2, 1, TAPS_1, 1, tmp, st));
+        P(pack_linear(m, sd, L_E3, "get_meanscale.6", m->EO, m->E3, 1, TAPS_1, 1, tmp, st));
+        P(pack_dual(m, sd, L_F0, "prtr_forward1", Cin, "prtr_forward2", N, tmp, st));
+        P(pack_gdn(m, sd, L_G0, "prtr_forward3.0", N, tmp, st));
+        P(pack_linear(m, sd, L_F1, "prtr_forward3.1", C2, N, 1, TAPS_1, 1, tmp, st));
+        P(pack_gdn(m, sd, L_G1, "prtr_forward3.2", C2, tmp, st));
+        P(pack_linear(m, sd, L_F2, "prtr_forward3.3", C3, C2, 1, TAPS_1, 1, tmp, st));
+        P(pack_gdn(m, sd, L_G2, "prtr_forward3.4", C3, tmp, st));
+        P(pack_linear(m, sd, L_F3, "prtr_forward3.5", M, C3, 1, TAPS_1, 1, tmp, st));
+        P(pack_dual(m, sd, L_D0, "prtr_inverse1", M, "prtr_inverse2", N, tmp, st));
+        P(pack_gdn(m, sd, L_IG0, "prtr_inverse3.0", N, tmp, st));
+        P(pack_linear(m, sd, L_D1, "prtr_inverse3.1", C2, N, 1, TAPS_1, 1, tmp, st));
+        P(pack_gdn(m, sd, L_IG1, "prtr_inverse3.2", C2, tmp, st));
+        P(pack_linear(m, sd, L_D2, "prtr_inverse3.3", C3, C2, 1, TAPS_1, 1, tmp, st));
+        P(pack_gdn(m, sd, L_IG2, "prtr_inverse3.4", C3, tmp, st));
+        P(pack_linear(m, sd, L_D3, "prtr_inverse3.5", Cin, C3, 1, TAPS_1, 1, tmp, st));
+#undef P
+    } while (0);
+    cudaError_t e = cudaStreamSynchronize(st);
+    free_all(tmp);
+    if (rc) return rc;
+    if (e != cudaSuccess) return lbic_fail(LBIC_ERR_CUDA, "weight packing failed: %s", cudaGetErrorString(e));
+    m->weights_loaded = true;
+    (void)TAPS_B;
+    return 0;
+}
+
+extern "C" int lbic_build_tables(lbic_model *m, const float *scale_table, int n_levels, double tail_mass,
+                                 void *stream) {
+    if (!m || !scale_table) return lbic_fail(LBIC_ERR_INVALID, "null argument");
+    if (n_levels != 64) return lbic_fail(LBIC_ERR_INVALID, "the codec path uses a 64-level scale table (NET:13-18)");
+    Active act(m);
+    return tables_build(m->tables, scale_table, n_levels, tail_mass, (cudaStream_t)stream);
+}
+
+extern "C" int lbic_set_tables(lbic_model *m, const float *scale_table, int n_levels, const int32_t *cdf,
+                               int cdf_stride, const int32_t *cdf_length, const int32_t *offset) {
+    if (!m || !scale_table || !cdf || !cdf_length || !offset) return lbic_fail(LBIC_ERR_INVALID, "null argument");
+    if (n_levels != 64 || cdf_stride < 3) return lbic_fail(LBIC_ERR_INVALID, "bad table shape");
+    Active act(m);
+    Tables &T = m->tables;
+    LBIC_CUDA(cudaDeviceSynchronize());
+    if (T.cdf) { cudaFree(T.cdf); cudaFree(T.cdf_length); cudaFree(T.offset); T.cdf = nullptr; }
+    LBIC_CUDA(cudaMalloc(&T.cdf, sizeof(int32_t) * (size_t)n_levels * cdf_stride));
+    LBIC_CUDA(cudaMalloc(&T.cdf_length, sizeof(int32_t) * 64));
+    LBIC_CUDA(cudaMalloc(&T.offset, sizeof(int32_t) * 64));
+    LBIC_CUDA(cudaMemcpy(T.cdf, cdf, sizeof(int32_t) * (size_t)n_levels * cdf_stride, cudaMemcpyHostToDevice));
+    LBIC_CUDA(cudaMemcpy(T.cdf_length, cdf_length, sizeof(int32_t) * n_levels, cudaMemcpyHostToDevice));
+    LBIC_CUDA(cudaMemcpy(T.offset, offset, sizeof(int32_t) * n_levels, cudaMemcpyHostToDevice));
+    T.n_levels = n_levels; T.stride = cdf_stride;
+    for (int i = 0; i < 64; ++i) T.scale_table[i] = scale_table[i];
+    if (!T.d_scale_table) LBIC_CUDA(cudaMalloc(&T.d_scale_table, sizeof(float) * 64));
+    LBIC_CUDA(cudaMemcpy(T.d_scale_table, T.scale_table, sizeof(float) * 64, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int lbic_get_tables(lbic_model *m, int *n_levels, int *cdf_stride, int32_t *cdf, int32_t *cdf_length,
+                               int32_t *offset) {
+    if (!m) return lbic_fail(LBIC_ERR_INVALID, "null model");
+    Tables &T = m->tables;
+    if (!T.cdf) return lbic_fail(LBIC_ERR_STATE, "Uninitialized CDFs. Run update() first");
+    Active act(m);
+    if (n_levels) *n_levels = T.n_levels;
+    if (cdf_stride) *cdf_stride = T.stride;
+    LBIC_CUDA(cudaDeviceSynchronize());
+    if (cdf) LBIC_CUDA(cudaMemcpy(cdf, T.cdf, sizeof(int32_t) * (size_t)T.n_levels * T.stride, cudaMemcpyDeviceToHost));
+    if (cdf_length) LBIC_CUDA(cudaMemcpy(cdf_length, T.cdf_length, sizeof(int32_t) * T.n_levels, cudaMemcpyDeviceToHost));
+    if (offset) LBIC_CUDA(cudaMemcpy(offset, T.offset, sizeof(int32_t) * T.n_levels, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" size_t lbic_stream_bound(const lbic_model *m, int Hb, int Wb, int lanes) {
+    if (!m) return 0;
+    return stream_bound(m, Hb, Wb, lanes == 1 ? 1 : Hb);
+}
+
+extern "C" int lbic_encode(lbic_model *m, const float *x, int n_img, int Hb, int Wb, float *zhat_out,
+                           int32_t *sym_out, uint8_t *idx_out, uint8_t *stream_out, size_t stream_cap,
+                           uint32_t *stream_len, int lanes, void *stream) {
+    LBIC_TRY(check_ready(m, stream_out != nullptr));
+    if (!x || n_img < 1 || Hb < 1 || Wb < 1) return lbic_fail(LBIC_ERR_INVALID, "bad arguments");
+    if (lanes != 0 && lanes != 1) return lbic_fail(LBIC_ERR_INVALID, "lanes must be 1 (reference) or 0 (per block row)");
+    if (stream_out && (!stream_len || stream_cap % 4)) return lbic_fail(LBIC_ERR_INVALID, "stream_cap must be a multiple of 4");
+    Active act(m);
+    cudaStream_t st = (cudaStream_t)stream;
+    LBIC_TRY(ensure_workspace(m, n_img, Hb, Wb));
+    Workspace &ws = m->ws;
+    const int HW = Hb * Wb;
+    const size_t nblk = (size_t)n_img * HW;
+    LBIC_TRY(launch_nchw_to_cl(x, ws.x_cl, n_img, m->Cin, HW, st));
+    LBIC_CUDA(cudaMemsetAsync(ws.zhat_cl, 0, sizeof(float) * nblk * m->Cin, st));   // NET:336
+    const bool want_syms = sym_out || idx_out || stream_out;
+    const int T_steps = Wb + 2 * (Hb - 1);
+    for (int t = 0; t < T_steps; ++t) {
+        StepDesc sd;
+        if (!wave_step(t, n_img, Hb, Wb, sd)) continue;
+        const int R = n_img * sd.nv;
+        LBIC_TRY(launch_gather(ws.x_cl, ws.zhat_cl, m->Cin, sd, R, ws.X.hi, ws.X.lo, ws.X.ld, ws.T.hi, ws.T.lo, ws.T.ld, st));
+        LBIC_TRY(run_ent(m, sd, R, st));
+        LBIC_TRY(run_enc(m, sd, R, want_syms ? ws.sym : nullptr, want_syms ? ws.idx : nullptr, st));
+        LBIC_TRY(run_dec(m, sd, R, st));
+    }
+    if (zhat_out) LBIC_TRY(launch_cl_to_nchw(ws.zhat_cl, zhat_out, n_img, m->Cin, HW, st));
+    if (sym_out) LBIC_CUDA(cudaMemcpyAsync(sym_out, ws.sym, sizeof(int32_t) * nblk * m->M, cudaMemcpyDeviceToDevice, st));
+    if (idx_out) LBIC_CUDA(cudaMemcpyAsync(idx_out, ws.idx, nblk * m->M, cudaMemcpyDeviceToDevice, st));
+    if (stream_out) {
+        const int L = lanes == 1 ? 1 : Hb;
+        const int n_streams = n_img * L;
+        const int64_t n_sym = (int64_t)HW * m->M / L;
+        const size_t per = (lanes == 1 ? stream_cap : (4 * (size_t)n_sym + 64)) / 4;   // scratch words per stream
+        LBIC_TRY(ensure_rans_scratch(m, (size_t)n_streams * per + 2 * (size_t)n_streams));
+        LBIC_TRY(launch_rans_encode(m->tables, ws.sym, ws.idx, n_streams, n_sym, n_sym, ws.rans_scratch, per,
+                                    lanes == 1 ? stream_out : nullptr, stream_cap, stream_len, m->err_flag, st));
+        if (lanes != 1)
+            LBIC_TRY(launch_lane_pack(ws.rans_scratch, per, n_img, L, stream_out, stream_cap, stream_len, m->err_flag, st));
+    }
+    return 0;
+}
+
+extern "C" int lbic_decode(lbic_model *m, const uint8_t *streams, const uint32_t *stream_len, size_t stream_cap,
+                           int n_img, int Hb, int Wb, float *zhat_out, int32_t *sym_out, int lanes, void *stream) {
+    LBIC_TRY(check_ready(m, true));
+    if (!streams || !stream_len || n_img < 1 || Hb < 1 || Wb < 1) return lbic_fail(LBIC_ERR_INVALID, "bad arguments");
+    if (lanes != 0 && lanes != 1) return lbic_fail(LBIC_ERR_INVALID, "lanes must be 1 (reference) or 0 (per block row)");
+    if (stream_cap % 4) return lbic_fail(LBIC_ERR_INVALID, "stream_cap must be a multiple of 4");
+    Active act(m);
+    cudaStream_t st = (cudaStream_t)stream;
+    LBIC_TRY(ensure_workspace(m, n_img, Hb, Wb));
+    Workspace &ws = m->ws;
+    const int HW = Hb * Wb;
+    const size_t nblk = (size_t)n_img * HW;
+    const int L = lanes == 1 ? 1 : Hb;
+    LBIC_CUDA(cudaMemsetAsync(ws.zhat_cl, 0, sizeof(float) * nblk * m->Cin, st));   // NET:417
+    LBIC_TRY(launch_rans_dec_init(streams, stream_len, stream_cap, n_img, L, ws.dec_states, ws.lane_ptr, m->err_flag, st));
+    auto one_step = [&](const StepDesc &sd, int R) -> int {
+        LBIC_TRY(launch_gather(nullptr, ws.zhat_cl, m->Cin, sd, R, nullptr, nullptr, 0, ws.T.hi, ws.T.lo, ws.T.ld, st));
+        LBIC_TRY(run_ent(m, sd, R, st));
+        LBIC_TRY(launch_rans_dec_step(m->tables, ws.dec_states, ws.lane_ptr, L, sd, R, m->M, ws.KSI, ws.ldKSI, ws.YQ.hi,
+                                      ws.YQ.lo, ws.YQ.ld, sym_out ? ws.sym : nullptr, st));
+        LBIC_TRY(run_dec(m, sd, R, st));
+        return 0;
+    };
+    if (L == 1) {
+        // reference container: the rANS state threads through the blocks in raster order (NET:420-450)
+        for (int v = 0; v < Hb; ++v)
+            for (int h = 0; h < Wb; ++h) {
+                StepDesc sd{n_img, 1, v, h + 2 * v, Hb, Wb};
+                LBIC_TRY(one_step(sd, n_img));
+            }
+    } else {
+        const int T_steps = Wb + 2 * (Hb - 1);
+        for (int t = 0; t < T_steps; ++t) {
+            StepDesc sd;
+            if (!wave_step(t, n_img, Hb, Wb, sd)) continue;
+            LBIC_TRY(one_step(sd, n_img * sd.nv));
+        }
+    }
+    if (zhat_out) LBIC_TRY(launch_cl_to_nchw(ws.zhat_cl, zhat_out, n_img, m->Cin, HW, st));
+    if (sym_out) LBIC_CUDA(cudaMemcpyAsync(sym_out, ws.sym, sizeof(int32_t) * nblk * m->M, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+namespace {
+int ensure_io(lbic_model *m, size_t bytes) {
+    if (m->io_bytes >= bytes) return 0;
+    if (m->io_dev) { cudaDeviceSynchronize(); cudaFree(m->io_dev); m->io_dev = nullptr; m->io_bytes = 0; }
+    cudaError_t e = cudaMalloc(&m->io_dev, bytes);
+    if (e != cudaSuccess) return lbic_fail(LBIC_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    m->io_bytes = bytes;
+    return 0;
+}
+size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+int check_async(lbic_model *m) {
+    int flag = 0;
+    LBIC_CUDA(cudaMemcpy(&flag, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+        cudaMemset(m->err_flag, 0, sizeof(int));
+        return lbic_fail(flag == 1 ? LBIC_ERR_OVERFLOW : LBIC_ERR_INVALID,
+                         flag == 1 ? "bitstream buffer too small (stream_cap)" : "malformed lane container");
+    }
+    return 0;
+}
+}  // namespace
+
+extern "C" int lbic_encode_host(lbic_model *m, const float *x, int n_img, int Hb, int Wb, float *zhat_out,
+                                uint8_t *stream_out, size_t stream_cap, uint32_t *stream_len, int lanes) {
+    LBIC_TRY(check_ready(m, stream_out != nullptr));
+    if (!x) return lbic_fail(LBIC_ERR_INVALID, "null input");
+    Active act(m);
+    const size_t nx = sizeof(float) * (size_t)n_img * m->Cin * Hb * Wb;
+    const size_t o_x = 0, o_z = align256(nx), o_len = o_z + align256(nx), o_s = o_len + align256(4 * (size_t)n_img);
+    LBIC_TRY(ensure_io(m, o_s + (stream_out ? (size_t)n_img * stream_cap : 0)));
+    uint8_t *io = (uint8_t *)m->io_dev;
+    cudaStream_t st = 0;
+    LBIC_CUDA(cudaMemcpyAsync(io + o_x, x, nx, cudaMemcpyHostToDevice, st));
+    LBIC_TRY(lbic_encode(m, (const float *)(io + o_x), n_img, Hb, Wb, zhat_out ? (float *)(io + o_z) : nullptr, nullptr,
+                         nullptr, stream_out ? io + o_s : nullptr, stream_cap, (uint32_t *)(io + o_len), lanes, st));
+    Active act2(m);
+    if (zhat_out) LBIC_CUDA(cudaMemcpyAsync(zhat_out, io + o_z, nx, cudaMemcpyDeviceToHost, st));
+    if (stream_out) {
+        LBIC_CUDA(cudaMemcpyAsync(stream_len, io + o_len, 4 * (size_t)n_img, cudaMemcpyDeviceToHost, st));
+        LBIC_CUDA(cudaStreamSynchronize(st));
+        LBIC_TRY(check_async(m));
+        for (int i = 0; i < n_img; ++i)
+            LBIC_CUDA(cudaMemcpyAsync(stream_out + (size_t)i * stream_cap, io + o_s + (size_t)i * stream_cap,
+                                      stream_len[i], cudaMemcpyDeviceToHost, st));
+    }
+    LBIC_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int lbic_decode_host(lbic_model *m, const uint8_t *streams, const uint32_t *stream_len, size_t stream_cap,
+                                int n_img, int Hb, int Wb, float *zhat_out, int lanes) {
+    LBIC_TRY(check_ready(m, true));
+    if (!streams || !stream_len || !zhat_out) return lbic_fail(LBIC_ERR_INVALID, "null argument");
+    Active act(m);
+    const size_t nx = sizeof(float) * (size_t)n_img * m->Cin * Hb * Wb;
+    const size_t o_z = 0, o_len = align256(nx), o_s = o_len + align256(4 * (size_t)n_img);
+    LBIC_TRY(ensure_io(m, o_s + (size_t)n_img * stream_cap));
+    uint8_t *io = (uint8_t *)m->io_dev;
+    cudaStream_t st = 0;
+    LBIC_CUDA(cudaMemcpyAsync(io + o_len, stream_len, 4 * (size_t)n_img, cudaMemcpyHostToDevice, st));
+    for (int i = 0; i < n_img; ++i) {
+        if (stream_len[i] > stream_cap) return lbic_fail(LBIC_ERR_INVALID, "stream %d longer than stream_cap", i);
+        LBIC_CUDA(cudaMemcpyAsync(io + o_s + (size_t)i * stream_cap, streams + (size_t)i * stream_cap, stream_len[i],
+                                  cudaMemcpyHostToDevice, st));
+    }
+    LBIC_TRY(lbic_decode(m, io + o_s, (const uint32_t *)(io + o_len), stream_cap, n_img, Hb, Wb, (float *)(io + o_z),
+                         nullptr, lanes, st));
+    Active act2(m);
+    LBIC_CUDA(cudaMemcpyAsync(zhat_out, io + o_z, nx, cudaMemcpyDeviceToHost, st));
+    LBIC_CUDA(cudaStreamSynchronize(st));
+    LBIC_TRY(check_async(m));
+    return 0;
+}
+
+extern "C" int lbic_space_to_depth(const float *img, float *blk, int n, int C, int Hb, int Wb, int B, void *stream) {
+    if (!img || !blk) return lbic_fail(LBIC_ERR_INVALID, "null argument");
+    return launch_space_to_depth(img, blk, n, C, Hb, Wb, B, (cudaStream_t)stream);
+}
+
+extern "C" int lbic_depth_to_space(const float *blk, float *img, int n, int C, int Hb, int Wb, int B, void *stream) {
+    if (!img || !blk) return lbic_fail(LBIC_ERR_INVALID, "null argument");
+    return launch_depth_to_space(blk, img, n, C, Hb, Wb, B, (cudaStream_t)stream);
+}
+
+extern "C" int lbic_rans_encode(lbic_model *m, const int32_t *symbols, const uint8_t *indexes, int n_streams,
+                                int64_t n_sym, uint8_t *stream_out, size_t stream_cap, uint32_t *stream_len,
+                                void *stream) {
+    if (!m || !symbols || !indexes || !stream_out || !stream_len) return lbic_fail(LBIC_ERR_INVALID, "null argument");
+    if (!m->tables.cdf) return lbic_fail(LBIC_ERR_STATE, "Uninitialized CDFs. Run update() first");
+    if (stream_cap % 4) return lbic_fail(LBIC_ERR_INVALID, "stream_cap must be a multiple of 4");
+    Active act(m);
+    if (m->ws.n_img == 0) LBIC_TRY(ensure_workspace(m, 1, 1, 2));
+    const size_t per = stream_cap / 4;
+    LBIC_TRY(ensure_rans_scratch(m, (size_t)n_streams * per + 2 * (size_t)n_streams));
+    return launch_rans_encode(m->tables, symbols, indexes, n_streams, n_sym, n_sym, m->ws.rans_scratch, per, stream_out,
+                              stream_cap, stream_len, m->err_flag, (cudaStream_t)stream);
+}
+
+extern "C" int lbic_rans_decode(lbic_model *m, const uint8_t *streams, const uint32_t *stream_len, size_t stream_cap,
+                                const uint8_t *indexes, int n_streams, int64_t n_sym, int32_t *symbols_out,
+                                void *stream) {
+    if (!m || !streams || !stream_len || !indexes || !symbols_out) return lbic_fail(LBIC_ERR_INVALID, "null argument");
+    Active act(m);
+    return launch_rans_decode_full(m->tables, streams, stream_len, stream_cap, indexes, n_streams, n_sym, symbols_out,
+                                   (cudaStream_t)stream);
+}
+
+extern "C" int lbic_debug_gemm(lbic_model *m, const float *A, const float *W, float *D, int R, int K, int cout,
+                               void *stream) {
+    if (!m || !A || !W || !D) return lbic_fail(LBIC_ERR_INVALID, "null argument");
+    if (K % 8 || cout % 16) return lbic_fail(LBIC_ERR_INVALID, "debug gemm needs K %% 8 == 0 and cout %% 16 == 0");
+    Active act(m);
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<void *> tmp;
+    bf16 *ah, *al, *wh, *wl;
+    int rc = 0;
+    do {
+#define P(call) if ((rc = (call)) != 0) break
+        P(dev_alloc(tmp, (void **)&ah, sizeof(bf16) * (size_t)R * K));
+        P(dev_alloc(tmp, (void **)&al, sizeof(bf16) * (size_t)R * K));
+        P(dev_alloc(tmp, (void **)&wh, sizeof(bf16) * (size_t)cout * K));
+        P(dev_alloc(tmp, (void **)&wl, sizeof(bf16) * (size_t)cout * K));
+        P(launch_split_f32(A, ah, al, (int64_t)R * K, st));
+        P(launch_split_f32(W, wh, wl, (int64_t)cout * K, st));
+        GemmCall g;
+        memset(&g, 0, sizeof(g));
+        g.R = R; g.cout = cout; g.bn = pick_bn(cout); g.nseg = 1; g.K[0] = K;
+        CUtensorMap ta_h, ta_l, tw_h, tw_l;
+        P(make_tmap_2d(&ta_h, ah, K, R, K, 64, 128));
+        P(make_tmap_2d(&ta_l, al, K, R, K, 64, 128));
+        P(make_tmap_2d(&tw_h, wh, K, cout, K, 64, g.bn));
+        P(make_tmap_2d(&tw_l, wl, K, cout, K, 64, g.bn));
+        g.A[0].hi = ah; g.A[0].lo = al; g.A[0].ld = K; g.A[0].tm_hi = &ta_h; g.A[0].tm_lo = &ta_l;
+        g.W[0].hi = wh; g.W[0].lo = wl; g.W[0].ld = K; g.W[0].tm_hi = &tw_h; g.W[0].tm_lo = &tw_l;
+        g.ep.mode = EPI_RAW; g.ep.R = R; g.ep.cout = cout; g.ep.out_f32 = D; g.ep.ld_f32 = cout;
+        P(m->gemm_core == 1 ? gemm_simt_launch(g, st) : gemm_tc_launch(g, st));
+#undef P
+    } while (0);
+    cudaError_t e = cudaStreamSynchronize(st);
+    free_all(tmp);
+    if (rc) return rc;
+    if (e != cudaSuccess) return lbic_fail(LBIC_ERR_CUDA, "debug gemm failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int64_t lbic_launch_count(const lbic_model *m) { return m ? m->launches[0] + m->launches[1] : 0; }
+
+extern "C" int lbic_set_profiling(lbic_model *m, int enabled) {
+    if (!m) return lbic_fail(LBIC_ERR_INVALID, "null model");
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    for (auto &r : m->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    m->prof.clear();
+    m->profiling = enabled ? 1 : 0;
+    return 0;
+}
+
+extern "C" int lbic_get_profile(lbic_model *m, int64_t *gemm_launches, double *gemm_ms, double *gemm_flops) {
+    if (!m) return lbic_fail(LBIC_ERR_INVALID, "null model");
+    cudaSetDevice(m->device);
+    LBIC_CUDA(cudaDeviceSynchronize());
+    double ms = 0, fl = 0;
+    for (auto &r : m->prof) {
+        float t = 0;
+        LBIC_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+        ms += t;
+        fl += r.flops;
+    }
+    if (gemm_launches) *gemm_launches = (int64_t)m->prof.size();
+    if (gemm_ms) *gemm_ms = ms;
+    if (gemm_flops) *gemm_flops = fl;
+    return 0;
+}

@@ -1,0 +1,290 @@
+// tcgen05 / TMEM / TMA GEMM core with fused layer epilogues (sm_100a only).
+//
+// D[R, cout] = sum over K segments of A_s[R, K_s] * W_s[cout, K_s]^T, fp32-grade accuracy from
+// bf16 tensor-core passes: every operand is stored as two bf16 planes (hi = bf16(v),
+// lo = bf16(v - hi)) and each 16-wide k-step issues three MMAs into one TMEM accumulator,
+//     Ahi*Whi + Ahi*Wlo + Alo*Whi          (the lo*lo term, ~2^-32 relative, is dropped),
+// in a fixed order, with no split-K: a row's result depends only on that row's inputs, never on
+// the tile it shares or on whether the encoder or the decoder computes it.
+//
+// CTA = one 128 x bn output tile (bn a multiple of 16, <= 256).  Warp roles:
+//   warp 0      TMA producer: per 64-wide k-block loads A hi/lo [128x64] and W hi/lo [bn x 64]
+//               (SWIZZLE_128B, K-major) into a multi-stage ring, mbarrier complete_tx
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit frees stages
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 16 columns at a time -> fused epilogue -> global
+#include "epilogue.cuh"
+
+#include <cstdio>
+#include <cstring>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_PLANE = BM * BK * 2;     // 16 KiB per bf16 plane
+constexpr int MAX_STAGES = 4;
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_LIMIT = 232448;       // 227 KiB opt-in maximum per CTA
+constexpr int SMEM_SLACK = 1024 + 256;   // 1024-B alignment of the ring + barrier block
+
+struct TcParams {
+    int kb[2];          // k-blocks per segment
+    int bn;
+    int stages;
+    uint32_t tmem_cols;
+    uint32_t idesc;
+    EpiParams ep;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a descriptor/transaction-count bug must fail the launch, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 22)) __trap();
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: 8-row atoms of 1024 B (SBO), LBO unused (1),
+// descriptor version 1 (sm_100), layout type 2.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant__ CUtensorMap tmA0l,
+               const __grid_constant__ CUtensorMap tmW0h, const __grid_constant__ CUtensorMap tmW0l,
+               const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
+               const __grid_constant__ CUtensorMap tmW1h, const __grid_constant__ CUtensorMap tmW1l,
+               const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t ring = (raw + 1023u) & ~1023u;                     // SWIZZLE_128B needs 1024-B alignment
+    const uint32_t w_plane = (uint32_t)p.bn * (BK * 2);
+    const uint32_t stage_bytes = 2 * A_PLANE + 2 * w_plane;
+    const uint32_t bars = ring + p.stages * stage_bytes;              // 8-B aligned (multiple of 1024)
+    // barrier block: full[4] | empty[4] | tmem_full | tmem base address
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (MAX_STAGES + s); };
+    const uint32_t tmem_full_bar = bars + 8u * (2 * MAX_STAGES);
+    const uint32_t tmem_slot = bars + 8u * (2 * MAX_STAGES + 1);
+    volatile uint32_t *tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * p.bn;
+    const int nkb = p.kb[0] + p.kb[1];
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA0h)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW0h)) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                     "r"(p.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_expect_tx(full_bar(s), stage_bytes);
+                const uint32_t sa = ring + s * stage_bytes;
+                const bool seg1 = kb >= p.kb[0];
+                const int kk = (seg1 ? kb - p.kb[0] : kb) * BK;
+                tma_load_2d(sa, seg1 ? &tmA1h : &tmA0h, full_bar(s), kk, m0);
+                tma_load_2d(sa + A_PLANE, seg1 ? &tmA1l : &tmA0l, full_bar(s), kk, m0);
+                tma_load_2d(sa + 2 * A_PLANE, seg1 ? &tmW1h : &tmW0h, full_bar(s), kk, n0);
+                tma_load_2d(sa + 2 * A_PLANE + w_plane, seg1 ? &tmW1l : &tmW0l, full_bar(s), kk, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t sa = ring + s * stage_bytes;
+                const uint64_t a_hi = make_smem_desc(sa);
+                const uint64_t a_lo = make_smem_desc(sa + A_PLANE);
+                const uint64_t w_hi = make_smem_desc(sa + 2 * A_PLANE);
+                const uint64_t w_lo = make_smem_desc(sa + 2 * A_PLANE + w_plane);
+                // each k16 step advances the start address by 32 B (= 2 in 16-B units)
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                    umma_bf16(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, p.idesc, 1u);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, p.idesc, 1u);
+                umma_commit(empty_bar(s));   // frees the stage once these MMAs have read it
+            }
+            umma_commit(tmem_full_bar);      // accumulator complete
+        }
+    } else {
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;                  // TMEM lane quarter this warp may access
+        const int r = m0 + q * 32 + lane;
+        const uint32_t lane_base = tmem_acc + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < p.bn; c0 += 16) {
+            float v[16];
+            tmem_ld_x16(lane_base + (uint32_t)c0, v);
+            const int c = n0 + c0;
+            if (r < p.ep.R && c < p.ep.cout) epilogue_store<16>(p.ep, r, c, v);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(p.tmem_cols)
+                     : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+
+}  // namespace
+
+int gemm_tc_init() {
+    if (g_encode_tiled) return 0;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    LBIC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess)
+        return lbic_fail(LBIC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+    LBIC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    return 0;
+}
+
+// bf16 row-major [outer][ld_elems] matrix, logical inner extent `inner`; out-of-bounds box elements
+// read as zero.
+int make_tmap_2d(CUtensorMap *tm, const void *base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                 uint32_t box_inner, uint32_t box_outer) {
+    LBIC_TRY(gemm_tc_init());
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld_elems * 2) & 15))
+        return lbic_fail(LBIC_ERR_INVALID, "TMA operand must be 16-byte aligned (base %p, ld %llu)", base,
+                         (unsigned long long)ld_elems);
+    cuuint64_t gdim[2] = {inner, outer};
+    cuuint64_t gstride[1] = {ld_elems * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult rc = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstride, box,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return lbic_fail(LBIC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)rc);
+    return 0;
+}
+
+int gemm_tc_launch(const GemmCall &g, cudaStream_t st) {
+    if (g.R <= 0) return 0;
+    LBIC_TRY(gemm_tc_init());
+    if (g.bn % 16 || g.bn < 16 || g.bn > 256) return lbic_fail(LBIC_ERR_INVALID, "bad tile N %d", g.bn);
+    TcParams p;
+    p.kb[0] = (g.K[0] + BK - 1) / BK;
+    p.kb[1] = g.nseg > 1 ? (g.K[1] + BK - 1) / BK : 0;
+    p.bn = g.bn;
+    const int stage_bytes = 2 * A_PLANE + 2 * g.bn * BK * 2;
+    int stages = (SMEM_LIMIT - SMEM_SLACK) / stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) return lbic_fail(LBIC_ERR_INVALID, "tile does not fit shared memory");
+    p.stages = stages;
+    uint32_t cols = 32;
+    while ((int)cols < g.bn) cols <<= 1;
+    p.tmem_cols = cols;
+    // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=bn, M=128
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    p.ep = g.ep;
+    const int s1 = g.nseg > 1 ? 1 : 0;
+    dim3 grid((g.R + BM - 1) / BM, (g.cout + g.bn - 1) / g.bn);
+    const size_t smem = (size_t)stages * stage_bytes + SMEM_SLACK;
+    gemm_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(*g.A[0].tm_hi, *g.A[0].tm_lo, *g.W[0].tm_hi, *g.W[0].tm_lo,
+                                                    *g.A[s1].tm_hi, *g.A[s1].tm_lo, *g.W[s1].tm_hi, *g.W[s1].tm_lo, p);
+    count_launch(0);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}

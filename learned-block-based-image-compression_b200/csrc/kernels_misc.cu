@@ -1,0 +1,227 @@
+// Layout, gather and weight-packing kernels (HBM-bound byte movers around the GEMM chain).
+#include "epilogue.cuh"
+
+namespace {
+
+// ---- (n, C, HW) <-> (n, HW, C) transposes -----------------------------------------------------
+__global__ void transpose_kernel(const float *__restrict__ src, float *__restrict__ dst, int rows, int cols) {
+    // src: [batch][rows][cols] -> dst: [batch][cols][rows]
+    __shared__ float tile[32][33];
+    const size_t base = (size_t)blockIdx.z * rows * cols;
+    int c = blockIdx.x * 32 + threadIdx.x;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        int r = blockIdx.y * 32 + j;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = src[base + (size_t)r * cols + c];
+    }
+    __syncthreads();
+    int r2 = blockIdx.y * 32 + threadIdx.x;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        int c2 = blockIdx.x * 32 + j;
+        if (r2 < rows && c2 < cols) dst[base + (size_t)c2 * rows + r2] = tile[threadIdx.x][j];
+    }
+}
+
+// ---- arrange_block_pixels_to_channel_dim / inverse (AGENT:853-873) ------------------------------
+// blk[n][(bv*B+bh)*C + c][v][h] = img[n][c][v*B+bv][h*B+bh]
+template <bool TO_DEPTH>
+__global__ void space_depth_kernel(const float *__restrict__ src, float *__restrict__ dst, int n, int C, int Hb, int Wb,
+                                   int B) {
+    const size_t total = (size_t)n * C * Hb * B * Wb * B;
+    const int W = Wb * B, H = Hb * B;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        // i indexes the image tensor (n, C, H, W)
+        int x = (int)(i % W);
+        size_t t = i / W;
+        int y = (int)(t % H);
+        t /= H;
+        int c = (int)(t % C);
+        int b = (int)(t / C);
+        int v = y / B, bv = y % B, h = x / B, bh = x % B;
+        size_t j = (((size_t)b * (C * B * B) + (size_t)(bv * B + bh) * C + c) * Hb + v) * Wb + h;
+        if (TO_DEPTH) dst[j] = src[i]; else dst[i] = src[j];
+    }
+}
+
+__global__ void split_kernel(const float *__restrict__ src, bf16 *__restrict__ hi, bf16 *__restrict__ lo, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        bf16 h, l;
+        split_bf16(src[i], h, l);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
+// ---- per-step gather ----------------------------------------------------------------------------
+// Row r = block (img, v, h) of the step.  X[r, :] = x(v,h); T[r, tap*Cin + c] = zhat(v+dv, h+dh)[c] for the
+// four live taps of a 3x3 mask-'A' kernel, (dv,dh) = (-1,-1), (-1,0), (-1,+1), (0,-1) (masked_conv2d.py:12-17),
+// zero outside the image (NET:349).
+__global__ void gather_kernel(const float *__restrict__ x_cl, const float *__restrict__ zhat_cl, int Cin, StepDesc s,
+                              int R, bf16 *__restrict__ X_hi, bf16 *__restrict__ X_lo, int ldX,
+                              bf16 *__restrict__ T_hi, bf16 *__restrict__ T_lo, int ldT) {
+    const int r = blockIdx.x;
+    if (r >= R) return;
+    int img, v, h;
+    step_row_to_block(s, r, img, v, h);
+    const int c4n = Cin >> 2;
+    const int first = X_hi ? 0 : 1;
+    for (int e = threadIdx.x + first * c4n; e < 5 * c4n; e += blockDim.x) {
+        const int seg = e / c4n, c = (e - seg * c4n) << 2;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        bf16 *ph, *pl;
+        if (seg == 0) {
+            val = *reinterpret_cast<const float4 *>(x_cl + (((size_t)img * s.Hb + v) * s.Wb + h) * Cin + c);
+            ph = X_hi + (size_t)r * ldX + c;
+            pl = X_lo + (size_t)r * ldX + c;
+        } else {
+            const int tap = seg - 1;
+            const int dv = (tap == 3) ? 0 : -1;
+            const int dh = (tap == 3) ? -1 : tap - 1;
+            const int vv = v + dv, hh = h + dh;
+            if (vv >= 0 && vv < s.Hb && hh >= 0 && hh < s.Wb)
+                val = *reinterpret_cast<const float4 *>(zhat_cl + (((size_t)img * s.Hb + vv) * s.Wb + hh) * Cin + c);
+            ph = T_hi + (size_t)r * ldT + tap * Cin + c;
+            pl = T_lo + (size_t)r * ldT + tap * Cin + c;
+        }
+        const float f[4] = {val.x, val.y, val.z, val.w};
+        store_hilo<4>(ph, pl, f);
+    }
+}
+
+// ---- weight packing -------------------------------------------------------------------------------
+struct TapList {
+    int n;
+    int kh[8], kw[8];
+};
+
+// out[co][t*cin + ci] = w[co][ci][kh_t][kw_t] * mask[co][ci][kh_t][kw_t]      (NET:381 weight * mask)
+__global__ void pack_conv_kernel(const float *__restrict__ w, const float *__restrict__ mask, int cout, int cin, int KH,
+                                 int KW, TapList taps, bf16 *__restrict__ hi, bf16 *__restrict__ lo, int ld) {
+    const size_t total = (size_t)cout * taps.n * cin;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % cin);
+        const int t = (int)((i / cin) % taps.n);
+        const int co = (int)(i / ((size_t)cin * taps.n));
+        const size_t src = (((size_t)co * cin + ci) * KH + taps.kh[t]) * KW + taps.kw[t];
+        const float val = w[src] * (mask ? mask[src] : 1.0f);
+        bf16 h, l;
+        split_bf16(val, h, l);
+        const size_t dst = (size_t)co * ld + (size_t)t * cin + ci;
+        hi[dst] = h;
+        lo[dst] = l;
+    }
+}
+
+// NonNegativeParametrizer.forward: max(p, bound)^2 - pedestal   (utils/parametrizers.py:45-48)
+__global__ void pack_gdn_kernel(const float *__restrict__ gamma, const float *__restrict__ beta, int C, float gbound,
+                                float gped, float bbound, float bped, bf16 *__restrict__ hi, bf16 *__restrict__ lo,
+                                int ld, float *__restrict__ beta_out) {
+    const size_t total = (size_t)C * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int rI = (int)(i / C), cI = (int)(i % C);
+        const float g = fmaxf(gamma[i], gbound);
+        const float val = g * g - gped;
+        bf16 h, l;
+        split_bf16(val, h, l);
+        hi[(size_t)rI * ld + cI] = h;
+        lo[(size_t)rI * ld + cI] = l;
+        if (i < (size_t)C) {
+            const float b = fmaxf(beta[i], bbound);
+            beta_out[i] = b * b - bped;
+        }
+    }
+}
+
+__global__ void add_vec_kernel(const float *a, const float *b, float *out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + (b ? b[i] : 0.0f);
+}
+
+inline int grid_for(size_t total, int block) {
+    size_t g = (total + block - 1) / block;
+    if (g > 148 * 16) g = 148 * 16;   // grid-stride loops; a multiple of the SM count
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace
+
+int launch_nchw_to_cl(const float *src, float *dst, int n, int C, int HW, cudaStream_t st) {
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, n), block(32, 8);
+    transpose_kernel<<<grid, block, 0, st>>>(src, dst, C, HW);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_cl_to_nchw(const float *src, float *dst, int n, int C, int HW, cudaStream_t st) {
+    dim3 grid((C + 31) / 32, (HW + 31) / 32, n), block(32, 8);
+    transpose_kernel<<<grid, block, 0, st>>>(src, dst, HW, C);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_space_to_depth(const float *img, float *blk, int n, int C, int Hb, int Wb, int B, cudaStream_t st) {
+    const size_t total = (size_t)n * C * Hb * B * Wb * B;
+    space_depth_kernel<true><<<grid_for(total, 256), 256, 0, st>>>(img, blk, n, C, Hb, Wb, B);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_depth_to_space(const float *blk, float *img, int n, int C, int Hb, int Wb, int B, cudaStream_t st) {
+    const size_t total = (size_t)n * C * Hb * B * Wb * B;
+    space_depth_kernel<false><<<grid_for(total, 256), 256, 0, st>>>(blk, img, n, C, Hb, Wb, B);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_split_f32(const float *src, bf16 *hi, bf16 *lo, int64_t n, cudaStream_t st) {
+    split_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(src, hi, lo, (size_t)n);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_gather(const float *x_cl, const float *zhat_cl, int Cin, const StepDesc &s, int R, bf16 *X_hi, bf16 *X_lo,
+                  int ldX, bf16 *T_hi, bf16 *T_lo, int ldT, cudaStream_t st) {
+    if (R <= 0) return 0;
+    int threads = 5 * (Cin / 4);
+    threads = threads > 256 ? 256 : ((threads + 31) / 32) * 32;
+    gather_kernel<<<R, threads, 0, st>>>(x_cl, zhat_cl, Cin, s, R, X_hi, X_lo, ldX, T_hi, T_lo, ldT);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_pack_conv(const float *w, const float *mask, int cout, int cin, int kh, int kw, const int *taps_host,
+                     int ntaps, bf16 *hi, bf16 *lo, int ld, cudaStream_t st) {
+    TapList tl;
+    tl.n = ntaps;
+    for (int i = 0; i < ntaps; ++i) {
+        tl.kh[i] = taps_host[2 * i];
+        tl.kw[i] = taps_host[2 * i + 1];
+    }
+    const size_t total = (size_t)cout * ntaps * cin;
+    pack_conv_kernel<<<grid_for(total, 256), 256, 0, st>>>(w, mask, cout, cin, kh, kw, tl, hi, lo, ld);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_pack_gdn(const float *gamma, const float *beta, int C, float gbound, float gped, float bbound, float bped,
+                    bf16 *hi, bf16 *lo, int ld, float *beta_out, cudaStream_t st) {
+    pack_gdn_kernel<<<grid_for((size_t)C * C, 256), 256, 0, st>>>(gamma, beta, C, gbound, gped, bbound, bped, hi, lo, ld,
+                                                                beta_out);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_add_vec(const float *a, const float *b, float *out, int n, cudaStream_t st) {
+    add_vec_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, b, out, n);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,158 @@
+// Internal declarations shared by the translation units of liblbic_b200.so.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/lbic.h"
+
+typedef __nv_bfloat16 bf16;
+
+int lbic_fail(int code, const char *fmt, ...);
+
+#define LBIC_CUDA(call)                                                                        \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return lbic_fail(LBIC_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,       \
+                             cudaGetErrorString(e__));                                         \
+    } while (0)
+
+#define LBIC_TRY(call)                  \
+    do {                                \
+        int rc__ = (call);              \
+        if (rc__ != 0) return rc__;     \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// A wavefront step.  Row r of a step's compact activation matrices is block
+//   img = r / nv,  v = vmin + r % nv,  h = t - 2 v        (slope-2 wavefront t = h + 2 v)
+// The raster-serial decode of the reference container uses nv = 1, vmin = v, t = h + 2 v.
+// ------------------------------------------------------------------------------------------------
+struct StepDesc {
+    int n_img, nv, vmin, t, Hb, Wb;
+};
+
+__host__ __device__ inline void step_row_to_block(const StepDesc &s, int r, int &img, int &v, int &h) {
+    img = r / s.nv;
+    v = s.vmin + (r - img * s.nv);
+    h = s.t - 2 * v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue of a GEMM layer (fused into both GEMM cores).
+// ------------------------------------------------------------------------------------------------
+enum EpiMode {
+    EPI_LRELU = 0,   // v = lrelu(acc+b)                      -> hi/lo           (NET:305-311)
+    EPI_PREGDN = 1,  // a = acc+b -> f32; a*a                 -> hi/lo           (GDNF:71 x**2)
+    EPI_GDN = 2,     // aux * rsqrt(acc+beta)                 -> hi/lo           (GDNF:71-78)
+    EPI_IGDN = 3,    // aux * sqrt(acc+beta)                  -> hi/lo
+    EPI_KSI = 4,     // acc+b                                 -> f32 (scales | means, NET:369)
+    EPI_QUANT = 5,   // y=acc+b; sym=rint(y-mean); idx; yq    -> hi/lo, sym, idx (NET:371-374)
+    EPI_RECON = 6,   // clamp(acc+b, -.5, .5)                 -> zhat (NET:357)
+    EPI_RAW = 7      // acc                                   -> f32 (debug gemm)
+};
+
+struct EpiParams {
+    int mode;
+    int R;              // valid rows
+    int cout;           // valid output columns
+    const float *bias;  // [cout] (beta for the GDN modes)
+    bf16 *out_hi, *out_lo;
+    int ld_out;
+    float *out_f32;
+    int ld_f32;
+    const float *aux;   // pre-GDN activations (GDN modes) or ksi (QUANT)
+    int ld_aux;
+    int M;              // latent channels (QUANT)
+    const float *scale_tab;   // device, 64 scale levels (QUANT)
+    int32_t *sym;       // (n_img,Hb,Wb,M) int32        (QUANT)
+    uint8_t *idx;       // (n_img,Hb,Wb,M) uint8        (QUANT)
+    float *zhat;        // (n_img,Hb,Wb,Cin) fp32 channel-last   (RECON)
+    StepDesc step;
+};
+
+// One K segment of a GEMM: A[R,K] (bf16 hi/lo planes, row stride ld) times W[cout,K]^T.
+struct GemmOperand {
+    const bf16 *hi, *lo;
+    int ld;                 // elements
+    const CUtensorMap *tm_hi, *tm_lo;   // host copies of the TMA descriptors
+};
+
+struct GemmCall {
+    int R, cout, bn;
+    int nseg;
+    int K[2];
+    GemmOperand A[2], W[2];
+    EpiParams ep;
+};
+
+int gemm_simt_launch(const GemmCall &g, cudaStream_t st);
+int gemm_tc_launch(const GemmCall &g, cudaStream_t st);
+int gemm_tc_init();   // resolves cuTensorMapEncodeTiled, sets smem attributes
+int make_tmap_2d(CUtensorMap *tm, const void *base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                 uint32_t box_inner, uint32_t box_outer);
+
+// ------------------------------------------------------------------------------------------------
+// elementwise / layout kernels (kernels_misc.cu)
+// ------------------------------------------------------------------------------------------------
+int launch_nchw_to_cl(const float *src, float *dst, int n, int C, int HW, cudaStream_t st);
+int launch_cl_to_nchw(const float *src, float *dst, int n, int C, int HW, cudaStream_t st);
+int launch_space_to_depth(const float *img, float *blk, int n, int C, int Hb, int Wb, int B, cudaStream_t st);
+int launch_depth_to_space(const float *blk, float *img, int n, int C, int Hb, int Wb, int B, cudaStream_t st);
+int launch_split_f32(const float *src, bf16 *hi, bf16 *lo, int64_t n, cudaStream_t st);
+// per-step gather of x and the four causal neighbour blocks of zhat
+int launch_gather(const float *x_cl, const float *zhat_cl, int Cin, const StepDesc &s, int R,
+                  bf16 *X_hi, bf16 *X_lo, int ldX, bf16 *T_hi, bf16 *T_lo, int ldT, cudaStream_t st);
+// weight packing
+int launch_pack_conv(const float *w, const float *mask, int cout, int cin, int kh, int kw,
+                     const int *taps_host, int ntaps, bf16 *hi, bf16 *lo, int ld, cudaStream_t st);
+int launch_pack_gdn(const float *gamma, const float *beta, int C, float gbound, float gped, float bbound,
+                    float bped, bf16 *hi, bf16 *lo, int ld, float *beta_out, cudaStream_t st);
+int launch_add_vec(const float *a, const float *b, float *out, int n, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------
+// entropy model tables + rANS (tables.cu, rans.cu)
+// ------------------------------------------------------------------------------------------------
+struct Tables {
+    int n_levels = 0, stride = 0;
+    int32_t *cdf = nullptr;       // device [n_levels][stride]
+    int32_t *cdf_length = nullptr;
+    int32_t *offset = nullptr;
+    float scale_table[64];
+    float *d_scale_table = nullptr;   // device copy, 64 floats
+};
+int tables_build(Tables &T, const float *scale_table_host, int n_levels, double tail_mass, cudaStream_t st);
+
+struct RansStreamState {   // one per stream, device resident between decode steps
+    unsigned long long x;
+    uint32_t pos;          // next word index within the stream
+    uint32_t nwords;
+};
+
+// symbols/indexes: for stream s, symbol k lives at  base + s*stream_stride + k   (elements).
+// scratch holds n_streams*scratch_words words followed by start_word[n_streams] and n_words[n_streams];
+// out may be NULL (lane mode: launch_lane_pack assembles the containers from the scratch).
+int launch_rans_encode(const Tables &T, const int32_t *sym, const uint8_t *idx, int n_streams, int64_t n_sym,
+                       int64_t stream_stride, uint32_t *scratch_words, size_t scratch_words_per_stream,
+                       uint8_t *out, size_t out_stride, uint32_t *out_len, int *err_flag, cudaStream_t st);
+// lane container: merges `lanes` consecutive single streams per image into header|lengths|payload
+int launch_lane_pack(const uint32_t *scratch, size_t scratch_words, int n_img, int lanes, uint8_t *out,
+                     size_t out_stride, uint32_t *out_len, int *err_flag, cudaStream_t st);
+int launch_rans_dec_init(const uint8_t *streams, const uint32_t *stream_len, size_t stream_stride, int n_img,
+                         int lanes, RansStreamState *states, const uint8_t **lane_ptr, int *err_flag, cudaStream_t st);
+// decode M symbols for every row of a step; writes yq = sym + mean (hi/lo) and optionally symbols
+int launch_rans_dec_step(const Tables &T, RansStreamState *states, const uint8_t *const *lane_ptr, int lanes,
+                         const StepDesc &s, int R, int M, const float *ksi, int ld_ksi, bf16 *yq_hi, bf16 *yq_lo,
+                         int ld_yq, int32_t *sym_out, cudaStream_t st);
+int launch_rans_decode_full(const Tables &T, const uint8_t *streams, const uint32_t *stream_len, size_t stream_stride,
+                            const uint8_t *idx, int n_streams, int64_t n_sym, int32_t *sym_out, cudaStream_t st);
+
+// launch bookkeeping
+void count_launch(int family);   // 0 = gemm, 1 = other
+extern thread_local int64_t *g_launch_counter;   // points into the active model

@@ -1,0 +1,406 @@
+// K5 / K6: rANS64 entropy coder on the GPU.
+//
+// Bit-compatible with the coder the reference binds from CompressAI (compressai.ans:
+// BufferedRansEncoder.encode_with_indexes + flush, RansDecoder.set_stream + decode_stream; call sites
+// graphs/models/BlockBasedImgCompLossy_net.py:328,359-360,409-410,439): one 64-bit state per stream,
+// RANS64_L = 2^31, 32-bit renormalisation words, 16-bit probabilities, 4-bit bypass escape for values outside
+// the table.  A stream's bytes are  [state lo][state hi][renorm words in decode order].
+//
+// Lanes: the reference container is ONE stream per image (symbols in raster block order, channels inner), so
+// its decode is serial in raster order.  The lane container (extension) holds one such stream per block row:
+//   u32 'LBML' | u32 lanes | u32 len[lanes] | lane 0 bytes | lane 1 bytes | ...
+// which lets the decoder follow the same slope-2 wavefront as the encoder.
+#include "epilogue.cuh"
+
+namespace {
+
+constexpr unsigned long long RANS_L = 1ull << 31;
+constexpr int PREC = 16;
+constexpr int BYPASS = 4;
+constexpr int MAX_BYPASS = 15;
+constexpr uint32_t LANE_MAGIC = 0x4C4D424Cu;   // "LBML"
+
+// ---------------------------------------------------------------------------------------------
+// encoder: one thread per stream walks its symbols backwards (flush() pops the pushed symbols in
+// reverse) and writes renormalisation words from the end of its scratch region towards the front.
+// ---------------------------------------------------------------------------------------------
+struct EncCursor {
+    unsigned long long x;
+    uint32_t *base;   // scratch region start
+    long pos;         // next free slot + 1 (we write base[--pos])
+    bool overflow;
+};
+
+__device__ __forceinline__ void enc_emit(EncCursor &c) {
+    if (c.pos <= 0) { c.overflow = true; return; }
+    c.base[--c.pos] = (uint32_t)c.x;
+    c.x >>= 32;
+}
+
+__device__ __forceinline__ void enc_put(EncCursor &c, uint32_t start, uint32_t range) {
+    const unsigned long long x_max = ((RANS_L >> PREC) << 32) * (unsigned long long)range;
+    if (c.x >= x_max) enc_emit(c);
+    c.x = ((c.x / range) << PREC) + (c.x % range) + start;
+}
+
+__device__ __forceinline__ void enc_put_bits(EncCursor &c, uint32_t val) {
+    const unsigned long long x_max = ((RANS_L >> PREC) << 32) * (unsigned long long)(1u << (PREC - BYPASS));
+    if (c.x >= x_max) enc_emit(c);
+    c.x = (c.x << BYPASS) | val;
+}
+
+__global__ void rans_encode_kernel(const int32_t *__restrict__ cdf, int cdf_stride, const int32_t *__restrict__ cdf_len,
+                                   const int32_t *__restrict__ offs, const int32_t *__restrict__ sym,
+                                   const uint8_t *__restrict__ idx, int n_streams, long n_sym, long stream_stride,
+                                   uint32_t *__restrict__ scratch, long scratch_words, uint32_t *__restrict__ start_word,
+                                   uint32_t *__restrict__ n_words, int *__restrict__ err) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    EncCursor c;
+    c.x = RANS_L;
+    c.base = scratch + (size_t)s * scratch_words;
+    c.pos = scratch_words;
+    c.overflow = false;
+    const int32_t *ps = sym + (size_t)s * stream_stride;
+    const uint8_t *pi = idx + (size_t)s * stream_stride;
+    for (long k = n_sym - 1; k >= 0; --k) {
+        const int ci = pi[k];
+        const int32_t *row = cdf + (size_t)ci * cdf_stride;
+        const int max_value = cdf_len[ci] - 2;
+        int value = ps[k] - offs[ci];
+        uint32_t raw = 0;
+        if (value < 0) {
+            raw = (uint32_t)(-2 * value - 1);
+            value = max_value;
+        } else if (value >= max_value) {
+            raw = (uint32_t)(2 * (value - max_value));
+            value = max_value;
+        }
+        if (value == max_value) {
+            // pushed order: main, count (15,15,...,rem), nibbles LSB first -> popped in reverse
+            int nb = 0;
+            while (nb < 8 && (raw >> (nb * BYPASS)) != 0) ++nb;
+            for (int j = nb - 1; j >= 0; --j) enc_put_bits(c, (raw >> (j * BYPASS)) & MAX_BYPASS);
+            const int q = nb / MAX_BYPASS, rem = nb - q * MAX_BYPASS;
+            enc_put_bits(c, (uint32_t)rem);
+            for (int j = 0; j < q; ++j) enc_put_bits(c, MAX_BYPASS);
+        }
+        const uint32_t start = (uint32_t)row[value];
+        enc_put(c, start, (uint32_t)row[value + 1] - start);
+    }
+    // Rans64EncFlush: two words, low half first in memory
+    if (c.pos < 2) c.overflow = true;
+    if (!c.overflow) {
+        c.base[--c.pos] = (uint32_t)(c.x >> 32);
+        c.base[--c.pos] = (uint32_t)(c.x);
+    }
+    if (c.overflow) {
+        atomicExch(err, 1);
+        start_word[s] = 0;
+        n_words[s] = 0xFFFFFFFFu;
+    } else {
+        start_word[s] = (uint32_t)c.pos;
+        n_words[s] = (uint32_t)(scratch_words - c.pos);
+    }
+}
+
+// move each stream's words to the front of its output slot (coalesced, one CTA per stream)
+__global__ void rans_compact_kernel(const uint32_t *__restrict__ scratch, long scratch_words,
+                                    const uint32_t *__restrict__ start_word, const uint32_t *__restrict__ n_words,
+                                    uint8_t *__restrict__ out, size_t out_stride, uint32_t *__restrict__ out_len,
+                                    int *__restrict__ err) {
+    const int s = blockIdx.x;
+    const uint32_t nw = n_words[s];
+    if (nw == 0xFFFFFFFFu || (size_t)nw * 4 > out_stride) {
+        if (threadIdx.x == 0) { out_len[s] = 0xFFFFFFFFu; atomicExch(err, 1); }
+        return;
+    }
+    const uint32_t *src = scratch + (size_t)s * scratch_words + start_word[s];
+    uint32_t *dst = reinterpret_cast<uint32_t *>(out + (size_t)s * out_stride);
+    for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x == 0) out_len[s] = nw * 4;
+}
+
+// lane container assembly: one CTA per image
+__global__ void lane_pack_kernel(const uint32_t *__restrict__ scratch, long scratch_words,
+                                 const uint32_t *__restrict__ start_word, const uint32_t *__restrict__ n_words,
+                                 int lanes, uint8_t *__restrict__ out, size_t out_stride, uint32_t *__restrict__ out_len,
+                                 int *__restrict__ err) {
+    extern __shared__ uint32_t lane_off[];   // lanes + 1 word offsets
+    const int img = blockIdx.x;
+    __shared__ int bad;
+    if (threadIdx.x == 0) {
+        bad = 0;
+        uint32_t run = 2 + (uint32_t)lanes;
+        for (int l = 0; l < lanes; ++l) {
+            lane_off[l] = run;
+            const uint32_t nw = n_words[(size_t)img * lanes + l];
+            if (nw == 0xFFFFFFFFu) bad = 1; else run += nw;
+        }
+        lane_off[lanes] = run;
+        if ((size_t)run * 4 > out_stride) bad = 1;
+    }
+    __syncthreads();
+    if (bad) {
+        if (threadIdx.x == 0) { out_len[img] = 0xFFFFFFFFu; atomicExch(err, 1); }
+        return;
+    }
+    uint32_t *dst = reinterpret_cast<uint32_t *>(out + (size_t)img * out_stride);
+    if (threadIdx.x == 0) { dst[0] = LANE_MAGIC; dst[1] = (uint32_t)lanes; out_len[img] = lane_off[lanes] * 4; }
+    for (int l = threadIdx.x; l < lanes; l += blockDim.x) dst[2 + l] = n_words[(size_t)img * lanes + l] * 4;
+    for (int l = 0; l < lanes; ++l) {
+        const size_t s = (size_t)img * lanes + l;
+        const uint32_t *src = scratch + s * scratch_words + start_word[s];
+        const uint32_t nw = n_words[s];
+        for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) dst[lane_off[l] + i] = src[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// decoder
+// ---------------------------------------------------------------------------------------------
+struct DecCursor {
+    unsigned long long x;
+    const uint32_t *words;
+    uint32_t pos, nwords;
+};
+
+__device__ __forceinline__ uint32_t dec_word(DecCursor &d) {
+    const uint32_t w = d.pos < d.nwords ? __ldg(d.words + d.pos) : 0u;   // a corrupt stream stays finite
+    d.pos++;
+    return w;
+}
+
+__device__ __forceinline__ int dec_bits(DecCursor &d) {
+    const int val = (int)(d.x & MAX_BYPASS);
+    d.x >>= BYPASS;
+    if (d.x < RANS_L) d.x = (d.x << 32) | dec_word(d);
+    return val;
+}
+
+// Decodes one symbol; warp-cooperative CDF search (all 32 lanes hold identical cursor state).
+__device__ __forceinline__ int dec_symbol_warp(DecCursor &d, const int32_t *__restrict__ row, int len, int off,
+                                               int lane) {
+    const uint32_t cf = (uint32_t)(d.x & 0xFFFFu);
+    const int max_value = len - 2;
+    // first k with row[k] > cf, searched in a 32-wide window around the distribution centre (value of symbol 0)
+    int g = -off - 15;
+    g = g < 0 ? 0 : g;
+    g = g > len - 32 ? (len - 32 < 0 ? 0 : len - 32) : g;
+    const int k = g + lane;
+    const bool gt = (k < len) && ((uint32_t)__ldg(row + k) > cf);
+    const unsigned ball = __ballot_sync(0xffffffffu, gt);
+    int s;
+    if ((ball & 1u) == 0 && ball != 0) {
+        s = g + (__ffs(ball) - 1) - 1;
+    } else {
+        // outside the window: upper_bound by bisection (identical result to the reference's linear find_if)
+        int lo = 0, hi = len - 1;   // row[len-1] = 65536 > cf always
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((uint32_t)__ldg(row + mid) > cf) hi = mid; else lo = mid + 1;
+        }
+        s = lo - 1;
+    }
+    const uint32_t start = (uint32_t)__ldg(row + s);
+    const uint32_t freq = (uint32_t)__ldg(row + s + 1) - start;
+    d.x = (unsigned long long)freq * (d.x >> PREC) + cf - start;
+    if (d.x < RANS_L) d.x = (d.x << 32) | dec_word(d);
+    int value = s;
+    if (value == max_value) {
+        int val = dec_bits(d);
+        int nb = val;
+        while (val == MAX_BYPASS) {
+            val = dec_bits(d);
+            nb += val;
+        }
+        int raw = 0;
+        for (int j = 0; j < nb; ++j) {
+            val = dec_bits(d);
+            raw |= val << (j * BYPASS);
+        }
+        value = raw >> 1;
+        if (raw & 1) value = -value - 1; else value += max_value;
+    }
+    return value + off;
+}
+
+// Parses the per-image container(s) and initialises one decoder state per lane.
+__global__ void rans_dec_init_kernel(const uint8_t *__restrict__ streams, const uint32_t *__restrict__ stream_len,
+                                     size_t stream_stride, int n_img, int lanes, RansStreamState *__restrict__ states,
+                                     const uint8_t **__restrict__ lane_ptr, int *__restrict__ err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_img * lanes) return;
+    const int img = i / lanes, l = i - img * lanes;
+    const uint8_t *base = streams + (size_t)img * stream_stride;
+    const uint32_t total = stream_len[img];
+    const uint8_t *p = base;
+    uint32_t nbytes = total;
+    if (lanes > 1) {
+        const uint32_t *hdr = reinterpret_cast<const uint32_t *>(base);
+        if (total < 8u + 4u * lanes || hdr[0] != LANE_MAGIC || hdr[1] != (uint32_t)lanes) {
+            atomicExch(err, 2);
+            nbytes = 0;
+        } else {
+            uint32_t o = 8u + 4u * lanes;
+            for (int j = 0; j < l; ++j) o += hdr[2 + j];
+            nbytes = hdr[2 + l];
+            p = base + o;
+            if (o + nbytes > total) { atomicExch(err, 2); nbytes = 0; }
+        }
+    }
+    RansStreamState st;
+    st.nwords = nbytes / 4;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(p);
+    const unsigned long long lo = st.nwords > 0 ? w[0] : 0u, hi = st.nwords > 1 ? w[1] : 0u;
+    st.x = lo | (hi << 32);
+    st.pos = 2;
+    states[i] = st;
+    lane_ptr[i] = p;
+}
+
+// One warp per row of the step: build_indexes from the predicted scales, decode M symbols from the row's
+// lane, dequantise (sym + mean, ENT:159-168) and emit the decoder-net input as bf16 hi/lo planes.
+__global__ void rans_dec_step_kernel(const int32_t *__restrict__ cdf, int cdf_stride,
+                                     const int32_t *__restrict__ cdf_len, const int32_t *__restrict__ offs,
+                                     const float *__restrict__ scale_tab, RansStreamState *__restrict__ states,
+                                     const uint8_t *const *__restrict__ lane_ptr, int lanes, StepDesc sd, int R, int M,
+                                     const float *__restrict__ ksi, int ld_ksi, bf16 *__restrict__ yq_hi,
+                                     bf16 *__restrict__ yq_lo, int ld_yq, int32_t *__restrict__ sym_out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= R) return;
+    int img, v, h;
+    step_row_to_block(sd, warp, img, v, h);
+    const int sidx = lanes > 1 ? img * lanes + v : img;
+    DecCursor d;
+    {
+        const RansStreamState st = states[sidx];
+        d.x = st.x; d.pos = st.pos; d.nwords = st.nwords;
+        d.words = reinterpret_cast<const uint32_t *>(lane_ptr[sidx]);
+    }
+    const float *krow = ksi + (size_t)warp * ld_ksi;
+    int my_idx[8];
+    int my_sym[8];
+    const int per = (M + 31) >> 5;   // M <= 256
+    for (int j = 0; j < per; ++j) {
+        const int c = j * 32 + lane;
+        my_idx[j] = c < M ? scale_to_index(krow[c], scale_tab) : 0;
+        my_sym[j] = 0;
+    }
+    for (int c = 0; c < M; ++c) {
+        const int ci = __shfl_sync(0xffffffffu, my_idx[c >> 5], c & 31);
+        const int sym = dec_symbol_warp(d, cdf + (size_t)ci * cdf_stride, cdf_len[ci], offs[ci], lane);
+        if (lane == (c & 31)) my_sym[c >> 5] = sym;
+    }
+    if (lane == 0) {
+        RansStreamState st;
+        st.x = d.x; st.pos = d.pos; st.nwords = d.nwords;
+        states[sidx] = st;
+    }
+    const size_t o = (((size_t)img * sd.Hb + v) * sd.Wb + h) * M;
+    for (int j = 0; j < per; ++j) {
+        const int c = j * 32 + lane;
+        if (c < M) {
+            const float yq = (float)my_sym[j] + krow[M + c];
+            bf16 hi, lo;
+            split_bf16(yq, hi, lo);
+            yq_hi[(size_t)warp * ld_yq + c] = hi;
+            yq_lo[(size_t)warp * ld_yq + c] = lo;
+            if (sym_out) sym_out[o + c] = my_sym[j];
+        }
+    }
+}
+
+// Whole-stream decode with given indexes (lbic_rans_decode): one warp per stream.
+__global__ void rans_decode_full_kernel(const int32_t *__restrict__ cdf, int cdf_stride,
+                                        const int32_t *__restrict__ cdf_len, const int32_t *__restrict__ offs,
+                                        const uint8_t *__restrict__ streams, const uint32_t *__restrict__ stream_len,
+                                        size_t stream_stride, const uint8_t *__restrict__ idx, int n_streams, long n_sym,
+                                        int32_t *__restrict__ sym_out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_streams) return;
+    DecCursor d;
+    d.words = reinterpret_cast<const uint32_t *>(streams + (size_t)warp * stream_stride);
+    d.nwords = stream_len[warp] / 4;
+    d.x = (unsigned long long)(d.nwords > 0 ? d.words[0] : 0u) | ((unsigned long long)(d.nwords > 1 ? d.words[1] : 0u) << 32);
+    d.pos = 2;
+    const uint8_t *pi = idx + (size_t)warp * n_sym;
+    int32_t *po = sym_out + (size_t)warp * n_sym;
+    for (long k = 0; k < n_sym; ++k) {
+        const int ci = pi[k];
+        const int sym = dec_symbol_warp(d, cdf + (size_t)ci * cdf_stride, cdf_len[ci], offs[ci], lane);
+        if (lane == 0) po[k] = sym;
+    }
+}
+
+}  // namespace
+
+// scratch layout: [n_streams * scratch_words] words, then start_word[n_streams], n_words[n_streams]
+int launch_rans_encode(const Tables &T, const int32_t *sym, const uint8_t *idx, int n_streams, int64_t n_sym,
+                       int64_t stream_stride, uint32_t *scratch, size_t scratch_words, uint8_t *out, size_t out_stride,
+                       uint32_t *out_len, int *err_flag, cudaStream_t st) {
+    if (!T.cdf) return lbic_fail(LBIC_ERR_STATE, "Uninitialized CDFs. Run update() first");
+    uint32_t *start_word = scratch + (size_t)n_streams * scratch_words;
+    uint32_t *n_words = start_word + n_streams;
+    const int threads = 32;
+    rans_encode_kernel<<<(n_streams + threads - 1) / threads, threads, 0, st>>>(
+        T.cdf, T.stride, T.cdf_length, T.offset, sym, idx, n_streams, (long)n_sym, (long)stream_stride, scratch,
+        (long)scratch_words, start_word, n_words, err_flag);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    if (out) {
+        rans_compact_kernel<<<n_streams, 256, 0, st>>>(scratch, (long)scratch_words, start_word, n_words, out,
+                                                       out_stride, out_len, err_flag);
+        count_launch(1);
+        LBIC_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+int launch_lane_pack(const uint32_t *scratch, size_t scratch_words, int n_img, int lanes, uint8_t *out,
+                     size_t out_stride, uint32_t *out_len, int *err_flag, cudaStream_t st) {
+    const uint32_t *start_word = scratch + (size_t)n_img * lanes * scratch_words;
+    const uint32_t *n_words = start_word + (size_t)n_img * lanes;
+    lane_pack_kernel<<<n_img, 256, sizeof(uint32_t) * (lanes + 1), st>>>(scratch, (long)scratch_words, start_word,
+                                                                        n_words, lanes, out, out_stride, out_len,
+                                                                        err_flag);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_rans_dec_init(const uint8_t *streams, const uint32_t *stream_len, size_t stream_stride, int n_img, int lanes,
+                         RansStreamState *states, const uint8_t **lane_ptr, int *err_flag, cudaStream_t st) {
+    const int n = n_img * lanes;
+    rans_dec_init_kernel<<<(n + 127) / 128, 128, 0, st>>>(streams, stream_len, stream_stride, n_img, lanes, states,
+                                                          lane_ptr, err_flag);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_rans_dec_step(const Tables &T, RansStreamState *states, const uint8_t *const *lane_ptr, int lanes,
+                         const StepDesc &s, int R, int M, const float *ksi, int ld_ksi, bf16 *yq_hi, bf16 *yq_lo,
+                         int ld_yq, int32_t *sym_out, cudaStream_t st) {
+    if (R <= 0) return 0;
+    if (M > 256) return lbic_fail(LBIC_ERR_INVALID, "M > 256 unsupported by the decode step");
+    const int warps_per_block = 4;
+    rans_dec_step_kernel<<<(R + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+        T.cdf, T.stride, T.cdf_length, T.offset, T.d_scale_table, states, lane_ptr, lanes, s, R, M, ksi, ld_ksi, yq_hi, yq_lo,
+        ld_yq, sym_out);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_rans_decode_full(const Tables &T, const uint8_t *streams, const uint32_t *stream_len, size_t stream_stride,
+                            const uint8_t *idx, int n_streams, int64_t n_sym, int32_t *sym_out, cudaStream_t st) {
+    if (!T.cdf) return lbic_fail(LBIC_ERR_STATE, "Uninitialized CDFs. Run update() first");
+    const int warps_per_block = 4;
+    rans_decode_full_kernel<<<(n_streams + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+        T.cdf, T.stride, T.cdf_length, T.offset, streams, stream_len, stream_stride, idx, n_streams, (long)n_sym,
+        sym_out);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}

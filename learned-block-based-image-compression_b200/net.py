@@ -1,0 +1,335 @@
+"""Host-side mirror of the reference model class for the codec path.
+
+`BlockBasedImgCompLossyNetv9` keeps the method surface eval_model() uses on the reference model
+(graphs/models/BlockBasedImgCompLossy_net.py:251-452, callers agents/blkbsdimgcomp_agent.py:555,
+592, 598 and agents/base.py:95-96):
+
+    Model(config)                      config.block_size / KS / N / M            NET:259-317
+    .load_state_dict(sd)               the reference state_dict, verbatim          base.py:95-96
+    .update(force=False) -> bool       entropy tables                              NET:121-125
+    .compress(x, LRU, chlat)           -> (bytes, zhat)                            NET:319-361
+    .decompress(bitstream, LRU, xshape, chlat, devc) -> zhat                       NET:400-452
+
+plus batched, device-resident variants.  All arithmetic runs in liblbic_b200.so (sm_100a CUDA);
+PyTorch only owns device memory and streams.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from collections import OrderedDict
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import load_config
+from .weights import layer_specs
+
+SCALES_MIN, SCALES_MAX, SCALES_LEVELS = 0.11, 256, 64   # NET:13-15
+
+
+def get_scale_table(mmin=SCALES_MIN, mmax=SCALES_MAX, levels=SCALES_LEVELS):
+    """NET:17-18 (same torch expression, so the 64 fp32 thresholds are bit-identical)."""
+    return torch.exp(torch.linspace(math.log(mmin), math.log(mmax), levels))
+
+
+def get_lru(KS):
+    """get_lru_(KS, 'compress') of the agent (AGENT:481-489)."""
+    r = sum(int(k) // 2 for k in KS)
+    return r, r, r
+
+
+class BlockBasedImgCompLossyNetv9:
+    def __init__(self, config, device=None):
+        self.config = load_config(config) if not hasattr(config, "block_size") else load_config(vars(config))
+        c = self.config
+        self.B, self.N, self.M = int(c.block_size), int(c.N), int(c.M)
+        self.KS = [int(k) for k in c.KS]
+        self.Cin = 3 * self.B * self.B
+        self._sd = None
+        self._handle = None
+        self._device = None
+        self._tables_ready = False
+        self.conditional_gaussian_model = SimpleNamespace(
+            quantized_cdf=torch.IntTensor(), cdf_length=torch.IntTensor(), offset=torch.IntTensor(),
+            scale_table=torch.Tensor(), tail_mass=1e-9)
+        self.training = False
+        if device is not None:
+            self.to(device)
+
+    # ---- nn.Module-like plumbing ------------------------------------------------------------
+    def eval(self):
+        self.training = False
+        return self
+
+    def to(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("lbic_b200 runs on sm_100a GPUs only; there is no CPU path")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if self._handle is not None and self._device.index == idx:
+            return self
+        self._destroy()
+        L = _lib.lib()
+        cfg = _lib.LbicConfig(self.B, (ctypes.c_int * 4)(*self.KS), self.N, self.M)
+        h = ctypes.c_void_p()
+        _lib.check(L.lbic_create(ctypes.byref(cfg), idx, ctypes.byref(h)))
+        self._handle, self._device = h, torch.device("cuda", idx)
+        if self._sd is not None:
+            self._upload()
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", torch.cuda.current_device() if device is None else device))
+
+    def _destroy(self):
+        if self._handle is not None:
+            _lib.lib().lbic_destroy(self._handle)
+            self._handle = None
+            self._tables_ready = False
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    def _need(self):
+        if self._handle is None:
+            if torch.cuda.is_available():
+                self.to(torch.device("cuda", torch.cuda.current_device()))
+            else:
+                raise RuntimeError("lbic_b200: no CUDA device; the B200 path has no CPU fallback")
+        return self._handle
+
+    def _stream(self):
+        return torch.cuda.current_stream(self._device).cuda_stream
+
+    def set_gemm_core(self, core: str):
+        """'tcgen05' (product path) or 'simt' (fp32 cross-check twin)."""
+        _lib.check(_lib.lib().lbic_set_option(self._need(), _lib.LBIC_OPT_GEMM_CORE, {"tcgen05": 0, "simt": 1}[core]))
+
+    # ---- state_dict ----------------------------------------------------------------------------
+    def expected_keys(self):
+        keys = []
+        for prefix, kind, _ in layer_specs(self.config):
+            if kind == "conv":
+                keys += [prefix + s for s in (".weight", ".bias", ".mask")]
+            else:
+                keys += [prefix + s for s in (".beta", ".gamma", ".beta_reparam.pedestal",
+                                              ".beta_reparam.lower_bound.bound", ".gamma_reparam.pedestal",
+                                              ".gamma_reparam.lower_bound.bound")]
+        return keys
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        """Accepts the reference `state_dict0` verbatim.  Keys under
+        conditional_gaussian_model.* are optional (they are empty in released checkpoints, AGENT:570);
+        non-empty table buffers are installed instead of being rebuilt."""
+        need = self.expected_keys()
+        missing = [k for k in need if k not in state_dict and not k.endswith(".mask") and "reparam" not in k]
+        if missing:
+            raise RuntimeError(f"Missing key(s) in state_dict: {missing[:6]}{' ...' if len(missing) > 6 else ''}")
+        if strict:
+            extra = [k for k in state_dict if k not in need and not k.startswith("conditional_gaussian_model.")]
+            if extra:
+                raise RuntimeError(f"Unexpected key(s) in state_dict: {extra[:6]}")
+        self._sd = OrderedDict((k, v.detach().clone()) for k, v in state_dict.items())
+        if self._handle is not None:
+            self._upload()
+        cg = "conditional_gaussian_model."
+        q = self._sd.get(cg + "_quantized_cdf")
+        if q is not None and q.numel() > 0:
+            self.conditional_gaussian_model.quantized_cdf = q.int().cpu()
+            self.conditional_gaussian_model.cdf_length = self._sd[cg + "_cdf_length"].int().cpu()
+            self.conditional_gaussian_model.offset = self._sd[cg + "_offset"].int().cpu()
+            st = self._sd.get(cg + "scale_table")
+            self.conditional_gaussian_model.scale_table = (st.float().cpu() if st is not None and st.numel() == 64
+                                                           else get_scale_table())
+            self._tables_ready = False
+            if self._handle is not None:
+                self._install_tables()
+        return SimpleNamespace(missing_keys=[], unexpected_keys=[])
+
+    def state_dict(self):
+        sd = OrderedDict(self._sd or {})
+        g = self.conditional_gaussian_model
+        sd["conditional_gaussian_model._offset"] = g.offset
+        sd["conditional_gaussian_model._quantized_cdf"] = g.quantized_cdf
+        sd["conditional_gaussian_model._cdf_length"] = g.cdf_length
+        sd["conditional_gaussian_model.scale_table"] = g.scale_table
+        return sd
+
+    def _upload(self):
+        L = _lib.lib()
+        keep, descs = [], []
+        for k, v in self._sd.items():
+            if k.startswith("conditional_gaussian_model.") or not v.dtype.is_floating_point or v.numel() == 0:
+                continue
+            t = v.detach().to(torch.float32).contiguous()
+            keep.append(t)
+            d = _lib.LbicTensorDesc()
+            d.name = k.encode()
+            d.data = t.data_ptr()
+            d.ndim = t.dim()
+            for i, s in enumerate(t.shape[:4]):
+                d.shape[i] = s
+            descs.append(d)
+        arr = (_lib.LbicTensorDesc * len(descs))(*descs)
+        with torch.cuda.device(self._device):
+            _lib.check(L.lbic_load_weights(self._handle, arr, len(descs), self._stream()))
+        if self.conditional_gaussian_model.quantized_cdf.numel() > 0 and not self._tables_ready:
+            self._install_tables()
+
+    # ---- entropy tables -------------------------------------------------------------------------
+    def _install_tables(self):
+        g = self.conditional_gaussian_model
+        cdf = np.ascontiguousarray(g.quantized_cdf.numpy().astype(np.int32))
+        ln = np.ascontiguousarray(g.cdf_length.numpy().astype(np.int32))
+        off = np.ascontiguousarray(g.offset.numpy().astype(np.int32))
+        st = np.ascontiguousarray(g.scale_table.numpy().astype(np.float32))
+        _lib.check(_lib.lib().lbic_set_tables(self._need(), st.ctypes.data, 64, cdf.ctypes.data, cdf.shape[1],
+                                              ln.ctypes.data, off.ctypes.data))
+        self._tables_ready = True
+
+    def update(self, force: bool = False) -> bool:
+        """NET:121-125 -> GaussianConditional.update_scale_table (ENT:579-588): rebuilds the quantised
+        CDF / cdf_length / offset tables, on the GPU.  Returns True if the tables were (re)built."""
+        h = self._need()
+        g = self.conditional_gaussian_model
+        if g.offset.numel() > 0 and not force:
+            if not self._tables_ready:
+                self._install_tables()
+            return False
+        st = get_scale_table().contiguous()
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.lib().lbic_build_tables(h, st.data_ptr(), 64, float(g.tail_mass), self._stream()))
+        n, stride = ctypes.c_int(), ctypes.c_int()
+        _lib.check(_lib.lib().lbic_get_tables(h, ctypes.byref(n), ctypes.byref(stride), None, None, None))
+        cdf = np.empty((n.value, stride.value), dtype=np.int32)
+        ln = np.empty(n.value, dtype=np.int32)
+        off = np.empty(n.value, dtype=np.int32)
+        _lib.check(_lib.lib().lbic_get_tables(h, None, None, cdf.ctypes.data, ln.ctypes.data, off.ctypes.data))
+        g.quantized_cdf, g.cdf_length, g.offset = torch.from_numpy(cdf), torch.from_numpy(ln), torch.from_numpy(off)
+        g.scale_table = st
+        self._tables_ready = True
+        return True
+
+    # ---- codec path -------------------------------------------------------------------------------
+    def _check_call(self, LRU, chlat):
+        if LRU is not None and [int(v) for v in LRU] != list(get_lru(self.KS)):
+            raise ValueError(f"LRU {list(LRU)} does not match KS {self.KS} (expected {list(get_lru(self.KS))})")
+        if chlat is not None and int(chlat) != self.M:
+            raise ValueError(f"chlat {chlat} != config.M {self.M}")
+
+    def stream_bound(self, Hb, Wb, lanes=1):
+        return int(_lib.lib().lbic_stream_bound(self._need(), Hb, Wb, lanes))
+
+    def encode_device(self, x, lanes: int = 1, want_symbols: bool = False, entropy_code: bool = True,
+                      stream_cap: int | None = None, out=None):
+        """Batched encode with everything left on the device (no host synchronisation).
+        x: (n, 3B^2, Hb, Wb) fp32 CUDA tensor in [-0.5, 0.5].
+        Returns a namespace: zhat (n,3B^2,Hb,Wb), streams (n, cap) uint8, lens (n,) int32 [bytes],
+        and sym (n,Hb,Wb,M) int32 / idx uint8 when want_symbols."""
+        h = self._need()
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == self.Cin):
+            raise ValueError(f"x must be a CUDA fp32 tensor of shape (n, {self.Cin}, Hb, Wb)")
+        x = x.contiguous()
+        n, _, Hb, Wb = x.shape
+        dev = x.device
+        o = out if out is not None else SimpleNamespace()
+        if out is None:
+            o.zhat = torch.empty_like(x)
+            o.sym = torch.empty(n, Hb, Wb, self.M, dtype=torch.int32, device=dev) if want_symbols else None
+            o.idx = torch.empty(n, Hb, Wb, self.M, dtype=torch.uint8, device=dev) if want_symbols else None
+            if entropy_code:
+                cap = stream_cap or self.stream_bound(Hb, Wb, lanes)
+                cap = (cap + 3) // 4 * 4
+                o.streams = torch.empty(n, cap, dtype=torch.uint8, device=dev)
+                o.lens = torch.zeros(n, dtype=torch.int32, device=dev)
+            else:
+                o.streams, o.lens = None, None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().lbic_encode(
+                h, x.data_ptr(), n, Hb, Wb, o.zhat.data_ptr(),
+                o.sym.data_ptr() if o.sym is not None else None,
+                o.idx.data_ptr() if o.idx is not None else None,
+                o.streams.data_ptr() if o.streams is not None else None,
+                o.streams.shape[1] if o.streams is not None else 0,
+                o.lens.data_ptr() if o.lens is not None else None, lanes, self._stream()))
+        return o
+
+    def decode_device(self, streams, lens, n, Hb, Wb, lanes: int = 1, want_symbols: bool = False):
+        """streams (n, cap) uint8 CUDA, lens (n,) int32 CUDA -> zhat (n,3B^2,Hb,Wb) [, sym]."""
+        h = self._need()
+        dev = streams.device
+        zhat = torch.empty(n, self.Cin, Hb, Wb, dtype=torch.float32, device=dev)
+        sym = torch.empty(n, Hb, Wb, self.M, dtype=torch.int32, device=dev) if want_symbols else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().lbic_decode(h, streams.data_ptr(), lens.data_ptr(), streams.shape[1], n, Hb, Wb,
+                                              zhat.data_ptr(), sym.data_ptr() if sym is not None else None, lanes,
+                                              self._stream()))
+        return (zhat, sym) if want_symbols else zhat
+
+    @staticmethod
+    def _gather_streams(o):
+        lens = o.lens.cpu().numpy().astype(np.int64)
+        if (lens < 0).any() or (lens > o.streams.shape[1]).any():
+            raise RuntimeError("bitstream buffer overflow (stream_cap too small)")
+        host = o.streams[:, : int(lens.max())].cpu().numpy()
+        return [host[i, : lens[i]].tobytes() for i in range(len(lens))]
+
+    def compress_batch(self, x, lanes: int = 1, return_symbols: bool = False):
+        """-> (list[bytes], zhat) or (list[bytes], zhat, sym, idx)."""
+        o = self.encode_device(x, lanes=lanes, want_symbols=return_symbols)
+        strings = self._gather_streams(o)
+        return (strings, o.zhat, o.sym, o.idx) if return_symbols else (strings, o.zhat)
+
+    def decompress_batch(self, strings, xshape, lanes: int = 1, device=None):
+        n, ch, Hb, Wb = [int(v) for v in xshape]
+        if len(strings) != n or ch != self.Cin:
+            raise ValueError("strings / xshape mismatch")
+        self._need()
+        dev = torch.device(device) if device is not None else self._device
+        cap = (max(len(s) for s in strings) + 3) // 4 * 4
+        host = np.zeros((n, cap), dtype=np.uint8)
+        for i, s in enumerate(strings):
+            host[i, : len(s)] = np.frombuffer(s, dtype=np.uint8)
+        streams = torch.from_numpy(host).to(dev)
+        lens = torch.tensor([len(s) for s in strings], dtype=torch.int32, device=dev)
+        return self.decode_device(streams, lens, n, Hb, Wb, lanes=lanes)
+
+    def compress(self, x, LRU=None, chlat=None):
+        """NET:319-361: one image (1, 3B^2, Hb, Wb) -> (bitstream bytes, zhat)."""
+        self._check_call(LRU, chlat)
+        if x.shape[0] != 1:
+            raise ValueError("compress() takes one image; use compress_batch() for more")
+        strings, zhat = self.compress_batch(x, lanes=1)
+        return strings[0], zhat
+
+    def decompress(self, bitstream, LRU=None, xshape=None, chlat=None, devc=None):
+        """NET:400-452: bitstream bytes -> zhat (1, 3B^2, Hb, Wb)."""
+        self._check_call(LRU, chlat)
+        return self.decompress_batch([bitstream], xshape, lanes=1, device=devc)
+
+    # ---- instrumentation ----------------------------------------------------------------------------
+    def launch_count(self) -> int:
+        return int(_lib.lib().lbic_launch_count(self._need()))
+
+    def set_profiling(self, on: bool):
+        _lib.check(_lib.lib().lbic_set_profiling(self._need(), 1 if on else 0))
+
+    def get_profile(self):
+        n, ms, fl = ctypes.c_int64(), ctypes.c_double(), ctypes.c_double()
+        _lib.check(_lib.lib().lbic_get_profile(self._need(), ctypes.byref(n), ctypes.byref(ms), ctypes.byref(fl)))
+        return dict(gemm_launches=n.value, gemm_ms=ms.value, gemm_flops=fl.value)
+
+    def debug_gemm(self, A, W):
+        """D = A @ W.T through the selected GEMM core (bring-up/test hook)."""
+        A, W = A.contiguous().float(), W.contiguous().float()
+        D = torch.empty(A.shape[0], W.shape[0], device=A.device, dtype=torch.float32)
+        with torch.cuda.device(A.device):
+            _lib.check(_lib.lib().lbic_debug_gemm(self._need(), A.data_ptr(), W.data_ptr(), D.data_ptr(), A.shape[0],
+                                                  A.shape[1], W.shape[0], self._stream()))
+        return D
