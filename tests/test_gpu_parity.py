@@ -126,8 +126,14 @@ def test_encode_matches_reference_golden(dev, case, core):
     sym_h, idx_h = sym[0].cpu().numpy(), idx[0].cpu().numpy()
     mism = int((sym_h != c["symbols"].astype(np.int32)).sum()) + int((idx_h != c["indexes"]).sum())
     assert mism == 0, f"{case}/{core}: {mism} symbol/index mismatches of {sym_h.size}"
-    zerr = float((zhat.cpu() - torch.from_numpy(c["zhat"])).abs().max())
-    assert zerr < 1e-4, f"{case}/{core}: zhat max abs diff {zerr:.2e}"
+    zref = torch.from_numpy(c["zhat"])
+    zerr = float((zhat.cpu() - zref).abs().max())
+    # fp32 accumulation-order noise: ~1e-5 normally; the "harsh" weights (decoder input at full scale, 86 % of
+    # samples clamped) amplify it to ~3e-4 even for plain fp32 FFMA (the SIMT twin), hence 1e-3 there.
+    assert zerr < (1e-3 if bool(c["harsh"]) else 1e-4), f"{case}/{core}: zhat max abs diff {zerr:.2e}"
+    xh = torch.from_numpy(c["x"])
+    psnr = lambda z: -10.0 * float(torch.log10(((xh - z) ** 2).mean()))
+    assert abs(psnr(zhat.cpu()) - psnr(zref)) < 0.01, "PSNR delta vs reference exceeds 0.01 dB"
     tabs_equal = np.array_equal(m.conditional_gaussian_model.quantized_cdf.numpy(), load_tables()["quantized_cdf"])
     if tabs_equal:
         assert strings[0] == c["stream"].tobytes(), "bitstream differs from the reference for identical symbols"
