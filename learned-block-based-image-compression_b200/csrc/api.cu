@@ -74,6 +74,10 @@ struct Workspace {
     float *A32 = nullptr, *KSI = nullptr;
     int ldA32 = 0, ldKSI = 0;
     ActView vX, vT, vYQ, vH1, vH2, vH3, vS[3], vU[3];
+    // KS[1] == 3 only: ring-extended hidden map g0, its per-step tap gather, and the taps of the ring-extended rows
+    int R_ext_cap = 0;
+    ActBuf G0, H1x5, Text;
+    ActView vH1x5, vText;
     int32_t *sym = nullptr;
     uint8_t *idx = nullptr;
     uint32_t *rans_scratch = nullptr;
@@ -286,6 +290,17 @@ int ensure_workspace(lbic_model *m, int n_img, int Hb, int Wb) {
     LBIC_TRY(alloc_act(ws, ws.T, 4 * m->Cin));
     LBIC_TRY(alloc_act(ws, ws.YQ, m->M));
     LBIC_TRY(alloc_act(ws, ws.H1, m->E1));
+    if (m->k1 == 3) {
+        ws.R_ext_cap = ((n_img * (max_nv + 2)) + 127) / 128 * 128;
+        const size_t npos = (size_t)n_img * (Hb + 1) * (Wb + 2);
+        ws.G0.ld = m->E1;
+        LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.G0.hi, sizeof(bf16) * npos * m->E1, true));
+        LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.G0.lo, sizeof(bf16) * npos * m->E1, true));
+        LBIC_TRY(alloc_act(ws, ws.H1x5, 5 * m->E1));
+        ws.Text.ld = 4 * m->Cin;
+        LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.Text.hi, sizeof(bf16) * (size_t)ws.R_ext_cap * ws.Text.ld, true));
+        LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.Text.lo, sizeof(bf16) * (size_t)ws.R_ext_cap * ws.Text.ld, true));
+    }
     LBIC_TRY(alloc_act(ws, ws.H2, m->E2));
     LBIC_TRY(alloc_act(ws, ws.H3, m->E3));
     LBIC_TRY(alloc_act(ws, ws.S, m->N));
@@ -297,6 +312,12 @@ int ensure_workspace(lbic_model *m, int n_img, int Hb, int Wb) {
     LBIC_TRY(make_view(ws, ws.vT, ws.T, 4 * m->Cin));
     LBIC_TRY(make_view(ws, ws.vYQ, ws.YQ, m->M));
     LBIC_TRY(make_view(ws, ws.vH1, ws.H1, m->E1));
+    if (m->k1 == 3) {
+        LBIC_TRY(make_view(ws, ws.vH1x5, ws.H1x5, 5 * m->E1));
+        ws.vText.buf = &ws.Text; ws.vText.K = 4 * m->Cin;
+        LBIC_TRY(make_tmap_2d(&ws.vText.tm_hi, ws.Text.hi, 4 * m->Cin, ws.R_ext_cap, ws.Text.ld, 64, 128));
+        LBIC_TRY(make_tmap_2d(&ws.vText.tm_lo, ws.Text.lo, 4 * m->Cin, ws.R_ext_cap, ws.Text.ld, 64, 128));
+    }
     LBIC_TRY(make_view(ws, ws.vH2, ws.H2, m->E2));
     LBIC_TRY(make_view(ws, ws.vH3, ws.H3, m->E3));
     const int wd[3] = {m->N, m->C2, m->C3};
@@ -368,11 +389,29 @@ EpiParams epi_hilo(int mode, const StepDesc &sd, const ActBuf &out) {
     return e;
 }
 
-// entropy-parameter net: T -> ksi   (get_meanscale_fast, NET:389-398; KS[1] == 1)
+// KS[1] == 3: hidden map g0 = lrelu(E0(zhat taps)) at the ring-extended positions `ext` (single-position or
+// diagonal steps with h in [-1, Wb]), scattered into the position-indexed store.
+int run_g0(lbic_model *m, const StepDesc &ext, int R_ext, cudaStream_t st) {
+    Workspace &ws = m->ws;
+    if (R_ext <= 0) return 0;
+    if (R_ext > ws.R_ext_cap) return lbic_fail(LBIC_ERR_INVALID, "internal: extended step exceeds its workspace");
+    LBIC_TRY(launch_gather(nullptr, ws.zhat_cl, m->Cin, ext, R_ext, nullptr, nullptr, 0, ws.Text.hi, ws.Text.lo,
+                           ws.Text.ld, st));
+    EpiParams e = epi_hilo(EPI_LRELU, ext, ws.G0);
+    e.out_pos = 1;
+    return run_gemm(m, L_E0, R_ext, &ws.vText, nullptr, e, st);
+}
+
+// entropy-parameter net: T (or the g0 store) -> ksi   (get_meanscale_fast, NET:389-398)
 int run_ent(lbic_model *m, const StepDesc &sd, int R, cudaStream_t st) {
     Workspace &ws = m->ws;
-    LBIC_TRY(run_gemm(m, L_E0, R, &ws.vT, nullptr, epi_hilo(EPI_LRELU, sd, ws.H1), st));
-    LBIC_TRY(run_gemm(m, L_E1, R, &ws.vH1, nullptr, epi_hilo(EPI_LRELU, sd, ws.H2), st));
+    if (m->k1 == 3) {
+        LBIC_TRY(launch_gather5(ws.G0.hi, ws.G0.lo, m->E1, sd, R, ws.H1x5.hi, ws.H1x5.lo, ws.H1x5.ld, st));
+        LBIC_TRY(run_gemm(m, L_E1, R, &ws.vH1x5, nullptr, epi_hilo(EPI_LRELU, sd, ws.H2), st));
+    } else {
+        LBIC_TRY(run_gemm(m, L_E0, R, &ws.vT, nullptr, epi_hilo(EPI_LRELU, sd, ws.H1), st));
+        LBIC_TRY(run_gemm(m, L_E1, R, &ws.vH1, nullptr, epi_hilo(EPI_LRELU, sd, ws.H2), st));
+    }
     LBIC_TRY(run_gemm(m, L_E2, R, &ws.vH2, nullptr, epi_hilo(EPI_LRELU, sd, ws.H3), st));
     EpiParams e = epi(EPI_KSI, sd);
     e.out_f32 = ws.KSI; e.ld_f32 = ws.ldKSI;
@@ -426,7 +465,21 @@ int run_dec(lbic_model *m, const StepDesc &sd, int R, cudaStream_t st) {
     return 0;
 }
 
+int floor_div2(int a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); }
+
+// ring-extended diagonal of step t (KS[1] == 3): positions (v, h = t - 2v) with v in [0, Hb-1], h in [-1, Wb]
+bool wave_step_ext(int t, int n_img, int Hb, int Wb, StepDesc &sd) {
+    int vmin = floor_div2(t - Wb + 1);   // ceil((t - Wb) / 2)
+    if (vmin < 0) vmin = 0;
+    int vmax = floor_div2(t + 1);
+    if (vmax > Hb - 1) vmax = Hb - 1;
+    if (vmax < vmin) return false;
+    sd.n_img = n_img; sd.nv = vmax - vmin + 1; sd.vmin = vmin; sd.t = t; sd.Hb = Hb; sd.Wb = Wb;
+    return true;
+}
+
 bool wave_step(int t, int n_img, int Hb, int Wb, StepDesc &sd) {
+    if (t < 0) return false;
     int vmin = t - (Wb - 1) <= 0 ? 0 : (t - (Wb - 1) + 1) / 2;
     int vmax = t / 2 < Hb - 1 ? t / 2 : Hb - 1;
     if (vmax < vmin) return false;
@@ -466,8 +519,6 @@ extern "C" int lbic_create(const lbic_config *cfg, int device, lbic_model **out)
                          prop.major, prop.minor);
     if (cfg->ks[0] != 3 || (cfg->ks[1] != 1 && cfg->ks[1] != 3) || cfg->ks[2] != 1 || cfg->ks[3] != 1)
         return lbic_fail(LBIC_ERR_INVALID, "unsupported KS [%d,%d,%d,%d]", cfg->ks[0], cfg->ks[1], cfg->ks[2], cfg->ks[3]);
-    if (cfg->ks[1] == 3)
-        return lbic_fail(LBIC_ERR_INVALID, "KS[1]=3 (5-tap entropy layer) is not implemented yet in this build");
     if (cfg->block_size < 1 || cfg->n % 8 || cfg->n < 16 || cfg->m % 16 || cfg->m < 16 || cfg->m > 256 ||
         (3 * cfg->block_size * cfg->block_size) % 16)
         return lbic_fail(LBIC_ERR_INVALID, "unsupported sizes B=%d N=%d M=%d (need 3B^2, M multiples of 16)",
@@ -543,7 +594,11 @@ extern "C" int lbic_load_weights(lbic_model *m, const lbic_tensor_desc *tensors,
         const int Cin = m->Cin, N = m->N, C2 = m->C2, C3 = m->C3, M = m->M;
 #define P(call) if ((rc = (call)) != 0) break
         P(pack_linear(m, sd, L_E0, "get_meanscale.0", m->E1, Cin, 3, TAPS_A, 4, tmp, st));
-        P(pack_linear(m, sd, L_E1, "get_meanscale.2", m->E2, m->E1, 1, TAPS_1, 1, tmp, st));
+        if (m->k1 == 3) {
+            P(pack_linear(m, sd, L_E1, "get_meanscale.2", m->E2, m->E1, 3, TAPS_B, 5, tmp, st));
+        } else {
+            P(pack_linear(m, sd, L_E1, "get_meanscale.2", m->E2, m->E1, 1, TAPS_1, 1, tmp, st));
+        }
         P(pack_linear(m, sd, L_E2, "get_meanscale.4", m->E3, m->E2, 1, TAPS_1, 1, tmp, st));
         P(pack_linear(m, sd, L_E3, "get_meanscale.6", m->EO, m->E3, 1, TAPS_1, 1, tmp, st));
         P(pack_dual(m, sd, L_F0, "prtr_forward1", Cin, "prtr_forward2", N, tmp, st));
@@ -567,7 +622,6 @@ extern "C" int lbic_load_weights(lbic_model *m, const lbic_tensor_desc *tensors,
     if (rc) return rc;
     if (e != cudaSuccess) return lbic_fail(LBIC_ERR_CUDA, "weight packing failed: %s", cudaGetErrorString(e));
     m->weights_loaded = true;
-    (void)TAPS_B;
     return 0;
 }
 
@@ -637,8 +691,10 @@ extern "C" int lbic_encode(lbic_model *m, const float *x, int n_img, int Hb, int
     LBIC_CUDA(cudaMemsetAsync(ws.zhat_cl, 0, sizeof(float) * nblk * m->Cin, st));   // NET:336
     const bool want_syms = sym_out || idx_out || stream_out;
     const int T_steps = Wb + 2 * (Hb - 1);
-    for (int t = 0; t < T_steps; ++t) {
-        StepDesc sd;
+    if (m->k1 == 3) LBIC_TRY(launch_fill_g0_top(m->L[L_E0].bias, m->E1, n_img, Hb, Wb, ws.G0.hi, ws.G0.lo, st));
+    for (int t = (m->k1 == 3 ? -1 : 0); t < T_steps; ++t) {
+        StepDesc sd, ext;
+        if (m->k1 == 3 && wave_step_ext(t, n_img, Hb, Wb, ext)) LBIC_TRY(run_g0(m, ext, n_img * ext.nv, st));
         if (!wave_step(t, n_img, Hb, Wb, sd)) continue;
         const int R = n_img * sd.nv;
         LBIC_TRY(launch_gather(ws.x_cl, ws.zhat_cl, m->Cin, sd, R, ws.X.hi, ws.X.lo, ws.X.ld, ws.T.hi, ws.T.lo, ws.T.ld, st));
@@ -686,17 +742,29 @@ extern "C" int lbic_decode(lbic_model *m, const uint8_t *streams, const uint32_t
         LBIC_TRY(run_dec(m, sd, R, st));
         return 0;
     };
+    if (m->k1 == 3) LBIC_TRY(launch_fill_g0_top(m->L[L_E0].bias, m->E1, n_img, Hb, Wb, ws.G0.hi, ws.G0.lo, st));
     if (L == 1) {
         // reference container: the rANS state threads through the blocks in raster order (NET:420-450)
         for (int v = 0; v < Hb; ++v)
             for (int h = 0; h < Wb; ++h) {
+                if (m->k1 == 3) {
+                    // hidden-map positions that become computable now: the ring columns of the row start, then (v,h)
+                    if (h == 0) {
+                        if (v >= 1) { StepDesc e{n_img, 1, v - 1, Wb + 2 * (v - 1), Hb, Wb}; LBIC_TRY(run_g0(m, e, n_img, st)); }
+                        StepDesc e{n_img, 1, v, -1 + 2 * v, Hb, Wb};
+                        LBIC_TRY(run_g0(m, e, n_img, st));
+                    }
+                    StepDesc e{n_img, 1, v, h + 2 * v, Hb, Wb};
+                    LBIC_TRY(run_g0(m, e, n_img, st));
+                }
                 StepDesc sd{n_img, 1, v, h + 2 * v, Hb, Wb};
                 LBIC_TRY(one_step(sd, n_img));
             }
     } else {
         const int T_steps = Wb + 2 * (Hb - 1);
-        for (int t = 0; t < T_steps; ++t) {
-            StepDesc sd;
+        for (int t = (m->k1 == 3 ? -1 : 0); t < T_steps; ++t) {
+            StepDesc sd, ext;
+            if (m->k1 == 3 && wave_step_ext(t, n_img, Hb, Wb, ext)) LBIC_TRY(run_g0(m, ext, n_img * ext.nv, st));
             if (!wave_step(t, n_img, Hb, Wb, sd)) continue;
             LBIC_TRY(one_step(sd, n_img * sd.nv));
         }

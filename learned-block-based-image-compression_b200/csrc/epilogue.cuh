@@ -59,23 +59,51 @@ __device__ __forceinline__ void load_f32(const float *__restrict__ p, float (&v)
     }
 }
 
+// Operands an epilogue needs besides the accumulator, fetched ahead of the TMEM load they are combined with
+// (the tcgen05 core software-pipelines: prefetch chunk i+1 while chunk i is being finished).
 template <int NV>
-__device__ __forceinline__ void epilogue_store(const EpiParams &p, int r, int c, const float (&acc)[NV]) {
+struct EpiPre {
+    float b[NV];    // bias / beta
+    float a[NV];    // pre-GDN activation (GDN modes) or predicted scale (QUANT)
+    float a2[NV];   // predicted mean (QUANT)
+};
+
+// bias: pointer to the bias of column c (global memory, or the CTA's shared-memory copy of its tile slice)
+template <int NV>
+__device__ __forceinline__ void epi_prefetch(const EpiParams &p, const float *__restrict__ bias, int r, int c,
+                                             EpiPre<NV> &pre) {
+    if (p.mode == EPI_RAW) return;
+    load_f32<NV>(bias, pre.b);
+    if (p.mode == EPI_GDN || p.mode == EPI_IGDN) {
+        load_f32<NV>(p.aux + (size_t)r * p.ld_aux + c, pre.a);
+    } else if (p.mode == EPI_QUANT) {
+        load_f32<NV>(p.aux + (size_t)r * p.ld_aux + c, pre.a);            // scales = ksi[:, :M]   (NET:369)
+        load_f32<NV>(p.aux + (size_t)r * p.ld_aux + p.M + c, pre.a2);     // means  = ksi[:, M:]
+    }
+}
+
+template <int NV>
+__device__ __forceinline__ void epi_apply(const EpiParams &p, int r, int c, const float (&acc)[NV],
+                                          const EpiPre<NV> &pre) {
     float v[NV];
     if (p.mode == EPI_RAW) {
         store_f32<NV>(p.out_f32 + (size_t)r * p.ld_f32 + c, acc);
         return;
     }
-    float b[NV];
-    load_f32<NV>(p.bias + c, b);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = acc[i] + b[i];
+    for (int i = 0; i < NV; ++i) v[i] = acc[i] + pre.b[i];
 
     switch (p.mode) {
     case EPI_LRELU: {
 #pragma unroll
         for (int i = 0; i < NV; ++i) v[i] = v[i] > 0.0f ? v[i] : v[i] * 0.01f;   // nn.LeakyReLU() default slope
-        store_hilo<NV>(p.out_hi + (size_t)r * p.ld_out + c, p.out_lo + (size_t)r * p.ld_out + c, v);
+        size_t orow = (size_t)r;
+        if (p.out_pos) {
+            int img, bv, bh;
+            step_row_to_block(p.step, r, img, bv, bh);
+            orow = g0_pos_index(img, bv, bh, p.step.Hb, p.step.Wb);
+        }
+        store_hilo<NV>(p.out_hi + orow * p.ld_out + c, p.out_lo + orow * p.ld_out + c, v);
     } break;
     case EPI_PREGDN: {
         store_f32<NV>(p.out_f32 + (size_t)r * p.ld_f32 + c, v);
@@ -85,13 +113,11 @@ __device__ __forceinline__ void epilogue_store(const EpiParams &p, int r, int c,
     } break;
     case EPI_GDN:
     case EPI_IGDN: {
-        float a[NV];
-        load_f32<NV>(p.aux + (size_t)r * p.ld_aux + c, a);
         const bool inv = (p.mode == EPI_IGDN);
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const float sq = __fsqrt_rn(v[i]);
-            v[i] = a[i] * (inv ? sq : __fdiv_rn(1.0f, sq));   // torch.sqrt / torch.rsqrt (GDNF:73-76)
+            v[i] = pre.a[i] * (inv ? sq : __fdiv_rn(1.0f, sq));   // torch.sqrt / torch.rsqrt (GDNF:73-76)
         }
         store_hilo<NV>(p.out_hi + (size_t)r * p.ld_out + c, p.out_lo + (size_t)r * p.ld_out + c, v);
     } break;
@@ -99,9 +125,6 @@ __device__ __forceinline__ void epilogue_store(const EpiParams &p, int r, int c,
         store_f32<NV>(p.out_f32 + (size_t)r * p.ld_f32 + c, v);
     } break;
     case EPI_QUANT: {
-        float sc[NV], mu[NV];
-        load_f32<NV>(p.aux + (size_t)r * p.ld_aux + c, sc);            // scales = ksi[:, :M]   (NET:369)
-        load_f32<NV>(p.aux + (size_t)r * p.ld_aux + p.M + c, mu);      // means  = ksi[:, M:]
         int img, bv, bh;
         step_row_to_block(p.step, r, img, bv, bh);
         const size_t o = (((size_t)img * p.step.Hb + bv) * p.step.Wb + bh) * p.M + c;
@@ -109,10 +132,10 @@ __device__ __forceinline__ void epilogue_store(const EpiParams &p, int r, int c,
         uint32_t packed_idx[NV / 4];
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-            const float q = rintf(v[i] - mu[i]);                       // torch.round: half to even (ENT:143)
+            const float q = rintf(v[i] - pre.a2[i]);                   // torch.round: half to even (ENT:143)
             s[i] = (int32_t)q;
-            v[i] = q + mu[i];                                          // y_qnt = y_sym + means (NET:374)
-            const int k = scale_to_index(sc[i], p.scale_tab);
+            v[i] = q + pre.a2[i];                                      // y_qnt = y_sym + means (NET:374)
+            const int k = scale_to_index(pre.a[i], p.scale_tab);
             if ((i & 3) == 0) packed_idx[i >> 2] = 0;
             packed_idx[i >> 2] |= (uint32_t)k << (8 * (i & 3));
         }
@@ -136,4 +159,11 @@ __device__ __forceinline__ void epilogue_store(const EpiParams &p, int r, int c,
     } break;
     default: break;
     }
+}
+
+template <int NV>
+__device__ __forceinline__ void epilogue_store(const EpiParams &p, int r, int c, const float (&acc)[NV]) {
+    EpiPre<NV> pre;
+    epi_prefetch<NV>(p, p.bias + c, r, c, pre);
+    epi_apply<NV>(p, r, c, acc, pre);
 }

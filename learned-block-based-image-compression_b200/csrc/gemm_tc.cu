@@ -11,7 +11,9 @@
 //   warp 0      TMA producer: per 64-wide k-block loads A hi/lo [128x64] and W hi/lo [bn x 64]
 //               (SWIZZLE_128B, K-major) into a multi-stage ring, mbarrier complete_tx
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit frees stages
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 16 columns at a time -> fused epilogue -> global
+//   warps 2..9  epilogue (two warps per TMEM lane quarter, each taking half of the tile's columns): stage the
+//               bias slice in shared memory while the mainloop runs, then software-pipelined
+//               tcgen05.ld (32 lanes x 16 columns) + operand prefetch -> fused epilogue -> global
 #include "epilogue.cuh"
 
 #include <cstdio>
@@ -23,9 +25,11 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_PLANE = BM * BK * 2;     // 16 KiB per bf16 plane
 constexpr int MAX_STAGES = 4;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;          // producer, MMA issuer, 8 epilogue warps
+constexpr int NUM_EPI_THREADS = 256;
 constexpr int SMEM_LIMIT = 232448;       // 227 KiB opt-in maximum per CTA
-constexpr int SMEM_SLACK = 1024 + 256;   // 1024-B alignment of the ring + barrier block
+constexpr int BAR_BLOCK = 128;           // full[4] | empty[4] | tmem_full | tmem base address
+constexpr int SMEM_SLACK = 1024 + BAR_BLOCK + 1024;   // ring alignment + barrier block + bias slice (<= 256 floats)
 
 struct TcParams {
     int kb[2];          // k-blocks per segment
@@ -103,17 +107,30 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
+// Asynchronous TMEM load of 16 consecutive fp32 columns of this warp's 32 lanes; the registers may only be
+// read after tmem_ld_wait (the "+r" operands there make that a data dependence the compiler must respect).
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+
+__device__ __forceinline__ void epi_chunk_apply(const EpiParams &ep, int r, int c, const uint32_t (&raw)[16],
+                                                const EpiPre<16> &pre) {
+    float v[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
+    epi_apply<16>(ep, r, c, v, pre);
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -202,16 +219,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
             umma_commit(tmem_full_bar);      // accumulator complete
         }
     } else {
+        const int q = warp & 3;                  // TMEM lane quarter this warp may access (warp id % 4)
+        const int half = (warp - 2) >> 2;        // which half of the tile's column chunks
+        // stage this tile's bias slice while the mainloop runs
+        float *sbias = reinterpret_cast<float *>(smem_raw + (bars + BAR_BLOCK - raw));
+        if (p.ep.mode != EPI_RAW)
+            for (int i = threadIdx.x - 64; i < p.bn; i += NUM_EPI_THREADS)
+                sbias[i] = (n0 + i < p.ep.cout) ? p.ep.bias[n0 + i] : 0.0f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int nch = p.bn >> 4;
+        const int ch_end = half ? nch : (nch + 1) >> 1;
+        int ch = half ? (nch + 1) >> 1 : 0;
+        const int r = m0 + q * 32 + lane;
+        const bool row_ok = r < p.ep.R;
+        const uint32_t lane_base = tmem_acc + ((uint32_t)(q * 32) << 16);
+        auto ok = [&](int chunk) { return row_ok && (n0 + chunk * 16 < p.ep.cout); };
+        EpiPre<16> preA, preB;
+        uint32_t accA[16], accB[16];
+        if (ch < ch_end && ok(ch)) epi_prefetch<16>(p.ep, sbias + ch * 16, r, n0 + ch * 16, preA);
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        const int q = warp & 3;                  // TMEM lane quarter this warp may access
-        const int r = m0 + q * 32 + lane;
-        const uint32_t lane_base = tmem_acc + ((uint32_t)(q * 32) << 16);
-        for (int c0 = 0; c0 < p.bn; c0 += 16) {
-            float v[16];
-            tmem_ld_x16(lane_base + (uint32_t)c0, v);
-            const int c = n0 + c0;
-            if (r < p.ep.R && c < p.ep.cout) epilogue_store<16>(p.ep, r, c, v);
+        if (ch < ch_end) {
+            tmem_ld_issue(lane_base + (uint32_t)(ch * 16), accA);
+            tmem_ld_wait(accA);
+        }
+        for (; ch < ch_end; ch += 2) {
+            const bool hasB = ch + 1 < ch_end;
+            if (hasB) {
+                tmem_ld_issue(lane_base + (uint32_t)((ch + 1) * 16), accB);
+                if (ok(ch + 1)) epi_prefetch<16>(p.ep, sbias + (ch + 1) * 16, r, n0 + (ch + 1) * 16, preB);
+            }
+            if (ok(ch)) epi_chunk_apply(p.ep, r, n0 + ch * 16, accA, preA);
+            if (hasB) {
+                tmem_ld_wait(accB);
+                const bool hasA = ch + 2 < ch_end;
+                if (hasA) {
+                    tmem_ld_issue(lane_base + (uint32_t)((ch + 2) * 16), accA);
+                    if (ok(ch + 2)) epi_prefetch<16>(p.ep, sbias + (ch + 2) * 16, r, n0 + (ch + 2) * 16, preA);
+                }
+                if (ok(ch + 1)) epi_chunk_apply(p.ep, r, n0 + (ch + 1) * 16, accB, preB);
+                if (hasA) tmem_ld_wait(accA);
+            }
         }
     }
     tc_fence_before();

@@ -87,6 +87,43 @@ __global__ void gather_kernel(const float *__restrict__ x_cl, const float *__res
     }
 }
 
+// KS[1] == 3: out[r, tap*E1 + c] = g0(v+dv, h+dh)[c] for the five live taps of a 3x3 mask-'B' kernel,
+// (dv,dh) = (-1,-1), (-1,0), (-1,+1), (0,-1), (0,0); every such position lies inside the ring-extended store.
+__global__ void gather5_kernel(const bf16 *__restrict__ g_hi, const bf16 *__restrict__ g_lo, int E1, StepDesc s, int R,
+                               bf16 *__restrict__ o_hi, bf16 *__restrict__ o_lo, int ld) {
+    const int r = blockIdx.x;
+    if (r >= R) return;
+    int img, v, h;
+    step_row_to_block(s, r, img, v, h);
+    const int c8n = E1 >> 3;   // 16-byte chunks per plane row
+    for (int e = threadIdx.x; e < 5 * c8n; e += blockDim.x) {
+        const int tap = e / c8n, c = (e - tap * c8n) << 3;
+        const int dv = (tap >= 3) ? 0 : -1;
+        const int dh = (tap >= 3) ? tap - 4 : tap - 1;
+        const size_t src = g0_pos_index(img, v + dv, h + dh, s.Hb, s.Wb) * E1 + c;
+        const size_t dst = (size_t)r * ld + (size_t)tap * E1 + c;
+        *reinterpret_cast<uint4 *>(o_hi + dst) = *reinterpret_cast<const uint4 *>(g_hi + src);
+        *reinterpret_cast<uint4 *>(o_lo + dst) = *reinterpret_cast<const uint4 *>(g_lo + src);
+    }
+}
+
+// KS[1] == 3: row v = -1 of the hidden map sees only zero padding, so g0(-1, h) = lrelu(0 + b_e0) for every h --
+// bit-identical to what the E0 GEMM epilogue produces from an all-zero accumulator.
+__global__ void fill_g0_top_kernel(const float *__restrict__ bias, int E1, int n_img, int Hb, int Wb,
+                                   bf16 *__restrict__ g_hi, bf16 *__restrict__ g_lo) {
+    const int pos = blockIdx.x;                 // img * (Wb+2) + (h+1)
+    const int img = pos / (Wb + 2), hp = pos - img * (Wb + 2);
+    const size_t row = g0_pos_index(img, -1, hp - 1, Hb, Wb);
+    for (int c = threadIdx.x; c < E1; c += blockDim.x) {
+        float v = 0.0f + bias[c];
+        v = v > 0.0f ? v : v * 0.01f;
+        bf16 h, l;
+        split_bf16(v, h, l);
+        g_hi[row * E1 + c] = h;
+        g_lo[row * E1 + c] = l;
+    }
+}
+
 // ---- weight packing -------------------------------------------------------------------------------
 struct TapList {
     int n;
@@ -190,6 +227,22 @@ int launch_gather(const float *x_cl, const float *zhat_cl, int Cin, const StepDe
     int threads = 5 * (Cin / 4);
     threads = threads > 256 ? 256 : ((threads + 31) / 32) * 32;
     gather_kernel<<<R, threads, 0, st>>>(x_cl, zhat_cl, Cin, s, R, X_hi, X_lo, ldX, T_hi, T_lo, ldT);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_gather5(const bf16 *g0_hi, const bf16 *g0_lo, int E1, const StepDesc &s, int R, bf16 *out_hi, bf16 *out_lo,
+                   int ld, cudaStream_t st) {
+    if (R <= 0) return 0;
+    gather5_kernel<<<R, 256, 0, st>>>(g0_hi, g0_lo, E1, s, R, out_hi, out_lo, ld);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_fill_g0_top(const float *bias, int E1, int n_img, int Hb, int Wb, bf16 *g_hi, bf16 *g_lo, cudaStream_t st) {
+    fill_g0_top_kernel<<<n_img * (Wb + 2), 256, 0, st>>>(bias, E1, n_img, Hb, Wb, g_hi, g_lo);
     count_launch(1);
     LBIC_CUDA(cudaGetLastError());
     return 0;

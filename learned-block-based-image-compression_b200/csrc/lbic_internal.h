@@ -38,6 +38,12 @@ struct StepDesc {
     int n_img, nv, vmin, t, Hb, Wb;
 };
 
+// Row of block position (v,h) of image img in the ring-extended hidden-map store used when KS[1] == 3:
+// rows v = -1..Hb-1, columns h = -1..Wb (g0 is evaluated on a one-block ring outside the image).
+__host__ __device__ inline size_t g0_pos_index(int img, int v, int h, int Hb, int Wb) {
+    return ((size_t)img * (Hb + 1) + (v + 1)) * (Wb + 2) + (h + 1);
+}
+
 __host__ __device__ inline void step_row_to_block(const StepDesc &s, int r, int &img, int &v, int &h) {
     img = r / s.nv;
     v = s.vmin + (r - img * s.nv);
@@ -65,6 +71,7 @@ struct EpiParams {
     const float *bias;  // [cout] (beta for the GDN modes)
     bf16 *out_hi, *out_lo;
     int ld_out;
+    int out_pos;        // 1: hi/lo output row = position in the ring-extended g0 store (KS[1]=3), see g0_pos_index
     float *out_f32;
     int ld_f32;
     const float *aux;   // pre-GDN activations (GDN modes) or ksi (QUANT)
@@ -114,6 +121,10 @@ int launch_pack_conv(const float *w, const float *mask, int cout, int cin, int k
                      const int *taps_host, int ntaps, bf16 *hi, bf16 *lo, int ld, cudaStream_t st);
 int launch_pack_gdn(const float *gamma, const float *beta, int C, float gbound, float gped, float bbound,
                     float bped, bf16 *hi, bf16 *lo, int ld, float *beta_out, cudaStream_t st);
+// KS[1]==3: A operand of get_meanscale[2] = the five mask-'B' taps of g0 around each block of the step
+int launch_gather5(const bf16 *g0_hi, const bf16 *g0_lo, int E1, const StepDesc &s, int R, bf16 *out_hi, bf16 *out_lo,
+                   int ld, cudaStream_t st);
+int launch_fill_g0_top(const float *bias, int E1, int n_img, int Hb, int Wb, bf16 *g_hi, bf16 *g_lo, cudaStream_t st);
 int launch_add_vec(const float *a, const float *b, float *out, int n, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------

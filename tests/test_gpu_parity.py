@@ -16,7 +16,7 @@ from conftest import golden_cases, load_case, load_tables
 
 pytestmark = pytest.mark.gpu
 
-KS3111_CASES = [c for c in golden_cases() if c.startswith(("B8_lowrate", "B16_lowrate"))]
+KS3111_CASES = golden_cases()   # all four reference topologies (KS3111 and KS3311)
 
 
 @pytest.fixture(scope="module")
@@ -157,7 +157,8 @@ def test_decode_roundtrip(dev, case, lanes):
     if lanes == 1:
         # and the reference's bitstream decodes to the reference's reconstruction
         zref = m.decompress(c["stream"].tobytes(), list(get_lru(m.KS)), x.shape, m.M, dev)
-        assert float((zref.cpu() - torch.from_numpy(c["zhat_dec"])).abs().max()) < 1e-4
+        tol = 1e-3 if bool(c["harsh"]) else 1e-4   # see test_encode_matches_reference_golden
+        assert float((zref.cpu() - torch.from_numpy(c["zhat_dec"])).abs().max()) < tol
 
 
 def test_batch_invariance_and_ragged_grids(dev):
