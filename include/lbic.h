@@ -60,6 +60,7 @@ typedef struct {
  *   1 = fp32 SIMT evaluation of the same split operands (bring-up / cross-check twin)      */
 #define LBIC_OPT_GEMM_CORE 1
 #define LBIC_OPT_USE_GRAPH 2   /* 1 = replay the per-(n,Hb,Wb) step sequence as a CUDA graph */
+#define LBIC_OPT_FORCE_BN 3    /* tuning hook: force the GEMM tile width (multiple of 16, <= 256); 0 = automatic */
 
 const char *lbic_last_error(void);
 const char *lbic_version(void);
@@ -140,6 +141,10 @@ int lbic_rans_decode(lbic_model *m, const uint8_t *streams, const uint32_t *stre
  * the selected GEMM core (A, W, D device fp32; the split into bf16 hi/lo planes happens inside). */
 int lbic_debug_gemm(lbic_model *m, const float *A, const float *W, float *D, int R, int K, int cout,
                     void *stream);
+
+/* Tuning hook: times `iters` back-to-back launches of the D = A W^T tile kernel (EPI_RAW or a PREGDN-style
+ * epilogue when with_epilogue != 0) on synthetic operands with CUDA events; returns the mean ms per launch. */
+int lbic_debug_gemm_bench(lbic_model *m, int R, int K, int cout, int with_epilogue, int iters, double *ms_per_launch);
 
 /* Number of kernels this library has launched on behalf of `m` since creation. */
 int64_t lbic_launch_count(const lbic_model *m);

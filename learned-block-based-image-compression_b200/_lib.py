@@ -23,6 +23,7 @@ class LbicTensorDesc(ctypes.Structure):
 
 LBIC_OPT_GEMM_CORE = 1
 LBIC_OPT_USE_GRAPH = 2
+LBIC_OPT_FORCE_BN = 3
 
 # every symbol include/lbic.h declares: (restype, argtypes)
 _vp, _i, _sz, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_int64
@@ -46,6 +47,7 @@ PROTOTYPES = {
     "lbic_rans_encode": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _sz, _vp, _vp]),
     "lbic_rans_decode": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _i64, _vp, _vp]),
     "lbic_debug_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "lbic_debug_gemm_bench": (_i, [_vp, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_double)]),
     "lbic_launch_count": (_i64, [_vp]),
     "lbic_set_profiling": (_i, [_vp, _i]),
     "lbic_get_profile": (_i, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_double),

@@ -44,14 +44,18 @@ enum LayerId {
     L_COUNT
 };
 
+constexpr int NBN = 3;   // tile-width variants per layer: wide (<= 256), 128, 64
+
 struct PackedSeg {
     int K = 0;
     bf16 *hi = nullptr, *lo = nullptr;
-    CUtensorMap tm_hi, tm_lo;
+    CUtensorMap tm_hi[NBN], tm_lo[NBN];   // TMA box = 64 x bn_v[i]
 };
 
 struct PackedLayer {
     int cout = 0, bn = 0, nseg = 0;
+    int bn_v[NBN] = {0, 0, 0};
+    int n_bn = 0;
     PackedSeg seg[2];
     float *bias = nullptr;
 };
@@ -105,6 +109,7 @@ struct lbic_model {
     Workspace ws;
     int gemm_core = 0;
     int use_graph = 0;
+    int force_bn = 0;
     int64_t launches[2] = {0, 0};
     int *err_flag = nullptr;
     // host-call staging
@@ -138,6 +143,17 @@ int dev_alloc(std::vector<void *> &list, void **p, size_t bytes, bool zero = fal
 void free_all(std::vector<void *> &list) {
     for (void *p : list) cudaFree(p);
     list.clear();
+}
+
+// tile-width candidates of a layer, widest first
+int bn_variants(int cout, int *out) {
+    const int ntiles = (cout + 255) / 256;
+    int wide = ((cout + ntiles - 1) / ntiles + 15) / 16 * 16;
+    int n = 0;
+    out[n++] = wide;
+    if (wide > 128) out[n++] = 128;
+    if (wide > 64) out[n++] = 64;
+    return n;
 }
 
 int pick_bn(int cout) {
@@ -198,8 +214,13 @@ int pack_conv_seg(lbic_model *m, const SdView &sd, const std::string &prefix, in
     LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&seg.hi, sizeof(bf16) * (size_t)cout * seg.K));
     LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&seg.lo, sizeof(bf16) * (size_t)cout * seg.K));
     LBIC_TRY(launch_pack_conv(w, mask, cout, cin, k, k, taps, ntaps, seg.hi, seg.lo, seg.K, st));
-    LBIC_TRY(make_tmap_2d(&seg.tm_hi, seg.hi, seg.K, cout, seg.K, 64, bn));
-    LBIC_TRY(make_tmap_2d(&seg.tm_lo, seg.lo, seg.K, cout, seg.K, 64, bn));
+    int bnv[NBN];
+    const int nb = bn_variants(cout, bnv);
+    (void)bn;
+    for (int i = 0; i < nb; ++i) {
+        LBIC_TRY(make_tmap_2d(&seg.tm_hi[i], seg.hi, seg.K, cout, seg.K, 64, bnv[i]));
+        LBIC_TRY(make_tmap_2d(&seg.tm_lo[i], seg.lo, seg.K, cout, seg.K, 64, bnv[i]));
+    }
     return 0;
 }
 
@@ -208,6 +229,7 @@ int pack_linear(lbic_model *m, const SdView &sd, int id, const std::string &pref
     PackedLayer &L = m->L[id];
     L.cout = cout;
     L.bn = pick_bn(cout);
+    L.n_bn = bn_variants(cout, L.bn_v);
     L.nseg = 1;
     float *b = nullptr;
     LBIC_TRY(pack_conv_seg(m, sd, prefix, cout, cin, k, taps, ntaps, L.bn, L.seg[0], &b, tmp, st));
@@ -222,6 +244,7 @@ int pack_dual(lbic_model *m, const SdView &sd, int id, const std::string &p1, in
     PackedLayer &L = m->L[id];
     L.cout = cout;
     L.bn = pick_bn(cout);
+    L.n_bn = bn_variants(cout, L.bn_v);
     L.nseg = 2;
     float *b1 = nullptr, *b2 = nullptr;
     LBIC_TRY(pack_conv_seg(m, sd, p1, cout, cin1, 1, TAPS_1, 1, L.bn, L.seg[0], &b1, tmp, st));
@@ -236,6 +259,7 @@ int pack_gdn(lbic_model *m, const SdView &sd, int id, const std::string &prefix,
     PackedLayer &L = m->L[id];
     L.cout = C;
     L.bn = pick_bn(C);
+    L.n_bn = bn_variants(C, L.bn_v);
     L.nseg = 1;
     float *g = nullptr, *b = nullptr;
     LBIC_TRY(stage(sd, prefix + ".gamma", (int64_t)C * C, tmp, &g, st));
@@ -253,8 +277,10 @@ int pack_gdn(lbic_model *m, const SdView &sd, int id, const std::string &prefix,
     LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&seg.lo, sizeof(bf16) * (size_t)C * C));
     LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&L.bias, sizeof(float) * C));
     LBIC_TRY(launch_pack_gdn(g, b, C, gbound, gped, bbound, bped, seg.hi, seg.lo, C, L.bias, st));
-    LBIC_TRY(make_tmap_2d(&seg.tm_hi, seg.hi, C, C, C, 64, L.bn));
-    LBIC_TRY(make_tmap_2d(&seg.tm_lo, seg.lo, C, C, C, 64, L.bn));
+    for (int i = 0; i < L.n_bn; ++i) {
+        LBIC_TRY(make_tmap_2d(&seg.tm_hi[i], seg.hi, C, C, C, 64, L.bn_v[i]));
+        LBIC_TRY(make_tmap_2d(&seg.tm_lo[i], seg.lo, C, C, C, 64, L.bn_v[i]));
+    }
     return 0;
 }
 
@@ -345,7 +371,17 @@ int ensure_rans_scratch(lbic_model *m, size_t words) {
 int run_gemm(lbic_model *m, int id, int R, const ActView *a0, const ActView *a1, EpiParams ep, cudaStream_t st) {
     const PackedLayer &L = m->L[id];
     GemmCall g;
-    g.R = R; g.cout = L.cout; g.bn = L.bn; g.nseg = L.nseg;
+    // Tile width: the widest variant that still gives about one CTA per SM; small steps (few rows) take narrower
+    // tiles so that more SMs share the layer -- the result does not depend on the choice (no split-K, fixed k order).
+    int vi = 0;
+    if (m->force_bn) {
+        for (int i = 0; i < L.n_bn; ++i)
+            if (L.bn_v[i] == m->force_bn) vi = i;
+    } else {
+        const int row_tiles = (R + 127) / 128;
+        while (vi + 1 < L.n_bn && row_tiles * ((L.cout + L.bn_v[vi] - 1) / L.bn_v[vi]) < 120) ++vi;
+    }
+    g.R = R; g.cout = L.cout; g.bn = L.bn_v[vi]; g.nseg = L.nseg;
     const ActView *av[2] = {a0, a1};
     double flops = 0;
     for (int s = 0; s < L.nseg; ++s) {
@@ -355,7 +391,7 @@ int run_gemm(lbic_model *m, int id, int R, const ActView *a0, const ActView *a1,
         g.A[s].hi = av[s]->buf->hi; g.A[s].lo = av[s]->buf->lo; g.A[s].ld = av[s]->buf->ld;
         g.A[s].tm_hi = &av[s]->tm_hi; g.A[s].tm_lo = &av[s]->tm_lo;
         g.W[s].hi = L.seg[s].hi; g.W[s].lo = L.seg[s].lo; g.W[s].ld = L.seg[s].K;
-        g.W[s].tm_hi = &L.seg[s].tm_hi; g.W[s].tm_lo = &L.seg[s].tm_lo;
+        g.W[s].tm_hi = &L.seg[s].tm_hi[vi]; g.W[s].tm_lo = &L.seg[s].tm_lo[vi];
         flops += 2.0 * R * (double)L.seg[s].K * L.cout;
     }
     ep.R = R; ep.cout = L.cout; ep.bias = L.bias;
@@ -571,6 +607,10 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
         return 0;
     case LBIC_OPT_USE_GRAPH:
         m->use_graph = value ? 1 : 0;
+        return 0;
+    case LBIC_OPT_FORCE_BN:
+        if (value != 0 && (value % 16 || value < 16 || value > 256)) return lbic_fail(LBIC_ERR_INVALID, "bad tile width");
+        m->force_bn = value;
         return 0;
     default:
         return lbic_fail(LBIC_ERR_INVALID, "unknown option %d", option);
@@ -918,6 +958,66 @@ extern "C" int lbic_debug_gemm(lbic_model *m, const float *A, const float *W, fl
     if (rc) return rc;
     if (e != cudaSuccess) return lbic_fail(LBIC_ERR_CUDA, "debug gemm failed: %s", cudaGetErrorString(e));
     return 0;
+}
+
+extern "C" int lbic_debug_gemm_bench(lbic_model *m, int R, int K, int cout, int with_epilogue, int iters,
+                                     double *ms_per_launch) {
+    if (!m || !ms_per_launch || R < 1 || K % 8 || cout % 16 || iters < 1) return lbic_fail(LBIC_ERR_INVALID, "bad argument");
+    Active act(m);
+    cudaStream_t st = 0;
+    std::vector<void *> tmp;
+    int rc = 0;
+    *ms_per_launch = 0;
+    do {
+#define P(call) if ((rc = (call)) != 0) break
+        const int Rp = (R + 127) / 128 * 128;
+        bf16 *ah, *al, *wh, *wl, *oh, *ol;
+        float *A, *W, *D, *bias;
+        P(dev_alloc(tmp, (void **)&A, sizeof(float) * (size_t)Rp * K, true));
+        P(dev_alloc(tmp, (void **)&W, sizeof(float) * (size_t)cout * K, true));
+        P(dev_alloc(tmp, (void **)&D, sizeof(float) * (size_t)Rp * cout, true));
+        P(dev_alloc(tmp, (void **)&bias, sizeof(float) * cout, true));
+        P(dev_alloc(tmp, (void **)&ah, sizeof(bf16) * (size_t)Rp * K, true));
+        P(dev_alloc(tmp, (void **)&al, sizeof(bf16) * (size_t)Rp * K, true));
+        P(dev_alloc(tmp, (void **)&wh, sizeof(bf16) * (size_t)cout * K, true));
+        P(dev_alloc(tmp, (void **)&wl, sizeof(bf16) * (size_t)cout * K, true));
+        P(dev_alloc(tmp, (void **)&oh, sizeof(bf16) * (size_t)Rp * cout, true));
+        P(dev_alloc(tmp, (void **)&ol, sizeof(bf16) * (size_t)Rp * cout, true));
+        GemmCall g;
+        memset(&g, 0, sizeof(g));
+        g.R = R; g.cout = cout; g.bn = m->force_bn ? m->force_bn : pick_bn(cout); g.nseg = 1; g.K[0] = K;
+        CUtensorMap ta_h, ta_l, tw_h, tw_l;
+        P(make_tmap_2d(&ta_h, ah, K, Rp, K, 64, 128));
+        P(make_tmap_2d(&ta_l, al, K, Rp, K, 64, 128));
+        P(make_tmap_2d(&tw_h, wh, K, cout, K, 64, g.bn));
+        P(make_tmap_2d(&tw_l, wl, K, cout, K, 64, g.bn));
+        g.A[0].hi = ah; g.A[0].lo = al; g.A[0].ld = K; g.A[0].tm_hi = &ta_h; g.A[0].tm_lo = &ta_l;
+        g.W[0].hi = wh; g.W[0].lo = wl; g.W[0].ld = K; g.W[0].tm_hi = &tw_h; g.W[0].tm_lo = &tw_l;
+        g.ep.R = R; g.ep.cout = cout;
+        if (with_epilogue) {
+            g.ep.mode = EPI_PREGDN; g.ep.bias = bias; g.ep.out_hi = oh; g.ep.out_lo = ol; g.ep.ld_out = cout;
+            g.ep.out_f32 = D; g.ep.ld_f32 = cout;
+        } else {
+            g.ep.mode = EPI_RAW; g.ep.out_f32 = D; g.ep.ld_f32 = cout;
+        }
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        for (int i = 0; i < 3 && rc == 0; ++i) rc = m->gemm_core == 1 ? gemm_simt_launch(g, st) : gemm_tc_launch(g, st);
+        if (rc) break;
+        cudaEventRecord(e0, st);
+        for (int i = 0; i < iters && rc == 0; ++i) rc = m->gemm_core == 1 ? gemm_simt_launch(g, st) : gemm_tc_launch(g, st);
+        cudaEventRecord(e1, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (rc == 0 && e != cudaSuccess) rc = lbic_fail(LBIC_ERR_CUDA, "gemm bench failed: %s", cudaGetErrorString(e));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *ms_per_launch = ms / iters;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+#undef P
+    } while (0);
+    cudaDeviceSynchronize();
+    free_all(tmp);
+    return rc;
 }
 
 extern "C" int64_t lbic_launch_count(const lbic_model *m) { return m ? m->launches[0] + m->launches[1] : 0; }

@@ -63,17 +63,12 @@ __device__ __forceinline__ void load_f32(const float *__restrict__ p, float (&v)
 // (the tcgen05 core software-pipelines: prefetch chunk i+1 while chunk i is being finished).
 template <int NV>
 struct EpiPre {
-    float b[NV];    // bias / beta
     float a[NV];    // pre-GDN activation (GDN modes) or predicted scale (QUANT)
     float a2[NV];   // predicted mean (QUANT)
 };
 
-// bias: pointer to the bias of column c (global memory, or the CTA's shared-memory copy of its tile slice)
 template <int NV>
-__device__ __forceinline__ void epi_prefetch(const EpiParams &p, const float *__restrict__ bias, int r, int c,
-                                             EpiPre<NV> &pre) {
-    if (p.mode == EPI_RAW) return;
-    load_f32<NV>(bias, pre.b);
+__device__ __forceinline__ void epi_prefetch(const EpiParams &p, int r, int c, EpiPre<NV> &pre) {
     if (p.mode == EPI_GDN || p.mode == EPI_IGDN) {
         load_f32<NV>(p.aux + (size_t)r * p.ld_aux + c, pre.a);
     } else if (p.mode == EPI_QUANT) {
@@ -82,34 +77,63 @@ __device__ __forceinline__ void epi_prefetch(const EpiParams &p, const float *__
     }
 }
 
+// Results of one epilogue chunk, still in registers.  Which planes are meaningful depends on the mode:
+//   f32 plane : RAW, PREGDN (a), KSI, RECON (zhat), QUANT (symbols, as int32 bit patterns)
+//   hi/lo     : LRELU, PREGDN (a*a), GDN, IGDN, QUANT (y_qnt)
+//   idx       : QUANT (CDF indexes, 4 per word)
 template <int NV>
-__device__ __forceinline__ void epi_apply(const EpiParams &p, int r, int c, const float (&acc)[NV],
-                                          const EpiPre<NV> &pre) {
-    float v[NV];
+struct EpiOut {
+    float f[NV];
+    uint32_t hi[NV / 2], lo[NV / 2];   // bf16 pairs, element 2j in the low half
+    uint32_t idx[NV / 4];
+};
+
+__host__ __device__ __forceinline__ bool epi_has_f32(int mode) {
+    return mode == EPI_RAW || mode == EPI_PREGDN || mode == EPI_KSI || mode == EPI_RECON || mode == EPI_QUANT;
+}
+__host__ __device__ __forceinline__ bool epi_has_hilo(int mode) {
+    return mode == EPI_LRELU || mode == EPI_PREGDN || mode == EPI_GDN || mode == EPI_IGDN || mode == EPI_QUANT;
+}
+
+template <int NV>
+__device__ __forceinline__ void pack_hilo(const float (&v)[NV], EpiOut<NV> &o) {
+#pragma unroll
+    for (int i = 0; i < NV; i += 2) {
+        bf16 h0, l0, h1, l1;
+        split_bf16(v[i], h0, l0);
+        split_bf16(v[i + 1], h1, l1);
+        o.hi[i >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        o.lo[i >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+}
+
+// The arithmetic of every fused epilogue.  bias: pointer to the bias / beta of the chunk's first column (global
+// memory, or the CTA's shared-memory copy of its tile slice).
+template <int NV>
+__device__ __forceinline__ void epi_compute(const EpiParams &p, const float *__restrict__ bias, const float (&acc)[NV],
+                                            const EpiPre<NV> &pre, EpiOut<NV> &o) {
     if (p.mode == EPI_RAW) {
-        store_f32<NV>(p.out_f32 + (size_t)r * p.ld_f32 + c, acc);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) o.f[i] = acc[i];
         return;
     }
+    float v[NV];
+    load_f32<NV>(bias, v);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = acc[i] + pre.b[i];
-
+    for (int i = 0; i < NV; ++i) v[i] = acc[i] + v[i];
     switch (p.mode) {
     case EPI_LRELU: {
 #pragma unroll
         for (int i = 0; i < NV; ++i) v[i] = v[i] > 0.0f ? v[i] : v[i] * 0.01f;   // nn.LeakyReLU() default slope
-        size_t orow = (size_t)r;
-        if (p.out_pos) {
-            int img, bv, bh;
-            step_row_to_block(p.step, r, img, bv, bh);
-            orow = g0_pos_index(img, bv, bh, p.step.Hb, p.step.Wb);
-        }
-        store_hilo<NV>(p.out_hi + orow * p.ld_out + c, p.out_lo + orow * p.ld_out + c, v);
+        pack_hilo<NV>(v, o);
     } break;
     case EPI_PREGDN: {
-        store_f32<NV>(p.out_f32 + (size_t)r * p.ld_f32 + c, v);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] = v[i] * v[i];
-        store_hilo<NV>(p.out_hi + (size_t)r * p.ld_out + c, p.out_lo + (size_t)r * p.ld_out + c, v);
+        for (int i = 0; i < NV; ++i) {
+            o.f[i] = v[i];
+            v[i] = v[i] * v[i];                                                   // x ** 2 (GDNF:71)
+        }
+        pack_hilo<NV>(v, o);
     } break;
     case EPI_GDN:
     case EPI_IGDN: {
@@ -119,51 +143,88 @@ __device__ __forceinline__ void epi_apply(const EpiParams &p, int r, int c, cons
             const float sq = __fsqrt_rn(v[i]);
             v[i] = pre.a[i] * (inv ? sq : __fdiv_rn(1.0f, sq));   // torch.sqrt / torch.rsqrt (GDNF:73-76)
         }
-        store_hilo<NV>(p.out_hi + (size_t)r * p.ld_out + c, p.out_lo + (size_t)r * p.ld_out + c, v);
+        pack_hilo<NV>(v, o);
     } break;
     case EPI_KSI: {
-        store_f32<NV>(p.out_f32 + (size_t)r * p.ld_f32 + c, v);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) o.f[i] = v[i];
     } break;
     case EPI_QUANT: {
-        int img, bv, bh;
-        step_row_to_block(p.step, r, img, bv, bh);
-        const size_t o = (((size_t)img * p.step.Hb + bv) * p.step.Wb + bh) * p.M + c;
-        int32_t s[NV];
-        uint32_t packed_idx[NV / 4];
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const float q = rintf(v[i] - pre.a2[i]);                   // torch.round: half to even (ENT:143)
-            s[i] = (int32_t)q;
+            o.f[i] = __int_as_float((int32_t)q);
             v[i] = q + pre.a2[i];                                      // y_qnt = y_sym + means (NET:374)
             const int k = scale_to_index(pre.a[i], p.scale_tab);
-            if ((i & 3) == 0) packed_idx[i >> 2] = 0;
-            packed_idx[i >> 2] |= (uint32_t)k << (8 * (i & 3));
+            if ((i & 3) == 0) o.idx[i >> 2] = 0;
+            o.idx[i >> 2] |= (uint32_t)k << (8 * (i & 3));
         }
-        store_hilo<NV>(p.out_hi + (size_t)r * p.ld_out + c, p.out_lo + (size_t)r * p.ld_out + c, v);
-        if (p.sym) {
-#pragma unroll
-            for (int i = 0; i < NV; i += 4)
-                *reinterpret_cast<int4 *>(p.sym + o + i) = make_int4(s[i], s[i + 1], s[i + 2], s[i + 3]);
-        }
-        if (p.idx) {
-#pragma unroll
-            for (int i = 0; i < NV / 4; ++i) *reinterpret_cast<uint32_t *>(p.idx + o + 4 * i) = packed_idx[i];
-        }
+        pack_hilo<NV>(v, o);
     } break;
     case EPI_RECON: {
-        int img, bv, bh;
-        step_row_to_block(p.step, r, img, bv, bh);
 #pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] = fminf(fmaxf(v[i], -0.5f), 0.5f);   // clamp_(-0.5, 0.5) NET:357
-        store_f32<NV>(p.zhat + (((size_t)img * p.step.Hb + bv) * p.step.Wb + bh) * p.cout + c, v);
+        for (int i = 0; i < NV; ++i) o.f[i] = fminf(fmaxf(v[i], -0.5f), 0.5f);   // clamp_(-0.5, 0.5) NET:357
     } break;
     default: break;
+    }
+}
+
+// Where row r of the step's compact matrices lands for each output plane (element offsets, column 0).
+struct EpiRowDst {
+    size_t f32, hilo, blk;   // blk: block index (img,v,h) for the scattered QUANT / RECON outputs
+};
+
+__device__ __forceinline__ EpiRowDst epi_row_dst(const EpiParams &p, int r) {
+    EpiRowDst d;
+    d.f32 = (size_t)r * p.ld_f32;
+    d.hilo = (size_t)r * p.ld_out;
+    d.blk = 0;
+    if (p.mode == EPI_QUANT || p.mode == EPI_RECON || (p.mode == EPI_LRELU && p.out_pos)) {
+        int img, bv, bh;
+        step_row_to_block(p.step, r, img, bv, bh);
+        d.blk = ((size_t)img * p.step.Hb + bv) * p.step.Wb + bh;
+        if (p.mode == EPI_LRELU) d.hilo = g0_pos_index(img, bv, bh, p.step.Hb, p.step.Wb) * p.ld_out;
+    }
+    return d;
+}
+
+// f32-plane destination pointer of (row, column c); nullptr if the mode has none / it is not requested
+__device__ __forceinline__ float *epi_f32_ptr(const EpiParams &p, const EpiRowDst &d, int c) {
+    switch (p.mode) {
+    case EPI_RAW: case EPI_PREGDN: case EPI_KSI: return p.out_f32 + d.f32 + c;
+    case EPI_RECON: return p.zhat + d.blk * p.cout + c;
+    case EPI_QUANT: return p.sym ? reinterpret_cast<float *>(p.sym) + d.blk * p.M + c : nullptr;
+    default: return nullptr;
+    }
+}
+
+// Direct (uncoalesced, one row per thread) store of a chunk: used by the SIMT twin.
+template <int NV>
+__device__ __forceinline__ void epi_store_direct(const EpiParams &p, int r, int c, const EpiOut<NV> &o) {
+    const EpiRowDst d = epi_row_dst(p, r);
+    float *pf = epi_f32_ptr(p, d, c);
+    if (pf) {
+#pragma unroll
+        for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4 *>(pf + i) = make_float4(o.f[i], o.f[i + 1], o.f[i + 2], o.f[i + 3]);
+    }
+    if (epi_has_hilo(p.mode)) {
+#pragma unroll
+        for (int i = 0; i < NV / 2; i += 2) {
+            *reinterpret_cast<uint2 *>(p.out_hi + d.hilo + c + 2 * i) = make_uint2(o.hi[i], o.hi[i + 1]);
+            *reinterpret_cast<uint2 *>(p.out_lo + d.hilo + c + 2 * i) = make_uint2(o.lo[i], o.lo[i + 1]);
+        }
+    }
+    if (p.mode == EPI_QUANT && p.idx) {
+#pragma unroll
+        for (int i = 0; i < NV / 4; ++i) *reinterpret_cast<uint32_t *>(p.idx + d.blk * p.M + c + 4 * i) = o.idx[i];
     }
 }
 
 template <int NV>
 __device__ __forceinline__ void epilogue_store(const EpiParams &p, int r, int c, const float (&acc)[NV]) {
     EpiPre<NV> pre;
-    epi_prefetch<NV>(p, p.bias + c, r, c, pre);
-    epi_apply<NV>(p, r, c, acc, pre);
+    EpiOut<NV> o;
+    epi_prefetch<NV>(p, r, c, pre);
+    epi_compute<NV>(p, p.bias + c, acc, pre, o);
+    epi_store_direct<NV>(p, r, c, o);
 }

@@ -8,12 +8,12 @@
 // the tile it shares or on whether the encoder or the decoder computes it.
 //
 // CTA = one 128 x bn output tile (bn a multiple of 16, <= 256).  Warp roles:
-//   warp 0      TMA producer: per 64-wide k-block loads A hi/lo [128x64] and W hi/lo [bn x 64]
-//               (SWIZZLE_128B, K-major) into a multi-stage ring, mbarrier complete_tx
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit frees stages
-//   warps 2..9  epilogue (two warps per TMEM lane quarter, each taking half of the tile's columns): stage the
-//               bias slice in shared memory while the mainloop runs, then software-pipelined
-//               tcgen05.ld (32 lanes x 16 columns) + operand prefetch -> fused epilogue -> global
+//   warp 0 lane 0   TMA producer: per 64-wide k-block loads A hi/lo [128x64] and W hi/lo [bn x 64]
+//                   (SWIZZLE_128B, K-major) into a multi-stage ring, mbarrier complete_tx
+//   warp 1 lane 0   single-thread tcgen05.mma issuer (warp 1 also owns the TMEM allocation);
+//                   tcgen05.commit frees stages and finally signals the accumulator
+//   all 8 warps     epilogue (two warps per TMEM lane quarter): software-pipelined tcgen05.ld (32 lanes x 16
+//                   columns) + operand prefetch -> fused epilogue -> staged in the idle ring -> coalesced stores
 #include "epilogue.cuh"
 
 #include <cstdio>
@@ -25,8 +25,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_PLANE = BM * BK * 2;     // 16 KiB per bf16 plane
 constexpr int MAX_STAGES = 4;
-constexpr int NUM_THREADS = 320;          // producer, MMA issuer, 8 epilogue warps
-constexpr int NUM_EPI_THREADS = 256;
+constexpr int NUM_THREADS = 256;          // 8 warps = 2 per SM sub-partition (255 registers available)
 constexpr int SMEM_LIMIT = 232448;       // 227 KiB opt-in maximum per CTA
 constexpr int BAR_BLOCK = 128;           // full[4] | empty[4] | tmem_full | tmem base address
 constexpr int SMEM_SLACK = 1024 + BAR_BLOCK + 1024;   // ring alignment + barrier block + bias slice (<= 256 floats)
@@ -37,6 +36,7 @@ struct TcParams {
     int stages;
     uint32_t tmem_cols;
     uint32_t idesc;
+    uint32_t ring_bytes;   // max(stages * stage_bytes, epilogue staging), multiple of 1024
     EpiParams ep;
 };
 
@@ -125,12 +125,89 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
                  : "memory");
 }
 
-__device__ __forceinline__ void epi_chunk_apply(const EpiParams &ep, int r, int c, const uint32_t (&raw)[16],
-                                                const EpiPre<16> &pre) {
+// ---- epilogue staging ---------------------------------------------------------------------------
+// Once the accumulator is complete every pipeline stage is idle, so the ring is reused to stage one 128-row x
+// (<=128)-column group of outputs: one thread per row writes its chunks (padded rows -> conflict-free 16-byte
+// shared stores), then whole warps copy each row to global memory as contiguous 16-byte-per-lane stores.  The
+// direct alternative (one row per lane, 16 B per store) costs one L1 tag lookup per lane per instruction and made
+// the epilogue 60 % of the kernel (profiles/r1_gemm_epilogue.md).
+constexpr int GROUP_COLS = 128;
+constexpr int STG_F_STRIDE = GROUP_COLS * 4 + 16;     // fp32 plane row stride (bytes)
+constexpr int STG_H_STRIDE = GROUP_COLS * 2 + 16;     // bf16 plane row stride
+constexpr int STG_I_STRIDE = GROUP_COLS + 16;         // uint8 index plane row stride
+constexpr int STG_F_OFF = 0;
+constexpr int STG_H_OFF = STG_F_OFF + BM * STG_F_STRIDE;
+constexpr int STG_L_OFF = STG_H_OFF + BM * STG_H_STRIDE;
+constexpr int STG_I_OFF = STG_L_OFF + BM * STG_H_STRIDE;
+constexpr int STG_BYTES = STG_I_OFF + BM * STG_I_STRIDE;   // 155,648 B
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+// thread = row `rl` of the tile; writes the 16 columns starting at group-local column gc
+__device__ __forceinline__ void stage_chunk(uint32_t stg, int mode, int rl, int gc, const EpiOut<16> &o) {
+    if (epi_has_f32(mode)) {
+        const uint32_t a = stg + STG_F_OFF + rl * STG_F_STRIDE + gc * 4;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+            sts128(a + i * 4, __float_as_uint(o.f[i]), __float_as_uint(o.f[i + 1]), __float_as_uint(o.f[i + 2]),
+                   __float_as_uint(o.f[i + 3]));
+    }
+    if (epi_has_hilo(mode)) {
+        const uint32_t h = stg + STG_H_OFF + rl * STG_H_STRIDE + gc * 2;
+        const uint32_t l = stg + STG_L_OFF + rl * STG_H_STRIDE + gc * 2;
+        sts128(h, o.hi[0], o.hi[1], o.hi[2], o.hi[3]);
+        sts128(h + 16, o.hi[4], o.hi[5], o.hi[6], o.hi[7]);
+        sts128(l, o.lo[0], o.lo[1], o.lo[2], o.lo[3]);
+        sts128(l + 16, o.lo[4], o.lo[5], o.lo[6], o.lo[7]);
+    }
+    if (mode == EPI_QUANT) sts128(stg + STG_I_OFF + rl * STG_I_STRIDE + gc, o.idx[0], o.idx[1], o.idx[2], o.idx[3]);
+}
+
+// one warp copies row `rl` (global row r) of the staged group: `ncols` valid columns starting at tile column c0
+__device__ __forceinline__ void store_row(const EpiParams &ep, uint32_t stg, int rl, int r, int c0, int ncols, int lane) {
+    const EpiRowDst d = epi_row_dst(ep, r);
+    float *pf = epi_f32_ptr(ep, d, c0);
+    if (pf) {
+        const uint32_t a = stg + STG_F_OFF + rl * STG_F_STRIDE;
+        for (int i = lane; i < (ncols >> 2); i += 32) {
+            const uint4 v = lds128(a + i * 16);
+            *reinterpret_cast<uint4 *>(pf + i * 4) = v;
+        }
+    }
+    if (epi_has_hilo(ep.mode)) {
+        // lanes 0..15 move the hi plane, lanes 16..31 the lo plane (ncols*2 bytes each, <= 256 B)
+        const int sub = lane & 15;
+        const bool is_lo = lane >= 16;
+        const uint32_t a = stg + (is_lo ? STG_L_OFF : STG_H_OFF) + rl * STG_H_STRIDE;
+        bf16 *dst = (is_lo ? ep.out_lo : ep.out_hi) + d.hilo + c0;
+        if (sub < (ncols >> 3)) {
+            const uint4 v = lds128(a + sub * 16);
+            *reinterpret_cast<uint4 *>(dst + sub * 8) = v;
+        }
+    }
+    if (ep.mode == EPI_QUANT && ep.idx) {
+        if (lane < (ncols >> 4)) {
+            const uint4 v = lds128(stg + STG_I_OFF + rl * STG_I_STRIDE + lane * 16);
+            *reinterpret_cast<uint4 *>(ep.idx + d.blk * ep.M + c0 + lane * 16) = v;
+        }
+    }
+}
+
+__device__ __forceinline__ void epi_chunk_stage(const EpiParams &ep, const float *bias, uint32_t stg, int rl, int gc,
+                                                const uint32_t (&raw)[16], const EpiPre<16> &pre) {
     float v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
-    epi_apply<16>(ep, r, c, v, pre);
+    EpiOut<16> o;
+    epi_compute<16>(ep, bias, v, pre, o);
+    stage_chunk(stg, ep.mode, rl, gc, o);
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -144,7 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     const uint32_t ring = (raw + 1023u) & ~1023u;                     // SWIZZLE_128B needs 1024-B alignment
     const uint32_t w_plane = (uint32_t)p.bn * (BK * 2);
     const uint32_t stage_bytes = 2 * A_PLANE + 2 * w_plane;
-    const uint32_t bars = ring + p.stages * stage_bytes;              // 8-B aligned (multiple of 1024)
+    const uint32_t bars = ring + p.ring_bytes;                        // after the ring / staging area
     // barrier block: full[4] | empty[4] | tmem_full | tmem base address
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (MAX_STAGES + s); };
@@ -173,6 +250,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // every thread helps staging this tile's bias slice (read back by the epilogue from shared memory)
+    float *sbias = reinterpret_cast<float *>(smem_raw + (bars + BAR_BLOCK - raw));
+    if (p.ep.mode != EPI_RAW)
+        for (int i = threadIdx.x; i < p.bn; i += NUM_THREADS) sbias[i] = (n0 + i < p.ep.cout) ? p.ep.bias[n0 + i] : 0.0f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -218,48 +299,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
             }
             umma_commit(tmem_full_bar);      // accumulator complete
         }
-    } else {
+    }
+    __syncwarp();
+    {
         const int q = warp & 3;                  // TMEM lane quarter this warp may access (warp id % 4)
-        const int half = (warp - 2) >> 2;        // which half of the tile's column chunks
-        // stage this tile's bias slice while the mainloop runs
-        float *sbias = reinterpret_cast<float *>(smem_raw + (bars + BAR_BLOCK - raw));
-        if (p.ep.mode != EPI_RAW)
-            for (int i = threadIdx.x - 64; i < p.bn; i += NUM_EPI_THREADS)
-                sbias[i] = (n0 + i < p.ep.cout) ? p.ep.bias[n0 + i] : 0.0f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int nch = p.bn >> 4;
-        const int ch_end = half ? nch : (nch + 1) >> 1;
-        int ch = half ? (nch + 1) >> 1 : 0;
-        const int r = m0 + q * 32 + lane;
+        const int ew = warp;                     // epilogue warp 0..7
+        const int sub = ew >> 2;                 // the two warps of a lane quarter split each group's chunks
+        const int rl = q * 32 + lane;
+        const int r = m0 + rl;
         const bool row_ok = r < p.ep.R;
         const uint32_t lane_base = tmem_acc + ((uint32_t)(q * 32) << 16);
-        auto ok = [&](int chunk) { return row_ok && (n0 + chunk * 16 < p.ep.cout); };
-        EpiPre<16> preA, preB;
-        uint32_t accA[16], accB[16];
-        if (ch < ch_end && ok(ch)) epi_prefetch<16>(p.ep, sbias + ch * 16, r, n0 + ch * 16, preA);
+        const uint32_t stg = ring;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        if (ch < ch_end) {
-            tmem_ld_issue(lane_base + (uint32_t)(ch * 16), accA);
-            tmem_ld_wait(accA);
-        }
-        for (; ch < ch_end; ch += 2) {
-            const bool hasB = ch + 1 < ch_end;
-            if (hasB) {
-                tmem_ld_issue(lane_base + (uint32_t)((ch + 1) * 16), accB);
-                if (ok(ch + 1)) epi_prefetch<16>(p.ep, sbias + (ch + 1) * 16, r, n0 + (ch + 1) * 16, preB);
+        for (int g0 = 0; g0 < p.bn; g0 += GROUP_COLS) {
+            const int gcols = (p.bn - g0) < GROUP_COLS ? (p.bn - g0) : GROUP_COLS;
+            const int gch = gcols >> 4;
+            const int ch_end = sub ? gch : (gch + 1) >> 1;
+            int ch = sub ? (gch + 1) >> 1 : 0;
+            // chunk `k` of this group covers tile columns g0 + 16k
+            auto ok = [&](int k) { return row_ok && (n0 + g0 + k * 16 < p.ep.cout); };
+            EpiPre<16> preA, preB;
+            uint32_t accA[16], accB[16];
+            if (ch < ch_end) {
+                if (ok(ch)) epi_prefetch<16>(p.ep, r, n0 + g0 + ch * 16, preA);
+                tmem_ld_issue(lane_base + (uint32_t)(g0 + ch * 16), accA);
+                tmem_ld_wait(accA);
             }
-            if (ok(ch)) epi_chunk_apply(p.ep, r, n0 + ch * 16, accA, preA);
-            if (hasB) {
-                tmem_ld_wait(accB);
-                const bool hasA = ch + 2 < ch_end;
-                if (hasA) {
-                    tmem_ld_issue(lane_base + (uint32_t)((ch + 2) * 16), accA);
-                    if (ok(ch + 2)) epi_prefetch<16>(p.ep, sbias + (ch + 2) * 16, r, n0 + (ch + 2) * 16, preA);
+            for (; ch < ch_end; ch += 2) {
+                const bool hasB = ch + 1 < ch_end;
+                if (hasB) {
+                    tmem_ld_issue(lane_base + (uint32_t)(g0 + (ch + 1) * 16), accB);
+                    if (ok(ch + 1)) epi_prefetch<16>(p.ep, r, n0 + g0 + (ch + 1) * 16, preB);
                 }
-                if (ok(ch + 1)) epi_chunk_apply(p.ep, r, n0 + (ch + 1) * 16, accB, preB);
-                if (hasA) tmem_ld_wait(accA);
+                if (ok(ch)) epi_chunk_stage(p.ep, sbias + g0 + ch * 16, stg, rl, ch * 16, accA, preA);
+                if (hasB) {
+                    tmem_ld_wait(accB);
+                    const bool hasA = ch + 2 < ch_end;
+                    if (hasA) {
+                        tmem_ld_issue(lane_base + (uint32_t)(g0 + (ch + 2) * 16), accA);
+                        if (ok(ch + 2)) epi_prefetch<16>(p.ep, r, n0 + g0 + (ch + 2) * 16, preA);
+                    }
+                    if (ok(ch + 1)) epi_chunk_stage(p.ep, sbias + g0 + (ch + 1) * 16, stg, rl, (ch + 1) * 16, accB, preB);
+                    if (hasA) tmem_ld_wait(accA);
+                }
             }
+            __syncthreads();                                      // the group is staged
+            int nvalid = p.ep.cout - (n0 + g0);
+            nvalid = nvalid < 0 ? 0 : (nvalid > gcols ? gcols : nvalid);
+            if (nvalid > 0) {
+                for (int row = ew; row < BM; row += 8) {
+                    const int rr = m0 + row;
+                    if (rr < p.ep.R) store_row(p.ep, stg, row, rr, n0 + g0, nvalid, lane);
+                }
+            }
+            if (g0 + GROUP_COLS < p.bn) __syncthreads();          // before restaging
         }
     }
     tc_fence_before();
@@ -329,7 +423,10 @@ int gemm_tc_launch(const GemmCall &g, cudaStream_t st) {
     p.ep = g.ep;
     const int s1 = g.nseg > 1 ? 1 : 0;
     dim3 grid((g.R + BM - 1) / BM, (g.cout + g.bn - 1) / g.bn);
-    const size_t smem = (size_t)stages * stage_bytes + SMEM_SLACK;
+    size_t ring_bytes = (size_t)stages * stage_bytes;
+    if (ring_bytes < (size_t)STG_BYTES) ring_bytes = (STG_BYTES + 1023) / 1024 * 1024;   // epilogue staging lives in the ring
+    p.ring_bytes = (uint32_t)ring_bytes;
+    const size_t smem = ring_bytes + SMEM_SLACK;
     gemm_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(*g.A[0].tm_hi, *g.A[0].tm_lo, *g.W[0].tm_hi, *g.W[0].tm_lo,
                                                     *g.A[s1].tm_hi, *g.A[s1].tm_lo, *g.W[s1].tm_hi, *g.W[s1].tm_lo, p);
     count_launch(0);
