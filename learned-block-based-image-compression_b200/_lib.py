@@ -24,6 +24,8 @@ class LbicTensorDesc(ctypes.Structure):
 LBIC_OPT_GEMM_CORE = 1
 LBIC_OPT_USE_GRAPH = 2
 LBIC_OPT_FORCE_BN = 3
+LBIC_OPT_CHAIN = 4
+LBIC_OPT_CLUSTER = 5
 
 # every symbol include/lbic.h declares: (restype, argtypes)
 _vp, _i, _sz, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_int64

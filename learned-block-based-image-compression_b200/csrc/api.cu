@@ -44,7 +44,7 @@ enum LayerId {
     L_COUNT
 };
 
-constexpr int NBN = 3;   // tile-width variants per layer: wide (<= 256), 128, 64
+constexpr int NBN = LBIC_NBN;
 
 struct PackedSeg {
     int K = 0;
@@ -88,6 +88,8 @@ struct Workspace {
     size_t rans_scratch_words = 0;   // total words allocated
     RansStreamState *dec_states = nullptr;
     const uint8_t **lane_ptr = nullptr;
+    std::vector<ChainLayer> h_chain;   // host copy of the per-layer chain descriptors (indexed by LayerId)
+    ChainLayer *d_chain = nullptr;
     std::vector<void *> allocs;
 };
 
@@ -110,6 +112,8 @@ struct lbic_model {
     int gemm_core = 0;
     int use_graph = 0;
     int force_bn = 0;
+    int use_chain = 1;     // persistent chain kernel per step (0: one launch per layer)
+    int force_cluster = 0;
     int64_t launches[2] = {0, 0};
     int *err_flag = nullptr;
     // host-call staging
@@ -300,6 +304,11 @@ int make_view(Workspace &ws, ActView &v, const ActBuf &b, int K) {
     return 0;
 }
 
+int build_chain(lbic_model *m);
+EpiParams epi(int mode, const StepDesc &sd);
+EpiParams epi_hilo(int mode, const StepDesc &sd, const ActBuf &out);
+EpiParams epi_pregdn(lbic_model *m, const StepDesc &sd);
+
 int ensure_workspace(lbic_model *m, int n_img, int Hb, int Wb) {
     Workspace &ws = m->ws;
     if (ws.n_img >= n_img && ws.Hb == Hb && ws.Wb == Wb) return 0;
@@ -355,7 +364,95 @@ int ensure_workspace(lbic_model *m, int n_img, int Hb, int Wb) {
     LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.idx, nblk * m->M));
     LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.dec_states, sizeof(RansStreamState) * (size_t)n_img * Hb));
     LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.lane_ptr, sizeof(void *) * (size_t)n_img * Hb));
+    LBIC_TRY(build_chain(m));
     return 0;
+}
+
+// Per-layer descriptors of the persistent chain kernel: the same operand views and epilogues run_ent / run_enc /
+// run_dec pass to the per-layer path, indexed by LayerId (so [L_E0, L_COUNT) is a whole encode step).
+int build_chain(lbic_model *m) {
+    Workspace &ws = m->ws;
+    ws.h_chain.assign(L_COUNT, ChainLayer());
+    StepDesc none;
+    memset(&none, 0, sizeof(none));
+    auto set = [&](int id, const ActView *a0, const ActView *a1, EpiParams ep) {
+        ChainLayer &c = ws.h_chain[id];
+        const PackedLayer &L = m->L[id];
+        memset(&c, 0, sizeof(c));
+        c.nseg = L.nseg; c.cout = L.cout; c.n_bn = L.n_bn;
+        const ActView *av[2] = {a0, a1};
+        for (int s = 0; s < L.nseg; ++s) {
+            c.kb[s] = (L.seg[s].K + 63) / 64;
+            c.tmA[s][0] = av[s]->tm_hi; c.tmA[s][1] = av[s]->tm_lo;
+            for (int v = 0; v < L.n_bn; ++v) { c.tmW[v][s][0] = L.seg[s].tm_hi[v]; c.tmW[v][s][1] = L.seg[s].tm_lo[v]; }
+        }
+        for (int v = 0; v < L.n_bn; ++v) c.bn_v[v] = L.bn_v[v];
+        ep.cout = L.cout; ep.bias = L.bias; ep.scale_tab = m->tables.d_scale_table;
+        c.ep = ep;
+    };
+    auto pre = [&]() { return epi_pregdn(m, none); };
+    auto gdn = [&](bool inv) {
+        EpiParams e = epi_hilo(inv ? EPI_IGDN : EPI_GDN, none, ws.U);
+        e.aux = ws.A32; e.ld_aux = ws.ldA32;
+        return e;
+    };
+    if (m->k1 == 3) {
+        set(L_E0, &ws.vText, nullptr, epi_hilo(EPI_LRELU, none, ws.G0));   // not run through the chain (ring rows)
+        set(L_E1, &ws.vH1x5, nullptr, epi_hilo(EPI_LRELU, none, ws.H2));
+    } else {
+        set(L_E0, &ws.vT, nullptr, epi_hilo(EPI_LRELU, none, ws.H1));
+        set(L_E1, &ws.vH1, nullptr, epi_hilo(EPI_LRELU, none, ws.H2));
+    }
+    set(L_E2, &ws.vH2, nullptr, epi_hilo(EPI_LRELU, none, ws.H3));
+    {
+        EpiParams e = epi(EPI_KSI, none);
+        e.out_f32 = ws.KSI; e.ld_f32 = ws.ldKSI;
+        set(L_E3, &ws.vH3, nullptr, e);
+    }
+    set(L_F0, &ws.vX, &ws.vT, pre());
+    set(L_G0, &ws.vS[0], nullptr, gdn(false));
+    set(L_F1, &ws.vU[0], nullptr, pre());
+    set(L_G1, &ws.vS[1], nullptr, gdn(false));
+    set(L_F2, &ws.vU[1], nullptr, pre());
+    set(L_G2, &ws.vS[2], nullptr, gdn(false));
+    {
+        EpiParams e = epi_hilo(EPI_QUANT, none, ws.YQ);
+        e.aux = ws.KSI; e.ld_aux = ws.ldKSI; e.M = m->M; e.sym = ws.sym; e.idx = ws.idx;
+        set(L_F3, &ws.vU[2], nullptr, e);
+    }
+    set(L_D0, &ws.vYQ, &ws.vT, pre());
+    set(L_IG0, &ws.vS[0], nullptr, gdn(true));
+    set(L_D1, &ws.vU[0], nullptr, pre());
+    set(L_IG1, &ws.vS[1], nullptr, gdn(true));
+    set(L_D2, &ws.vU[1], nullptr, pre());
+    set(L_IG2, &ws.vS[2], nullptr, gdn(true));
+    {
+        EpiParams e = epi(EPI_RECON, none);
+        e.zhat = ws.zhat_cl;
+        set(L_D3, &ws.vU[2], nullptr, e);
+    }
+    LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.d_chain, sizeof(ChainLayer) * L_COUNT));
+    LBIC_CUDA(cudaMemcpy(ws.d_chain, ws.h_chain.data(), sizeof(ChainLayer) * L_COUNT, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int run_chain(lbic_model *m, int l0, int l1, const StepDesc &sd, int R, cudaStream_t st) {
+    Workspace &ws = m->ws;
+    ProfRec rec;
+    if (m->profiling) {
+        double fl = 0;
+        for (int l = l0; l < l1; ++l)
+            for (int s = 0; s < m->L[l].nseg; ++s) fl += 2.0 * R * (double)m->L[l].seg[s].K * m->L[l].cout;
+        cudaEventCreate(&rec.a); cudaEventCreate(&rec.b);
+        rec.flops = fl;
+        cudaEventRecord(rec.a, st);
+    }
+    const int rc = gemm_chain_launch(ws.d_chain, ws.h_chain.data(), l0, l1, R, sd, m->force_cluster, st);
+    if (m->profiling) {
+        cudaEventRecord(rec.b, st);
+        m->prof.push_back(rec);
+    }
+    return rc;
 }
 
 int ensure_rans_scratch(lbic_model *m, size_t words) {
@@ -608,6 +705,14 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
     case LBIC_OPT_USE_GRAPH:
         m->use_graph = value ? 1 : 0;
         return 0;
+    case LBIC_OPT_CHAIN:
+        m->use_chain = value ? 1 : 0;
+        return 0;
+    case LBIC_OPT_CLUSTER:
+        if (value != 0 && value != 1 && value != 2 && value != 3 && value != 4 && value != 6 && value != 8)
+            return lbic_fail(LBIC_ERR_INVALID, "cluster size must be one of 0 (auto), 1, 2, 3, 4, 6, 8");
+        m->force_cluster = value;
+        return 0;
     case LBIC_OPT_FORCE_BN:
         if (value != 0 && (value % 16 || value < 16 || value > 256)) return lbic_fail(LBIC_ERR_INVALID, "bad tile width");
         m->force_bn = value;
@@ -738,9 +843,15 @@ extern "C" int lbic_encode(lbic_model *m, const float *x, int n_img, int Hb, int
         if (!wave_step(t, n_img, Hb, Wb, sd)) continue;
         const int R = n_img * sd.nv;
         LBIC_TRY(launch_gather(ws.x_cl, ws.zhat_cl, m->Cin, sd, R, ws.X.hi, ws.X.lo, ws.X.ld, ws.T.hi, ws.T.lo, ws.T.ld, st));
-        LBIC_TRY(run_ent(m, sd, R, st));
-        LBIC_TRY(run_enc(m, sd, R, want_syms ? ws.sym : nullptr, want_syms ? ws.idx : nullptr, st));
-        LBIC_TRY(run_dec(m, sd, R, st));
+        if (m->use_chain && m->gemm_core == 0) {
+            // the whole step (entropy net, encoder net + quantisation, decoder net) in one persistent launch
+            if (m->k1 == 3) LBIC_TRY(launch_gather5(ws.G0.hi, ws.G0.lo, m->E1, sd, R, ws.H1x5.hi, ws.H1x5.lo, ws.H1x5.ld, st));
+            LBIC_TRY(run_chain(m, m->k1 == 3 ? L_E1 : L_E0, L_COUNT, sd, R, st));
+        } else {
+            LBIC_TRY(run_ent(m, sd, R, st));
+            LBIC_TRY(run_enc(m, sd, R, want_syms ? ws.sym : nullptr, want_syms ? ws.idx : nullptr, st));
+            LBIC_TRY(run_dec(m, sd, R, st));
+        }
     }
     if (zhat_out) LBIC_TRY(launch_cl_to_nchw(ws.zhat_cl, zhat_out, n_img, m->Cin, HW, st));
     if (sym_out) LBIC_CUDA(cudaMemcpyAsync(sym_out, ws.sym, sizeof(int32_t) * nblk * m->M, cudaMemcpyDeviceToDevice, st));
@@ -776,10 +887,16 @@ extern "C" int lbic_decode(lbic_model *m, const uint8_t *streams, const uint32_t
     LBIC_TRY(launch_rans_dec_init(streams, stream_len, stream_cap, n_img, L, ws.dec_states, ws.lane_ptr, m->err_flag, st));
     auto one_step = [&](const StepDesc &sd, int R) -> int {
         LBIC_TRY(launch_gather(nullptr, ws.zhat_cl, m->Cin, sd, R, nullptr, nullptr, 0, ws.T.hi, ws.T.lo, ws.T.ld, st));
-        LBIC_TRY(run_ent(m, sd, R, st));
+        const bool chain = m->use_chain && m->gemm_core == 0;
+        if (chain) {
+            if (m->k1 == 3) LBIC_TRY(launch_gather5(ws.G0.hi, ws.G0.lo, m->E1, sd, R, ws.H1x5.hi, ws.H1x5.lo, ws.H1x5.ld, st));
+            LBIC_TRY(run_chain(m, m->k1 == 3 ? L_E1 : L_E0, L_F0, sd, R, st));
+        } else {
+            LBIC_TRY(run_ent(m, sd, R, st));
+        }
         LBIC_TRY(launch_rans_dec_step(m->tables, ws.dec_states, ws.lane_ptr, L, sd, R, m->M, ws.KSI, ws.ldKSI, ws.YQ.hi,
                                       ws.YQ.lo, ws.YQ.ld, sym_out ? ws.sym : nullptr, st));
-        LBIC_TRY(run_dec(m, sd, R, st));
+        if (chain) LBIC_TRY(run_chain(m, L_D0, L_COUNT, sd, R, st)); else LBIC_TRY(run_dec(m, sd, R, st));
         return 0;
     };
     if (m->k1 == 3) LBIC_TRY(launch_fill_g0_top(m->L[L_E0].bias, m->E1, n_img, Hb, Wb, ws.G0.hi, ws.G0.lo, st));

@@ -99,6 +99,21 @@ struct GemmCall {
     EpiParams ep;
 };
 
+// One layer of a persistent chain launch (gemm_chain.cu), resident in device memory.
+constexpr int LBIC_NBN = 3;   // tile-width variants per layer: wide (<= 256), 128, 64
+struct alignas(64) ChainLayer {
+    CUtensorMap tmA[2][2];              // [segment][hi, lo]   box 64 x 128
+    CUtensorMap tmW[LBIC_NBN][2][2];    // [variant][segment][hi, lo]   box 64 x bn_v[variant]
+    int kb[2];                          // 64-wide k-blocks per segment
+    int nseg;
+    int cout;
+    int bn_v[LBIC_NBN];
+    int n_bn;
+    EpiParams ep;                       // R and step are filled in per launch
+};
+int gemm_chain_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int l0, int l1, int R,
+                      const StepDesc &step, int force_S, cudaStream_t st);
+
 int gemm_simt_launch(const GemmCall &g, cudaStream_t st);
 int gemm_tc_launch(const GemmCall &g, cudaStream_t st);
 int gemm_tc_init();   // resolves cuTensorMapEncodeTiled, sets smem attributes

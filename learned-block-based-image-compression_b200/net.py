@@ -111,6 +111,13 @@ class BlockBasedImgCompLossyNetv9:
         """'tcgen05' (product path) or 'simt' (fp32 cross-check twin)."""
         _lib.check(_lib.lib().lbic_set_option(self._need(), _lib.LBIC_OPT_GEMM_CORE, {"tcgen05": 0, "simt": 1}[core]))
 
+    def set_option(self, name: str, value: int):
+        """Tuning hooks: 'chain' (1 = persistent chain kernel per step, default), 'cluster' (forced cluster size),
+        'force_bn' (forced tile width), 'graph'."""
+        opt = {"chain": _lib.LBIC_OPT_CHAIN, "cluster": _lib.LBIC_OPT_CLUSTER, "force_bn": _lib.LBIC_OPT_FORCE_BN,
+               "graph": _lib.LBIC_OPT_USE_GRAPH}[name]
+        _lib.check(_lib.lib().lbic_set_option(self._need(), opt, int(value)))
+
     # ---- state_dict ----------------------------------------------------------------------------
     def expected_keys(self):
         keys = []

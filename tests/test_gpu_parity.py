@@ -179,6 +179,32 @@ def test_batch_invariance_and_ragged_grids(dev):
         assert torch.equal(zdec, zhat)
 
 
+@pytest.mark.parametrize("cfgname", ["B8_lowrate", "B4_highrate"])
+def test_chain_kernel_equals_per_layer_launches(dev, cfgname):
+    """The persistent chain kernel (any cluster size) and the one-launch-per-layer path run the same tiles in the
+    same k order: symbols, indexes, reconstruction and bytes must be bit-identical."""
+    m = get_model(cfgname, 1337, False, dev)
+    B = m.B
+    from lbic_b200.layout import arrange_block_pixels_to_channel_dim
+    img = weights.synth_images(6, 7 * B, 11 * B, seed0=77)
+    x = arrange_block_pixels_to_channel_dim((img - 0.5).to(dev), B)
+    m.set_option("chain", 0)
+    ref = m.compress_batch(x, lanes=0, return_symbols=True)
+    zdec_ref = m.decompress_batch(ref[0], x.shape, lanes=0)
+    try:
+        for S in (0, 1, 2, 3, 4, 6, 8):
+            m.set_option("chain", 1)
+            m.set_option("cluster", S)
+            got = m.compress_batch(x, lanes=0, return_symbols=True)
+            assert got[0] == ref[0], f"cluster {S}: bitstreams differ"
+            assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2]) and torch.equal(got[3], ref[3])
+            zdec = m.decompress_batch(got[0], x.shape, lanes=0)
+            assert torch.equal(zdec, zdec_ref) and torch.equal(zdec, got[1])
+    finally:
+        m.set_option("chain", 1)
+        m.set_option("cluster", 0)
+
+
 def test_layout_kernels_match_reference_definition(dev):
     from lbic_b200.layout import arrange_block_pixels_to_channel_dim, arrange_channel_dim_to_block_pixels
     from oracle import nets
