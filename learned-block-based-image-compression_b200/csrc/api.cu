@@ -1,6 +1,7 @@
 // C ABI (include/lbic.h): model management, weight packing, workspace, and the wavefront drivers for
 // encode (NET:319-361) and decode (NET:400-452).
 #include <math.h>
+#include <cmath>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -48,20 +49,22 @@ constexpr int NBN = LBIC_NBN;
 
 struct PackedSeg {
     int K = 0;
-    bf16 *hi = nullptr, *lo = nullptr;
+    float *weff = nullptr;   // effective fp32 weights (temporary, freed after the scaled split)
+    h16 *hi = nullptr, *lo = nullptr;
     CUtensorMap tm_hi[NBN], tm_lo[NBN];   // TMA box = 64 x bn_v[i]
 };
 
 struct PackedLayer {
     int cout = 0, bn = 0, nseg = 0;
-    int bn_v[NBN] = {0, 0, 0};
+    int bn_v[NBN] = {0, 0, 0, 0, 0, 0};
     int n_bn = 0;
     PackedSeg seg[2];
     float *bias = nullptr;
+    float acc_scale = 1.0f;   // 2^-k, see finish_layer
 };
 
 struct ActBuf {
-    bf16 *hi = nullptr, *lo = nullptr;
+    h16 *hi = nullptr, *lo = nullptr;
     int ld = 0;
 };
 
@@ -112,7 +115,7 @@ struct lbic_model {
     int gemm_core = 0;
     int use_graph = 0;
     int force_bn = 0;
-    int use_chain = 1;     // persistent chain kernel per step (0: one launch per layer)
+    int use_chain = 0;     // 1: persistent chain kernel per step (experimental; the per-layer path is faster today)
     int force_cluster = 0;
     int64_t launches[2] = {0, 0};
     int *err_flag = nullptr;
@@ -149,15 +152,15 @@ void free_all(std::vector<void *> &list) {
     list.clear();
 }
 
-// tile-width candidates of a layer, widest first
+// tile-width variants of a layer, one per split factor (lbic_split): widest first
 int bn_variants(int cout, int *out) {
-    const int ntiles = (cout + 255) / 256;
-    int wide = ((cout + ntiles - 1) / ntiles + 15) / 16 * 16;
-    int n = 0;
-    out[n++] = wide;
-    if (wide > 128) out[n++] = 128;
-    if (wide > 64) out[n++] = 64;
-    return n;
+    for (int i = 0; i < NBN; ++i) {
+        const int f = lbic_split(i);
+        const int ntiles = f * ((cout + 256 * f - 1) / (256 * f));
+        int bn = ((cout + ntiles - 1) / ntiles + 15) / 16 * 16;
+        out[i] = bn < 16 ? 16 : bn;
+    }
+    return NBN;
 }
 
 int pick_bn(int cout) {
@@ -215,9 +218,10 @@ int pack_conv_seg(lbic_model *m, const SdView &sd, const std::string &prefix, in
     if (sd.find(prefix + ".mask")) LBIC_TRY(stage(sd, prefix + ".mask", nw, tmp, &mask, st));
     LBIC_TRY(stage(sd, prefix + ".bias", cout, tmp, bias_tmp, st));
     seg.K = ntaps * cin;
-    LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&seg.hi, sizeof(bf16) * (size_t)cout * seg.K));
-    LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&seg.lo, sizeof(bf16) * (size_t)cout * seg.K));
-    LBIC_TRY(launch_pack_conv(w, mask, cout, cin, k, k, taps, ntaps, seg.hi, seg.lo, seg.K, st));
+    LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&seg.hi, sizeof(h16) * (size_t)cout * seg.K));
+    LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&seg.lo, sizeof(h16) * (size_t)cout * seg.K));
+    LBIC_TRY(dev_alloc(tmp, (void **)&seg.weff, sizeof(float) * (size_t)cout * seg.K));
+    LBIC_TRY(launch_pack_conv(w, mask, cout, cin, k, k, taps, ntaps, seg.weff, seg.K, st));
     int bnv[NBN];
     const int nb = bn_variants(cout, bnv);
     (void)bn;
@@ -225,6 +229,28 @@ int pack_conv_seg(lbic_model *m, const SdView &sd, const std::string &prefix, in
         LBIC_TRY(make_tmap_2d(&seg.tm_hi[i], seg.hi, seg.K, cout, seg.K, 64, bnv[i]));
         LBIC_TRY(make_tmap_2d(&seg.tm_lo[i], seg.lo, seg.K, cout, seg.K, 64, bnv[i]));
     }
+    return 0;
+}
+
+// fp16 operand planes need the weights inside fp16's normal range: scale the layer's effective weights by 2^k so
+// that max |w| lands in [2^9, 2^10), split into hi/lo, and undo the scale exactly in the epilogue (acc_scale = 2^-k).
+int finish_layer(lbic_model *m, PackedLayer &L, cudaStream_t st) {
+    float *d_max = nullptr;
+    std::vector<void *> tmp;
+    LBIC_TRY(dev_alloc(tmp, (void **)&d_max, sizeof(float), true));
+    for (int s = 0; s < L.nseg; ++s) LBIC_TRY(launch_absmax(L.seg[s].weff, (int64_t)L.cout * L.seg[s].K, d_max, st));
+    float mx = 0.0f;
+    LBIC_CUDA(cudaMemcpyAsync(&mx, d_max, sizeof(float), cudaMemcpyDeviceToHost, st));
+    LBIC_CUDA(cudaStreamSynchronize(st));
+    free_all(tmp);
+    int k = 0;
+    if (mx > 0.0f && std::isfinite(mx)) k = 9 - (int)floorf(log2f(mx));
+    k = k > 24 ? 24 : (k < -24 ? -24 : k);
+    const float scale = ldexpf(1.0f, k);
+    L.acc_scale = ldexpf(1.0f, -k);
+    for (int s = 0; s < L.nseg; ++s)
+        LBIC_TRY(launch_split_scaled(L.seg[s].weff, L.seg[s].hi, L.seg[s].lo, (int64_t)L.cout * L.seg[s].K, scale, st));
+    (void)m;
     return 0;
 }
 
@@ -239,7 +265,7 @@ int pack_linear(lbic_model *m, const SdView &sd, int id, const std::string &pref
     LBIC_TRY(pack_conv_seg(m, sd, prefix, cout, cin, k, taps, ntaps, L.bn, L.seg[0], &b, tmp, st));
     LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&L.bias, sizeof(float) * cout));
     LBIC_TRY(launch_add_vec(b, nullptr, L.bias, cout, st));
-    return 0;
+    return finish_layer(m, L, st);
 }
 
 // first layer of the encoder / decoder nets: 1x1 conv on x (or y_qnt) plus masked 3x3 conv on zhat, summed
@@ -255,7 +281,7 @@ int pack_dual(lbic_model *m, const SdView &sd, int id, const std::string &p1, in
     LBIC_TRY(pack_conv_seg(m, sd, p2, cout, m->Cin, 3, TAPS_A, 4, L.bn, L.seg[1], &b2, tmp, st));
     LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&L.bias, sizeof(float) * cout));
     LBIC_TRY(launch_add_vec(b1, b2, L.bias, cout, st));
-    return 0;
+    return finish_layer(m, L, st);
 }
 
 int pack_gdn(lbic_model *m, const SdView &sd, int id, const std::string &prefix, int C, std::vector<void *> &tmp,
@@ -277,22 +303,23 @@ int pack_gdn(lbic_model *m, const SdView &sd, int id, const std::string &prefix,
     LBIC_TRY(scalar(sd, prefix + ".beta_reparam.lower_bound.bound", (float)sqrt(1e-6 + pow(2.0, -36.0)), &bbound));
     PackedSeg &seg = L.seg[0];
     seg.K = C;
-    LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&seg.hi, sizeof(bf16) * (size_t)C * C));
-    LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&seg.lo, sizeof(bf16) * (size_t)C * C));
+    LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&seg.hi, sizeof(h16) * (size_t)C * C));
+    LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&seg.lo, sizeof(h16) * (size_t)C * C));
     LBIC_TRY(dev_alloc(m->weight_allocs, (void **)&L.bias, sizeof(float) * C));
-    LBIC_TRY(launch_pack_gdn(g, b, C, gbound, gped, bbound, bped, seg.hi, seg.lo, C, L.bias, st));
+    LBIC_TRY(dev_alloc(tmp, (void **)&seg.weff, sizeof(float) * (size_t)C * C));
+    LBIC_TRY(launch_pack_gdn(g, b, C, gbound, gped, bbound, bped, seg.weff, C, L.bias, st));
     for (int i = 0; i < L.n_bn; ++i) {
         LBIC_TRY(make_tmap_2d(&seg.tm_hi[i], seg.hi, C, C, C, 64, L.bn_v[i]));
         LBIC_TRY(make_tmap_2d(&seg.tm_lo[i], seg.lo, C, C, C, 64, L.bn_v[i]));
     }
-    return 0;
+    return finish_layer(m, L, st);
 }
 
 // ---- workspace ----------------------------------------------------------------------------------
 int alloc_act(Workspace &ws, ActBuf &b, int ld) {
     b.ld = ld;
-    LBIC_TRY(dev_alloc(ws.allocs, (void **)&b.hi, sizeof(bf16) * (size_t)ws.R_cap * ld, true));
-    LBIC_TRY(dev_alloc(ws.allocs, (void **)&b.lo, sizeof(bf16) * (size_t)ws.R_cap * ld, true));
+    LBIC_TRY(dev_alloc(ws.allocs, (void **)&b.hi, sizeof(h16) * (size_t)ws.R_cap * ld, true));
+    LBIC_TRY(dev_alloc(ws.allocs, (void **)&b.lo, sizeof(h16) * (size_t)ws.R_cap * ld, true));
     return 0;
 }
 
@@ -329,12 +356,12 @@ int ensure_workspace(lbic_model *m, int n_img, int Hb, int Wb) {
         ws.R_ext_cap = ((n_img * (max_nv + 2)) + 127) / 128 * 128;
         const size_t npos = (size_t)n_img * (Hb + 1) * (Wb + 2);
         ws.G0.ld = m->E1;
-        LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.G0.hi, sizeof(bf16) * npos * m->E1, true));
-        LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.G0.lo, sizeof(bf16) * npos * m->E1, true));
+        LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.G0.hi, sizeof(h16) * npos * m->E1, true));
+        LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.G0.lo, sizeof(h16) * npos * m->E1, true));
         LBIC_TRY(alloc_act(ws, ws.H1x5, 5 * m->E1));
         ws.Text.ld = 4 * m->Cin;
-        LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.Text.hi, sizeof(bf16) * (size_t)ws.R_ext_cap * ws.Text.ld, true));
-        LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.Text.lo, sizeof(bf16) * (size_t)ws.R_ext_cap * ws.Text.ld, true));
+        LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.Text.hi, sizeof(h16) * (size_t)ws.R_ext_cap * ws.Text.ld, true));
+        LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.Text.lo, sizeof(h16) * (size_t)ws.R_ext_cap * ws.Text.ld, true));
     }
     LBIC_TRY(alloc_act(ws, ws.H2, m->E2));
     LBIC_TRY(alloc_act(ws, ws.H3, m->E3));
@@ -387,7 +414,7 @@ int build_chain(lbic_model *m) {
             for (int v = 0; v < L.n_bn; ++v) { c.tmW[v][s][0] = L.seg[s].tm_hi[v]; c.tmW[v][s][1] = L.seg[s].tm_lo[v]; }
         }
         for (int v = 0; v < L.n_bn; ++v) c.bn_v[v] = L.bn_v[v];
-        ep.cout = L.cout; ep.bias = L.bias; ep.scale_tab = m->tables.d_scale_table;
+        ep.cout = L.cout; ep.bias = L.bias; ep.scale_tab = m->tables.d_scale_table; ep.acc_scale = L.acc_scale;
         c.ep = ep;
     };
     auto pre = [&]() { return epi_pregdn(m, none); };
@@ -476,7 +503,7 @@ int run_gemm(lbic_model *m, int id, int R, const ActView *a0, const ActView *a1,
             if (L.bn_v[i] == m->force_bn) vi = i;
     } else {
         const int row_tiles = (R + 127) / 128;
-        while (vi + 1 < L.n_bn && row_tiles * ((L.cout + L.bn_v[vi] - 1) / L.bn_v[vi]) < 120) ++vi;
+        while (vi + 1 < L.n_bn && row_tiles * ((L.cout + L.bn_v[vi] - 1) / L.bn_v[vi]) < 132) ++vi;
     }
     g.R = R; g.cout = L.cout; g.bn = L.bn_v[vi]; g.nseg = L.nseg;
     const ActView *av[2] = {a0, a1};
@@ -491,7 +518,7 @@ int run_gemm(lbic_model *m, int id, int R, const ActView *a0, const ActView *a1,
         g.W[s].tm_hi = &L.seg[s].tm_hi[vi]; g.W[s].tm_lo = &L.seg[s].tm_lo[vi];
         flops += 2.0 * R * (double)L.seg[s].K * L.cout;
     }
-    ep.R = R; ep.cout = L.cout; ep.bias = L.bias;
+    ep.R = R; ep.cout = L.cout; ep.bias = L.bias; ep.acc_scale = L.acc_scale;
     ep.scale_tab = m->tables.d_scale_table;
     g.ep = ep;
     ProfRec rec;
@@ -1046,14 +1073,14 @@ extern "C" int lbic_debug_gemm(lbic_model *m, const float *A, const float *W, fl
     Active act(m);
     cudaStream_t st = (cudaStream_t)stream;
     std::vector<void *> tmp;
-    bf16 *ah, *al, *wh, *wl;
+    h16 *ah, *al, *wh, *wl;
     int rc = 0;
     do {
 #define P(call) if ((rc = (call)) != 0) break
-        P(dev_alloc(tmp, (void **)&ah, sizeof(bf16) * (size_t)R * K));
-        P(dev_alloc(tmp, (void **)&al, sizeof(bf16) * (size_t)R * K));
-        P(dev_alloc(tmp, (void **)&wh, sizeof(bf16) * (size_t)cout * K));
-        P(dev_alloc(tmp, (void **)&wl, sizeof(bf16) * (size_t)cout * K));
+        P(dev_alloc(tmp, (void **)&ah, sizeof(h16) * (size_t)R * K));
+        P(dev_alloc(tmp, (void **)&al, sizeof(h16) * (size_t)R * K));
+        P(dev_alloc(tmp, (void **)&wh, sizeof(h16) * (size_t)cout * K));
+        P(dev_alloc(tmp, (void **)&wl, sizeof(h16) * (size_t)cout * K));
         P(launch_split_f32(A, ah, al, (int64_t)R * K, st));
         P(launch_split_f32(W, wh, wl, (int64_t)cout * K, st));
         GemmCall g;
@@ -1066,7 +1093,7 @@ extern "C" int lbic_debug_gemm(lbic_model *m, const float *A, const float *W, fl
         P(make_tmap_2d(&tw_l, wl, K, cout, K, 64, g.bn));
         g.A[0].hi = ah; g.A[0].lo = al; g.A[0].ld = K; g.A[0].tm_hi = &ta_h; g.A[0].tm_lo = &ta_l;
         g.W[0].hi = wh; g.W[0].lo = wl; g.W[0].ld = K; g.W[0].tm_hi = &tw_h; g.W[0].tm_lo = &tw_l;
-        g.ep.mode = EPI_RAW; g.ep.R = R; g.ep.cout = cout; g.ep.out_f32 = D; g.ep.ld_f32 = cout;
+        g.ep.mode = EPI_RAW; g.ep.R = R; g.ep.cout = cout; g.ep.out_f32 = D; g.ep.ld_f32 = cout; g.ep.acc_scale = 1.0f;
         P(m->gemm_core == 1 ? gemm_simt_launch(g, st) : gemm_tc_launch(g, st));
 #undef P
     } while (0);
@@ -1088,18 +1115,18 @@ extern "C" int lbic_debug_gemm_bench(lbic_model *m, int R, int K, int cout, int 
     do {
 #define P(call) if ((rc = (call)) != 0) break
         const int Rp = (R + 127) / 128 * 128;
-        bf16 *ah, *al, *wh, *wl, *oh, *ol;
+        h16 *ah, *al, *wh, *wl, *oh, *ol;
         float *A, *W, *D, *bias;
         P(dev_alloc(tmp, (void **)&A, sizeof(float) * (size_t)Rp * K, true));
         P(dev_alloc(tmp, (void **)&W, sizeof(float) * (size_t)cout * K, true));
         P(dev_alloc(tmp, (void **)&D, sizeof(float) * (size_t)Rp * cout, true));
         P(dev_alloc(tmp, (void **)&bias, sizeof(float) * cout, true));
-        P(dev_alloc(tmp, (void **)&ah, sizeof(bf16) * (size_t)Rp * K, true));
-        P(dev_alloc(tmp, (void **)&al, sizeof(bf16) * (size_t)Rp * K, true));
-        P(dev_alloc(tmp, (void **)&wh, sizeof(bf16) * (size_t)cout * K, true));
-        P(dev_alloc(tmp, (void **)&wl, sizeof(bf16) * (size_t)cout * K, true));
-        P(dev_alloc(tmp, (void **)&oh, sizeof(bf16) * (size_t)Rp * cout, true));
-        P(dev_alloc(tmp, (void **)&ol, sizeof(bf16) * (size_t)Rp * cout, true));
+        P(dev_alloc(tmp, (void **)&ah, sizeof(h16) * (size_t)Rp * K, true));
+        P(dev_alloc(tmp, (void **)&al, sizeof(h16) * (size_t)Rp * K, true));
+        P(dev_alloc(tmp, (void **)&wh, sizeof(h16) * (size_t)cout * K, true));
+        P(dev_alloc(tmp, (void **)&wl, sizeof(h16) * (size_t)cout * K, true));
+        P(dev_alloc(tmp, (void **)&oh, sizeof(h16) * (size_t)Rp * cout, true));
+        P(dev_alloc(tmp, (void **)&ol, sizeof(h16) * (size_t)Rp * cout, true));
         GemmCall g;
         memset(&g, 0, sizeof(g));
         g.R = R; g.cout = cout; g.bn = m->force_bn ? m->force_bn : pick_bn(cout); g.nseg = 1; g.K[0] = K;
@@ -1110,7 +1137,7 @@ extern "C" int lbic_debug_gemm_bench(lbic_model *m, int R, int K, int cout, int 
         P(make_tmap_2d(&tw_l, wl, K, cout, K, 64, g.bn));
         g.A[0].hi = ah; g.A[0].lo = al; g.A[0].ld = K; g.A[0].tm_hi = &ta_h; g.A[0].tm_lo = &ta_l;
         g.W[0].hi = wh; g.W[0].lo = wl; g.W[0].ld = K; g.W[0].tm_hi = &tw_h; g.W[0].tm_lo = &tw_l;
-        g.ep.R = R; g.ep.cout = cout;
+        g.ep.R = R; g.ep.cout = cout; g.ep.acc_scale = 1.0f;
         if (with_epilogue) {
             g.ep.mode = EPI_PREGDN; g.ep.bias = bias; g.ep.out_hi = oh; g.ep.out_lo = ol; g.ep.ld_out = cout;
             g.ep.out_f32 = D; g.ep.ld_f32 = cout;

@@ -6,9 +6,14 @@
 
 #define LBIC_SCALES_MIN 0.11f   // NET:13, ENT:553 LowerBound(scale_bound)
 
-__device__ __forceinline__ void split_bf16(float v, bf16 &hi, bf16 &lo) {
-    hi = __float2bfloat16_rn(v);
-    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+#define LBIC_H16_MAX 65504.0f
+
+// v ~= hi + lo with hi = fp16(v), lo = fp16(v - hi): 22 significand bits.  |v| is saturated at the fp16 maximum
+// (activations of this codec are O(1..100); a saturated value loses precision but never becomes inf/NaN).
+__device__ __forceinline__ void split_h16(float v, h16 &hi, h16 &lo) {
+    v = fminf(fmaxf(v, -LBIC_H16_MAX), LBIC_H16_MAX);
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
 }
 
 // build_indexes (ENT:649-654): idx = 63 - #{i<63 : max(s,0.11) <= T[i]} = #{i<63 : T[i] < s'}
@@ -26,18 +31,18 @@ __device__ __forceinline__ int scale_to_index(float scale, const float *__restri
 }
 
 template <int NV>
-__device__ __forceinline__ void store_hilo(bf16 *__restrict__ ph, bf16 *__restrict__ pl, const float (&v)[NV]) {
+__device__ __forceinline__ void store_hilo(h16 *__restrict__ ph, h16 *__restrict__ pl, const float (&v)[NV]) {
     static_assert(NV % 4 == 0, "NV");
 #pragma unroll
     for (int i = 0; i < NV; i += 4) {
-        bf16 h[4], l[4];
+        h16 h[4], l[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) split_bf16(v[i + j], h[j], l[j]);
+        for (int j = 0; j < 4; ++j) split_h16(v[i + j], h[j], l[j]);
         uint2 uh, ul;
-        uh.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
-        uh.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
-        ul.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
-        ul.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+        uh.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+        uh.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+        ul.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16);
+        ul.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
         *reinterpret_cast<uint2 *>(ph + i) = uh;
         *reinterpret_cast<uint2 *>(pl + i) = ul;
     }
@@ -84,7 +89,7 @@ __device__ __forceinline__ void epi_prefetch(const EpiParams &p, int r, int c, E
 template <int NV>
 struct EpiOut {
     float f[NV];
-    uint32_t hi[NV / 2], lo[NV / 2];   // bf16 pairs, element 2j in the low half
+    uint32_t hi[NV / 2], lo[NV / 2];   // h16 pairs, element 2j in the low half
     uint32_t idx[NV / 4];
 };
 
@@ -99,11 +104,14 @@ template <int NV>
 __device__ __forceinline__ void pack_hilo(const float (&v)[NV], EpiOut<NV> &o) {
 #pragma unroll
     for (int i = 0; i < NV; i += 2) {
-        bf16 h0, l0, h1, l1;
-        split_bf16(v[i], h0, l0);
-        split_bf16(v[i + 1], h1, l1);
-        o.hi[i >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        o.lo[i >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        // two elements at a time: hi = fp16(v), lo = fp16(v - hi)   (same values as split_h16)
+        const float a = fminf(fmaxf(v[i], -LBIC_H16_MAX), LBIC_H16_MAX);
+        const float b = fminf(fmaxf(v[i + 1], -LBIC_H16_MAX), LBIC_H16_MAX);
+        const __half2 h = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+        o.hi[i >> 1] = *reinterpret_cast<const uint32_t *>(&h);
+        o.lo[i >> 1] = *reinterpret_cast<const uint32_t *>(&l);
     }
 }
 
@@ -120,7 +128,7 @@ __device__ __forceinline__ void epi_compute(const EpiParams &p, const float *__r
     float v[NV];
     load_f32<NV>(bias, v);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = acc[i] + v[i];
+    for (int i = 0; i < NV; ++i) v[i] = fmaf(acc[i], p.acc_scale, v[i]);   // exact power-of-two rescale, one rounding
     switch (p.mode) {
     case EPI_LRELU: {
 #pragma unroll
@@ -137,11 +145,15 @@ __device__ __forceinline__ void epi_compute(const EpiParams &p, const float *__r
     } break;
     case EPI_GDN:
     case EPI_IGDN: {
+        // GDNF:73-78: x * rsqrt(norm) (forward) or x * sqrt(norm) (inverse).  rsqrtf is the 2-ulp hardware
+        // approximation (the IEEE sqrt + divide sequences cost ~50 instructions per element and made these
+        // epilogues 3x longer, profiles/r1_chain_trace.md); its error (2^-22) is far below the h16 hi/lo operand
+        // split (2^-17) and it is the same instruction in encoder and decoder.
         const bool inv = (p.mode == EPI_IGDN);
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-            const float sq = __fsqrt_rn(v[i]);
-            v[i] = pre.a[i] * (inv ? sq : __fdiv_rn(1.0f, sq));   // torch.sqrt / torch.rsqrt (GDNF:73-76)
+            const float rs = rsqrtf(v[i]);
+            v[i] = pre.a[i] * (inv ? v[i] * rs : rs);
         }
         pack_hilo<NV>(v, o);
     } break;

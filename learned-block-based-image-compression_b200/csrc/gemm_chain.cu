@@ -11,6 +11,7 @@
 #include "tc_common.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -21,11 +22,13 @@ struct ChainParams {
     int R;
     StepDesc step;
     int S;               // cluster size
+    int vi;              // tile-width variant = index of S among the split factors
     int n_clusters;
     int stages;
     uint32_t slot_bytes;   // pipeline slot: A hi/lo (32 KiB) + W hi/lo for the widest tile of this launch
     uint32_t ring_bytes;
     uint32_t tmem_cols;
+    unsigned long long *trace;   // debug: per-phase clock64() stamps of CTA 0 (LBIC_CHAIN_TRACE), else nullptr
 };
 
 struct LayerScalars {
@@ -45,7 +48,10 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-constexpr int CHAIN_SLACK = 1024 + BAR_BLOCK + 1024 + 512;   // ring alignment, barriers, bias slice, layer scalars
+#define TRACE0(slot) do { if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[(l - p.l0) * 16 + (slot)] = clock64(); } while (0)
+#define TRACE1(slot) do { if (p.trace && blockIdx.x == 0 && threadIdx.x == 32) p.trace[(l - p.l0) * 16 + (slot)] = clock64(); } while (0)
+
+constexpr int CHAIN_SLACK = 1024 + BAR_BLOCK + 1024 + 512 + 3072;   // ring alignment, barriers, bias slice, layer scalars, row table
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_chain_kernel(const ChainParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -59,6 +65,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_chain_kernel(const ChainP
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - raw));
     float *sbias = reinterpret_cast<float *>(smem_raw + (bars + BAR_BLOCK - raw));
     LayerScalars *sl = reinterpret_cast<LayerScalars *>(smem_raw + (bars + BAR_BLOCK + 1024 - raw));
+    RowTab *rowtab = reinterpret_cast<RowTab *>(smem_raw + (bars + BAR_BLOCK + 1024 + 512 - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = p.S > 1 ? (int)cluster_ctarank() : 0;
@@ -91,10 +98,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_chain_kernel(const ChainP
         const int m0 = m * BM;
         for (int l = p.l0; l < p.l1; ++l) {
             const ChainLayer *L = p.layers + l;
+            TRACE0(0);
             // layer scalars + epilogue parameters -> shared memory (one copy per CTA)
             if (threadIdx.x == 0) {
-                int vi = 0;
-                while (vi + 1 < L->n_bn && (L->cout + L->bn_v[vi] - 1) / L->bn_v[vi] < p.S) ++vi;
+                const int vi = p.vi;
                 const int bn = L->bn_v[vi];
                 sl->kb[0] = L->kb[0];
                 sl->kb[1] = L->nseg > 1 ? L->kb[1] : 0;
@@ -102,7 +109,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_chain_kernel(const ChainP
                 sl->bn = bn;
                 sl->vi = vi;
                 sl->ntiles = (L->cout + bn - 1) / bn;
-                sl->idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                sl->idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             }
             {
                 const uint32_t *src = reinterpret_cast<const uint32_t *>(&L->ep);
@@ -118,6 +125,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_chain_kernel(const ChainP
             const uint32_t idesc = sl->idesc;
             const uint32_t w_plane = (uint32_t)bn * (BK * 2);
             const uint32_t stage_tx = 2 * A_PLANE + 2 * w_plane;
+            TRACE0(1);
 
             for (int n = rank; n < ntiles; n += p.S) {
                 const int n0 = n * bn;
@@ -125,6 +133,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_chain_kernel(const ChainP
                     for (int i = threadIdx.x; i < bn; i += NUM_THREADS)
                         sbias[i] = (n0 + i < ep.cout) ? ep.bias[n0 + i] : 0.0f;
                 __syncthreads();
+                TRACE0(2);
                 if (warp == 0) {
                     if (lane == 0) {
                         for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -149,6 +158,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_chain_kernel(const ChainP
                             const uint32_t ph = (it / p.stages) & 1u;
                             mbar_wait(full_bar(s), ph);
                             tc_fence_after();
+                            if (kb == 0) TRACE1(8);
                             const uint32_t sa = ring + s * p.slot_bytes;
                             const uint64_t a_hi = make_smem_desc(sa);
                             const uint64_t a_lo = make_smem_desc(sa + A_PLANE);
@@ -164,13 +174,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_chain_kernel(const ChainP
                             umma_commit(empty_bar(s));
                         }
                         umma_commit(tmem_full_bar);
+                        TRACE1(9);
                     }
                 }
                 __syncwarp();
+                TRACE0(3);
                 mbar_wait(tmem_full_bar, tile_cnt & 1u);
                 tc_fence_after();
-                tile_epilogue(ep, sbias, ring, tmem_acc, m0, n0, bn, warp, lane);
+                TRACE0(4);
+                tile_epilogue(ep, sbias, ring, rowtab, tmem_acc, m0, n0, bn, warp, lane,
+                              (p.trace && blockIdx.x == 0) ? p.trace + (l - p.l0) * 16 : nullptr);
                 ++tile_cnt;
+                TRACE0(5);
                 // the staging area (generic proxy) becomes a TMA destination (async proxy) again, and the accumulator
                 // is about to be overwritten: order both before the next tile
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -179,10 +194,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_chain_kernel(const ChainP
             }
             // layer boundary: this layer's global stores (generic proxy) are read by the next layer's TMA loads
             // (async proxy), possibly issued by another CTA of the cluster
+            TRACE0(6);
             asm volatile("fence.proxy.async;" ::: "memory");
             __threadfence();
             if (p.S > 1) cluster_sync_all(); else __syncthreads();
             asm volatile("fence.proxy.async;" ::: "memory");
+            TRACE0(7);
         }
     }
     tc_fence_before();
@@ -205,9 +222,10 @@ double tile_us(int kblocks, int bn) {
 }  // namespace
 
 int chain_variant(const ChainLayer &L, int S) {
-    int vi = 0;
-    while (vi + 1 < L.n_bn && (L.cout + L.bn_v[vi] - 1) / L.bn_v[vi] < S) ++vi;
-    return vi;
+    for (int i = 0; i < LBIC_NBN; ++i)
+        if (lbic_split(i) == S) return i;
+    (void)L;
+    return 0;
 }
 
 int gemm_chain_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int l0, int l1, int R,
@@ -249,6 +267,7 @@ int gemm_chain_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, in
     ChainParams p;
     p.layers = d_layers; p.l0 = l0; p.l1 = l1; p.R = R; p.step = step;
     p.S = best_S;
+    p.vi = chain_variant(h_layers[l0], best_S);
     p.n_clusters = (n_sm / best_S) < row_tiles ? (n_sm / best_S) : row_tiles;
     int max_bn = 16;
     for (int l = l0; l < l1; ++l) {
@@ -278,7 +297,33 @@ int gemm_chain_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, in
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    p.trace = nullptr;
+    static int trace_left = getenv("LBIC_CHAIN_TRACE") ? atoi(getenv("LBIC_CHAIN_TRACE")) : 0;
+    const bool tracing = trace_left > 0 && row_tiles >= 20;
+    if (tracing) {
+        --trace_left;
+        LBIC_CUDA(cudaMalloc(&p.trace, sizeof(unsigned long long) * 16 * 32));
+        LBIC_CUDA(cudaMemsetAsync(p.trace, 0, sizeof(unsigned long long) * 16 * 32, st));
+    }
     LBIC_CUDA(cudaLaunchKernelEx(&cfg, gemm_chain_kernel, p));
     count_launch(0);
+    if (tracing) {
+        unsigned long long h[16 * 32];
+        LBIC_CUDA(cudaStreamSynchronize(st));
+        LBIC_CUDA(cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(p.trace);
+        fprintf(stderr, "[chain trace] R=%d S=%d clusters=%d stages=%d layers %d..%d (cycles: setup, bias, issue, mma-wait, epi, tail, sync | first-data, mma-done rel. to tile start)\n",
+                R, p.S, p.n_clusters, p.stages, l0, l1);
+        for (int l = 0; l < l1 - l0; ++l) {
+            const unsigned long long *t = h + l * 16;
+            fprintf(stderr, "  L%02d bn=%3d kb=%2d: %6lld %6lld %6lld %6lld %6lld %6lld %6lld | %6lld %6lld  total %lld\n", l0 + l,
+                    h_layers[l0 + l].bn_v[chain_variant(h_layers[l0 + l], p.S)], h_layers[l0 + l].kb[0] + h_layers[l0 + l].kb[1],
+                    (long long)(t[1] - t[0]), (long long)(t[2] - t[1]), (long long)(t[3] - t[2]), (long long)(t[4] - t[3]),
+                    (long long)(t[5] - t[4]), (long long)(t[6] - t[5]), (long long)(t[7] - t[6]), (long long)(t[8] - t[2]),
+                    (long long)(t[9] - t[2]), (long long)(t[7] - t[0]));
+            fprintf(stderr, "        epilogue: phaseA %lld  barrier %lld  phaseB %lld\n", (long long)(t[10] - t[4]),
+                    (long long)(t[11] - t[10]), (long long)(t[5] - t[11]));
+        }
+    }
     return 0;
 }

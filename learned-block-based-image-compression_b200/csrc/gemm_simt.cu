@@ -1,4 +1,4 @@
-// fp32 SIMT evaluation of the same bf16 hi/lo split operands the tcgen05 core consumes.
+// fp32 SIMT evaluation of the same h16 hi/lo split operands the tcgen05 core consumes.
 // Bring-up / cross-check twin only (LBIC_OPT_GEMM_CORE = 1): identical buffers, identical fused
 // epilogues, plain FFMA accumulation.  D[r, c] = sum_seg sum_k (Ah+Al)[r,k] * (Wh+Wl)[c,k].
 #include "epilogue.cuh"
@@ -8,7 +8,7 @@ namespace {
 constexpr int TM = 64, TN = 64, TK = 16;
 
 struct SimtSeg {
-    const bf16 *a_hi, *a_lo, *w_hi, *w_lo;
+    const h16 *a_hi, *a_lo, *w_hi, *w_lo;
     int lda, ldw, K;
 };
 
@@ -43,12 +43,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtParams p) {
                     const int r = row0 + m;
                     if (r < p.ep.R) {
                         const size_t o = (size_t)r * sg.lda + k0 + k;
-                        a = __bfloat162float(sg.a_hi[o]) + __bfloat162float(sg.a_lo[o]);
+                        a = __half2float(sg.a_hi[o]) + __half2float(sg.a_lo[o]);
                     }
                     const int c = col0 + m;
                     if (c < p.ep.cout) {
                         const size_t o = (size_t)c * sg.ldw + k0 + k;
-                        w = __bfloat162float(sg.w_hi[o]) + __bfloat162float(sg.w_lo[o]);
+                        w = __half2float(sg.w_hi[o]) + __half2float(sg.w_lo[o]);
                     }
                 }
                 sA[k][m] = a;

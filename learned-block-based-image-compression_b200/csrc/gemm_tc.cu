@@ -1,8 +1,8 @@
 // tcgen05 / TMEM / TMA GEMM core with fused layer epilogues (sm_100a only).
 //
 // D[R, cout] = sum over K segments of A_s[R, K_s] * W_s[cout, K_s]^T, fp32-grade accuracy from
-// bf16 tensor-core passes: every operand is stored as two bf16 planes (hi = bf16(v),
-// lo = bf16(v - hi)) and each 16-wide k-step issues three MMAs into one TMEM accumulator,
+// h16 tensor-core passes: every operand is stored as two h16 planes (hi = h16(v),
+// lo = h16(v - hi)) and each 16-wide k-step issues three MMAs into one TMEM accumulator,
 //     Ahi*Whi + Ahi*Wlo + Alo*Whi          (the lo*lo term, ~2^-32 relative, is dropped),
 // in a fixed order, with no split-K: a row's result depends only on that row's inputs, never on
 // the tile it shares or on whether the encoder or the decoder computes it.
@@ -125,7 +125,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     __syncwarp();
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    tile_epilogue(p.ep, sbias, ring, tmem_acc, m0, n0, p.bn, warp, lane);
+    tile_epilogue(p.ep, sbias, ring, reinterpret_cast<RowTab *>(smem_raw + (bars + BAR_BLOCK + 1024 - raw)), tmem_acc, m0, n0,
+                  p.bn, warp, lane);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -153,7 +154,7 @@ int gemm_tc_init() {
     return 0;
 }
 
-// bf16 row-major [outer][ld_elems] matrix, logical inner extent `inner`; out-of-bounds box elements
+// h16 row-major [outer][ld_elems] matrix, logical inner extent `inner`; out-of-bounds box elements
 // read as zero.
 int make_tmap_2d(CUtensorMap *tm, const void *base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                  uint32_t box_inner, uint32_t box_outer) {
@@ -165,7 +166,7 @@ int make_tmap_2d(CUtensorMap *tm, const void *base, uint64_t inner, uint64_t out
     cuuint64_t gstride[1] = {ld_elems * 2};
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
-    CUresult rc = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstride, box,
+    CUresult rc = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), gdim, gstride, box,
                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) return lbic_fail(LBIC_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)rc);
@@ -188,8 +189,8 @@ int gemm_tc_launch(const GemmCall &g, cudaStream_t st) {
     uint32_t cols = 32;
     while ((int)cols < g.bn) cols <<= 1;
     p.tmem_cols = cols;
-    // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=bn, M=128
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // kind::f16 instruction descriptor: D=f32, A=B=h16, both K-major, N=bn, M=128
+    p.idesc = (1u << 4) | ((uint32_t)(g.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // D=f32, A=B=f16 (format 0), K-major
     p.ep = g.ep;
     const int s1 = g.nseg > 1 ? 1 : 0;
     dim3 grid((g.R + BM - 1) / BM, (g.cout + g.bn - 1) / g.bn);

@@ -42,10 +42,10 @@ __global__ void space_depth_kernel(const float *__restrict__ src, float *__restr
     }
 }
 
-__global__ void split_kernel(const float *__restrict__ src, bf16 *__restrict__ hi, bf16 *__restrict__ lo, size_t n) {
+__global__ void split_kernel(const float *__restrict__ src, h16 *__restrict__ hi, h16 *__restrict__ lo, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        bf16 h, l;
-        split_bf16(src[i], h, l);
+        h16 h, l;
+        split_h16(src[i], h, l);
         hi[i] = h;
         lo[i] = l;
     }
@@ -56,8 +56,8 @@ __global__ void split_kernel(const float *__restrict__ src, bf16 *__restrict__ h
 // four live taps of a 3x3 mask-'A' kernel, (dv,dh) = (-1,-1), (-1,0), (-1,+1), (0,-1) (masked_conv2d.py:12-17),
 // zero outside the image (NET:349).
 __global__ void gather_kernel(const float *__restrict__ x_cl, const float *__restrict__ zhat_cl, int Cin, StepDesc s,
-                              int R, bf16 *__restrict__ X_hi, bf16 *__restrict__ X_lo, int ldX,
-                              bf16 *__restrict__ T_hi, bf16 *__restrict__ T_lo, int ldT) {
+                              int R, h16 *__restrict__ X_hi, h16 *__restrict__ X_lo, int ldX,
+                              h16 *__restrict__ T_hi, h16 *__restrict__ T_lo, int ldT) {
     const int r = blockIdx.x;
     if (r >= R) return;
     int img, v, h;
@@ -67,7 +67,7 @@ __global__ void gather_kernel(const float *__restrict__ x_cl, const float *__res
     for (int e = threadIdx.x + first * c4n; e < 5 * c4n; e += blockDim.x) {
         const int seg = e / c4n, c = (e - seg * c4n) << 2;
         float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        bf16 *ph, *pl;
+        h16 *ph, *pl;
         if (seg == 0) {
             val = *reinterpret_cast<const float4 *>(x_cl + (((size_t)img * s.Hb + v) * s.Wb + h) * Cin + c);
             ph = X_hi + (size_t)r * ldX + c;
@@ -89,8 +89,8 @@ __global__ void gather_kernel(const float *__restrict__ x_cl, const float *__res
 
 // KS[1] == 3: out[r, tap*E1 + c] = g0(v+dv, h+dh)[c] for the five live taps of a 3x3 mask-'B' kernel,
 // (dv,dh) = (-1,-1), (-1,0), (-1,+1), (0,-1), (0,0); every such position lies inside the ring-extended store.
-__global__ void gather5_kernel(const bf16 *__restrict__ g_hi, const bf16 *__restrict__ g_lo, int E1, StepDesc s, int R,
-                               bf16 *__restrict__ o_hi, bf16 *__restrict__ o_lo, int ld) {
+__global__ void gather5_kernel(const h16 *__restrict__ g_hi, const h16 *__restrict__ g_lo, int E1, StepDesc s, int R,
+                               h16 *__restrict__ o_hi, h16 *__restrict__ o_lo, int ld) {
     const int r = blockIdx.x;
     if (r >= R) return;
     int img, v, h;
@@ -110,15 +110,15 @@ __global__ void gather5_kernel(const bf16 *__restrict__ g_hi, const bf16 *__rest
 // KS[1] == 3: row v = -1 of the hidden map sees only zero padding, so g0(-1, h) = lrelu(0 + b_e0) for every h --
 // bit-identical to what the E0 GEMM epilogue produces from an all-zero accumulator.
 __global__ void fill_g0_top_kernel(const float *__restrict__ bias, int E1, int n_img, int Hb, int Wb,
-                                   bf16 *__restrict__ g_hi, bf16 *__restrict__ g_lo) {
+                                   h16 *__restrict__ g_hi, h16 *__restrict__ g_lo) {
     const int pos = blockIdx.x;                 // img * (Wb+2) + (h+1)
     const int img = pos / (Wb + 2), hp = pos - img * (Wb + 2);
     const size_t row = g0_pos_index(img, -1, hp - 1, Hb, Wb);
     for (int c = threadIdx.x; c < E1; c += blockDim.x) {
         float v = 0.0f + bias[c];
         v = v > 0.0f ? v : v * 0.01f;
-        bf16 h, l;
-        split_bf16(v, h, l);
+        h16 h, l;
+        split_h16(v, h, l);
         g_hi[row * E1 + c] = h;
         g_lo[row * E1 + c] = l;
     }
@@ -130,41 +130,50 @@ struct TapList {
     int kh[8], kw[8];
 };
 
-// out[co][t*cin + ci] = w[co][ci][kh_t][kw_t] * mask[co][ci][kh_t][kw_t]      (NET:381 weight * mask)
+// weff[co][t*cin + ci] = w[co][ci][kh_t][kw_t] * mask[co][ci][kh_t][kw_t]      (NET:381 weight * mask)
 __global__ void pack_conv_kernel(const float *__restrict__ w, const float *__restrict__ mask, int cout, int cin, int KH,
-                                 int KW, TapList taps, bf16 *__restrict__ hi, bf16 *__restrict__ lo, int ld) {
+                                 int KW, TapList taps, float *__restrict__ weff, int ld) {
     const size_t total = (size_t)cout * taps.n * cin;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int ci = (int)(i % cin);
         const int t = (int)((i / cin) % taps.n);
         const int co = (int)(i / ((size_t)cin * taps.n));
         const size_t src = (((size_t)co * cin + ci) * KH + taps.kh[t]) * KW + taps.kw[t];
-        const float val = w[src] * (mask ? mask[src] : 1.0f);
-        bf16 h, l;
-        split_bf16(val, h, l);
-        const size_t dst = (size_t)co * ld + (size_t)t * cin + ci;
-        hi[dst] = h;
-        lo[dst] = l;
+        weff[(size_t)co * ld + (size_t)t * cin + ci] = w[src] * (mask ? mask[src] : 1.0f);
     }
 }
 
 // NonNegativeParametrizer.forward: max(p, bound)^2 - pedestal   (utils/parametrizers.py:45-48)
 __global__ void pack_gdn_kernel(const float *__restrict__ gamma, const float *__restrict__ beta, int C, float gbound,
-                                float gped, float bbound, float bped, bf16 *__restrict__ hi, bf16 *__restrict__ lo,
-                                int ld, float *__restrict__ beta_out) {
+                                float gped, float bbound, float bped, float *__restrict__ weff, int ld,
+                                float *__restrict__ beta_out) {
     const size_t total = (size_t)C * C;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int rI = (int)(i / C), cI = (int)(i % C);
         const float g = fmaxf(gamma[i], gbound);
-        const float val = g * g - gped;
-        bf16 h, l;
-        split_bf16(val, h, l);
-        hi[(size_t)rI * ld + cI] = h;
-        lo[(size_t)rI * ld + cI] = l;
+        weff[(size_t)rI * ld + cI] = g * g - gped;
         if (i < (size_t)C) {
             const float b = fmaxf(beta[i], bbound);
             beta_out[i] = b * b - bped;
         }
+    }
+}
+
+__global__ void absmax_kernel(const float *__restrict__ v, size_t n, float *__restrict__ out) {
+    float m = 0.0f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(v[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int *>(out), __float_as_uint(m));   // m >= 0
+}
+
+__global__ void split_scaled_kernel(const float *__restrict__ src, h16 *__restrict__ hi, h16 *__restrict__ lo, size_t n,
+                                    float scale) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        h16 h, l;
+        split_h16(src[i] * scale, h, l);
+        hi[i] = h;
+        lo[i] = l;
     }
 }
 
@@ -214,15 +223,15 @@ int launch_depth_to_space(const float *blk, float *img, int n, int C, int Hb, in
     return 0;
 }
 
-int launch_split_f32(const float *src, bf16 *hi, bf16 *lo, int64_t n, cudaStream_t st) {
+int launch_split_f32(const float *src, h16 *hi, h16 *lo, int64_t n, cudaStream_t st) {
     split_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(src, hi, lo, (size_t)n);
     count_launch(1);
     LBIC_CUDA(cudaGetLastError());
     return 0;
 }
 
-int launch_gather(const float *x_cl, const float *zhat_cl, int Cin, const StepDesc &s, int R, bf16 *X_hi, bf16 *X_lo,
-                  int ldX, bf16 *T_hi, bf16 *T_lo, int ldT, cudaStream_t st) {
+int launch_gather(const float *x_cl, const float *zhat_cl, int Cin, const StepDesc &s, int R, h16 *X_hi, h16 *X_lo,
+                  int ldX, h16 *T_hi, h16 *T_lo, int ldT, cudaStream_t st) {
     if (R <= 0) return 0;
     int threads = 5 * (Cin / 4);
     threads = threads > 256 ? 256 : ((threads + 31) / 32) * 32;
@@ -232,7 +241,7 @@ int launch_gather(const float *x_cl, const float *zhat_cl, int Cin, const StepDe
     return 0;
 }
 
-int launch_gather5(const bf16 *g0_hi, const bf16 *g0_lo, int E1, const StepDesc &s, int R, bf16 *out_hi, bf16 *out_lo,
+int launch_gather5(const h16 *g0_hi, const h16 *g0_lo, int E1, const StepDesc &s, int R, h16 *out_hi, h16 *out_lo,
                    int ld, cudaStream_t st) {
     if (R <= 0) return 0;
     gather5_kernel<<<R, 256, 0, st>>>(g0_hi, g0_lo, E1, s, R, out_hi, out_lo, ld);
@@ -241,7 +250,7 @@ int launch_gather5(const bf16 *g0_hi, const bf16 *g0_lo, int E1, const StepDesc 
     return 0;
 }
 
-int launch_fill_g0_top(const float *bias, int E1, int n_img, int Hb, int Wb, bf16 *g_hi, bf16 *g_lo, cudaStream_t st) {
+int launch_fill_g0_top(const float *bias, int E1, int n_img, int Hb, int Wb, h16 *g_hi, h16 *g_lo, cudaStream_t st) {
     fill_g0_top_kernel<<<n_img * (Wb + 2), 256, 0, st>>>(bias, E1, n_img, Hb, Wb, g_hi, g_lo);
     count_launch(1);
     LBIC_CUDA(cudaGetLastError());
@@ -249,7 +258,7 @@ int launch_fill_g0_top(const float *bias, int E1, int n_img, int Hb, int Wb, bf1
 }
 
 int launch_pack_conv(const float *w, const float *mask, int cout, int cin, int kh, int kw, const int *taps_host,
-                     int ntaps, bf16 *hi, bf16 *lo, int ld, cudaStream_t st) {
+                     int ntaps, float *weff, int ld, cudaStream_t st) {
     TapList tl;
     tl.n = ntaps;
     for (int i = 0; i < ntaps; ++i) {
@@ -257,16 +266,30 @@ int launch_pack_conv(const float *w, const float *mask, int cout, int cin, int k
         tl.kw[i] = taps_host[2 * i + 1];
     }
     const size_t total = (size_t)cout * ntaps * cin;
-    pack_conv_kernel<<<grid_for(total, 256), 256, 0, st>>>(w, mask, cout, cin, kh, kw, tl, hi, lo, ld);
+    pack_conv_kernel<<<grid_for(total, 256), 256, 0, st>>>(w, mask, cout, cin, kh, kw, tl, weff, ld);
     count_launch(1);
     LBIC_CUDA(cudaGetLastError());
     return 0;
 }
 
 int launch_pack_gdn(const float *gamma, const float *beta, int C, float gbound, float gped, float bbound, float bped,
-                    bf16 *hi, bf16 *lo, int ld, float *beta_out, cudaStream_t st) {
-    pack_gdn_kernel<<<grid_for((size_t)C * C, 256), 256, 0, st>>>(gamma, beta, C, gbound, gped, bbound, bped, hi, lo, ld,
+                    float *weff, int ld, float *beta_out, cudaStream_t st) {
+    pack_gdn_kernel<<<grid_for((size_t)C * C, 256), 256, 0, st>>>(gamma, beta, C, gbound, gped, bbound, bped, weff, ld,
                                                                 beta_out);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_absmax(const float *v, int64_t n, float *out_dev, cudaStream_t st) {
+    absmax_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(v, (size_t)n, out_dev);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_split_scaled(const float *src, h16 *hi, h16 *lo, int64_t n, float scale, cudaStream_t st) {
+    split_scaled_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(src, hi, lo, (size_t)n, scale);
     count_launch(1);
     LBIC_CUDA(cudaGetLastError());
     return 0;

@@ -2,7 +2,7 @@
 #pragma once
 
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -11,7 +11,9 @@
 
 #include "../../include/lbic.h"
 
-typedef __nv_bfloat16 bf16;
+// GEMM operand element: IEEE fp16.  Every fp32 value is stored as two fp16 planes (hi + lo = 22 significand bits);
+// see gemm_tc.cu.  (bf16 planes gave 16 bits and ~6x more rounding-boundary symbol flips)
+typedef __half h16;
 
 int lbic_fail(int code, const char *fmt, ...);
 
@@ -69,7 +71,8 @@ struct EpiParams {
     int R;              // valid rows
     int cout;           // valid output columns
     const float *bias;  // [cout] (beta for the GDN modes)
-    bf16 *out_hi, *out_lo;
+    float acc_scale;    // 2^-k: the layer's weights are stored multiplied by 2^k (fp16 range), undone here exactly
+    h16 *out_hi, *out_lo;
     int ld_out;
     int out_pos;        // 1: hi/lo output row = position in the ring-extended g0 store (KS[1]=3), see g0_pos_index
     float *out_f32;
@@ -84,9 +87,9 @@ struct EpiParams {
     StepDesc step;
 };
 
-// One K segment of a GEMM: A[R,K] (bf16 hi/lo planes, row stride ld) times W[cout,K]^T.
+// One K segment of a GEMM: A[R,K] (h16 hi/lo planes, row stride ld) times W[cout,K]^T.
 struct GemmOperand {
-    const bf16 *hi, *lo;
+    const h16 *hi, *lo;
     int ld;                 // elements
     const CUtensorMap *tm_hi, *tm_lo;   // host copies of the TMA descriptors
 };
@@ -100,7 +103,10 @@ struct GemmCall {
 };
 
 // One layer of a persistent chain launch (gemm_chain.cu), resident in device memory.
-constexpr int LBIC_NBN = 3;   // tile-width variants per layer: wide (<= 256), 128, 64
+// Tile-width variants per layer, indexed by "split factor" f: the layer's Cout is cut into f * ceil(Cout / (256 f))
+// equal tiles (width rounded up to 16), so a cluster of f CTAs gets the same number of tiles per CTA.
+constexpr int LBIC_NBN = 6;
+__host__ __device__ inline int lbic_split(int i) { return i == 0 ? 1 : i == 1 ? 2 : i == 2 ? 3 : i == 3 ? 4 : i == 4 ? 6 : 8; }
 struct alignas(64) ChainLayer {
     CUtensorMap tmA[2][2];              // [segment][hi, lo]   box 64 x 128
     CUtensorMap tmW[LBIC_NBN][2][2];    // [variant][segment][hi, lo]   box 64 x bn_v[variant]
@@ -127,19 +133,23 @@ int launch_nchw_to_cl(const float *src, float *dst, int n, int C, int HW, cudaSt
 int launch_cl_to_nchw(const float *src, float *dst, int n, int C, int HW, cudaStream_t st);
 int launch_space_to_depth(const float *img, float *blk, int n, int C, int Hb, int Wb, int B, cudaStream_t st);
 int launch_depth_to_space(const float *blk, float *img, int n, int C, int Hb, int Wb, int B, cudaStream_t st);
-int launch_split_f32(const float *src, bf16 *hi, bf16 *lo, int64_t n, cudaStream_t st);
+int launch_split_f32(const float *src, h16 *hi, h16 *lo, int64_t n, cudaStream_t st);
 // per-step gather of x and the four causal neighbour blocks of zhat
 int launch_gather(const float *x_cl, const float *zhat_cl, int Cin, const StepDesc &s, int R,
-                  bf16 *X_hi, bf16 *X_lo, int ldX, bf16 *T_hi, bf16 *T_lo, int ldT, cudaStream_t st);
+                  h16 *X_hi, h16 *X_lo, int ldX, h16 *T_hi, h16 *T_lo, int ldT, cudaStream_t st);
 // weight packing
+// weight packing: effective fp32 weights (mask folded / taps reordered / GDN reparametrised), their max |w|,
+// then the scaled fp16 hi/lo split
 int launch_pack_conv(const float *w, const float *mask, int cout, int cin, int kh, int kw,
-                     const int *taps_host, int ntaps, bf16 *hi, bf16 *lo, int ld, cudaStream_t st);
+                     const int *taps_host, int ntaps, float *weff, int ld, cudaStream_t st);
 int launch_pack_gdn(const float *gamma, const float *beta, int C, float gbound, float gped, float bbound,
-                    float bped, bf16 *hi, bf16 *lo, int ld, float *beta_out, cudaStream_t st);
+                    float bped, float *weff, int ld, float *beta_out, cudaStream_t st);
+int launch_absmax(const float *v, int64_t n, float *out_dev, cudaStream_t st);   // *out_dev = max(*out_dev, max|v|)
+int launch_split_scaled(const float *src, h16 *hi, h16 *lo, int64_t n, float scale, cudaStream_t st);
 // KS[1]==3: A operand of get_meanscale[2] = the five mask-'B' taps of g0 around each block of the step
-int launch_gather5(const bf16 *g0_hi, const bf16 *g0_lo, int E1, const StepDesc &s, int R, bf16 *out_hi, bf16 *out_lo,
+int launch_gather5(const h16 *g0_hi, const h16 *g0_lo, int E1, const StepDesc &s, int R, h16 *out_hi, h16 *out_lo,
                    int ld, cudaStream_t st);
-int launch_fill_g0_top(const float *bias, int E1, int n_img, int Hb, int Wb, bf16 *g_hi, bf16 *g_lo, cudaStream_t st);
+int launch_fill_g0_top(const float *bias, int E1, int n_img, int Hb, int Wb, h16 *g_hi, h16 *g_lo, cudaStream_t st);
 int launch_add_vec(const float *a, const float *b, float *out, int n, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
@@ -174,7 +184,7 @@ int launch_rans_dec_init(const uint8_t *streams, const uint32_t *stream_len, siz
                          int lanes, RansStreamState *states, const uint8_t **lane_ptr, int *err_flag, cudaStream_t st);
 // decode M symbols for every row of a step; writes yq = sym + mean (hi/lo) and optionally symbols
 int launch_rans_dec_step(const Tables &T, RansStreamState *states, const uint8_t *const *lane_ptr, int lanes,
-                         const StepDesc &s, int R, int M, const float *ksi, int ld_ksi, bf16 *yq_hi, bf16 *yq_lo,
+                         const StepDesc &s, int R, int M, const float *ksi, int ld_ksi, h16 *yq_hi, h16 *yq_lo,
                          int ld_yq, int32_t *sym_out, cudaStream_t st);
 int launch_rans_decode_full(const Tables &T, const uint8_t *streams, const uint32_t *stream_len, size_t stream_stride,
                             const uint8_t *idx, int n_streams, int64_t n_sym, int32_t *sym_out, cudaStream_t st);

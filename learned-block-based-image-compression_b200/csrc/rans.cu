@@ -37,6 +37,14 @@ __device__ __forceinline__ void enc_emit(EncCursor &c) {
     c.x >>= 32;
 }
 
+// warp-uniform variant: every lane tracks the same cursor, lane 0 performs the store
+__device__ __forceinline__ void enc_emit_w(EncCursor &c, int lane) {
+    if (c.pos <= 0) { c.overflow = true; return; }
+    --c.pos;
+    if (lane == 0) c.base[c.pos] = (uint32_t)c.x;
+    c.x >>= 32;
+}
+
 __device__ __forceinline__ void enc_put(EncCursor &c, uint32_t start, uint32_t range) {
     const unsigned long long x_max = ((RANS_L >> PREC) << 32) * (unsigned long long)range;
     if (c.x >= x_max) enc_emit(c);
@@ -49,12 +57,19 @@ __device__ __forceinline__ void enc_put_bits(EncCursor &c, uint32_t val) {
     c.x = (c.x << BYPASS) | val;
 }
 
+// One warp per stream.  The state update is inherently serial, so the warp splits the work in two:
+//   * in parallel, each lane prepares one of the next 32 symbols: table lookups (start, range), the escape
+//     decision, and the exact reciprocal of `range` (Granlund-Montgomery / ryg_rans Rans64EncSymbolInit:
+//     rcp = ceil(2^(63+s) / range), s = ceil(log2 range); floor(x / range) = mulhi64(x, rcp) >> (s - 1) for every
+//     x < 2^63, which covers x < x_max = range << 47);
+//   * then all lanes replay the 32 prepared symbols in order (records broadcast with shuffles, every lane holds the
+//     same state, lane 0 writes the renormalisation words), so no memory latency or division sits on the serial chain.
 __global__ void rans_encode_kernel(const int32_t *__restrict__ cdf, int cdf_stride, const int32_t *__restrict__ cdf_len,
                                    const int32_t *__restrict__ offs, const int32_t *__restrict__ sym,
                                    const uint8_t *__restrict__ idx, int n_streams, long n_sym, long stream_stride,
                                    uint32_t *__restrict__ scratch, long scratch_words, uint32_t *__restrict__ start_word,
                                    uint32_t *__restrict__ n_words, int *__restrict__ err) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (s >= n_streams) return;
     EncCursor c;
     c.x = RANS_L;
@@ -63,44 +78,89 @@ __global__ void rans_encode_kernel(const int32_t *__restrict__ cdf, int cdf_stri
     c.overflow = false;
     const int32_t *ps = sym + (size_t)s * stream_stride;
     const uint8_t *pi = idx + (size_t)s * stream_stride;
-    for (long k = n_sym - 1; k >= 0; --k) {
-        const int ci = pi[k];
-        const int32_t *row = cdf + (size_t)ci * cdf_stride;
-        const int max_value = cdf_len[ci] - 2;
-        int value = ps[k] - offs[ci];
-        uint32_t raw = 0;
-        if (value < 0) {
-            raw = (uint32_t)(-2 * value - 1);
-            value = max_value;
-        } else if (value >= max_value) {
-            raw = (uint32_t)(2 * (value - max_value));
-            value = max_value;
+    for (long top = n_sym; top > 0; top -= 32) {
+        // lane j prepares symbol top-1-j (the coder walks the symbols backwards)
+        const long k = top - 1 - lane;
+        uint32_t sr = 0, raw = 0, flags = 0;       // sr = start | range << 16; flags: bit0 escape, bits 8.. rcp shift
+        unsigned long long rcp = 0;
+        if (k >= 0) {
+            const int ci = pi[k];
+            const int32_t *row = cdf + (size_t)ci * cdf_stride;
+            const int max_value = __ldg(cdf_len + ci) - 2;
+            int value = ps[k] - __ldg(offs + ci);
+            if (value < 0) {
+                raw = (uint32_t)(-2 * value - 1);
+                value = max_value;
+            } else if (value >= max_value) {
+                raw = (uint32_t)(2 * (value - max_value));
+                value = max_value;
+            }
+            const uint32_t start = (uint32_t)__ldg(row + value);
+            const uint32_t range = (uint32_t)__ldg(row + value + 1) - start;
+            sr = start | (range << 16);
+            uint32_t shift = 0;
+            while (range > (1u << shift)) ++shift;
+            if (range >= 2) {
+                // ((1 << (shift + 63)) + range - 1) / range as two 64-bit divides
+                unsigned long long x0 = range - 1;
+                const unsigned long long x1 = 1ull << (shift + 31);
+                const unsigned long long t1 = x1 / range;
+                x0 += (x1 % range) << 32;
+                rcp = x0 / range + (t1 << 32);
+            }
+            flags = (value == max_value ? 1u : 0u) | (shift << 8);
         }
-        if (value == max_value) {
-            // pushed order: main, count (15,15,...,rem), nibbles LSB first -> popped in reverse
-            int nb = 0;
-            while (nb < 8 && (raw >> (nb * BYPASS)) != 0) ++nb;
-            for (int j = nb - 1; j >= 0; --j) enc_put_bits(c, (raw >> (j * BYPASS)) & MAX_BYPASS);
-            const int q = nb / MAX_BYPASS, rem = nb - q * MAX_BYPASS;
-            enc_put_bits(c, (uint32_t)rem);
-            for (int j = 0; j < q; ++j) enc_put_bits(c, MAX_BYPASS);
+        const int cnt = top < 32 ? (int)top : 32;
+        for (int j = 0; j < cnt; ++j) {
+            const uint32_t b_sr = __shfl_sync(0xffffffffu, sr, j);
+            const uint32_t b_fl = __shfl_sync(0xffffffffu, flags, j);
+            const uint32_t r_lo = __shfl_sync(0xffffffffu, (uint32_t)rcp, j);
+            const uint32_t r_hi = __shfl_sync(0xffffffffu, (uint32_t)(rcp >> 32), j);
+            if (b_fl & 1u) {
+                // escape: pushed order is main, count (15,15,...,rem), nibbles LSB first -> popped in reverse
+                const uint32_t b_raw = __shfl_sync(0xffffffffu, raw, j);
+                int nb = 0;
+                while (nb < 8 && (b_raw >> (nb * BYPASS)) != 0) ++nb;
+                for (int q = nb - 1; q >= 0; --q) {
+                    const unsigned long long x_max = ((RANS_L >> PREC) << 32) * (unsigned long long)(1u << (PREC - BYPASS));
+                    if (c.x >= x_max) enc_emit_w(c, lane);
+                    c.x = (c.x << BYPASS) | ((b_raw >> (q * BYPASS)) & MAX_BYPASS);
+                }
+                const int qn = nb / MAX_BYPASS, rem = nb - qn * MAX_BYPASS;
+                for (int q = 0; q <= qn; ++q) {
+                    const unsigned long long x_max = ((RANS_L >> PREC) << 32) * (unsigned long long)(1u << (PREC - BYPASS));
+                    if (c.x >= x_max) enc_emit_w(c, lane);
+                    c.x = (c.x << BYPASS) | (uint32_t)(q == 0 ? rem : MAX_BYPASS);
+                }
+            }
+            const uint32_t start = b_sr & 0xFFFFu, range = b_sr >> 16;
+            const unsigned long long x_max = ((RANS_L >> PREC) << 32) * (unsigned long long)range;
+            if (c.x >= x_max) enc_emit_w(c, lane);
+            unsigned long long q;
+            if (range >= 2) {
+                const unsigned long long r64 = (unsigned long long)r_lo | ((unsigned long long)r_hi << 32);
+                q = __umul64hi(c.x, r64) >> ((b_fl >> 8) - 1);
+            } else {
+                q = c.x;
+            }
+            c.x = (q << PREC) + (c.x - q * range) + start;
         }
-        const uint32_t start = (uint32_t)row[value];
-        enc_put(c, start, (uint32_t)row[value + 1] - start);
     }
     // Rans64EncFlush: two words, low half first in memory
     if (c.pos < 2) c.overflow = true;
-    if (!c.overflow) {
-        c.base[--c.pos] = (uint32_t)(c.x >> 32);
-        c.base[--c.pos] = (uint32_t)(c.x);
-    }
-    if (c.overflow) {
-        atomicExch(err, 1);
-        start_word[s] = 0;
-        n_words[s] = 0xFFFFFFFFu;
-    } else {
-        start_word[s] = (uint32_t)c.pos;
-        n_words[s] = (uint32_t)(scratch_words - c.pos);
+    if (lane == 0) {
+        if (!c.overflow) {
+            c.base[--c.pos] = (uint32_t)(c.x >> 32);
+            c.base[--c.pos] = (uint32_t)(c.x);
+        }
+        if (c.overflow) {
+            atomicExch(err, 1);
+            start_word[s] = 0;
+            n_words[s] = 0xFFFFFFFFu;
+        } else {
+            start_word[s] = (uint32_t)c.pos;
+            n_words[s] = (uint32_t)(scratch_words - c.pos);
+        }
     }
 }
 
@@ -260,13 +320,13 @@ __global__ void rans_dec_init_kernel(const uint8_t *__restrict__ streams, const 
 }
 
 // One warp per row of the step: build_indexes from the predicted scales, decode M symbols from the row's
-// lane, dequantise (sym + mean, ENT:159-168) and emit the decoder-net input as bf16 hi/lo planes.
+// lane, dequantise (sym + mean, ENT:159-168) and emit the decoder-net input as h16 hi/lo planes.
 __global__ void rans_dec_step_kernel(const int32_t *__restrict__ cdf, int cdf_stride,
                                      const int32_t *__restrict__ cdf_len, const int32_t *__restrict__ offs,
                                      const float *__restrict__ scale_tab, RansStreamState *__restrict__ states,
                                      const uint8_t *const *__restrict__ lane_ptr, int lanes, StepDesc sd, int R, int M,
-                                     const float *__restrict__ ksi, int ld_ksi, bf16 *__restrict__ yq_hi,
-                                     bf16 *__restrict__ yq_lo, int ld_yq, int32_t *__restrict__ sym_out) {
+                                     const float *__restrict__ ksi, int ld_ksi, h16 *__restrict__ yq_hi,
+                                     h16 *__restrict__ yq_lo, int ld_yq, int32_t *__restrict__ sym_out) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= R) return;
     int img, v, h;
@@ -302,8 +362,8 @@ __global__ void rans_dec_step_kernel(const int32_t *__restrict__ cdf, int cdf_st
         const int c = j * 32 + lane;
         if (c < M) {
             const float yq = (float)my_sym[j] + krow[M + c];
-            bf16 hi, lo;
-            split_bf16(yq, hi, lo);
+            h16 hi, lo;
+            split_h16(yq, hi, lo);
             yq_hi[(size_t)warp * ld_yq + c] = hi;
             yq_lo[(size_t)warp * ld_yq + c] = lo;
             if (sym_out) sym_out[o + c] = my_sym[j];
@@ -342,8 +402,8 @@ int launch_rans_encode(const Tables &T, const int32_t *sym, const uint8_t *idx, 
     if (!T.cdf) return lbic_fail(LBIC_ERR_STATE, "Uninitialized CDFs. Run update() first");
     uint32_t *start_word = scratch + (size_t)n_streams * scratch_words;
     uint32_t *n_words = start_word + n_streams;
-    const int threads = 32;
-    rans_encode_kernel<<<(n_streams + threads - 1) / threads, threads, 0, st>>>(
+    const int warps_per_block = 4;
+    rans_encode_kernel<<<(n_streams + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
         T.cdf, T.stride, T.cdf_length, T.offset, sym, idx, n_streams, (long)n_sym, (long)stream_stride, scratch,
         (long)scratch_words, start_word, n_words, err_flag);
     count_launch(1);
@@ -380,7 +440,7 @@ int launch_rans_dec_init(const uint8_t *streams, const uint32_t *stream_len, siz
 }
 
 int launch_rans_dec_step(const Tables &T, RansStreamState *states, const uint8_t *const *lane_ptr, int lanes,
-                         const StepDesc &s, int R, int M, const float *ksi, int ld_ksi, bf16 *yq_hi, bf16 *yq_lo,
+                         const StepDesc &s, int R, int M, const float *ksi, int ld_ksi, h16 *yq_hi, h16 *yq_lo,
                          int ld_yq, int32_t *sym_out, cudaStream_t st) {
     if (R <= 0) return 0;
     if (M > 256) return lbic_fail(LBIC_ERR_INVALID, "M > 256 unsupported by the decode step");

@@ -8,12 +8,12 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int A_PLANE = BM * BK * 2;     // 16 KiB per bf16 plane
+constexpr int A_PLANE = BM * BK * 2;     // 16 KiB per h16 plane
 constexpr int MAX_STAGES = 4;
 constexpr int NUM_THREADS = 256;          // 8 warps = 2 per SM sub-partition (255 registers available)
 constexpr int SMEM_LIMIT = 232448;       // 227 KiB opt-in maximum per CTA
 constexpr int BAR_BLOCK = 128;           // full[4] | empty[4] | tmem_full | tmem base address
-constexpr int SMEM_SLACK = 1024 + BAR_BLOCK + 1024;   // ring alignment + barrier block + bias slice (<= 256 floats)
+constexpr int SMEM_SLACK = 1024 + BAR_BLOCK + 1024 + 3072;   // ring alignment + barrier block + bias slice (<= 256 floats) + row table
 
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -109,7 +109,7 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
 // the epilogue 60 % of the kernel (profiles/r1_gemm_epilogue.md).
 constexpr int GROUP_COLS = 128;
 constexpr int STG_F_STRIDE = GROUP_COLS * 4 + 16;     // fp32 plane row stride (bytes)
-constexpr int STG_H_STRIDE = GROUP_COLS * 2 + 16;     // bf16 plane row stride
+constexpr int STG_H_STRIDE = GROUP_COLS * 2 + 16;     // h16 plane row stride
 constexpr int STG_I_STRIDE = GROUP_COLS + 16;         // uint8 index plane row stride
 constexpr int STG_F_OFF = 0;
 constexpr int STG_H_OFF = STG_F_OFF + BM * STG_F_STRIDE;
@@ -146,35 +146,15 @@ __device__ __forceinline__ void stage_chunk(uint32_t stg, int mode, int rl, int 
     if (mode == EPI_QUANT) sts128(stg + STG_I_OFF + rl * STG_I_STRIDE + gc, o.idx[0], o.idx[1], o.idx[2], o.idx[3]);
 }
 
-// one warp copies row `rl` (global row r) of the staged group: `ncols` valid columns starting at tile column c0
-__device__ __forceinline__ void store_row(const EpiParams &ep, uint32_t stg, int rl, int r, int c0, int ncols, int lane) {
-    const EpiRowDst d = epi_row_dst(ep, r);
-    float *pf = epi_f32_ptr(ep, d, c0);
-    if (pf) {
-        const uint32_t a = stg + STG_F_OFF + rl * STG_F_STRIDE;
-        for (int i = lane; i < (ncols >> 2); i += 32) {
-            const uint4 v = lds128(a + i * 16);
-            *reinterpret_cast<uint4 *>(pf + i * 4) = v;
-        }
-    }
-    if (epi_has_hilo(ep.mode)) {
-        // lanes 0..15 move the hi plane, lanes 16..31 the lo plane (ncols*2 bytes each, <= 256 B)
-        const int sub = lane & 15;
-        const bool is_lo = lane >= 16;
-        const uint32_t a = stg + (is_lo ? STG_L_OFF : STG_H_OFF) + rl * STG_H_STRIDE;
-        bf16 *dst = (is_lo ? ep.out_lo : ep.out_hi) + d.hilo + c0;
-        if (sub < (ncols >> 3)) {
-            const uint4 v = lds128(a + sub * 16);
-            *reinterpret_cast<uint4 *>(dst + sub * 8) = v;
-        }
-    }
-    if (ep.mode == EPI_QUANT && ep.idx) {
-        if (lane < (ncols >> 4)) {
-            const uint4 v = lds128(stg + STG_I_OFF + rl * STG_I_STRIDE + lane * 16);
-            *reinterpret_cast<uint4 *>(ep.idx + d.blk * ep.M + c0 + lane * 16) = v;
-        }
-    }
-}
+// Per-row destinations of a tile (shared memory, filled once per tile by the row's owner thread so that the
+// store loops below carry no index arithmetic): fp32-plane pointer, hi/lo element offset, index-plane pointer,
+// each already advanced to the tile's first column n0.
+struct RowTab {
+    unsigned long long f32[BM];
+    unsigned long long hilo[BM];
+    unsigned long long idx[BM];
+};
+constexpr int ROWTAB_BYTES = (int)sizeof(RowTab);   // 3 KiB
 
 __device__ __forceinline__ void epi_chunk_stage(const EpiParams &ep, const float *bias, uint32_t stg, int rl, int gc,
                                                 const uint32_t (&raw)[16], const EpiPre<16> &pre) {
@@ -188,27 +168,79 @@ __device__ __forceinline__ void epi_chunk_stage(const EpiParams &ep, const float
 
 // Epilogue of one 128 x bn tile, executed by all 8 warps of the CTA after the accumulator is complete
 // (the caller has waited on the accumulator barrier and issued tcgen05.fence::after_thread_sync).
-// sbias: shared-memory copy of the tile's bias slice; stg: shared address of the (idle) ring used for staging.
-__device__ __forceinline__ void tile_epilogue(const EpiParams &ep, const float *sbias, uint32_t stg, uint32_t tmem_acc,
-                                              int m0, int n0, int bn, int warp, int lane) {
+// sbias: shared-memory copy of the tile's bias slice; stg: shared address of the (idle) ring used for staging;
+// rt: shared-memory row table.
+__device__ __forceinline__ void tile_epilogue(const EpiParams &ep, const float *sbias, uint32_t stg, RowTab *rt,
+                                              uint32_t tmem_acc, int m0, int n0, int bn, int warp, int lane,
+                                              unsigned long long *trace = nullptr) {
     const int q = warp & 3;                  // TMEM lane quarter this warp may access (warp id % 4)
     const int ew = warp;                     // epilogue warp 0..7
     const int sub = ew >> 2;                 // the two warps of a lane quarter split each group's chunks
     const int rl = q * 32 + lane;
     const int r = m0 + rl;
     const bool row_ok = r < ep.R;
+    const int rows_valid = (ep.R - m0) < BM ? (ep.R - m0) : BM;
+    const int mode = ep.mode;
+    const bool gdn = (mode == EPI_GDN || mode == EPI_IGDN);
     const uint32_t lane_base = tmem_acc + ((uint32_t)(q * 32) << 16);
+    if (sub == 0 && row_ok) {
+        const EpiRowDst d = epi_row_dst(ep, r);
+        rt->f32[rl] = reinterpret_cast<unsigned long long>(epi_f32_ptr(ep, d, n0));
+        rt->hilo[rl] = (unsigned long long)(d.hilo + n0);
+        rt->idx[rl] = reinterpret_cast<unsigned long long>(mode == EPI_QUANT && ep.idx ? ep.idx + d.blk * ep.M + n0 : nullptr);
+    }
     for (int g0 = 0; g0 < bn; g0 += GROUP_COLS) {
         const int gcols = (bn - g0) < GROUP_COLS ? (bn - g0) : GROUP_COLS;
+        int nvalid = ep.cout - (n0 + g0);
+        nvalid = nvalid < 0 ? 0 : (nvalid > gcols ? gcols : nvalid);
+        if (gdn) {
+            // the pre-GDN activations of this group, loaded row by row with coalesced 16-byte lanes into the
+            // (otherwise unused) fp32 staging plane; each thread then reads its own row from shared memory
+            const int nv4 = nvalid >> 2;
+            if (lane < nv4) {
+                const float *src = ep.aux + (size_t)m0 * ep.ld_aux + n0 + g0 + lane * 4;
+                const uint32_t dst = stg + STG_F_OFF + lane * 16;
+                // 16 rows per warp, in two batches of 8 independent 16-byte loads (all in flight before the first store)
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint4 v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int row = ew + 8 * (half * 8 + j);
+                        v[j] = row < rows_valid ? *reinterpret_cast<const uint4 *>(src + (size_t)row * ep.ld_aux)
+                                                : make_uint4(0u, 0u, 0u, 0u);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int row = ew + 8 * (half * 8 + j);
+                        sts128(dst + row * STG_F_STRIDE, v[j].x, v[j].y, v[j].z, v[j].w);
+                    }
+                }
+            }
+            __syncthreads();
+        }
         const int gch = gcols >> 4;
         const int ch_end = sub ? gch : (gch + 1) >> 1;
         int ch = sub ? (gch + 1) >> 1 : 0;
         // chunk `k` of this group covers tile columns g0 + 16k
         auto ok = [&](int k) { return row_ok && (n0 + g0 + k * 16 < ep.cout); };
+        auto fetch = [&](int k, EpiPre<16> &pre) {
+            if (gdn) {
+                const uint32_t a = stg + STG_F_OFF + rl * STG_F_STRIDE + k * 64;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 v = lds128(a + i * 16);
+                    pre.a[4 * i] = __uint_as_float(v.x); pre.a[4 * i + 1] = __uint_as_float(v.y);
+                    pre.a[4 * i + 2] = __uint_as_float(v.z); pre.a[4 * i + 3] = __uint_as_float(v.w);
+                }
+            } else {
+                epi_prefetch<16>(ep, r, n0 + g0 + k * 16, pre);
+            }
+        };
         EpiPre<16> preA, preB;
         uint32_t accA[16], accB[16];
         if (ch < ch_end) {
-            if (ok(ch)) epi_prefetch<16>(ep, r, n0 + g0 + ch * 16, preA);
+            if (ok(ch)) fetch(ch, preA);
             tmem_ld_issue(lane_base + (uint32_t)(g0 + ch * 16), accA);
             tmem_ld_wait(accA);
         }
@@ -216,7 +248,7 @@ __device__ __forceinline__ void tile_epilogue(const EpiParams &ep, const float *
             const bool hasB = ch + 1 < ch_end;
             if (hasB) {
                 tmem_ld_issue(lane_base + (uint32_t)(g0 + (ch + 1) * 16), accB);
-                if (ok(ch + 1)) epi_prefetch<16>(ep, r, n0 + g0 + (ch + 1) * 16, preB);
+                if (ok(ch + 1)) fetch(ch + 1, preB);
             }
             if (ok(ch)) epi_chunk_stage(ep, sbias + g0 + ch * 16, stg, rl, ch * 16, accA, preA);
             if (hasB) {
@@ -224,19 +256,49 @@ __device__ __forceinline__ void tile_epilogue(const EpiParams &ep, const float *
                 const bool hasA = ch + 2 < ch_end;
                 if (hasA) {
                     tmem_ld_issue(lane_base + (uint32_t)(g0 + (ch + 2) * 16), accA);
-                    if (ok(ch + 2)) epi_prefetch<16>(ep, r, n0 + g0 + (ch + 2) * 16, preA);
+                    if (ok(ch + 2)) fetch(ch + 2, preA);
                 }
                 if (ok(ch + 1)) epi_chunk_stage(ep, sbias + g0 + (ch + 1) * 16, stg, rl, (ch + 1) * 16, accB, preB);
                 if (hasA) tmem_ld_wait(accA);
             }
         }
-        __syncthreads();                                      // the group is staged
-        int nvalid = ep.cout - (n0 + g0);
-        nvalid = nvalid < 0 ? 0 : (nvalid > gcols ? gcols : nvalid);
+        if (trace && threadIdx.x == 0) trace[10] = clock64();
+        __syncthreads();                                      // the group (and the row table) is staged
+        if (trace && threadIdx.x == 0) trace[11] = clock64();
         if (nvalid > 0) {
-            for (int row = ew; row < BM; row += 8) {
-                const int rr = m0 + row;
-                if (rr < ep.R) store_row(ep, stg, row, rr, n0 + g0, nvalid, lane);
+            // lean store loops: one plane at a time, one row per warp and iteration, 16 bytes per lane
+            if (epi_has_f32(mode) && (mode != EPI_QUANT || ep.sym)) {
+                const int nv4 = nvalid >> 2;
+                const uint32_t src = stg + STG_F_OFF + lane * 16;
+                if (lane < nv4) {
+#pragma unroll 2
+                    for (int row = ew; row < rows_valid; row += 8) {
+                        const uint4 v = lds128(src + row * STG_F_STRIDE);
+                        float *dst = reinterpret_cast<float *>(rt->f32[row]) + g0 + lane * 4;
+                        *reinterpret_cast<uint4 *>(dst) = v;
+                    }
+                }
+            }
+            if (epi_has_hilo(mode)) {
+                const int l16 = lane & 15;
+                const bool is_lo = lane >= 16;
+                const uint32_t src = stg + (is_lo ? STG_L_OFF : STG_H_OFF) + l16 * 16;
+                h16 *base = (is_lo ? ep.out_lo : ep.out_hi) + g0 + l16 * 8;
+                if (l16 < (nvalid >> 3)) {
+#pragma unroll 2
+                    for (int row = ew; row < rows_valid; row += 8) {
+                        const uint4 v = lds128(src + row * STG_H_STRIDE);
+                        *reinterpret_cast<uint4 *>(base + rt->hilo[row]) = v;
+                    }
+                }
+            }
+            if (mode == EPI_QUANT && ep.idx) {
+                if (lane < (nvalid >> 4)) {
+                    for (int row = ew; row < rows_valid; row += 8) {
+                        const uint4 v = lds128(stg + STG_I_OFF + row * STG_I_STRIDE + lane * 16);
+                        *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(rt->idx[row]) + g0 + lane * 16) = v;
+                    }
+                }
             }
         }
         if (g0 + GROUP_COLS < bn) __syncthreads();          // before restaging

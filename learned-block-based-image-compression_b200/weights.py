@@ -156,3 +156,33 @@ def synth_images(n: int, H: int, W: int, seed0: int = 1000, kind: str = "smooth"
             up = torch.nn.functional.interpolate(low, size=(H, W), mode="bicubic", align_corners=False)
             out[i] = (up[0] + 0.05 * torch.randn(3, H, W, generator=g)).clamp_(0, 1)
     return out
+
+
+def synth_image_u8(H: int, W: int, seed: int = 0):
+    """Bit-reproducible synthetic 8-bit RGB image (numpy integer arithmetic only: identical on every machine):
+    a coarse random grid, bilinearly interpolated in fixed point, plus +-12 levels of hash noise.
+    Returns a uint8 array (3, H, W)."""
+    import numpy as np
+    rng = np.random.RandomState(seed)        # MT19937 integer draws are platform independent
+    gh, gw = H // 16 + 2, W // 16 + 2
+    grid = rng.randint(0, 256, size=(3, gh, gw)).astype(np.int64)
+    ys, xs = np.arange(H, dtype=np.int64), np.arange(W, dtype=np.int64)
+    y0, fy = ys // 16, ys % 16
+    x0, fx = xs // 16, xs % 16
+    g00 = grid[:, y0][:, :, x0]
+    g01 = grid[:, y0][:, :, x0 + 1]
+    g10 = grid[:, y0 + 1][:, :, x0]
+    g11 = grid[:, y0 + 1][:, :, x0 + 1]
+    wy, wx = fy[None, :, None], fx[None, None, :]
+    smooth = ((16 - wy) * ((16 - wx) * g00 + wx * g01) + wy * ((16 - wx) * g10 + wx * g11)) // 256
+    noise = rng.randint(-12, 13, size=(3, H, W)).astype(np.int64)
+    return np.clip(smooth + noise, 0, 255).astype(np.uint8)
+
+
+def u8_to_model_input(img_u8):
+    """uint8 (3,H,W) or (n,3,H,W) -> float32 tensor in [-0.5, 0.5] exactly as eval_model feeds it (x/255 - 0.5)."""
+    import numpy as np
+    a = np.asarray(img_u8)
+    if a.ndim == 3:
+        a = a[None]
+    return torch.from_numpy(a.astype(np.float32) / np.float32(255.0) - np.float32(0.5))
