@@ -62,6 +62,7 @@ typedef struct {
 #define LBIC_OPT_USE_GRAPH 2   /* 1 = replay the per-(n,Hb,Wb) step sequence as a CUDA graph */
 #define LBIC_OPT_CHAIN 4       /* 1 = one persistent chain kernel per wavefront step (experimental); 0 (default) = one launch per layer */
 #define LBIC_OPT_CLUSTER 5     /* tuning hook: force the chain kernel's cluster size (1,2,3,4,6,8); 0 = cost model */
+#define LBIC_OPT_WS 6          /* 1 (default) = persistent warp-specialised kernel for steps with >= 2 tiles per SM */
 #define LBIC_OPT_FORCE_BN 3    /* tuning hook: force the GEMM tile width (multiple of 16, <= 256); 0 = automatic */
 
 const char *lbic_last_error(void);

@@ -56,7 +56,7 @@ struct PackedSeg {
 
 struct PackedLayer {
     int cout = 0, bn = 0, nseg = 0;
-    int bn_v[NBN] = {0, 0, 0, 0, 0, 0};
+    int bn_v[NBN] = {0, 0, 0, 0, 0, 0, 0};
     int n_bn = 0;
     PackedSeg seg[2];
     float *bias = nullptr;
@@ -117,6 +117,7 @@ struct lbic_model {
     int force_bn = 0;
     int use_chain = 0;     // 1: persistent chain kernel per step (experimental; the per-layer path is faster today)
     int force_cluster = 0;
+    int use_ws = 1;        // warp-specialised persistent kernel for large steps
     int64_t launches[2] = {0, 0};
     int *err_flag = nullptr;
     // host-call staging
@@ -155,6 +156,12 @@ void free_all(std::vector<void *> &list) {
 // tile-width variants of a layer, one per split factor (lbic_split): widest first
 int bn_variants(int cout, int *out) {
     for (int i = 0; i < NBN; ++i) {
+        if (i == LBIC_WS_VARIANT) {
+            const int wmax = gemm_ws_max_bn();
+            const int nt = (cout + wmax - 1) / wmax;
+            out[i] = ((cout + nt - 1) / nt + 15) / 16 * 16;
+            continue;
+        }
         const int f = lbic_split(i);
         const int ntiles = f * ((cout + 256 * f - 1) / (256 * f));
         int bn = ((cout + ntiles - 1) / ntiles + 15) / 16 * 16;
@@ -498,12 +505,19 @@ int run_gemm(lbic_model *m, int id, int R, const ActView *a0, const ActView *a1,
     // Tile width: the widest variant that still gives about one CTA per SM; small steps (few rows) take narrower
     // tiles so that more SMs share the layer -- the result does not depend on the choice (no split-K, fixed k order).
     int vi = 0;
+    bool ws = false;
+    const int row_tiles = (R + 127) / 128;
     if (m->force_bn) {
         for (int i = 0; i < L.n_bn; ++i)
             if (L.bn_v[i] == m->force_bn) vi = i;
+    } else if (m->gemm_core == 0 && m->use_ws &&
+               (m->use_ws == 2 ||
+                row_tiles * ((L.cout + L.bn_v[LBIC_WS_VARIANT] - 1) / L.bn_v[LBIC_WS_VARIANT]) >= 2 * 148)) {
+        // at least two tiles per SM: the persistent kernel overlaps each tile's epilogue with the next mainloop
+        vi = LBIC_WS_VARIANT;
+        ws = true;
     } else {
-        const int row_tiles = (R + 127) / 128;
-        while (vi + 1 < L.n_bn && row_tiles * ((L.cout + L.bn_v[vi] - 1) / L.bn_v[vi]) < 132) ++vi;
+        while (vi + 1 < LBIC_WS_VARIANT && row_tiles * ((L.cout + L.bn_v[vi] - 1) / L.bn_v[vi]) < 132) ++vi;
     }
     g.R = R; g.cout = L.cout; g.bn = L.bn_v[vi]; g.nseg = L.nseg;
     const ActView *av[2] = {a0, a1};
@@ -527,7 +541,7 @@ int run_gemm(lbic_model *m, int id, int R, const ActView *a0, const ActView *a1,
         rec.flops = flops;
         cudaEventRecord(rec.a, st);
     }
-    const int rc = m->gemm_core == 1 ? gemm_simt_launch(g, st) : gemm_tc_launch(g, st);
+    const int rc = m->gemm_core == 1 ? gemm_simt_launch(g, st) : (ws ? gemm_ws_launch(g, st) : gemm_tc_launch(g, st));
     if (m->profiling) {
         cudaEventRecord(rec.b, st);
         m->prof.push_back(rec);
@@ -739,6 +753,9 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
         if (value != 0 && value != 1 && value != 2 && value != 3 && value != 4 && value != 6 && value != 8)
             return lbic_fail(LBIC_ERR_INVALID, "cluster size must be one of 0 (auto), 1, 2, 3, 4, 6, 8");
         m->force_cluster = value;
+        return 0;
+    case LBIC_OPT_WS:
+        m->use_ws = value < 0 ? 0 : (value > 2 ? 2 : value);   // 2 = always (testing)
         return 0;
     case LBIC_OPT_FORCE_BN:
         if (value != 0 && (value % 16 || value < 16 || value > 256)) return lbic_fail(LBIC_ERR_INVALID, "bad tile width");

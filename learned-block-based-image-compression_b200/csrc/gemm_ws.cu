@@ -1,0 +1,361 @@
+// Warp-specialised, persistent tcgen05 GEMM: the throughput kernel for large wavefront steps.
+//
+// profiles/r1_chain_trace.md showed that in gemm_tc_kernel the epilogue (TMEM -> fused math -> staged, coalesced
+// stores) takes about as long as the mainloop, and that every tile also pays prologue / pipeline fill / drain.  Here a
+// CTA stays resident, loops over output tiles, and runs the three stages of consecutive tiles concurrently:
+//
+//   warp 0 lane 0   TMA producer: runs ahead over tile boundaries, gated only by the stage ring
+//   warp 1 lane 0   tcgen05.mma issuer: accumulates tile i into TMEM buffer (i & 1) as soon as the epilogue has
+//                   drained that buffer (acc_empty), tcgen05.commit -> acc_full
+//   warps 2..9      epilogue of tile i-1 from the other TMEM buffer, in 32-column groups staged through a small
+//                   dedicated shared-memory area (so the ring keeps streaming), then coalesced row stores
+//
+// Tiles are 128 x bn with bn <= 192 (2 stages of 80 KiB + 44 KiB staging fit the 227 KiB of shared memory).  Same
+// operand planes, same k order and same epilogue arithmetic as gemm_tc_kernel: results are bit-identical.
+#include "tc_common.cuh"
+
+#include <cstdio>
+#include <cstring>
+
+namespace {
+
+constexpr int WS_THREADS = 320;
+constexpr int WS_EPI_THREADS = 256;
+constexpr int WS_MAX_BN = 192;
+constexpr int WS_ACC_STRIDE = 256;          // TMEM columns between the two accumulators
+constexpr int GC = 32;                      // columns per staged group
+constexpr int WF_STRIDE = GC * 4 + 16;      // 144 B
+constexpr int WH_STRIDE = GC * 2 + 16;      // 80 B
+constexpr int WI_STRIDE = GC + 16;          // 48 B
+constexpr int WF_OFF = 0;
+constexpr int WH_OFF = WF_OFF + BM * WF_STRIDE;
+constexpr int WL_OFF = WH_OFF + BM * WH_STRIDE;
+constexpr int WI_OFF = WL_OFF + BM * WH_STRIDE;
+constexpr int WSTG_BYTES = WI_OFF + BM * WI_STRIDE;   // 45,056 B
+constexpr int WS_BAR_BLOCK = 128;           // full[4] empty[4] acc_full[2] acc_empty[2] tmem slot
+constexpr int WS_TAIL = WS_BAR_BLOCK + 2 * 1024 + ROWTAB_BYTES;   // barriers, two bias slices, row table
+
+struct WsParams {
+    int kb[2];
+    int bn, ntiles_n, total_tiles;
+    int stages;
+    uint32_t slot_bytes, ring_bytes;
+    uint32_t idesc;
+    EpiParams ep;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant__ CUtensorMap tmA0l,
+               const __grid_constant__ CUtensorMap tmW0h, const __grid_constant__ CUtensorMap tmW0l,
+               const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
+               const __grid_constant__ CUtensorMap tmW1h, const __grid_constant__ CUtensorMap tmW1l,
+               const WsParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t ring = (raw + 1023u) & ~1023u;
+    const uint32_t stg = ring + p.ring_bytes;                 // dedicated epilogue staging (1024-aligned)
+    const uint32_t bars = stg + ((WSTG_BYTES + 127) / 128) * 128;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (MAX_STAGES + s); };
+    auto acc_full = [&](int a) { return bars + 8u * (2 * MAX_STAGES + a); };
+    auto acc_empty = [&](int a) { return bars + 8u * (2 * MAX_STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * MAX_STAGES + 4);
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - raw));
+    float *sbias = reinterpret_cast<float *>(smem_raw + (bars + WS_BAR_BLOCK - raw));        // [2][256]
+    RowTab *rt = reinterpret_cast<RowTab *>(smem_raw + (bars + WS_BAR_BLOCK + 2048 - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = p.kb[0] + p.kb[1];
+    const uint32_t w_plane = (uint32_t)p.bn * (BK * 2);
+    const uint32_t stage_tx = 2 * A_PLANE + 2 * w_plane;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(acc_full(a), 1);
+            mbar_init(acc_empty(a), WS_EPI_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA0h)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW0h)) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const int m0 = (t / p.ntiles_n) * BM, n0 = (t % p.ntiles_n) * p.bn;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_expect_tx(full_bar(s), stage_tx);
+                    const uint32_t sa = ring + s * p.slot_bytes;
+                    const bool seg1 = kb >= p.kb[0];
+                    const int kk = (seg1 ? kb - p.kb[0] : kb) * BK;
+                    tma_load_2d(sa, seg1 ? &tmA1h : &tmA0h, full_bar(s), kk, m0);
+                    tma_load_2d(sa + A_PLANE, seg1 ? &tmA1l : &tmA0l, full_bar(s), kk, m0);
+                    tma_load_2d(sa + 2 * A_PLANE, seg1 ? &tmW1h : &tmW0h, full_bar(s), kk, n0);
+                    tma_load_2d(sa + 2 * A_PLANE + w_plane, seg1 ? &tmW1l : &tmW0l, full_bar(s), kk, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t it = 0, ti = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
+                const uint32_t a = ti & 1u;
+                mbar_wait(acc_empty(a), ((ti >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_acc = tmem_base + a * WS_ACC_STRIDE;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1u;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = ring + s * p.slot_bytes;
+                    const uint64_t a_hi = make_smem_desc(sa);
+                    const uint64_t a_lo = make_smem_desc(sa + A_PLANE);
+                    const uint64_t w_hi = make_smem_desc(sa + 2 * A_PLANE);
+                    const uint64_t w_lo = make_smem_desc(sa + 2 * A_PLANE + w_plane);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, p.idesc, 1u);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, p.idesc, 1u);
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(acc_full(a));
+            }
+        }
+    } else {
+        // ---- epilogue warps 2..9 ----------------------------------------------------------------------
+        const int ew = warp - 2;                 // 0..7
+        const int q = warp & 3;                  // TMEM lane quarter (warp id % 4)
+        const int sub = ew >> 2;                 // which 16-column chunk of a 32-column group
+        const int et = threadIdx.x - 64;         // 0..255
+        const int rl = q * 32 + lane;
+        const EpiParams &ep = p.ep;
+        const int mode = ep.mode;
+        const bool gdn = (mode == EPI_GDN || mode == EPI_IGDN);
+        uint32_t ti = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
+            const uint32_t a = ti & 1u;
+            const int m0 = (t / p.ntiles_n) * BM, n0 = (t % p.ntiles_n) * p.bn;
+            const int r = m0 + rl;
+            const bool row_ok = r < ep.R;
+            const int rows_valid = (ep.R - m0) < BM ? (ep.R - m0) : BM;
+            float *sb = sbias + a * 256;
+            // per-tile setup (overlaps the mainloop of this tile): bias slice, row table
+            epi_bar();                           // previous tile's stores have finished reading rt / sbias
+            if (mode != EPI_RAW)
+                for (int i = et; i < p.bn; i += WS_EPI_THREADS) sb[i] = (n0 + i < ep.cout) ? ep.bias[n0 + i] : 0.0f;
+            if (sub == 0 && row_ok) {
+                const EpiRowDst d = epi_row_dst(ep, r);
+                rt->f32[rl] = reinterpret_cast<unsigned long long>(epi_f32_ptr(ep, d, n0));
+                rt->hilo[rl] = (unsigned long long)(d.hilo + n0);
+                rt->idx[rl] = reinterpret_cast<unsigned long long>(mode == EPI_QUANT && ep.idx ? ep.idx + d.blk * ep.M + n0 : nullptr);
+            }
+            epi_bar();
+            mbar_wait(acc_full(a), (ti >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t lane_base = tmem_base + a * WS_ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+            const int ngroups = (p.bn + GC - 1) / GC;   // the last group may hold a single 16-column chunk
+            for (int g = 0; g < ngroups; ++g) {
+                const int g0 = g * GC;
+                int nvalid = ep.cout - (n0 + g0);
+                nvalid = nvalid < 0 ? 0 : (nvalid > GC ? GC : nvalid);
+                if (nvalid > p.bn - g0) nvalid = p.bn - g0;   // a 16-column tail group must not spill into the next tile
+                if (gdn) {
+                    // pre-GDN activations of the group: 128 B per row, 4 rows per warp instruction
+                    const int rsub = lane >> 3, c16 = lane & 7;
+                    uint4 v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int row = ew * 16 + j * 4 + rsub;
+                        v[j] = (row < rows_valid && c16 * 4 < nvalid)
+                                   ? *reinterpret_cast<const uint4 *>(ep.aux + (size_t)(m0 + row) * ep.ld_aux + n0 + g0 + c16 * 4)
+                                   : make_uint4(0u, 0u, 0u, 0u);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int row = ew * 16 + j * 4 + rsub;
+                        sts128(stg + WF_OFF + row * WF_STRIDE + c16 * 16, v[j].x, v[j].y, v[j].z, v[j].w);
+                    }
+                    epi_bar();
+                }
+                // phase A: this warp's 16-column chunk of the group
+                {
+                    const int c = n0 + g0 + sub * 16;
+                    uint32_t acc[16];
+                    tmem_ld_issue(lane_base + (uint32_t)(g0 + sub * 16), acc);
+                    EpiPre<16> pre;
+                    const bool ok = row_ok && c < ep.cout && (g0 + sub * 16) < p.bn;
+                    if (ok) {
+                        if (gdn) {
+                            const uint32_t src = stg + WF_OFF + rl * WF_STRIDE + sub * 64;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const uint4 v = lds128(src + i * 16);
+                                pre.a[4 * i] = __uint_as_float(v.x); pre.a[4 * i + 1] = __uint_as_float(v.y);
+                                pre.a[4 * i + 2] = __uint_as_float(v.z); pre.a[4 * i + 3] = __uint_as_float(v.w);
+                            }
+                        } else {
+                            epi_prefetch<16>(ep, r, c, pre);
+                        }
+                    }
+                    tmem_ld_wait(acc);
+                    if (g == ngroups - 1) {
+                        // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc_empty(a));
+                    }
+                    if (ok) {
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
+                        EpiOut<16> o;
+                        epi_compute<16>(ep, sb + g0 + sub * 16, v, pre, o);
+                        const int gc = sub * 16;
+                        if (epi_has_f32(mode)) {
+                            const uint32_t d = stg + WF_OFF + rl * WF_STRIDE + gc * 4;
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4)
+                                sts128(d + i * 4, __float_as_uint(o.f[i]), __float_as_uint(o.f[i + 1]),
+                                       __float_as_uint(o.f[i + 2]), __float_as_uint(o.f[i + 3]));
+                        }
+                        if (epi_has_hilo(mode)) {
+                            const uint32_t h = stg + WH_OFF + rl * WH_STRIDE + gc * 2;
+                            const uint32_t l = stg + WL_OFF + rl * WH_STRIDE + gc * 2;
+                            sts128(h, o.hi[0], o.hi[1], o.hi[2], o.hi[3]);
+                            sts128(h + 16, o.hi[4], o.hi[5], o.hi[6], o.hi[7]);
+                            sts128(l, o.lo[0], o.lo[1], o.lo[2], o.lo[3]);
+                            sts128(l + 16, o.lo[4], o.lo[5], o.lo[6], o.lo[7]);
+                        }
+                        if (mode == EPI_QUANT)
+                            sts128(stg + WI_OFF + rl * WI_STRIDE + gc, o.idx[0], o.idx[1], o.idx[2], o.idx[3]);
+                    }
+                }
+                epi_bar();                       // group staged
+                // phase B: coalesced stores, 4 rows per warp instruction
+                if (nvalid > 0) {
+                    const int rsub = lane >> 3;
+                    if (epi_has_f32(mode) && (mode != EPI_QUANT || ep.sym)) {
+                        const int c16 = lane & 7;
+                        if (c16 * 4 < nvalid) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int row = ew * 16 + j * 4 + rsub;
+                                if (row < rows_valid) {
+                                    const uint4 v = lds128(stg + WF_OFF + row * WF_STRIDE + c16 * 16);
+                                    float *dst = reinterpret_cast<float *>(rt->f32[row]) + g0 + c16 * 4;
+                                    *reinterpret_cast<uint4 *>(dst) = v;
+                                }
+                            }
+                        }
+                    }
+                    if (epi_has_hilo(mode)) {
+                        const int c8 = lane & 3;                 // 16-byte chunk within the 64-byte plane row
+                        const bool is_lo = (lane >> 2) & 1;
+                        if (c8 * 8 < nvalid) {
+                            h16 *base = (is_lo ? ep.out_lo : ep.out_hi) + g0 + c8 * 8;
+                            const uint32_t src = stg + (is_lo ? WL_OFF : WH_OFF) + c8 * 16;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int row = ew * 16 + j * 4 + rsub;
+                                if (row < rows_valid) {
+                                    const uint4 v = lds128(src + row * WH_STRIDE);
+                                    *reinterpret_cast<uint4 *>(base + rt->hilo[row]) = v;
+                                }
+                            }
+                        }
+                    }
+                    if (mode == EPI_QUANT && ep.idx) {
+                        const int c16 = lane & 7;                // 2 x 16 B per row
+                        if (c16 < 2 && c16 * 16 < nvalid) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int row = ew * 16 + j * 4 + rsub;
+                                if (row < rows_valid) {
+                                    const uint4 v = lds128(stg + WI_OFF + row * WI_STRIDE + c16 * 16);
+                                    *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(rt->idx[row]) + g0 + c16 * 16) = v;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (g + 1 < ngroups) epi_bar();   // stores have read the staging area
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+bool g_ws_attr = false;
+
+}  // namespace
+
+int gemm_ws_max_bn() { return WS_MAX_BN; }
+
+int gemm_ws_launch(const GemmCall &g, cudaStream_t st) {
+    if (g.R <= 0) return 0;
+    LBIC_TRY(gemm_tc_init());
+    if (g.bn % 16 || g.bn < 16 || g.bn > WS_MAX_BN) return lbic_fail(LBIC_ERR_INVALID, "ws kernel: bad tile N %d", g.bn);
+    if (!g_ws_attr) {
+        LBIC_CUDA(cudaFuncSetAttribute(gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        g_ws_attr = true;
+    }
+    WsParams p;
+    p.kb[0] = (g.K[0] + BK - 1) / BK;
+    p.kb[1] = g.nseg > 1 ? (g.K[1] + BK - 1) / BK : 0;
+    p.bn = g.bn;
+    p.ntiles_n = (g.cout + g.bn - 1) / g.bn;
+    p.total_tiles = ((g.R + BM - 1) / BM) * p.ntiles_n;
+    p.slot_bytes = 2 * A_PLANE + 2 * (uint32_t)g.bn * BK * 2;
+    const int avail = SMEM_LIMIT - 1024 - WSTG_BYTES - 128 - WS_TAIL;
+    int stages = avail / (int)p.slot_bytes;
+    stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+    if (stages < 2) return lbic_fail(LBIC_ERR_INVALID, "ws kernel: tile does not fit shared memory");
+    p.stages = stages;
+    p.ring_bytes = (uint32_t)stages * p.slot_bytes;
+    p.idesc = (1u << 4) | ((uint32_t)(g.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    p.ep = g.ep;
+    int n_sm = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;
+    const int s1 = g.nseg > 1 ? 1 : 0;
+    const size_t smem = 1024 + (size_t)p.ring_bytes + ((WSTG_BYTES + 127) / 128) * 128 + WS_TAIL;
+    gemm_ws_kernel<<<grid, WS_THREADS, smem, st>>>(*g.A[0].tm_hi, *g.A[0].tm_lo, *g.W[0].tm_hi, *g.W[0].tm_lo,
+                                                   *g.A[s1].tm_hi, *g.A[s1].tm_lo, *g.W[s1].tm_hi, *g.W[s1].tm_lo, p);
+    count_launch(0);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}

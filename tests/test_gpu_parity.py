@@ -252,6 +252,27 @@ def test_chain_kernel_equals_per_layer_launches(dev, cfgname):
         m.set_option("cluster", 0)
 
 
+@pytest.mark.parametrize("cfgname", ["B8_lowrate", "B4_highrate", "B16_lowrate"])
+def test_warp_specialised_kernel_equals_per_tile_kernel(dev, cfgname):
+    """gemm_ws_kernel (persistent, overlapped epilogue, 192-wide tiles) must be bit-identical to gemm_tc_kernel."""
+    m = get_model(cfgname, 1337, False, dev)
+    B = m.B
+    from lbic_b200.layout import arrange_block_pixels_to_channel_dim
+    img = weights.synth_images(24, 6 * B, 13 * B, seed0=91)
+    x = arrange_block_pixels_to_channel_dim((img - 0.5).to(dev), B)
+    try:
+        m.set_option("ws", 0)
+        ref = m.compress_batch(x, lanes=0, return_symbols=True)
+        m.set_option("ws", 2)
+        got = m.compress_batch(x, lanes=0, return_symbols=True)
+        assert got[0] == ref[0], "bitstreams differ"
+        assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2]) and torch.equal(got[3], ref[3])
+        zdec = m.decompress_batch(got[0], x.shape, lanes=0)
+        assert torch.equal(zdec, got[1])
+    finally:
+        m.set_option("ws", 1)
+
+
 @pytest.mark.parametrize("cfgname,H,W", [("B8_lowrate", 512, 768), ("B4_highrate", 128, 192), ("B16_lowrate", 256, 256)])
 def test_full_size_fixed_point_vs_oracle(dev, cfgname, H, W):
     """BASELINE-size check through a size-independent property: the closed-loop result is
