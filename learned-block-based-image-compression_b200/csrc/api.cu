@@ -512,8 +512,8 @@ int run_gemm(lbic_model *m, int id, int R, const ActView *a0, const ActView *a1,
             if (L.bn_v[i] == m->force_bn) vi = i;
     } else if (m->gemm_core == 0 && m->use_ws &&
                (m->use_ws == 2 ||
-                row_tiles * ((L.cout + L.bn_v[LBIC_WS_VARIANT] - 1) / L.bn_v[LBIC_WS_VARIANT]) >= 2 * 148)) {
-        // at least two tiles per SM: the persistent kernel overlaps each tile's epilogue with the next mainloop
+                row_tiles * ((L.cout + L.bn_v[LBIC_WS_VARIANT] - 1) / L.bn_v[LBIC_WS_VARIANT]) >= 148)) {
+        // at least one tile per SM: the persistent kernel overlaps each tile's epilogue with the next mainloop
         vi = LBIC_WS_VARIANT;
         ws = true;
     } else {
@@ -1146,7 +1146,9 @@ extern "C" int lbic_debug_gemm_bench(lbic_model *m, int R, int K, int cout, int 
         P(dev_alloc(tmp, (void **)&ol, sizeof(h16) * (size_t)Rp * cout, true));
         GemmCall g;
         memset(&g, 0, sizeof(g));
+        const bool ws = m->use_ws == 2;
         g.R = R; g.cout = cout; g.bn = m->force_bn ? m->force_bn : pick_bn(cout); g.nseg = 1; g.K[0] = K;
+        if (ws && !m->force_bn) { const int nt = (cout + gemm_ws_max_bn() - 1) / gemm_ws_max_bn(); g.bn = ((cout + nt - 1) / nt + 15) / 16 * 16; }
         CUtensorMap ta_h, ta_l, tw_h, tw_l;
         P(make_tmap_2d(&ta_h, ah, K, Rp, K, 64, 128));
         P(make_tmap_2d(&ta_l, al, K, Rp, K, 64, 128));
@@ -1163,10 +1165,10 @@ extern "C" int lbic_debug_gemm_bench(lbic_model *m, int R, int K, int cout, int 
         }
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
-        for (int i = 0; i < 3 && rc == 0; ++i) rc = m->gemm_core == 1 ? gemm_simt_launch(g, st) : gemm_tc_launch(g, st);
+        for (int i = 0; i < 3 && rc == 0; ++i) rc = m->gemm_core == 1 ? gemm_simt_launch(g, st) : (ws ? gemm_ws_launch(g, st) : gemm_tc_launch(g, st));
         if (rc) break;
         cudaEventRecord(e0, st);
-        for (int i = 0; i < iters && rc == 0; ++i) rc = m->gemm_core == 1 ? gemm_simt_launch(g, st) : gemm_tc_launch(g, st);
+        for (int i = 0; i < iters && rc == 0; ++i) rc = m->gemm_core == 1 ? gemm_simt_launch(g, st) : (ws ? gemm_ws_launch(g, st) : gemm_tc_launch(g, st));
         cudaEventRecord(e1, st);
         cudaError_t e = cudaStreamSynchronize(st);
         if (rc == 0 && e != cudaSuccess) rc = lbic_fail(LBIC_ERR_CUDA, "gemm bench failed: %s", cudaGetErrorString(e));
