@@ -27,6 +27,7 @@ LBIC_OPT_FORCE_BN = 3
 LBIC_OPT_CHAIN = 4
 LBIC_OPT_CLUSTER = 5
 LBIC_OPT_WS = 6
+LBIC_OPT_PDL = 7
 
 # every symbol include/lbic.h declares: (restype, argtypes)
 _vp, _i, _sz, _i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_int64

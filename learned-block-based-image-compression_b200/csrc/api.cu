@@ -754,6 +754,9 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
             return lbic_fail(LBIC_ERR_INVALID, "cluster size must be one of 0 (auto), 1, 2, 3, 4, 6, 8");
         m->force_cluster = value;
         return 0;
+    case LBIC_OPT_PDL:
+        gemm_set_pdl(value);
+        return 0;
     case LBIC_OPT_WS:
         m->use_ws = value < 0 ? 0 : (value > 2 ? 2 : value);   // 2 = always (testing)
         return 0;

@@ -80,6 +80,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_slot_ptr;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch, bias
+    // staging of static weights) overlapped the previous kernel's tail; its outputs are only read below.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         if (lane == 0) {
@@ -139,8 +143,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode_tiled = nullptr;
+bool g_use_pdl = true;
 
 }  // namespace
+
+void gemm_set_pdl(int on) { g_use_pdl = on != 0; }
+int gemm_get_pdl() { return g_use_pdl ? 1 : 0; }
 
 int gemm_tc_init() {
     if (g_encode_tiled) return 0;
@@ -198,8 +206,19 @@ int gemm_tc_launch(const GemmCall &g, cudaStream_t st) {
     if (ring_bytes < (size_t)STG_BYTES) ring_bytes = (STG_BYTES + 1023) / 1024 * 1024;   // epilogue staging lives in the ring
     p.ring_bytes = (uint32_t)ring_bytes;
     const size_t smem = ring_bytes + SMEM_SLACK;
-    gemm_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(*g.A[0].tm_hi, *g.A[0].tm_lo, *g.W[0].tm_hi, *g.W[0].tm_lo,
-                                                    *g.A[s1].tm_hi, *g.A[s1].tm_lo, *g.W[s1].tm_hi, *g.W[s1].tm_lo, p);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    LBIC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel, *g.A[0].tm_hi, *g.A[0].tm_lo, *g.W[0].tm_hi, *g.W[0].tm_lo,
+                                 *g.A[s1].tm_hi, *g.A[s1].tm_lo, *g.W[s1].tm_hi, *g.W[s1].tm_lo, p));
     count_launch(0);
     LBIC_CUDA(cudaGetLastError());
     return 0;

@@ -96,6 +96,8 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    asm volatile("griddepcontrol.wait;" ::: "memory");             // PDL: see gemm_tc.cu
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         if (lane == 0) {
@@ -353,8 +355,19 @@ int gemm_ws_launch(const GemmCall &g, cudaStream_t st) {
     const int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;
     const int s1 = g.nseg > 1 ? 1 : 0;
     const size_t smem = 1024 + (size_t)p.ring_bytes + ((WSTG_BYTES + 127) / 128) * 128 + WS_TAIL;
-    gemm_ws_kernel<<<grid, WS_THREADS, smem, st>>>(*g.A[0].tm_hi, *g.A[0].tm_lo, *g.W[0].tm_hi, *g.W[0].tm_lo,
-                                                   *g.A[s1].tm_hi, *g.A[s1].tm_lo, *g.W[s1].tm_hi, *g.W[s1].tm_lo, p);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(WS_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = gemm_get_pdl() ? 1 : 0;
+    LBIC_CUDA(cudaLaunchKernelEx(&cfg, gemm_ws_kernel, *g.A[0].tm_hi, *g.A[0].tm_lo, *g.W[0].tm_hi, *g.W[0].tm_lo,
+                                 *g.A[s1].tm_hi, *g.A[s1].tm_lo, *g.W[s1].tm_hi, *g.W[s1].tm_lo, p));
     count_launch(0);
     LBIC_CUDA(cudaGetLastError());
     return 0;

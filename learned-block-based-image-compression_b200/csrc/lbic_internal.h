@@ -123,6 +123,8 @@ int gemm_chain_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, in
 
 int gemm_ws_launch(const GemmCall &g, cudaStream_t st);   // persistent warp-specialised kernel (gemm_ws.cu)
 int gemm_ws_max_bn();
+void gemm_set_pdl(int on);   // programmatic dependent launch between consecutive GEMM kernels (default on)
+int gemm_get_pdl();
 int gemm_simt_launch(const GemmCall &g, cudaStream_t st);
 int gemm_tc_launch(const GemmCall &g, cudaStream_t st);
 int gemm_tc_init();   // resolves cuTensorMapEncodeTiled, sets smem attributes

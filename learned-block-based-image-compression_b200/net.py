@@ -115,7 +115,7 @@ class BlockBasedImgCompLossyNetv9:
         """Tuning hooks: 'chain' (1 = persistent chain kernel per step, default), 'cluster' (forced cluster size),
         'force_bn' (forced tile width), 'graph'."""
         opt = {"chain": _lib.LBIC_OPT_CHAIN, "cluster": _lib.LBIC_OPT_CLUSTER, "force_bn": _lib.LBIC_OPT_FORCE_BN,
-               "graph": _lib.LBIC_OPT_USE_GRAPH, "ws": _lib.LBIC_OPT_WS}[name]
+               "graph": _lib.LBIC_OPT_USE_GRAPH, "ws": _lib.LBIC_OPT_WS, "pdl": _lib.LBIC_OPT_PDL}[name]
         _lib.check(_lib.lib().lbic_set_option(self._need(), opt, int(value)))
 
     # ---- state_dict ----------------------------------------------------------------------------
