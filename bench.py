@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="B8_lowrate")
-    ap.add_argument("--images", type=int, default=512, help="images per GPU per step")
+    ap.add_argument("--images", type=int, default=1024, help="images per GPU per step")
     ap.add_argument("--height", type=int, default=512)
     ap.add_argument("--width", type=int, default=768)
     ap.add_argument("--lanes", type=int, default=0, help="1 = reference container, 0 = lane container")
@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--core", default="tcgen05", choices=["tcgen05", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-reference-container", action="store_true")
     args = ap.parse_args()
 
     import lbic_b200
@@ -277,7 +278,23 @@ def main():
                     launches=prof["gemm_launches"], avg_launch_us=1e3 * prof["gemm_ms"] / max(1, prof["gemm_launches"]),
                     gemm_share_of_encode=prof["gemm_ms"] / (ms_enc / args.steps),
                     algorithmic_flop_per_pixel=dict(encode=2 * macs["encode"] / (B * B), decode=2 * macs["decode"] / (B * B)),
-                    traffic=None)
+                    traffic=None,
+                    traffic_note="ncu dram bytes per launch for the dominant shapes are in profiles/r1_gemm_ws.md "
+                                 "(196 MB measured vs 229 MB algorithmic for a 24k x 768 x 768 PREGDN launch)")
+
+    # the reference's own container (one rANS stream per image, NET:359-360): its decode is serial in raster order,
+    # so it is reported beside the headline instead of inside it
+    refc = None
+    if args.lanes != 1 and not args.no_reference_container:
+        o1 = m.encode_device(x, lanes=1)
+        torch.cuda.synchronize()
+        ms_e1 = timed(lambda: m.encode_device(x, lanes=1, out=o1), 1)
+        ms_d1 = timed(lambda: m.decode_device(o1.streams, o1.lens, n, Hb, Wb, lanes=1), 1)
+        z1 = m.decode_device(o1.streams, o1.lens, n, Hb, Wb, lanes=1)
+        refc = dict(container="reference (1 rANS64 stream per image)", images_per_gpu=n,
+                    encode_mpix_s=pixels_step / (ms_e1 * 1e-3) / 1e6, decode_mpix_s=pixels_step / (ms_d1 * 1e-3) / 1e6,
+                    enc_dec_identical=bool(torch.equal(z1, o1.zhat)), bpp=8.0 * int(o1.lens.sum().item()) / (n * H * W))
+        del o1, z1
 
     # end to end through the host-buffer C ABI (pinned host memory, H2D + D2H inside the timed region)
     e2e = None
@@ -325,6 +342,7 @@ def main():
                     decode_mpix_s=pixels_step * args.steps / (ms_dec * 1e-3) / 1e6,
                     bpp=8.0 * bytes_total / (n * H * W), enc_dec_identical=parity_ok,
                     gpu_launches=int(launches), clocks=clocks, roofline=roofline, e2e=e2e, cpu_baseline=cpu,
+                    reference_container=refc,
                     gemm_core=args.core)
         print(json.dumps(line), flush=True)
     if dist is not None:

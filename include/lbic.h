@@ -115,6 +115,13 @@ int lbic_encode(lbic_model *m, const float *x, int n_img, int Hb, int Wb, float 
 int lbic_decode(lbic_model *m, const uint8_t *streams, const uint32_t *stream_len, size_t stream_cap,
                 int n_img, int Hb, int Wb, float *zhat_out, int32_t *sym_out, int lanes, void *stream);
 
+/* Closed-loop reconstruction WITHOUT entropy coding plus the rate estimate -- the loop of validate_recu_reco_fast
+ * (AGENT:491-549): zhat_out as lbic_encode; selfinfo_out device, (n_img, M, Hb, Wb) fp32 = -log2 of the
+ * Gaussian-conditional likelihood of every quantised latent (ENT:615-647).  Block windows follow the codec path's
+ * border rule; for KS[1]=1 that is exactly what model.forward() computes in the reference loop. */
+int lbic_validate(lbic_model *m, const float *x, int n_img, int Hb, int Wb, float *zhat_out, float *selfinfo_out,
+                  void *stream);
+
 /* Same two calls with HOST buffers (pageable or pinned): the copies are part of the call and the
  * call returns after the results are in host memory.  This is what a reference-side binding
  *  calls from eval_model (AGENT:591-599). */

@@ -118,6 +118,7 @@ struct lbic_model {
     int use_chain = 0;     // 1: persistent chain kernel per step (experimental; the per-layer path is faster today)
     int force_cluster = 0;
     int use_ws = 1;        // warp-specialised persistent kernel for large steps
+    float *selfinfo_cl = nullptr;   // set by lbic_validate for the duration of the call: (n,Hb,Wb,M) self-information
     int64_t launches[2] = {0, 0};
     int *err_flag = nullptr;
     // host-call staging
@@ -881,7 +882,7 @@ extern "C" int lbic_encode(lbic_model *m, const float *x, int n_img, int Hb, int
     const size_t nblk = (size_t)n_img * HW;
     LBIC_TRY(launch_nchw_to_cl(x, ws.x_cl, n_img, m->Cin, HW, st));
     LBIC_CUDA(cudaMemsetAsync(ws.zhat_cl, 0, sizeof(float) * nblk * m->Cin, st));   // NET:336
-    const bool want_syms = sym_out || idx_out || stream_out;
+    const bool want_syms = sym_out || idx_out || stream_out || m->selfinfo_cl;
     const int T_steps = Wb + 2 * (Hb - 1);
     if (m->k1 == 3) LBIC_TRY(launch_fill_g0_top(m->L[L_E0].bias, m->E1, n_img, Hb, Wb, ws.G0.hi, ws.G0.lo, st));
     for (int t = (m->k1 == 3 ? -1 : 0); t < T_steps; ++t) {
@@ -899,6 +900,8 @@ extern "C" int lbic_encode(lbic_model *m, const float *x, int n_img, int Hb, int
             LBIC_TRY(run_enc(m, sd, R, want_syms ? ws.sym : nullptr, want_syms ? ws.idx : nullptr, st));
             LBIC_TRY(run_dec(m, sd, R, st));
         }
+        if (m->selfinfo_cl)
+            LBIC_TRY(launch_selfinfo_step(sd, R, m->M, ws.KSI, ws.ldKSI, ws.sym, m->selfinfo_cl, st));
     }
     if (zhat_out) LBIC_TRY(launch_cl_to_nchw(ws.zhat_cl, zhat_out, n_img, m->Cin, HW, st));
     if (sym_out) LBIC_CUDA(cudaMemcpyAsync(sym_out, ws.sym, sizeof(int32_t) * nblk * m->M, cudaMemcpyDeviceToDevice, st));
@@ -915,6 +918,26 @@ extern "C" int lbic_encode(lbic_model *m, const float *x, int n_img, int Hb, int
             LBIC_TRY(launch_lane_pack(ws.rans_scratch, per, n_img, L, stream_out, stream_cap, stream_len, m->err_flag, st));
     }
     return 0;
+}
+
+extern "C" int lbic_validate(lbic_model *m, const float *x, int n_img, int Hb, int Wb, float *zhat_out,
+                             float *selfinfo_out, void *stream) {
+    LBIC_TRY(check_ready(m, false));
+    if (!x || !selfinfo_out || n_img < 1) return lbic_fail(LBIC_ERR_INVALID, "bad arguments");
+    Active act(m);
+    cudaStream_t st = (cudaStream_t)stream;
+    LBIC_TRY(ensure_workspace(m, n_img, Hb, Wb));
+    float *cl = nullptr;
+    std::vector<void *> tmp;
+    LBIC_TRY(dev_alloc(tmp, (void **)&cl, sizeof(float) * (size_t)n_img * Hb * Wb * m->M));
+    m->selfinfo_cl = cl;
+    int rc = lbic_encode(m, x, n_img, Hb, Wb, zhat_out, nullptr, nullptr, nullptr, 0, nullptr, 1, stream);
+    m->selfinfo_cl = nullptr;
+    Active act2(m);
+    if (rc == 0) rc = launch_cl_to_nchw(cl, selfinfo_out, n_img, m->M, Hb * Wb, st);   // -> (n, M, Hb, Wb) as AGENT:509
+    cudaStreamSynchronize(st);
+    free_all(tmp);
+    return rc;
 }
 
 extern "C" int lbic_decode(lbic_model *m, const uint8_t *streams, const uint32_t *stream_len, size_t stream_cap,

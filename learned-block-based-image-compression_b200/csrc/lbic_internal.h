@@ -191,6 +191,8 @@ int launch_rans_dec_init(const uint8_t *streams, const uint32_t *stream_len, siz
 int launch_rans_dec_step(const Tables &T, RansStreamState *states, const uint8_t *const *lane_ptr, int lanes,
                          const StepDesc &s, int R, int M, const float *ksi, int ld_ksi, h16 *yq_hi, h16 *yq_lo,
                          int ld_yq, int32_t *sym_out, cudaStream_t st);
+int launch_selfinfo_step(const StepDesc &s, int R, int M, const float *ksi, int ld_ksi, const int32_t *sym, float *info,
+                         cudaStream_t st);
 int launch_rans_decode_full(const Tables &T, const uint8_t *streams, const uint32_t *stream_len, size_t stream_stride,
                             const uint8_t *idx, int n_streams, int64_t n_sym, int32_t *sym_out, cudaStream_t st);
 

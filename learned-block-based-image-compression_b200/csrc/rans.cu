@@ -371,6 +371,26 @@ __global__ void rans_dec_step_kernel(const int32_t *__restrict__ cdf, int cdf_st
     }
 }
 
+// Closed-loop validation without entropy coding (AGENT:491-549 validate_recu_reco_fast): the rate is estimated as
+// -log2 of the Gaussian-conditional likelihood of each quantised latent (ENT:615-647, eval mode: values = |sym|,
+// scales lower-bounded at 0.11, likelihood lower-bounded at 1e-9).  One thread per (row, channel) of the step.
+__global__ void selfinfo_step_kernel(StepDesc sd, int R, int M, const float *__restrict__ ksi, int ld_ksi,
+                                     const int32_t *__restrict__ sym, float *__restrict__ info) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R * M) return;
+    const int r = i / M, c = i - r * M;
+    int img, v, h;
+    step_row_to_block(sd, r, img, v, h);
+    const size_t o = (((size_t)img * sd.Hb + v) * sd.Wb + h) * M + c;
+    const float s = fmaxf(ksi[(size_t)r * ld_ksi + c], LBIC_SCALES_MIN);
+    const float val = fabsf((float)sym[o]);
+    const float k = (float)(-0.70710678118654752440);
+    const float upper = 0.5f * erfcf(k * ((0.5f - val) / s));
+    const float lower = 0.5f * erfcf(k * ((-0.5f - val) / s));
+    const float lik = fmaxf(upper - lower, 1e-9f);
+    info[o] = -log2f(lik);
+}
+
 // Whole-stream decode with given indexes (lbic_rans_decode): one warp per stream.
 __global__ void rans_decode_full_kernel(const int32_t *__restrict__ cdf, int cdf_stride,
                                         const int32_t *__restrict__ cdf_len, const int32_t *__restrict__ offs,
@@ -448,6 +468,16 @@ int launch_rans_dec_step(const Tables &T, RansStreamState *states, const uint8_t
     rans_dec_step_kernel<<<(R + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
         T.cdf, T.stride, T.cdf_length, T.offset, T.d_scale_table, states, lane_ptr, lanes, s, R, M, ksi, ld_ksi, yq_hi, yq_lo,
         ld_yq, sym_out);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_selfinfo_step(const StepDesc &s, int R, int M, const float *ksi, int ld_ksi, const int32_t *sym, float *info,
+                         cudaStream_t st) {
+    if (R <= 0) return 0;
+    const int n = R * M;
+    selfinfo_step_kernel<<<(n + 255) / 256, 256, 0, st>>>(s, R, M, ksi, ld_ksi, sym, info);
     count_launch(1);
     LBIC_CUDA(cudaGetLastError());
     return 0;

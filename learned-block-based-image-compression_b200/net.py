@@ -267,6 +267,20 @@ class BlockBasedImgCompLossyNetv9:
                 o.lens.data_ptr() if o.lens is not None else None, lanes, self._stream()))
         return o
 
+    def validate_recu_reco(self, x):
+        """Closed loop without entropy coding + rate estimate (validate_recu_reco_fast, AGENT:491-549).
+        x: (n, 3B^2, Hb, Wb) CUDA fp32 -> (zhat, self_infos (n, M, Hb, Wb)); rate as the reference's loss computes it
+        (graphs/losses/rate_dist.py:44): self_infos.sum() / x.numel() * 3  [bits per pixel]."""
+        h = self._need()
+        x = x.contiguous()
+        n, _, Hb, Wb = x.shape
+        zhat = torch.empty_like(x)
+        info = torch.empty(n, self.M, Hb, Wb, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().lbic_validate(h, x.data_ptr(), n, Hb, Wb, zhat.data_ptr(), info.data_ptr(),
+                                                self._stream()))
+        return zhat, info
+
     def decode_device(self, streams, lens, n, Hb, Wb, lanes: int = 1, want_symbols: bool = False):
         """streams (n, cap) uint8 CUDA, lens (n,) int32 CUDA -> zhat (n,3B^2,Hb,Wb) [, sym]."""
         h = self._need()

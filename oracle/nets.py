@@ -274,6 +274,17 @@ def whole_image_eval(P, x, zhat, dtype=torch.float32):
     return (sym.permute(0, 2, 3, 1).contiguous(), idx.permute(0, 2, 3, 1).contiguous(), xhat, y, ksi)
 
 
+def self_information(sym, scales, likelihood_bound: float = 1e-9):
+    """-log2 likelihood of quantised latents: ENT:615-647 (eval mode: values = |round(y - mean)|, scales lower-bounded
+    at 0.11, likelihood lower-bounded), as summed by validate_recu_reco_fast (AGENT:509-519)."""
+    s = torch.max(scales.float(), torch.tensor([SCALES_MIN]))
+    v = sym.float().abs()
+    c = float(-(2 ** -0.5))
+    upper = 0.5 * torch.erfc(c * ((0.5 - v) / s))
+    lower = 0.5 * torch.erfc(c * ((-0.5 - v) / s))
+    return -torch.log2(torch.max(upper - lower, torch.tensor([likelihood_bound])))
+
+
 # ----------------------------------------------------------------------------------------------
 # layout (AGENT:853-873)
 # ----------------------------------------------------------------------------------------------

@@ -352,6 +352,31 @@ def test_full_size_image_vs_reference_closed_loop(dev):
     assert torch.equal(zdec, zhat)
 
 
+def test_validation_rate_estimate(dev):
+    """validate_recu_reco_fast (AGENT:491-549): closed loop without entropy coding + -log2 pmf.  The reconstruction
+    must equal compress()'s; the self-information must match the oracle's on the same symbols/scales (1e-3 relative:
+    erfc differs by a few ulp between CUDA and torch); the estimated rate is of the order of the coded rate (with
+    random-init weights the predicted scales are poor, so the two need not be close)."""
+    from lbic_b200.layout import arrange_block_pixels_to_channel_dim
+    from oracle import nets
+    cfg = lbic_b200.load_config("B8_lowrate")
+    m = get_model("B8_lowrate", 1337, False, dev)
+    img = weights.synth_images(3, 5 * 8, 9 * 8, seed0=300)
+    x = arrange_block_pixels_to_channel_dim((img - 0.5).to(dev), 8)
+    zhat, info = m.validate_recu_reco(x)
+    strings, zhat2, sym, idx = m.compress_batch(x, lanes=1, return_symbols=True)
+    assert torch.equal(zhat, zhat2)
+    P = nets.effective_params(weights.synth_state_dict(cfg, 1337), cfg)
+    s2, i2, _, _, ksi = nets.whole_image_eval(P, x.cpu(), zhat.cpu())
+    want = nets.self_information(sym.cpu().permute(0, 3, 1, 2), ksi[:, :m.M])
+    got = info.cpu()
+    same = (s2 == sym.cpu()).permute(0, 3, 1, 2)
+    rel = ((got - want).abs() / want.clamp(min=1e-3))[same]
+    assert float(rel.max()) < 1e-3, f"self-information differs by {float(rel.max()):.2e}"
+    est_bits, coded_bits = float(got.sum()), 8.0 * sum(len(s) for s in strings)
+    assert 0.5 * coded_bits < est_bits < 2.0 * coded_bits, (est_bits, coded_bits)
+
+
 def test_layout_kernels_match_reference_definition(dev):
     from lbic_b200.layout import arrange_block_pixels_to_channel_dim, arrange_channel_dim_to_block_pixels
     from oracle import nets

@@ -196,3 +196,36 @@ def test_oracle_equals_reference_live():
     for k in sd:
         if not k.startswith("conditional_gaussian_model._") and "scale_table" not in k:
             assert tuple(ref_sd[k].shape) == tuple(sd[k].shape), k
+
+
+@pytest.mark.needs_reference
+def test_validation_loop_equals_reference_forward_loop():
+    """validate_recu_reco_fast (AGENT:491-549) run with the UNMODIFIED reference model vs the oracle's codec loop +
+    self_information, KS3111 (for KS[1]=1 the forward() windows and the codec-path windows coincide)."""
+    from oracle.ref_shim import load_reference
+    if not load_reference.available():
+        pytest.skip("/root/reference not present")
+    ref = load_reference.load()
+    cfg = lbic_b200.load_config("B8_lowrate")
+    sd = weights.synth_state_dict(cfg, 5)
+    m = ref.BlockBasedImgCompLossyNetv9(cfg).eval()
+    m.load_state_dict(sd, strict=False)
+    img = weights.synth_images(1, 32, 40, seed0=9)
+    x = nets.arrange_block_pixels_to_channel_dim(img - 0.5, 8)
+    bt, ch, hg, wd = x.shape
+    L = R = U = 1                                                    # get_lru_(KS, 'validation') for [3,1,1,1]
+    zhat = torch.zeros_like(x)
+    infos = torch.zeros(bt, cfg.M, hg, wd)
+    with torch.no_grad():
+        for v in range(hg):
+            for h in range(wd):
+                LL, RR, UU = max(0, h - L), min(wd, h + R + 1), max(0, v - U)
+                xh, si = m(zhat[:, :, UU:v + 1, LL:RR], x[:, :, UU:v + 1, LL:RR])
+                infos[:, :, v, h] = si[:, :, v - UU, h - LL]
+                zhat[:, :, v, h] = xh[:, :, v - UU, h - LL].clamp_(-0.5, 0.5)
+    P = nets.effective_params(sd, cfg)
+    syms, idxs, ozhat = nets.compress_loop(P, x)
+    assert float((ozhat - zhat).abs().max()) < 1e-5
+    _, _, _, _, ksi = nets.whole_image_eval(P, x, ozhat)
+    want = nets.self_information(syms.permute(2, 0, 1)[None], ksi[:, :cfg.M])
+    assert float((want - infos).abs().max()) < 1e-3 * float(infos.abs().max())
