@@ -272,7 +272,7 @@ def main():
     peaks = load_peaks()
     ach = prof["gemm_flops"] / (prof["gemm_ms"] * 1e-3) / 1e12 if prof["gemm_ms"] > 0 else 0.0
     macs = macs_per_block(cfg)
-    roofline = dict(bound="tensor", kernel="gemm_tc_kernel (tcgen05 bf16 hi/lo split, 3 MMAs per product)",
+    roofline = dict(bound="tensor", kernel="gemm_ws_kernel + gemm_tc_kernel (tcgen05 kind::f16, fp16 hi/lo operand split, 3 MMAs per product, fp32 TMEM accumulate)",
                     achieved=ach, peak=peaks["tf_sustained"], unit="TFLOP/s", frac=ach / peaks["tf_sustained"],
                     passes=3, frac_pass_adjusted=3 * ach / peaks["tf_sustained"], peak_source=peaks["source"] + " sustained",
                     launches=prof["gemm_launches"], avg_launch_us=1e3 * prof["gemm_ms"] / max(1, prof["gemm_launches"]),

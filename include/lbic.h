@@ -56,7 +56,7 @@ typedef struct {
 } lbic_tensor_desc;
 
 /* GEMM core selection (lbic_set_option LBIC_OPT_GEMM_CORE):
- *   0 = tcgen05/TMEM/TMA tensor-core tiles, bf16 hi/lo split, 3 MMAs per product (product path)
+ *   0 = tcgen05/TMEM/TMA tensor-core tiles, fp16 hi/lo operand split, 3 MMAs per product (product path)
  *   1 = fp32 SIMT evaluation of the same split operands (bring-up / cross-check twin)      */
 #define LBIC_OPT_GEMM_CORE 1
 #define LBIC_OPT_USE_GRAPH 2   /* 1 = replay the per-(n,Hb,Wb) step sequence as a CUDA graph */
@@ -76,7 +76,7 @@ int lbic_set_option(lbic_model *m, int option, int value);
 
 /* model.load_state_dict(sd) -- agents/base.py:95-96.  Consumes every `*.weight/bias/mask`,
  * `*.beta/gamma` and GDN reparam buffer of Appendix A.7; folds the masks (NET:381), applies the
- * non-negative reparametrisation (utils/parametrizers.py:45-48) and packs bf16 hi/lo planes on
+ * non-negative reparametrisation (utils/parametrizers.py:45-48) and packs fp16 hi/lo planes (scaled by 2^k per layer) on
  * the device.  The library keeps no reference to the caller's memory. */
 int lbic_load_weights(lbic_model *m, const lbic_tensor_desc *tensors, int n_tensors, void *stream);
 
@@ -149,7 +149,7 @@ int lbic_rans_decode(lbic_model *m, const uint8_t *streams, const uint32_t *stre
                      void *stream);
 
 /* Bring-up / test hook: D[R,cout] = A[R,K] * W[cout,K]^T with fp32 host-visible results, through
- * the selected GEMM core (A, W, D device fp32; the split into bf16 hi/lo planes happens inside). */
+ * the selected GEMM core (A, W, D device fp32; the split into fp16 hi/lo planes happens inside). */
 int lbic_debug_gemm(lbic_model *m, const float *A, const float *W, float *D, int R, int K, int cout,
                     void *stream);
 

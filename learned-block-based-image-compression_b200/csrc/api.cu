@@ -31,7 +31,7 @@ void count_launch(int family) {
 }
 
 extern "C" const char *lbic_last_error(void) { return g_err; }
-extern "C" const char *lbic_version(void) { return "lbic_b200 0.1 (sm_100a; tcgen05 bf16x3 + SIMT twin)"; }
+extern "C" const char *lbic_version(void) { return "lbic_b200 0.1 (sm_100a; tcgen05 fp16 hi/lo x3 + SIMT twin)"; }
 
 // ------------------------------------------------------------------------------------------------
 // model

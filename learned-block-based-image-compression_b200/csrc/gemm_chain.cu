@@ -166,11 +166,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_chain_kernel(const ChainP
                             const uint64_t w_lo = make_smem_desc(sa + 2 * A_PLANE + w_plane);
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k)
-                                umma_bf16(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                                umma_f16(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
 #pragma unroll
-                            for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
+                            for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
 #pragma unroll
-                            for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
+                            for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
                             umma_commit(empty_bar(s));
                         }
                         umma_commit(tmem_full_bar);

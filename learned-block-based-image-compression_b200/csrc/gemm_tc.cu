@@ -1,9 +1,9 @@
 // tcgen05 / TMEM / TMA GEMM core with fused layer epilogues (sm_100a only).
 //
 // D[R, cout] = sum over K segments of A_s[R, K_s] * W_s[cout, K_s]^T, fp32-grade accuracy from
-// h16 tensor-core passes: every operand is stored as two h16 planes (hi = h16(v),
-// lo = h16(v - hi)) and each 16-wide k-step issues three MMAs into one TMEM accumulator,
-//     Ahi*Whi + Ahi*Wlo + Alo*Whi          (the lo*lo term, ~2^-32 relative, is dropped),
+// fp16 tensor-core passes: every operand is stored as two fp16 planes (hi = fp16(v),
+// lo = fp16(v - hi)) and each 16-wide k-step issues three MMAs into one TMEM accumulator,
+//     Ahi*Whi + Ahi*Wlo + Alo*Whi          (the lo*lo term, ~2^-22 x 2^-22, is dropped),
 // in a fixed order, with no split-K: a row's result depends only on that row's inputs, never on
 // the tile it shares or on whether the encoder or the decoder computes it.
 //
@@ -116,11 +116,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
                 // each k16 step advances the start address by 32 B (= 2 in 16-B units)
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k)
-                    umma_bf16(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_f16(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, p.idesc, 1u);
+                for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, p.idesc, 1u);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, p.idesc, 1u);
+                for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, p.idesc, 1u);
                 umma_commit(empty_bar(s));   // frees the stage once these MMAs have read it
             }
             umma_commit(tmem_full_bar);      // accumulator complete

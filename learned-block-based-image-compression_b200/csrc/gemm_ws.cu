@@ -139,11 +139,11 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
                     const uint64_t w_lo = make_smem_desc(sa + 2 * A_PLANE + w_plane);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        umma_bf16(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_f16(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, p.idesc, 1u);
+                    for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, p.idesc, 1u);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, p.idesc, 1u);
+                    for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, p.idesc, 1u);
                     umma_commit(empty_bar(s));
                 }
                 umma_commit(acc_full(a));
@@ -182,34 +182,47 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
             tc_fence_after();
             const uint32_t lane_base = tmem_base + a * WS_ACC_STRIDE + ((uint32_t)(q * 32) << 16);
             const int ngroups = (p.bn + GC - 1) / GC;   // the last group may hold a single 16-column chunk
+            // Software pipeline over the 32-column groups: the TMEM load of group g+1 is issued before group g is
+            // finished, and (GDN modes) the pre-activations of group g+1 are fetched from global memory while group g
+            // is being stored, then dropped into the fp32 staging plane, which those modes do not use for output.
+            const int rsub = lane >> 3, c16 = lane & 7;
+            auto group_valid = [&](int g) {
+                int nv = ep.cout - (n0 + g * GC);
+                nv = nv < 0 ? 0 : (nv > GC ? GC : nv);
+                return nv > p.bn - g * GC ? p.bn - g * GC : nv;
+            };
+            auto aux_load = [&](int g, uint4 (&v)[4]) {
+                const int nv = group_valid(g);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int row = ew * 16 + j * 4 + rsub;
+                    v[j] = (row < rows_valid && c16 * 4 < nv)
+                               ? *reinterpret_cast<const uint4 *>(ep.aux + (size_t)(m0 + row) * ep.ld_aux + n0 + g * GC + c16 * 4)
+                               : make_uint4(0u, 0u, 0u, 0u);
+                }
+            };
+            auto aux_store = [&](const uint4 (&v)[4]) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int row = ew * 16 + j * 4 + rsub;
+                    sts128(stg + WF_OFF + row * WF_STRIDE + c16 * 16, v[j].x, v[j].y, v[j].z, v[j].w);
+                }
+            };
+            uint32_t accA[16], accB[16];
+            tmem_ld_issue(lane_base + (uint32_t)(sub * 16), accA);
+            if (gdn) {
+                uint4 v[4];
+                aux_load(0, v);
+                aux_store(v);
+                epi_bar();
+            }
             for (int g = 0; g < ngroups; ++g) {
                 const int g0 = g * GC;
-                int nvalid = ep.cout - (n0 + g0);
-                nvalid = nvalid < 0 ? 0 : (nvalid > GC ? GC : nvalid);
-                if (nvalid > p.bn - g0) nvalid = p.bn - g0;   // a 16-column tail group must not spill into the next tile
-                if (gdn) {
-                    // pre-GDN activations of the group: 128 B per row, 4 rows per warp instruction
-                    const int rsub = lane >> 3, c16 = lane & 7;
-                    uint4 v[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int row = ew * 16 + j * 4 + rsub;
-                        v[j] = (row < rows_valid && c16 * 4 < nvalid)
-                                   ? *reinterpret_cast<const uint4 *>(ep.aux + (size_t)(m0 + row) * ep.ld_aux + n0 + g0 + c16 * 4)
-                                   : make_uint4(0u, 0u, 0u, 0u);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int row = ew * 16 + j * 4 + rsub;
-                        sts128(stg + WF_OFF + row * WF_STRIDE + c16 * 16, v[j].x, v[j].y, v[j].z, v[j].w);
-                    }
-                    epi_bar();
-                }
+                const int nvalid = group_valid(g);
+                const bool even = (g & 1) == 0;
                 // phase A: this warp's 16-column chunk of the group
                 {
                     const int c = n0 + g0 + sub * 16;
-                    uint32_t acc[16];
-                    tmem_ld_issue(lane_base + (uint32_t)(g0 + sub * 16), acc);
                     EpiPre<16> pre;
                     const bool ok = row_ok && c < ep.cout && (g0 + sub * 16) < p.bn;
                     if (ok) {
@@ -225,8 +238,11 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
                             epi_prefetch<16>(ep, r, c, pre);
                         }
                     }
-                    tmem_ld_wait(acc);
-                    if (g == ngroups - 1) {
+                    if (even) tmem_ld_wait(accA); else tmem_ld_wait(accB);
+                    if (g + 1 < ngroups) {
+                        if (even) tmem_ld_issue(lane_base + (uint32_t)(g0 + GC + sub * 16), accB);
+                        else tmem_ld_issue(lane_base + (uint32_t)(g0 + GC + sub * 16), accA);
+                    } else {
                         // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
                         tc_fence_before();
                         __syncwarp();
@@ -235,7 +251,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
                     if (ok) {
                         float v[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(even ? accA[i] : accB[i]);
                         EpiOut<16> o;
                         epi_compute<16>(ep, sb + g0 + sub * 16, v, pre, o);
                         const int gc = sub * 16;
@@ -258,12 +274,13 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
                             sts128(stg + WI_OFF + rl * WI_STRIDE + gc, o.idx[0], o.idx[1], o.idx[2], o.idx[3]);
                     }
                 }
-                epi_bar();                       // group staged
+                epi_bar();                       // group staged (and, GDN: every thread has read its pre-activations)
+                uint4 nxt[4];
+                const bool fetch_next = gdn && g + 1 < ngroups;
+                if (fetch_next) aux_load(g + 1, nxt);
                 // phase B: coalesced stores, 4 rows per warp instruction
                 if (nvalid > 0) {
-                    const int rsub = lane >> 3;
                     if (epi_has_f32(mode) && (mode != EPI_QUANT || ep.sym)) {
-                        const int c16 = lane & 7;
                         if (c16 * 4 < nvalid) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -293,8 +310,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
                         }
                     }
                     if (mode == EPI_QUANT && ep.idx) {
-                        const int c16 = lane & 7;                // 2 x 16 B per row
-                        if (c16 < 2 && c16 * 16 < nvalid) {
+                        if (c16 < 2 && c16 * 16 < nvalid) {      // 2 x 16 B per row
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const int row = ew * 16 + j * 4 + rsub;
@@ -306,7 +322,8 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
                         }
                     }
                 }
-                if (g + 1 < ngroups) epi_bar();   // stores have read the staging area
+                if (fetch_next) aux_store(nxt);
+                if (g + 1 < ngroups) epi_bar();   // stores have read the staging area; next pre-activations visible
             }
         }
     }
