@@ -880,6 +880,7 @@ extern "C" int lbic_encode(lbic_model *m, const float *x, int n_img, int Hb, int
     Workspace &ws = m->ws;
     const int HW = Hb * Wb;
     const size_t nblk = (size_t)n_img * HW;
+    LBIC_CUDA(cudaMemsetAsync(m->err_flag, 0, sizeof(int), st));
     LBIC_TRY(launch_nchw_to_cl(x, ws.x_cl, n_img, m->Cin, HW, st));
     LBIC_CUDA(cudaMemsetAsync(ws.zhat_cl, 0, sizeof(float) * nblk * m->Cin, st));   // NET:336
     const bool want_syms = sym_out || idx_out || stream_out || m->selfinfo_cl;
@@ -953,6 +954,7 @@ extern "C" int lbic_decode(lbic_model *m, const uint8_t *streams, const uint32_t
     const int HW = Hb * Wb;
     const size_t nblk = (size_t)n_img * HW;
     const int L = lanes == 1 ? 1 : Hb;
+    LBIC_CUDA(cudaMemsetAsync(m->err_flag, 0, sizeof(int), st));
     LBIC_CUDA(cudaMemsetAsync(ws.zhat_cl, 0, sizeof(float) * nblk * m->Cin, st));   // NET:417
     LBIC_TRY(launch_rans_dec_init(streams, stream_len, stream_cap, n_img, L, ws.dec_states, ws.lane_ptr, m->err_flag, st));
     auto one_step = [&](const StepDesc &sd, int R) -> int {

@@ -402,3 +402,29 @@ def test_error_behaviour(dev):
     with pytest.raises(ValueError):
         m.compress(x, [2, 2, 2], m.M)        # LRU inconsistent with KS
     m.compress(x, [1, 1, 1], m.M)
+
+
+def test_stream_capacity_and_corrupt_streams(dev):
+    """Error behaviour of the entropy stage: a too-small caller buffer is reported (never written past), a damaged
+    lane container is rejected, a damaged reference stream decodes to something finite (the coder reads zeros past the
+    end, like a corrupt CompressAI stream yields garbage symbols, never a crash), and the model stays usable."""
+    from lbic_b200.layout import arrange_block_pixels_to_channel_dim
+    m = get_model("B8_lowrate", 1337, False, dev)
+    img = weights.synth_images(2, 4 * 8, 6 * 8, seed0=12)
+    x = arrange_block_pixels_to_channel_dim((img - 0.5).to(dev), 8)
+    good, zhat = m.compress_batch(x, lanes=1)
+    o = m.encode_device(x, lanes=1, stream_cap=64)                 # real streams are ~2 kB
+    with pytest.raises(RuntimeError):
+        m._gather_streams(o)
+    lane_strings, _ = m.compress_batch(x, lanes=0)
+    bad = bytearray(lane_strings[0]); bad[0] ^= 0xFF               # break the 'LBML' magic
+    zb = m.decompress_batch([bytes(bad), lane_strings[1]], x.shape, lanes=0)
+    torch.cuda.synchronize()
+    assert torch.equal(zb[1], zhat[1])                             # the intact image is unaffected
+    cut = good[0][: len(good[0]) // 2 // 4 * 4]
+    zc = m.decompress_batch([cut, good[1]], x.shape, lanes=1)
+    assert bool(torch.isfinite(zc).all()) and torch.equal(zc[1], zhat[1])
+    again, zhat2 = m.compress_batch(x, lanes=1)
+    assert again == good and torch.equal(zhat2, zhat)
+    with pytest.raises((RuntimeError, ValueError)):
+        m.compress_batch(x[:0], lanes=1)
