@@ -62,6 +62,7 @@ typedef struct {
 #define LBIC_OPT_USE_GRAPH 2   /* 1 = replay the per-(n,Hb,Wb) step sequence as a CUDA graph */
 #define LBIC_OPT_CHAIN 4       /* 1 = one persistent chain kernel per wavefront step (experimental); 0 (default) = one launch per layer */
 #define LBIC_OPT_CLUSTER 5     /* tuning hook: force the chain kernel's cluster size (1,2,3,4,6,8); 0 = cost model */
+#define LBIC_OPT_PAIR 8        /* 1 (default) = CTA-pair (cta_group::2) form of the persistent kernel: 256-row tiles, half the weight traffic per SM */
 #define LBIC_OPT_WS 6          /* 1 (default) = persistent warp-specialised kernel for steps with >= 2 tiles per SM */
 #define LBIC_OPT_PDL 7         /* 1 (default) = programmatic dependent launch between consecutive GEMM kernels (process-wide) */
 #define LBIC_OPT_FORCE_BN 3    /* tuning hook: force the GEMM tile width (multiple of 16, <= 256); 0 = automatic */
@@ -163,6 +164,10 @@ int64_t lbic_launch_count(const lbic_model *m);
  * the GEMM family; used by bench.py for the roofline line. */
 int lbic_set_profiling(lbic_model *m, int enabled);
 int lbic_get_profile(lbic_model *m, int64_t *gemm_launches, double *gemm_ms, double *gemm_flops);
+/* The same records split by layer, in the order E0 E1 E2 E3 | F0 G0 F1 G1 F2 G2 F3 | D0 IG0 D1 IG1 D2 IG2 D3
+ * (get_meanscale / prtr_forward* / prtr_inverse* of graphs/models/BlockBasedImgCompLossy_net.py:262-302; G = the GDN
+ * gamma product).  Fills at most max_layers entries of each array and returns the number filled (18), or < 0. */
+int lbic_get_layer_profile(lbic_model *m, int max_layers, int64_t *launches, double *ms, double *flops);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,7 @@ LBIC_OPT_FORCE_BN = 3
 LBIC_OPT_CHAIN = 4
 LBIC_OPT_CLUSTER = 5
 LBIC_OPT_WS = 6
+LBIC_OPT_PAIR = 8
 LBIC_OPT_PDL = 7
 
 # every symbol include/lbic.h declares: (restype, argtypes)
@@ -57,6 +58,8 @@ PROTOTYPES = {
     "lbic_set_profiling": (_i, [_vp, _i]),
     "lbic_get_profile": (_i, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_double),
                               ctypes.POINTER(ctypes.c_double)]),
+    "lbic_get_layer_profile": (_i, [_vp, _i, ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_double),
+                                    ctypes.POINTER(ctypes.c_double)]),
 }
 
 

@@ -99,6 +99,7 @@ struct Workspace {
 struct ProfRec {
     cudaEvent_t a, b;
     double flops;
+    int layer;     // LayerId, or -1 for a chain launch covering several layers
 };
 
 }  // namespace
@@ -118,6 +119,7 @@ struct lbic_model {
     int use_chain = 0;     // 1: persistent chain kernel per step (experimental; the per-layer path is faster today)
     int force_cluster = 0;
     int use_ws = 1;        // warp-specialised persistent kernel for large steps
+    int use_pair = 1;      // CTA-pair (cta_group::2) form of the persistent kernel
     float *selfinfo_cl = nullptr;   // set by lbic_validate for the duration of the call: (n,Hb,Wb,M) self-information
     int64_t launches[2] = {0, 0};
     int *err_flag = nullptr;
@@ -157,7 +159,7 @@ void free_all(std::vector<void *> &list) {
 // tile-width variants of a layer, one per split factor (lbic_split): widest first
 int bn_variants(int cout, int *out) {
     for (int i = 0; i < NBN; ++i) {
-        if (i == LBIC_WS_VARIANT) {
+        if (i == LBIC_WS_VARIANT || i == LBIC_PAIR_VARIANT) {
             const int wmax = gemm_ws_max_bn();
             const int nt = (cout + wmax - 1) / wmax;
             out[i] = ((cout + nt - 1) / nt + 15) / 16 * 16;
@@ -234,8 +236,9 @@ int pack_conv_seg(lbic_model *m, const SdView &sd, const std::string &prefix, in
     const int nb = bn_variants(cout, bnv);
     (void)bn;
     for (int i = 0; i < nb; ++i) {
-        LBIC_TRY(make_tmap_2d(&seg.tm_hi[i], seg.hi, seg.K, cout, seg.K, 64, bnv[i]));
-        LBIC_TRY(make_tmap_2d(&seg.tm_lo[i], seg.lo, seg.K, cout, seg.K, 64, bnv[i]));
+        const int box = i == LBIC_PAIR_VARIANT ? bnv[i] / 2 : bnv[i];   // a CTA pair loads half the tile per CTA
+        LBIC_TRY(make_tmap_2d(&seg.tm_hi[i], seg.hi, seg.K, cout, seg.K, 64, box));
+        LBIC_TRY(make_tmap_2d(&seg.tm_lo[i], seg.lo, seg.K, cout, seg.K, 64, box));
     }
     return 0;
 }
@@ -317,8 +320,9 @@ int pack_gdn(lbic_model *m, const SdView &sd, int id, const std::string &prefix,
     LBIC_TRY(dev_alloc(tmp, (void **)&seg.weff, sizeof(float) * (size_t)C * C));
     LBIC_TRY(launch_pack_gdn(g, b, C, gbound, gped, bbound, bped, seg.weff, C, L.bias, st));
     for (int i = 0; i < L.n_bn; ++i) {
-        LBIC_TRY(make_tmap_2d(&seg.tm_hi[i], seg.hi, C, C, C, 64, L.bn_v[i]));
-        LBIC_TRY(make_tmap_2d(&seg.tm_lo[i], seg.lo, C, C, C, 64, L.bn_v[i]));
+        const int box = i == LBIC_PAIR_VARIANT ? L.bn_v[i] / 2 : L.bn_v[i];
+        LBIC_TRY(make_tmap_2d(&seg.tm_hi[i], seg.hi, C, C, C, 64, box));
+        LBIC_TRY(make_tmap_2d(&seg.tm_lo[i], seg.lo, C, C, C, 64, box));
     }
     return finish_layer(m, L, st);
 }
@@ -480,6 +484,7 @@ int run_chain(lbic_model *m, int l0, int l1, const StepDesc &sd, int R, cudaStre
             for (int s = 0; s < m->L[l].nseg; ++s) fl += 2.0 * R * (double)m->L[l].seg[s].K * m->L[l].cout;
         cudaEventCreate(&rec.a); cudaEventCreate(&rec.b);
         rec.flops = fl;
+        rec.layer = -1;
         cudaEventRecord(rec.a, st);
     }
     const int rc = gemm_chain_launch(ws.d_chain, ws.h_chain.data(), l0, l1, R, sd, m->force_cluster, st);
@@ -509,13 +514,13 @@ int run_gemm(lbic_model *m, int id, int R, const ActView *a0, const ActView *a1,
     bool ws = false;
     const int row_tiles = (R + 127) / 128;
     if (m->force_bn) {
-        for (int i = 0; i < L.n_bn; ++i)
+        for (int i = 0; i < L.n_bn && i < LBIC_PAIR_VARIANT; ++i)
             if (L.bn_v[i] == m->force_bn) vi = i;
     } else if (m->gemm_core == 0 && m->use_ws &&
                (m->use_ws == 2 ||
                 row_tiles * ((L.cout + L.bn_v[LBIC_WS_VARIANT] - 1) / L.bn_v[LBIC_WS_VARIANT]) >= 148)) {
         // at least one tile per SM: the persistent kernel overlaps each tile's epilogue with the next mainloop
-        vi = LBIC_WS_VARIANT;
+        vi = m->use_pair ? LBIC_PAIR_VARIANT : LBIC_WS_VARIANT;
         ws = true;
     } else {
         while (vi + 1 < LBIC_WS_VARIANT && row_tiles * ((L.cout + L.bn_v[vi] - 1) / L.bn_v[vi]) < 132) ++vi;
@@ -540,9 +545,11 @@ int run_gemm(lbic_model *m, int id, int R, const ActView *a0, const ActView *a1,
     if (m->profiling) {
         cudaEventCreate(&rec.a); cudaEventCreate(&rec.b);
         rec.flops = flops;
+        rec.layer = id;
         cudaEventRecord(rec.a, st);
     }
-    const int rc = m->gemm_core == 1 ? gemm_simt_launch(g, st) : (ws ? gemm_ws_launch(g, st) : gemm_tc_launch(g, st));
+    const int rc = m->gemm_core == 1 ? gemm_simt_launch(g, st)
+                                     : (ws ? gemm_ws_launch(g, st, vi == LBIC_PAIR_VARIANT) : gemm_tc_launch(g, st));
     if (m->profiling) {
         cudaEventRecord(rec.b, st);
         m->prof.push_back(rec);
@@ -760,6 +767,9 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
         return 0;
     case LBIC_OPT_WS:
         m->use_ws = value < 0 ? 0 : (value > 2 ? 2 : value);   // 2 = always (testing)
+        return 0;
+    case LBIC_OPT_PAIR:
+        m->use_pair = value ? 1 : 0;
         return 0;
     case LBIC_OPT_FORCE_BN:
         if (value != 0 && (value % 16 || value < 16 || value > 256)) return lbic_fail(LBIC_ERR_INVALID, "bad tile width");
@@ -1131,15 +1141,18 @@ extern "C" int lbic_debug_gemm(lbic_model *m, const float *A, const float *W, fl
         GemmCall g;
         memset(&g, 0, sizeof(g));
         g.R = R; g.cout = cout; g.bn = pick_bn(cout); g.nseg = 1; g.K[0] = K;
+        const bool ws = m->gemm_core == 0 && m->use_ws == 2;   // forced persistent kernel (optionally its CTA-pair form)
+        const int pair = ws && m->use_pair;
+        if (ws) { const int nt = (cout + gemm_ws_max_bn() - 1) / gemm_ws_max_bn(); g.bn = ((cout + nt - 1) / nt + 15) / 16 * 16; }
         CUtensorMap ta_h, ta_l, tw_h, tw_l;
         P(make_tmap_2d(&ta_h, ah, K, R, K, 64, 128));
         P(make_tmap_2d(&ta_l, al, K, R, K, 64, 128));
-        P(make_tmap_2d(&tw_h, wh, K, cout, K, 64, g.bn));
-        P(make_tmap_2d(&tw_l, wl, K, cout, K, 64, g.bn));
+        P(make_tmap_2d(&tw_h, wh, K, cout, K, 64, pair ? g.bn / 2 : g.bn));
+        P(make_tmap_2d(&tw_l, wl, K, cout, K, 64, pair ? g.bn / 2 : g.bn));
         g.A[0].hi = ah; g.A[0].lo = al; g.A[0].ld = K; g.A[0].tm_hi = &ta_h; g.A[0].tm_lo = &ta_l;
         g.W[0].hi = wh; g.W[0].lo = wl; g.W[0].ld = K; g.W[0].tm_hi = &tw_h; g.W[0].tm_lo = &tw_l;
         g.ep.mode = EPI_RAW; g.ep.R = R; g.ep.cout = cout; g.ep.out_f32 = D; g.ep.ld_f32 = cout; g.ep.acc_scale = 1.0f;
-        P(m->gemm_core == 1 ? gemm_simt_launch(g, st) : gemm_tc_launch(g, st));
+        P(m->gemm_core == 1 ? gemm_simt_launch(g, st) : (ws ? gemm_ws_launch(g, st, pair) : gemm_tc_launch(g, st)));
 #undef P
     } while (0);
     cudaError_t e = cudaStreamSynchronize(st);
@@ -1175,28 +1188,48 @@ extern "C" int lbic_debug_gemm_bench(lbic_model *m, int R, int K, int cout, int 
         GemmCall g;
         memset(&g, 0, sizeof(g));
         const bool ws = m->use_ws == 2;
+        const int pair = ws && m->use_pair;
         g.R = R; g.cout = cout; g.bn = m->force_bn ? m->force_bn : pick_bn(cout); g.nseg = 1; g.K[0] = K;
         if (ws && !m->force_bn) { const int nt = (cout + gemm_ws_max_bn() - 1) / gemm_ws_max_bn(); g.bn = ((cout + nt - 1) / nt + 15) / 16 * 16; }
         CUtensorMap ta_h, ta_l, tw_h, tw_l;
         P(make_tmap_2d(&ta_h, ah, K, Rp, K, 64, 128));
         P(make_tmap_2d(&ta_l, al, K, Rp, K, 64, 128));
-        P(make_tmap_2d(&tw_h, wh, K, cout, K, 64, g.bn));
-        P(make_tmap_2d(&tw_l, wl, K, cout, K, 64, g.bn));
+        P(make_tmap_2d(&tw_h, wh, K, cout, K, 64, pair ? g.bn / 2 : g.bn));
+        P(make_tmap_2d(&tw_l, wl, K, cout, K, 64, pair ? g.bn / 2 : g.bn));
         g.A[0].hi = ah; g.A[0].lo = al; g.A[0].ld = K; g.A[0].tm_hi = &ta_h; g.A[0].tm_lo = &ta_l;
         g.W[0].hi = wh; g.W[0].lo = wl; g.W[0].ld = K; g.W[0].tm_hi = &tw_h; g.W[0].tm_lo = &tw_l;
         g.ep.R = R; g.ep.cout = cout; g.ep.acc_scale = 1.0f;
-        if (with_epilogue) {
-            g.ep.mode = EPI_PREGDN; g.ep.bias = bias; g.ep.out_hi = oh; g.ep.out_lo = ol; g.ep.ld_out = cout;
+        // with_epilogue: 0 RAW, 1 PREGDN, 2 GDN, 3 QUANT, 4 LRELU, 5 KSI, 6 RECON  (synthetic operands; row r = block r)
+        g.ep.bias = bias; g.ep.scale_tab = m->tables.d_scale_table;
+        g.ep.step.n_img = R; g.ep.step.nv = 1; g.ep.step.vmin = 0; g.ep.step.t = 0; g.ep.step.Hb = 1; g.ep.step.Wb = 1;
+        switch (with_epilogue) {
+        case 0: g.ep.mode = EPI_RAW; g.ep.out_f32 = D; g.ep.ld_f32 = cout; break;
+        case 1:
+            g.ep.mode = EPI_PREGDN; g.ep.out_hi = oh; g.ep.out_lo = ol; g.ep.ld_out = cout;
             g.ep.out_f32 = D; g.ep.ld_f32 = cout;
-        } else {
-            g.ep.mode = EPI_RAW; g.ep.out_f32 = D; g.ep.ld_f32 = cout;
+            break;
+        case 2: g.ep.mode = EPI_GDN; g.ep.out_hi = oh; g.ep.out_lo = ol; g.ep.ld_out = cout; g.ep.aux = D; g.ep.ld_aux = cout; break;
+        case 3: {
+            float *ksi; int32_t *sym; uint8_t *idx;
+            P(dev_alloc(tmp, (void **)&ksi, sizeof(float) * (size_t)Rp * 2 * cout, true));
+            P(dev_alloc(tmp, (void **)&sym, sizeof(int32_t) * (size_t)Rp * cout, true));
+            P(dev_alloc(tmp, (void **)&idx, (size_t)Rp * cout, true));
+            if (!m->tables.d_scale_table) { rc = lbic_fail(LBIC_ERR_INVALID, "QUANT bench needs entropy tables (call update first)"); break; }
+            g.ep.mode = EPI_QUANT; g.ep.out_hi = oh; g.ep.out_lo = ol; g.ep.ld_out = cout;
+            g.ep.aux = ksi; g.ep.ld_aux = 2 * cout; g.ep.M = cout; g.ep.sym = sym; g.ep.idx = idx;
+        } break;
+        case 4: g.ep.mode = EPI_LRELU; g.ep.out_hi = oh; g.ep.out_lo = ol; g.ep.ld_out = cout; break;
+        case 5: g.ep.mode = EPI_KSI; g.ep.out_f32 = D; g.ep.ld_f32 = cout; break;
+        case 6: g.ep.mode = EPI_RECON; g.ep.zhat = D; break;
+        default: rc = lbic_fail(LBIC_ERR_INVALID, "unknown epilogue selector"); break;
         }
+        if (rc) break;
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
-        for (int i = 0; i < 3 && rc == 0; ++i) rc = m->gemm_core == 1 ? gemm_simt_launch(g, st) : (ws ? gemm_ws_launch(g, st) : gemm_tc_launch(g, st));
+        for (int i = 0; i < 3 && rc == 0; ++i) rc = m->gemm_core == 1 ? gemm_simt_launch(g, st) : (ws ? gemm_ws_launch(g, st, pair) : gemm_tc_launch(g, st));
         if (rc) break;
         cudaEventRecord(e0, st);
-        for (int i = 0; i < iters && rc == 0; ++i) rc = m->gemm_core == 1 ? gemm_simt_launch(g, st) : (ws ? gemm_ws_launch(g, st) : gemm_tc_launch(g, st));
+        for (int i = 0; i < iters && rc == 0; ++i) rc = m->gemm_core == 1 ? gemm_simt_launch(g, st) : (ws ? gemm_ws_launch(g, st, pair) : gemm_tc_launch(g, st));
         cudaEventRecord(e1, st);
         cudaError_t e = cudaStreamSynchronize(st);
         if (rc == 0 && e != cudaSuccess) rc = lbic_fail(LBIC_ERR_CUDA, "gemm bench failed: %s", cudaGetErrorString(e));
@@ -1209,6 +1242,21 @@ extern "C" int lbic_debug_gemm_bench(lbic_model *m, int R, int K, int cout, int 
     cudaDeviceSynchronize();
     free_all(tmp);
     return rc;
+}
+
+extern "C" int lbic_get_layer_profile(lbic_model *m, int max_layers, int64_t *launches, double *ms, double *flops) {
+    if (!m || !launches || !ms || !flops || max_layers < 0) return lbic_fail(LBIC_ERR_INVALID, "bad argument");
+    cudaSetDevice(m->device);
+    LBIC_CUDA(cudaDeviceSynchronize());
+    const int n = max_layers < L_COUNT ? max_layers : L_COUNT;
+    for (int i = 0; i < n; ++i) { launches[i] = 0; ms[i] = 0; flops[i] = 0; }
+    for (auto &r : m->prof) {
+        if (r.layer < 0 || r.layer >= n) continue;
+        float t = 0;
+        LBIC_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+        launches[r.layer] += 1; ms[r.layer] += t; flops[r.layer] += r.flops;
+    }
+    return n;
 }
 
 extern "C" int64_t lbic_launch_count(const lbic_model *m) { return m ? m->launches[0] + m->launches[1] : 0; }

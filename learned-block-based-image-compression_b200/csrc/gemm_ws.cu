@@ -12,6 +12,14 @@
 //
 // Tiles are 128 x bn with bn <= 192 (2 stages of 80 KiB + 44 KiB staging fit the 227 KiB of shared memory).  Same
 // operand planes, same k order and same epilogue arithmetic as gemm_tc_kernel: results are bit-identical.
+//
+// PAIR = true is the CTA-pair form (cluster of 2, tcgen05 cta_group::2).  The single-CTA kernel turned out to be bound
+// by L2 -> SM bandwidth, not by the tensor pipe: a 128 x 192 tile moves (128 + 192) x 64 x 4 B per k-block for 12 MMAs,
+// i.e. 71 B/clk/SM against a chip-wide L2 limit of ~43 B/clk/SM (profiles/r1_l2_bound.md).  A pair computes a 256 x bn
+// tile: each CTA loads its own 128 activation rows but only HALF of the weight tile, and the tensor cores of both SMs
+// read both halves, which cuts the bytes per flop by 30 %.  The leader CTA (rank 0) issues every MMA; full barriers live
+// in the leader, empty / acc_full barriers are signalled in both CTAs by multicast commits, and both epilogues report
+// to the leader's acc_empty barrier.
 #include "tc_common.cuh"
 
 #include <cstdio>
@@ -49,6 +57,52 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// ---- CTA-pair helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+        "}" ::"r"(bar), "r"(cta) : "memory");
+}
+// TMA load issued by either CTA of a pair; the transaction bytes are credited to the LEADER's barrier (the shared
+// window of the odd CTA differs from the even one in bit 24 of the cluster address).
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of all prior MMAs of the pair -> arrive on the barrier at this offset in both CTAs
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+template <bool PAIR>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant__ CUtensorMap tmA0l,
                const __grid_constant__ CUtensorMap tmW0h, const __grid_constant__ CUtensorMap tmW0l,
@@ -71,29 +125,40 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.kb[0] + p.kb[1];
-    const uint32_t w_plane = (uint32_t)p.bn * (BK * 2);
-    const uint32_t stage_tx = 2 * A_PLANE + 2 * w_plane;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;            // 0 = leader
+    const int w_rows = PAIR ? p.bn / 2 : p.bn;                      // weight rows this CTA loads per stage
+    const uint32_t w_plane = (uint32_t)w_rows * (BK * 2);
+    const uint32_t stage_tx = (2 * A_PLANE + 2 * w_plane) * (PAIR ? 2u : 1u);
+    const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int tile_rows = PAIR ? 2 * BM : BM;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(full_bar(s), 1);
+            mbar_init(full_bar(s), PAIR ? 2 : 1);          // pair: one arrival per CTA's producer, on the leader
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(acc_full(a), 1);
-            mbar_init(acc_empty(a), WS_EPI_THREADS / 32);
+            mbar_init(acc_empty(a), (PAIR ? 2 : 1) * (WS_EPI_THREADS / 32));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA0h)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW0h)) : "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     asm volatile("griddepcontrol.wait;" ::: "memory");             // PDL: see gemm_tc.cu
@@ -102,27 +167,37 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-                const int m0 = (t / p.ntiles_n) * BM, n0 = (t % p.ntiles_n) * p.bn;
+            for (int t = tile_first; t < p.total_tiles; t += tile_stride) {
+                const int m0 = (t / p.ntiles_n) * tile_rows + (int)rank * BM;
+                const int n0 = (t % p.ntiles_n) * p.bn + (int)rank * w_rows;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1u;
                     mbar_wait(empty_bar(s), ph ^ 1u);
-                    mbar_expect_tx(full_bar(s), stage_tx);
                     const uint32_t sa = ring + s * p.slot_bytes;
                     const bool seg1 = kb >= p.kb[0];
                     const int kk = (seg1 ? kb - p.kb[0] : kb) * BK;
-                    tma_load_2d(sa, seg1 ? &tmA1h : &tmA0h, full_bar(s), kk, m0);
-                    tma_load_2d(sa + A_PLANE, seg1 ? &tmA1l : &tmA0l, full_bar(s), kk, m0);
-                    tma_load_2d(sa + 2 * A_PLANE, seg1 ? &tmW1h : &tmW0h, full_bar(s), kk, n0);
-                    tma_load_2d(sa + 2 * A_PLANE + w_plane, seg1 ? &tmW1l : &tmW0l, full_bar(s), kk, n0);
+                    if (PAIR) {
+                        if (rank == 0) mbar_expect_tx(full_bar(s), stage_tx);
+                        else mbar_arrive_remote(full_bar(s), 0);
+                        tma_load_2d_pair(sa, seg1 ? &tmA1h : &tmA0h, full_bar(s), kk, m0);
+                        tma_load_2d_pair(sa + A_PLANE, seg1 ? &tmA1l : &tmA0l, full_bar(s), kk, m0);
+                        tma_load_2d_pair(sa + 2 * A_PLANE, seg1 ? &tmW1h : &tmW0h, full_bar(s), kk, n0);
+                        tma_load_2d_pair(sa + 2 * A_PLANE + w_plane, seg1 ? &tmW1l : &tmW0l, full_bar(s), kk, n0);
+                    } else {
+                        mbar_expect_tx(full_bar(s), stage_tx);
+                        tma_load_2d(sa, seg1 ? &tmA1h : &tmA0h, full_bar(s), kk, m0);
+                        tma_load_2d(sa + A_PLANE, seg1 ? &tmA1l : &tmA0l, full_bar(s), kk, m0);
+                        tma_load_2d(sa + 2 * A_PLANE, seg1 ? &tmW1h : &tmW0h, full_bar(s), kk, n0);
+                        tma_load_2d(sa + 2 * A_PLANE + w_plane, seg1 ? &tmW1l : &tmW0l, full_bar(s), kk, n0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {
             uint32_t it = 0, ti = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
+            for (int t = tile_first; t < p.total_tiles; t += tile_stride, ++ti) {
                 const uint32_t a = ti & 1u;
                 mbar_wait(acc_empty(a), ((ti >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator
                 tc_fence_after();
@@ -137,16 +212,19 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
                     const uint64_t a_lo = make_smem_desc(sa + A_PLANE);
                     const uint64_t w_hi = make_smem_desc(sa + 2 * A_PLANE);
                     const uint64_t w_lo = make_smem_desc(sa + 2 * A_PLANE + w_plane);
+                    auto mma = [&](uint64_t ad, uint64_t wd, uint32_t acc) {
+                        if (PAIR) umma_f16_pair(tmem_acc, ad, wd, p.idesc, acc);
+                        else umma_f16(tmem_acc, ad, wd, p.idesc, acc);
+                    };
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_f16(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BK / 16; ++k) mma(a_hi + 2 * k, w_hi + 2 * k, (kb | k) != 0 ? 1u : 0u);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, p.idesc, 1u);
+                    for (int k = 0; k < BK / 16; ++k) mma(a_hi + 2 * k, w_lo + 2 * k, 1u);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, p.idesc, 1u);
-                    umma_commit(empty_bar(s));
+                    for (int k = 0; k < BK / 16; ++k) mma(a_lo + 2 * k, w_hi + 2 * k, 1u);
+                    if (PAIR) umma_commit_pair(empty_bar(s)); else umma_commit(empty_bar(s));
                 }
-                umma_commit(acc_full(a));
+                if (PAIR) umma_commit_pair(acc_full(a)); else umma_commit(acc_full(a));
             }
         }
     } else {
@@ -160,9 +238,9 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
         const int mode = ep.mode;
         const bool gdn = (mode == EPI_GDN || mode == EPI_IGDN);
         uint32_t ti = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
+        for (int t = tile_first; t < p.total_tiles; t += tile_stride, ++ti) {
             const uint32_t a = ti & 1u;
-            const int m0 = (t / p.ntiles_n) * BM, n0 = (t % p.ntiles_n) * p.bn;
+            const int m0 = (t / p.ntiles_n) * tile_rows + (int)rank * BM, n0 = (t % p.ntiles_n) * p.bn;
             const int r = m0 + rl;
             const bool row_ok = r < ep.R;
             const int rows_valid = (ep.R - m0) < BM ? (ep.R - m0) : BM;
@@ -246,7 +324,10 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
                         // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(acc_empty(a));
+                        if (lane == 0) {
+                            if (PAIR) mbar_arrive_remote(acc_empty(a), 0);
+                            else mbar_arrive(acc_empty(a));
+                        }
                     }
                     if (ok) {
                         float v[16];
@@ -328,40 +409,48 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();   // pair: the peer's shared memory / barriers stay live until both are done
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
-bool g_ws_attr = false;
+bool g_ws_attr[2] = {false, false};
 
 }  // namespace
 
 int gemm_ws_max_bn() { return WS_MAX_BN; }
 
-int gemm_ws_launch(const GemmCall &g, cudaStream_t st) {
+// pair != 0: CTA-pair kernel; g.W[*] tensor maps must then have a box of bn / 2 rows.
+int gemm_ws_launch(const GemmCall &g, cudaStream_t st, int pair) {
     if (g.R <= 0) return 0;
     LBIC_TRY(gemm_tc_init());
     if (g.bn % 16 || g.bn < 16 || g.bn > WS_MAX_BN) return lbic_fail(LBIC_ERR_INVALID, "ws kernel: bad tile N %d", g.bn);
-    if (!g_ws_attr) {
-        LBIC_CUDA(cudaFuncSetAttribute(gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        g_ws_attr = true;
+    pair = pair ? 1 : 0;
+    if (!g_ws_attr[pair]) {
+        if (pair) LBIC_CUDA(cudaFuncSetAttribute(gemm_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        else LBIC_CUDA(cudaFuncSetAttribute(gemm_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        g_ws_attr[pair] = true;
     }
     WsParams p;
+    const int tile_rows = pair ? 2 * BM : BM;
+    const int w_rows = pair ? g.bn / 2 : g.bn;
     p.kb[0] = (g.K[0] + BK - 1) / BK;
     p.kb[1] = g.nseg > 1 ? (g.K[1] + BK - 1) / BK : 0;
     p.bn = g.bn;
     p.ntiles_n = (g.cout + g.bn - 1) / g.bn;
-    p.total_tiles = ((g.R + BM - 1) / BM) * p.ntiles_n;
-    p.slot_bytes = 2 * A_PLANE + 2 * (uint32_t)g.bn * BK * 2;
+    p.total_tiles = ((g.R + tile_rows - 1) / tile_rows) * p.ntiles_n;
+    p.slot_bytes = 2 * A_PLANE + 2 * (uint32_t)w_rows * BK * 2;
     const int avail = SMEM_LIMIT - 1024 - WSTG_BYTES - 128 - WS_TAIL;
     int stages = avail / (int)p.slot_bytes;
     stages = stages > MAX_STAGES ? MAX_STAGES : stages;
     if (stages < 2) return lbic_fail(LBIC_ERR_INVALID, "ws kernel: tile does not fit shared memory");
     p.stages = stages;
     p.ring_bytes = (uint32_t)stages * p.slot_bytes;
-    p.idesc = (1u << 4) | ((uint32_t)(g.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    p.idesc = (1u << 4) | ((uint32_t)(g.bn >> 3) << 17) | ((uint32_t)(tile_rows >> 4) << 24);
     p.ep = g.ep;
     int n_sm = 148;
     {
@@ -369,7 +458,8 @@ int gemm_ws_launch(const GemmCall &g, cudaStream_t st) {
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;
+    int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;
+    if (pair) grid = 2 * (p.total_tiles < n_sm / 2 ? p.total_tiles : n_sm / 2);
     const int s1 = g.nseg > 1 ? 1 : 0;
     const size_t smem = 1024 + (size_t)p.ring_bytes + ((WSTG_BYTES + 127) / 128) * 128 + WS_TAIL;
     cudaLaunchConfig_t cfg;
@@ -378,13 +468,26 @@ int gemm_ws_launch(const GemmCall &g, cudaStream_t st) {
     cfg.blockDim = dim3(WS_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pair) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (gemm_get_pdl()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = gemm_get_pdl() ? 1 : 0;
-    LBIC_CUDA(cudaLaunchKernelEx(&cfg, gemm_ws_kernel, *g.A[0].tm_hi, *g.A[0].tm_lo, *g.W[0].tm_hi, *g.W[0].tm_lo,
-                                 *g.A[s1].tm_hi, *g.A[s1].tm_lo, *g.W[s1].tm_hi, *g.W[s1].tm_lo, p));
+    cfg.numAttrs = na;
+    if (pair)
+        LBIC_CUDA(cudaLaunchKernelEx(&cfg, gemm_ws_kernel<true>, *g.A[0].tm_hi, *g.A[0].tm_lo, *g.W[0].tm_hi, *g.W[0].tm_lo,
+                                     *g.A[s1].tm_hi, *g.A[s1].tm_lo, *g.W[s1].tm_hi, *g.W[s1].tm_lo, p));
+    else
+        LBIC_CUDA(cudaLaunchKernelEx(&cfg, gemm_ws_kernel<false>, *g.A[0].tm_hi, *g.A[0].tm_lo, *g.W[0].tm_hi, *g.W[0].tm_lo,
+                                     *g.A[s1].tm_hi, *g.A[s1].tm_lo, *g.W[s1].tm_hi, *g.W[s1].tm_lo, p));
     count_launch(0);
     LBIC_CUDA(cudaGetLastError());
     return 0;

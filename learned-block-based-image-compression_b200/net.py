@@ -112,10 +112,12 @@ class BlockBasedImgCompLossyNetv9:
         _lib.check(_lib.lib().lbic_set_option(self._need(), _lib.LBIC_OPT_GEMM_CORE, {"tcgen05": 0, "simt": 1}[core]))
 
     def set_option(self, name: str, value: int):
-        """Tuning hooks: 'chain' (1 = persistent chain kernel per step, default), 'cluster' (forced cluster size),
-        'force_bn' (forced tile width), 'graph'."""
+        """Tuning hooks: 'chain' (1 = persistent chain kernel per step; default 0), 'cluster' (forced cluster size),
+        'force_bn' (forced tile width), 'graph', 'ws' (0 off / 1 auto / 2 always: persistent kernel),
+        'pair' (CTA-pair form of the persistent kernel), 'pdl'."""
         opt = {"chain": _lib.LBIC_OPT_CHAIN, "cluster": _lib.LBIC_OPT_CLUSTER, "force_bn": _lib.LBIC_OPT_FORCE_BN,
-               "graph": _lib.LBIC_OPT_USE_GRAPH, "ws": _lib.LBIC_OPT_WS, "pdl": _lib.LBIC_OPT_PDL}[name]
+               "graph": _lib.LBIC_OPT_USE_GRAPH, "ws": _lib.LBIC_OPT_WS, "pdl": _lib.LBIC_OPT_PDL,
+               "pair": _lib.LBIC_OPT_PAIR}[name]
         _lib.check(_lib.lib().lbic_set_option(self._need(), opt, int(value)))
 
     # ---- state_dict ----------------------------------------------------------------------------
@@ -345,6 +347,19 @@ class BlockBasedImgCompLossyNetv9:
         n, ms, fl = ctypes.c_int64(), ctypes.c_double(), ctypes.c_double()
         _lib.check(_lib.lib().lbic_get_profile(self._need(), ctypes.byref(n), ctypes.byref(ms), ctypes.byref(fl)))
         return dict(gemm_launches=n.value, gemm_ms=ms.value, gemm_flops=fl.value)
+
+    LAYER_NAMES = ("E0", "E1", "E2", "E3", "F0", "G0", "F1", "G1", "F2", "G2", "F3",
+                   "D0", "IG0", "D1", "IG1", "D2", "IG2", "D3")
+
+    def get_layer_profile(self):
+        """Per-layer launch count, device ms and algorithmic FLOPs of the GEMM launches recorded since
+        set_profiling(True)."""
+        n = len(self.LAYER_NAMES)
+        cnt, ms, fl = (ctypes.c_int64 * n)(), (ctypes.c_double * n)(), (ctypes.c_double * n)()
+        got = _lib.lib().lbic_get_layer_profile(self._need(), n, cnt, ms, fl)
+        if got < 0:
+            _lib.check(got)
+        return {self.LAYER_NAMES[i]: dict(launches=cnt[i], ms=ms[i], flops=fl[i]) for i in range(got)}
 
     def debug_gemm(self, A, W):
         """D = A @ W.T through the selected GEMM core (bring-up/test hook)."""

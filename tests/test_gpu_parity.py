@@ -254,7 +254,8 @@ def test_chain_kernel_equals_per_layer_launches(dev, cfgname):
 
 @pytest.mark.parametrize("cfgname", ["B8_lowrate", "B4_highrate", "B16_lowrate"])
 def test_warp_specialised_kernel_equals_per_tile_kernel(dev, cfgname):
-    """gemm_ws_kernel (persistent, overlapped epilogue, 192-wide tiles) must be bit-identical to gemm_tc_kernel."""
+    """gemm_ws_kernel (persistent, overlapped epilogue, 192-wide tiles), in its single-CTA and CTA-pair (cta_group::2,
+    256-row tiles) forms, must be bit-identical to gemm_tc_kernel."""
     m = get_model(cfgname, 1337, False, dev)
     B = m.B
     from lbic_b200.layout import arrange_block_pixels_to_channel_dim
@@ -263,14 +264,17 @@ def test_warp_specialised_kernel_equals_per_tile_kernel(dev, cfgname):
     try:
         m.set_option("ws", 0)
         ref = m.compress_batch(x, lanes=0, return_symbols=True)
-        m.set_option("ws", 2)
-        got = m.compress_batch(x, lanes=0, return_symbols=True)
-        assert got[0] == ref[0], "bitstreams differ"
-        assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2]) and torch.equal(got[3], ref[3])
-        zdec = m.decompress_batch(got[0], x.shape, lanes=0)
-        assert torch.equal(zdec, got[1])
+        for pair in (0, 1):
+            m.set_option("ws", 2)
+            m.set_option("pair", pair)
+            got = m.compress_batch(x, lanes=0, return_symbols=True)
+            assert got[0] == ref[0], f"bitstreams differ (pair={pair})"
+            assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2]) and torch.equal(got[3], ref[3])
+            zdec = m.decompress_batch(got[0], x.shape, lanes=0)
+            assert torch.equal(zdec, got[1])
     finally:
         m.set_option("ws", 1)
+        m.set_option("pair", 1)
 
 
 @pytest.mark.parametrize("cfgname,H,W", [("B8_lowrate", 512, 768), ("B4_highrate", 128, 192), ("B16_lowrate", 256, 256)])
