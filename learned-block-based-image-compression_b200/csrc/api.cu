@@ -159,8 +159,8 @@ void free_all(std::vector<void *> &list) {
 // tile-width variants of a layer, one per split factor (lbic_split): widest first
 int bn_variants(int cout, int *out) {
     for (int i = 0; i < NBN; ++i) {
-        if (i == LBIC_WS_VARIANT || i == LBIC_PAIR_VARIANT) {
-            const int wmax = gemm_ws_max_bn();
+        if (i == LBIC_WS_VARIANT || i == LBIC_PAIR_VARIANT || i == LBIC_PAIR_WIDE) {
+            const int wmax = i == LBIC_PAIR_WIDE ? gemm_pair_max_bn() : gemm_ws_max_bn();
             const int nt = (cout + wmax - 1) / wmax;
             out[i] = ((cout + nt - 1) / nt + 15) / 16 * 16;
             continue;
@@ -236,7 +236,7 @@ int pack_conv_seg(lbic_model *m, const SdView &sd, const std::string &prefix, in
     const int nb = bn_variants(cout, bnv);
     (void)bn;
     for (int i = 0; i < nb; ++i) {
-        const int box = i == LBIC_PAIR_VARIANT ? bnv[i] / 2 : bnv[i];   // a CTA pair loads half the tile per CTA
+        const int box = (i == LBIC_PAIR_VARIANT || i == LBIC_PAIR_WIDE) ? bnv[i] / 2 : bnv[i];   // a CTA pair loads half the tile per CTA
         LBIC_TRY(make_tmap_2d(&seg.tm_hi[i], seg.hi, seg.K, cout, seg.K, 64, box));
         LBIC_TRY(make_tmap_2d(&seg.tm_lo[i], seg.lo, seg.K, cout, seg.K, 64, box));
     }
@@ -320,7 +320,7 @@ int pack_gdn(lbic_model *m, const SdView &sd, int id, const std::string &prefix,
     LBIC_TRY(dev_alloc(tmp, (void **)&seg.weff, sizeof(float) * (size_t)C * C));
     LBIC_TRY(launch_pack_gdn(g, b, C, gbound, gped, bbound, bped, seg.weff, C, L.bias, st));
     for (int i = 0; i < L.n_bn; ++i) {
-        const int box = i == LBIC_PAIR_VARIANT ? L.bn_v[i] / 2 : L.bn_v[i];
+        const int box = (i == LBIC_PAIR_VARIANT || i == LBIC_PAIR_WIDE) ? L.bn_v[i] / 2 : L.bn_v[i];
         LBIC_TRY(make_tmap_2d(&seg.tm_hi[i], seg.hi, C, C, C, 64, box));
         LBIC_TRY(make_tmap_2d(&seg.tm_lo[i], seg.lo, C, C, C, 64, box));
     }
@@ -520,8 +520,27 @@ int run_gemm(lbic_model *m, int id, int R, const ActView *a0, const ActView *a1,
                (m->use_ws == 2 ||
                 row_tiles * ((L.cout + L.bn_v[LBIC_WS_VARIANT] - 1) / L.bn_v[LBIC_WS_VARIANT]) >= 148)) {
         // at least one tile per SM: the persistent kernel overlaps each tile's epilogue with the next mainloop
-        vi = m->use_pair ? LBIC_PAIR_VARIANT : LBIC_WS_VARIANT;
+        vi = LBIC_WS_VARIANT;
         ws = true;
+        if (m->use_pair) {
+            // Both pair tilings are L2-bandwidth bound: pick the one that moves fewer bytes per SM over the launch,
+            // rounds of tiles (74 clusters) x bytes per tile (operand loads of one CTA + its output rows).
+            int ktot = 0;
+            for (int s = 0; s < L.nseg; ++s) ktot += (L.seg[s].K + 63) / 64 * 64;
+            const int md = ep.mode;   // bytes per output element: fp32 plane, hi+lo planes, (GDN) pre-activation read back
+            const int out_b = ((md == EPI_RAW || md == EPI_PREGDN || md == EPI_KSI || md == EPI_RECON || md == EPI_QUANT) ? 4 : 0) +
+                              ((md == EPI_LRELU || md == EPI_PREGDN || md == EPI_GDN || md == EPI_IGDN || md == EPI_QUANT) ? 4 : 0) +
+                              ((md == EPI_GDN || md == EPI_IGDN) ? 4 : 0);
+            const int rt2 = (R + 255) / 256;
+            double best = 0;
+            const int cand[2] = {LBIC_PAIR_VARIANT, LBIC_PAIR_WIDE};
+            for (int c = 0; c < (m->use_pair == 2 ? 1 : 2); ++c) {
+                const int bnc = L.bn_v[cand[c]];
+                const int tiles = rt2 * ((L.cout + bnc - 1) / bnc);
+                const double cost = (double)((tiles + 73) / 74) * ((double)ktot * (128 + bnc / 2) * 4 + 128.0 * bnc * out_b);
+                if (c == 0 || cost < best) { best = cost; vi = cand[c]; }
+            }
+        }
     } else {
         while (vi + 1 < LBIC_WS_VARIANT && row_tiles * ((L.cout + L.bn_v[vi] - 1) / L.bn_v[vi]) < 132) ++vi;
     }
@@ -549,7 +568,7 @@ int run_gemm(lbic_model *m, int id, int R, const ActView *a0, const ActView *a1,
         cudaEventRecord(rec.a, st);
     }
     const int rc = m->gemm_core == 1 ? gemm_simt_launch(g, st)
-                                     : (ws ? gemm_ws_launch(g, st, vi == LBIC_PAIR_VARIANT) : gemm_tc_launch(g, st));
+                                     : (ws ? gemm_ws_launch(g, st, vi >= LBIC_PAIR_VARIANT) : gemm_tc_launch(g, st));
     if (m->profiling) {
         cudaEventRecord(rec.b, st);
         m->prof.push_back(rec);
@@ -769,7 +788,7 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
         m->use_ws = value < 0 ? 0 : (value > 2 ? 2 : value);   // 2 = always (testing)
         return 0;
     case LBIC_OPT_PAIR:
-        m->use_pair = value ? 1 : 0;
+        m->use_pair = value < 0 ? 0 : (value > 3 ? 3 : value);   // 2 = narrow (<= 192) tiles only, 3 = wide (<= 256) in the microbench
         return 0;
     case LBIC_OPT_FORCE_BN:
         if (value != 0 && (value % 16 || value < 16 || value > 256)) return lbic_fail(LBIC_ERR_INVALID, "bad tile width");
@@ -1143,7 +1162,11 @@ extern "C" int lbic_debug_gemm(lbic_model *m, const float *A, const float *W, fl
         g.R = R; g.cout = cout; g.bn = pick_bn(cout); g.nseg = 1; g.K[0] = K;
         const bool ws = m->gemm_core == 0 && m->use_ws == 2;   // forced persistent kernel (optionally its CTA-pair form)
         const int pair = ws && m->use_pair;
-        if (ws) { const int nt = (cout + gemm_ws_max_bn() - 1) / gemm_ws_max_bn(); g.bn = ((cout + nt - 1) / nt + 15) / 16 * 16; }
+        if (ws) {
+            const int wmax = (pair && m->use_pair == 3) ? gemm_pair_max_bn() : gemm_ws_max_bn();
+            const int nt = (cout + wmax - 1) / wmax;
+            g.bn = ((cout + nt - 1) / nt + 15) / 16 * 16;
+        }
         CUtensorMap ta_h, ta_l, tw_h, tw_l;
         P(make_tmap_2d(&ta_h, ah, K, R, K, 64, 128));
         P(make_tmap_2d(&ta_l, al, K, R, K, 64, 128));
@@ -1190,7 +1213,11 @@ extern "C" int lbic_debug_gemm_bench(lbic_model *m, int R, int K, int cout, int 
         const bool ws = m->use_ws == 2;
         const int pair = ws && m->use_pair;
         g.R = R; g.cout = cout; g.bn = m->force_bn ? m->force_bn : pick_bn(cout); g.nseg = 1; g.K[0] = K;
-        if (ws && !m->force_bn) { const int nt = (cout + gemm_ws_max_bn() - 1) / gemm_ws_max_bn(); g.bn = ((cout + nt - 1) / nt + 15) / 16 * 16; }
+        if (ws && !m->force_bn) {
+            const int wmax = (pair && m->use_pair == 3) ? gemm_pair_max_bn() : gemm_ws_max_bn();
+            const int nt = (cout + wmax - 1) / wmax;
+            g.bn = ((cout + nt - 1) / nt + 15) / 16 * 16;
+        }
         CUtensorMap ta_h, ta_l, tw_h, tw_l;
         P(make_tmap_2d(&ta_h, ah, K, Rp, K, 64, 128));
         P(make_tmap_2d(&ta_l, al, K, Rp, K, 64, 128));

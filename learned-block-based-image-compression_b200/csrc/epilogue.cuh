@@ -17,17 +17,48 @@ __device__ __forceinline__ void split_h16(float v, h16 &hi, h16 &lo) {
 }
 
 // build_indexes (ENT:649-654): idx = 63 - #{i<63 : max(s,0.11) <= T[i]} = #{i<63 : T[i] < s'}
-__device__ __forceinline__ int scale_to_index(float scale, const float *__restrict__ tab) {
-    const float s = fmaxf(scale, LBIC_SCALES_MIN);
+// `tab` may point to global memory or to a shared-memory copy of the table (plain generic loads).  The tensor-core
+// kernels configure almost the whole L1 as shared memory, so a table left in global memory misses L1 and every probe
+// costs an L2 round trip (profiles/r1_quant_epilogue.md); they pass a shared-memory copy.
+__device__ __forceinline__ int scale_to_index_bisect(float s, const float *tab) {
     int lo = 0, hi = 63;   // first i in [0,63] with T[i] >= s  (63 = none)
 #pragma unroll
     for (int it = 0; it < 6; ++it) {
         const int mid = (lo + hi) >> 1;
-        const bool lt = (mid < 63) && (__ldg(tab + mid) < s);
+        const bool lt = (mid < 63) && (tab[mid] < s);
         lo = lt ? mid + 1 : lo;
         hi = lt ? hi : mid;
     }
     return lo;
+}
+static __device__ __noinline__ int scale_to_index_slow(float s, const float *tab) { return scale_to_index_bisect(s, tab); }
+
+// Hint for tables that are geometric, like the reference's (ENT:22-28: exp(linspace(log 0.11, log 256, 64))):
+// log(s) then lands within a fraction of an entry of the answer.
+struct ScaleHint {
+    float t0, log_t0, inv_step;
+};
+__device__ __forceinline__ ScaleHint scale_hint(const float *tab) {
+    ScaleHint h;
+    h.t0 = tab[0];
+    h.log_t0 = __logf(h.t0);
+    h.inv_step = 63.0f / (__logf(tab[63]) - h.log_t0);
+    return h;
+}
+
+// Candidate index from the hint; *ok says whether the table itself confirms it (T[c-1] < s <= T[c], two independent
+// probes instead of six dependent ones).  A confirmed candidate IS the bisection's answer for any increasing table.
+__device__ __forceinline__ int scale_to_index_hinted(float s, const float *tab, const ScaleHint &h, bool *ok) {
+    int c = (int)ceilf((__logf(s) - h.log_t0) * h.inv_step);
+    c = c < 0 ? 0 : (c > 63 ? 63 : c);
+    c = h.t0 < s ? c : 0;   // scales clamped to the lower bound equal T[0] exactly: rounding in the line above may say 1
+    const float below = tab[c > 0 ? c - 1 : 0];
+    const float at = tab[c < 63 ? c : 62];
+    *ok = (c == 0 || below < s) && (c == 63 || !(at < s));
+    return c;
+}
+__device__ __forceinline__ int scale_to_index(float scale, const float *tab) {
+    return scale_to_index_bisect(fmaxf(scale, LBIC_SCALES_MIN), tab);
 }
 
 template <int NV>
@@ -119,7 +150,7 @@ __device__ __forceinline__ void pack_hilo(const float (&v)[NV], EpiOut<NV> &o) {
 // memory, or the CTA's shared-memory copy of its tile slice).
 template <int NV>
 __device__ __forceinline__ void epi_compute(const EpiParams &p, const float *__restrict__ bias, const float (&acc)[NV],
-                                            const EpiPre<NV> &pre, EpiOut<NV> &o) {
+                                            const EpiPre<NV> &pre, EpiOut<NV> &o, const float *stab = nullptr) {
     if (p.mode == EPI_RAW) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) o.f[i] = acc[i];
@@ -162,15 +193,26 @@ __device__ __forceinline__ void epi_compute(const EpiParams &p, const float *__r
         for (int i = 0; i < NV; ++i) o.f[i] = v[i];
     } break;
     case EPI_QUANT: {
+        const float *tab = stab ? stab : p.scale_tab;
+        const ScaleHint hint = scale_hint(tab);
+        int k[NV];
+        bool all_ok = true;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const float q = rintf(v[i] - pre.a2[i]);                   // torch.round: half to even (ENT:143)
             o.f[i] = __int_as_float((int32_t)q);
             v[i] = q + pre.a2[i];                                      // y_qnt = y_sym + means (NET:374)
-            const int k = scale_to_index(pre.a[i], p.scale_tab);
-            if ((i & 3) == 0) o.idx[i >> 2] = 0;
-            o.idx[i >> 2] |= (uint32_t)k << (8 * (i & 3));
+            bool ok;
+            k[i] = scale_to_index_hinted(fmaxf(pre.a[i], LBIC_SCALES_MIN), tab, hint, &ok);
+            all_ok = all_ok && ok;
         }
+        if (!all_ok) {   // a table that is not geometric (or a candidate off by one): bisect
+#pragma unroll
+            for (int i = 0; i < NV; ++i) k[i] = scale_to_index_slow(fmaxf(pre.a[i], LBIC_SCALES_MIN), tab);
+        }
+#pragma unroll
+        for (int i = 0; i < NV; i += 4)
+            o.idx[i >> 2] = (uint32_t)k[i] | ((uint32_t)k[i + 1] << 8) | ((uint32_t)k[i + 2] << 16) | ((uint32_t)k[i + 3] << 24);
         pack_hilo<NV>(v, o);
     } break;
     case EPI_RECON: {

@@ -51,7 +51,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 #define TRACE0(slot) do { if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[(l - p.l0) * 16 + (slot)] = clock64(); } while (0)
 #define TRACE1(slot) do { if (p.trace && blockIdx.x == 0 && threadIdx.x == 32) p.trace[(l - p.l0) * 16 + (slot)] = clock64(); } while (0)
 
-constexpr int CHAIN_SLACK = 1024 + BAR_BLOCK + 1024 + 512 + 3072;   // ring alignment, barriers, bias slice, layer scalars, row table
+constexpr int CHAIN_SLACK = 1024 + BAR_BLOCK + 1024 + 512 + 3072 + STAB_BYTES;   // ring alignment, barriers, bias slice, layer scalars, row table
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_chain_kernel(const ChainParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_chain_kernel(const ChainP
                 if (ep.mode != EPI_RAW)
                     for (int i = threadIdx.x; i < bn; i += NUM_THREADS)
                         sbias[i] = (n0 + i < ep.cout) ? ep.bias[n0 + i] : 0.0f;
+                fill_scale_tab(reinterpret_cast<float *>(rowtab + 1), ep, threadIdx.x);
                 __syncthreads();
                 TRACE0(2);
                 if (warp == 0) {

@@ -76,6 +76,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     float *sbias = reinterpret_cast<float *>(smem_raw + (bars + BAR_BLOCK - raw));
     if (p.ep.mode != EPI_RAW)
         for (int i = threadIdx.x; i < p.bn; i += NUM_THREADS) sbias[i] = (n0 + i < p.ep.cout) ? p.ep.bias[n0 + i] : 0.0f;
+    fill_scale_tab(reinterpret_cast<float *>(smem_raw + (bars + BAR_BLOCK + 1024 + ROWTAB_BYTES - raw)), p.ep, threadIdx.x);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();

@@ -41,7 +41,7 @@ constexpr int WL_OFF = WH_OFF + BM * WH_STRIDE;
 constexpr int WI_OFF = WL_OFF + BM * WH_STRIDE;
 constexpr int WSTG_BYTES = WI_OFF + BM * WI_STRIDE;   // 45,056 B
 constexpr int WS_BAR_BLOCK = 128;           // full[4] empty[4] acc_full[2] acc_empty[2] tmem slot
-constexpr int WS_TAIL = WS_BAR_BLOCK + 2 * 1024 + ROWTAB_BYTES;   // barriers, two bias slices, row table
+constexpr int WS_TAIL = WS_BAR_BLOCK + 2 * 1024 + ROWTAB_BYTES + STAB_BYTES;   // barriers, two bias slices, row table, scale table
 
 struct WsParams {
     int kb[2];
@@ -122,6 +122,8 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - raw));
     float *sbias = reinterpret_cast<float *>(smem_raw + (bars + WS_BAR_BLOCK - raw));        // [2][256]
     RowTab *rt = reinterpret_cast<RowTab *>(smem_raw + (bars + WS_BAR_BLOCK + 2048 - raw));
+    float *stab = reinterpret_cast<float *>(rt + 1);
+    fill_scale_tab(stab, p.ep, threadIdx.x);                       // visible after the setup barrier below
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.kb[0] + p.kb[1];
@@ -298,6 +300,11 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
                 const int g0 = g * GC;
                 const int nvalid = group_valid(g);
                 const bool even = (g & 1) == 0;
+                // GDN modes: the next group's pre-activations are requested now and land in shared memory after this
+                // group's stores, so the global-load latency hides behind a whole group of work
+                uint4 nxt[4];
+                const bool fetch_next = gdn && g + 1 < ngroups;
+                if (fetch_next) aux_load(g + 1, nxt);
                 // phase A: this warp's 16-column chunk of the group
                 {
                     const int c = n0 + g0 + sub * 16;
@@ -334,7 +341,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(even ? accA[i] : accB[i]);
                         EpiOut<16> o;
-                        epi_compute<16>(ep, sb + g0 + sub * 16, v, pre, o);
+                        epi_compute<16>(ep, sb + g0 + sub * 16, v, pre, o, stab);
                         const int gc = sub * 16;
                         if (epi_has_f32(mode)) {
                             const uint32_t d = stg + WF_OFF + rl * WF_STRIDE + gc * 4;
@@ -356,9 +363,6 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
                     }
                 }
                 epi_bar();                       // group staged (and, GDN: every thread has read its pre-activations)
-                uint4 nxt[4];
-                const bool fetch_next = gdn && g + 1 < ngroups;
-                if (fetch_next) aux_load(g + 1, nxt);
                 // phase B: coalesced stores, 4 rows per warp instruction
                 if (nvalid > 0) {
                     if (epi_has_f32(mode) && (mode != EPI_QUANT || ep.sym)) {
@@ -423,13 +427,15 @@ bool g_ws_attr[2] = {false, false};
 }  // namespace
 
 int gemm_ws_max_bn() { return WS_MAX_BN; }
+int gemm_pair_max_bn() { return WS_ACC_STRIDE; }
 
 // pair != 0: CTA-pair kernel; g.W[*] tensor maps must then have a box of bn / 2 rows.
 int gemm_ws_launch(const GemmCall &g, cudaStream_t st, int pair) {
     if (g.R <= 0) return 0;
     LBIC_TRY(gemm_tc_init());
-    if (g.bn % 16 || g.bn < 16 || g.bn > WS_MAX_BN) return lbic_fail(LBIC_ERR_INVALID, "ws kernel: bad tile N %d", g.bn);
     pair = pair ? 1 : 0;
+    if (g.bn % 16 || g.bn < 16 || g.bn > (pair ? WS_ACC_STRIDE : WS_MAX_BN))
+        return lbic_fail(LBIC_ERR_INVALID, "ws kernel: bad tile N %d", g.bn);
     if (!g_ws_attr[pair]) {
         if (pair) LBIC_CUDA(cudaFuncSetAttribute(gemm_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         else LBIC_CUDA(cudaFuncSetAttribute(gemm_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));

@@ -13,7 +13,8 @@ constexpr int MAX_STAGES = 4;
 constexpr int NUM_THREADS = 256;          // 8 warps = 2 per SM sub-partition (255 registers available)
 constexpr int SMEM_LIMIT = 232448;       // 227 KiB opt-in maximum per CTA
 constexpr int BAR_BLOCK = 128;           // full[4] | empty[4] | tmem_full | tmem base address
-constexpr int SMEM_SLACK = 1024 + BAR_BLOCK + 1024 + 3072;   // ring alignment + barrier block + bias slice (<= 256 floats) + row table
+constexpr int STAB_BYTES = 256;          // shared-memory copy of the 64-entry scale table (QUANT epilogue), right after the row table
+constexpr int SMEM_SLACK = 1024 + BAR_BLOCK + 1024 + 3072 + STAB_BYTES;   // ring alignment + barrier block + bias slice (<= 256 floats) + row table + scale table
 
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -156,13 +157,18 @@ struct RowTab {
 };
 constexpr int ROWTAB_BYTES = (int)sizeof(RowTab);   // 3 KiB
 
+// copy of the scale table for the QUANT epilogue; the caller synchronises before the epilogue reads it
+__device__ __forceinline__ void fill_scale_tab(float *stab, const EpiParams &ep, int tid) {
+    if (ep.mode == EPI_QUANT && tid < 64) stab[tid] = ep.scale_tab[tid];
+}
+
 __device__ __forceinline__ void epi_chunk_stage(const EpiParams &ep, const float *bias, uint32_t stg, int rl, int gc,
-                                                const uint32_t (&raw)[16], const EpiPre<16> &pre) {
+                                                const uint32_t (&raw)[16], const EpiPre<16> &pre, const float *stab) {
     float v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
     EpiOut<16> o;
-    epi_compute<16>(ep, bias, v, pre, o);
+    epi_compute<16>(ep, bias, v, pre, o, stab);
     stage_chunk(stg, ep.mode, rl, gc, o);
 }
 
@@ -183,6 +189,7 @@ __device__ __forceinline__ void tile_epilogue(const EpiParams &ep, const float *
     const int mode = ep.mode;
     const bool gdn = (mode == EPI_GDN || mode == EPI_IGDN);
     const uint32_t lane_base = tmem_acc + ((uint32_t)(q * 32) << 16);
+    const float *stab = reinterpret_cast<const float *>(rt + 1);   // filled by the caller (fill_scale_tab)
     if (sub == 0 && row_ok) {
         const EpiRowDst d = epi_row_dst(ep, r);
         rt->f32[rl] = reinterpret_cast<unsigned long long>(epi_f32_ptr(ep, d, n0));
@@ -250,7 +257,7 @@ __device__ __forceinline__ void tile_epilogue(const EpiParams &ep, const float *
                 tmem_ld_issue(lane_base + (uint32_t)(g0 + (ch + 1) * 16), accB);
                 if (ok(ch + 1)) fetch(ch + 1, preB);
             }
-            if (ok(ch)) epi_chunk_stage(ep, sbias + g0 + ch * 16, stg, rl, ch * 16, accA, preA);
+            if (ok(ch)) epi_chunk_stage(ep, sbias + g0 + ch * 16, stg, rl, ch * 16, accA, preA, stab);
             if (hasB) {
                 tmem_ld_wait(accB);
                 const bool hasA = ch + 2 < ch_end;
@@ -258,7 +265,7 @@ __device__ __forceinline__ void tile_epilogue(const EpiParams &ep, const float *
                     tmem_ld_issue(lane_base + (uint32_t)(g0 + (ch + 2) * 16), accA);
                     if (ok(ch + 2)) fetch(ch + 2, preA);
                 }
-                if (ok(ch + 1)) epi_chunk_stage(ep, sbias + g0 + (ch + 1) * 16, stg, rl, (ch + 1) * 16, accB, preB);
+                if (ok(ch + 1)) epi_chunk_stage(ep, sbias + g0 + (ch + 1) * 16, stg, rl, (ch + 1) * 16, accB, preB, stab);
                 if (hasA) tmem_ld_wait(accA);
             }
         }
