@@ -755,7 +755,7 @@ extern "C" void lbic_destroy(lbic_model *m) {
     cudaDeviceSynchronize();
     free_all(m->ws.allocs);
     free_all(m->weight_allocs);
-    if (m->tables.cdf) { cudaFree(m->tables.cdf); cudaFree(m->tables.cdf_length); cudaFree(m->tables.offset); }
+    tables_free(m->tables);
     if (m->tables.d_scale_table) cudaFree(m->tables.d_scale_table);
     if (m->err_flag) cudaFree(m->err_flag);
     if (m->io_dev) cudaFree(m->io_dev);
@@ -786,6 +786,9 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
         return 0;
     case LBIC_OPT_WS:
         m->use_ws = value < 0 ? 0 : (value > 2 ? 2 : value);   // 2 = always (testing)
+        return 0;
+    case LBIC_OPT_DEC_THREAD_ROWS:
+        rans_set_dec_thread_min_rows(value);
         return 0;
     case LBIC_OPT_PAIR:
         m->use_pair = value < 0 ? 0 : (value > 3 ? 3 : value);   // 2 = narrow (<= 192) tiles only, 3 = wide (<= 256) in the microbench
@@ -862,7 +865,7 @@ extern "C" int lbic_set_tables(lbic_model *m, const float *scale_table, int n_le
     Active act(m);
     Tables &T = m->tables;
     LBIC_CUDA(cudaDeviceSynchronize());
-    if (T.cdf) { cudaFree(T.cdf); cudaFree(T.cdf_length); cudaFree(T.offset); T.cdf = nullptr; }
+    tables_free(T);
     LBIC_CUDA(cudaMalloc(&T.cdf, sizeof(int32_t) * (size_t)n_levels * cdf_stride));
     LBIC_CUDA(cudaMalloc(&T.cdf_length, sizeof(int32_t) * 64));
     LBIC_CUDA(cudaMalloc(&T.offset, sizeof(int32_t) * 64));
@@ -873,7 +876,7 @@ extern "C" int lbic_set_tables(lbic_model *m, const float *scale_table, int n_le
     for (int i = 0; i < 64; ++i) T.scale_table[i] = scale_table[i];
     if (!T.d_scale_table) LBIC_CUDA(cudaMalloc(&T.d_scale_table, sizeof(float) * 64));
     LBIC_CUDA(cudaMemcpy(T.d_scale_table, T.scale_table, sizeof(float) * 64, cudaMemcpyHostToDevice));
-    return 0;
+    return tables_compact(T, 0);
 }
 
 extern "C" int lbic_get_tables(lbic_model *m, int *n_levels, int *cdf_stride, int32_t *cdf, int32_t *cdf_length,

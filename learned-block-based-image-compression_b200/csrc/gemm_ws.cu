@@ -23,6 +23,7 @@
 #include "tc_common.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -453,6 +454,11 @@ int gemm_ws_launch(const GemmCall &g, cudaStream_t st, int pair) {
     const int avail = SMEM_LIMIT - 1024 - WSTG_BYTES - 128 - WS_TAIL;
     int stages = avail / (int)p.slot_bytes;
     stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+    {
+        static int cap = -1;   // tuning hook: LBIC_WS_STAGES caps the pipeline depth
+        if (cap < 0) { const char *e = getenv("LBIC_WS_STAGES"); cap = e ? atoi(e) : 0; }
+        if (cap >= 2 && stages > cap) stages = cap;
+    }
     if (stages < 2) return lbic_fail(LBIC_ERR_INVALID, "ws kernel: tile does not fit shared memory");
     p.stages = stages;
     p.ring_bytes = (uint32_t)stages * p.slot_bytes;

@@ -170,8 +170,16 @@ struct Tables {
     int32_t *offset = nullptr;
     float scale_table[64];
     float *d_scale_table = nullptr;   // device copy, 64 floats
+    // Compact form for the thread-per-stream decode kernel (rans.cu), which keeps it in shared memory: the rows
+    // back to back as 16-bit values without their final 65536 (row l starts at cdf16_off[l]) followed by a
+    // 257-entry bucket table per level: lut[l][b] = first k with cdf[l][k] > 256 b, lut[l][256] = len - 1.
+    uint16_t *cdf16 = nullptr;        // [cdf16_total] rows | [n_levels][257] bucket table
+    int32_t *cdf16_off = nullptr;     // device [65]
+    int cdf16_total = 0;              // 0: not available (tables too large for shared memory)
 };
 int tables_build(Tables &T, const float *scale_table_host, int n_levels, double tail_mass, cudaStream_t st);
+int tables_compact(Tables &T, cudaStream_t st);   // (re)builds the compact form from cdf / cdf_length
+void tables_free(Tables &T);
 
 struct RansStreamState {   // one per stream, device resident between decode steps
     unsigned long long x;
@@ -191,6 +199,7 @@ int launch_lane_pack(const uint32_t *scratch, size_t scratch_words, int n_img, i
 int launch_rans_dec_init(const uint8_t *streams, const uint32_t *stream_len, size_t stream_stride, int n_img,
                          int lanes, RansStreamState *states, const uint8_t **lane_ptr, int *err_flag, cudaStream_t st);
 // decode M symbols for every row of a step; writes yq = sym + mean (hi/lo) and optionally symbols
+void rans_set_dec_thread_min_rows(int rows);   // steps with at least this many rows use the thread-per-stream kernel
 int launch_rans_dec_step(const Tables &T, RansStreamState *states, const uint8_t *const *lane_ptr, int lanes,
                          const StepDesc &s, int R, int M, const float *ksi, int ld_ksi, h16 *yq_hi, h16 *yq_lo,
                          int ld_yq, int32_t *sym_out, cudaStream_t st);

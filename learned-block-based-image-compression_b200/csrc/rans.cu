@@ -371,6 +371,145 @@ __global__ void rans_dec_step_kernel(const int32_t *__restrict__ cdf, int cdf_st
     }
 }
 
+// ---- thread-per-stream form of the decode step ---------------------------------------------------
+// With hundreds of images in flight a step has tens of thousands of independent streams, so one THREAD per stream
+// (instead of one warp) keeps every lane busy; what makes that affordable is that all probes of the CDF search hit
+// shared memory: the CTA holds the compact 16-bit tables (Tables::cdf16, ~88 KiB for the reference's scale table)
+// and each symbol costs one bucket lookup plus a bisection over the few entries of that bucket.  Same symbols as
+// dec_symbol_warp by construction: both return (first k with cdf[k] > slot) - 1.
+constexpr int DEC_T_THREADS = 256;
+
+// Per-thread cursor with the next stream word already in a register: lanes of a warp need a new word at different
+// symbols, and a load issued only when needed would stall the whole warp for a memory round trip at nearly every
+// symbol.  The word is requested right after the previous one is consumed and is not needed for ~4 symbols.
+struct DecCursorT {
+    unsigned long long x;
+    const uint32_t *words;
+    uint32_t pos, nwords, w_next;
+};
+__device__ __forceinline__ uint32_t dec_word_t(DecCursorT &d) {
+    const uint32_t w = d.w_next;
+    d.pos++;
+    d.w_next = d.pos < d.nwords ? __ldg(d.words + d.pos) : 0u;   // a corrupt stream stays finite
+    return w;
+}
+__device__ __forceinline__ int dec_bits_t(DecCursorT &d) {
+    const int val = (int)(d.x & MAX_BYPASS);
+    d.x >>= BYPASS;
+    if (d.x < RANS_L) d.x = (d.x << 32) | dec_word_t(d);
+    return val;
+}
+
+__device__ __forceinline__ int dec_symbol_thread(DecCursorT &d, const uint16_t *__restrict__ row,
+                                                 const uint16_t *__restrict__ lut, int len, int off) {
+    const uint32_t cf = (uint32_t)(d.x & 0xFFFFu);
+    const int max_value = len - 2;
+    const uint32_t b = cf >> 8;
+    int lo = lut[b], hi = lut[b + 1];           // first k with row[k] > 256 b  /  > 256 (b + 1)   (<= len - 1)
+    while (lo < hi) {                            // mid < hi <= len - 1, so row[mid] is a stored (16-bit) entry
+        const int mid = (lo + hi) >> 1;
+        if ((uint32_t)row[mid] > cf) hi = mid; else lo = mid + 1;
+    }
+    const int s = lo - 1;
+    const uint32_t start = row[s];
+    const uint32_t next = (s + 1 == len - 1) ? 65536u : (uint32_t)row[s + 1];
+    d.x = (unsigned long long)(next - start) * (d.x >> PREC) + cf - start;
+    if (d.x < RANS_L) d.x = (d.x << 32) | dec_word_t(d);
+    int value = s;
+    if (value == max_value) {
+        int val = dec_bits_t(d);
+        int nb = val;
+        while (val == MAX_BYPASS) {
+            val = dec_bits_t(d);
+            nb += val;
+        }
+        int raw = 0;
+        for (int j = 0; j < nb; ++j) {
+            val = dec_bits_t(d);
+            raw |= val << (j * BYPASS);
+        }
+        value = raw >> 1;
+        if (raw & 1) value = -value - 1; else value += max_value;
+    }
+    return value + off;
+}
+
+__global__ void __launch_bounds__(DEC_T_THREADS)
+rans_dec_step_thread_kernel(const uint16_t *__restrict__ cdf16, const int32_t *__restrict__ off16, int total,
+                            const int32_t *__restrict__ cdf_len, const int32_t *__restrict__ offs,
+                            const float *__restrict__ scale_tab, RansStreamState *__restrict__ states,
+                            const uint8_t *const *__restrict__ lane_ptr, int lanes, StepDesc sd, int R, int M,
+                            const float *__restrict__ ksi, int ld_ksi, h16 *__restrict__ yq_hi,
+                            h16 *__restrict__ yq_lo, int ld_yq, int32_t *__restrict__ sym_out) {
+    extern __shared__ uint4 dec_smem[];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = r < R;
+    // this thread's stream state and first operands are requested before the table copy so their latency overlaps it
+    int img = 0, v = 0, h = 0, sidx = 0;
+    DecCursorT d;
+    d.x = 0; d.words = nullptr; d.pos = 0; d.nwords = 0; d.w_next = 0;
+    const float *krow = ksi;
+    float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), mu = sc;
+    if (active) {
+        step_row_to_block(sd, r, img, v, h);
+        sidx = lanes > 1 ? img * lanes + v : img;
+        const RansStreamState st = states[sidx];
+        d.x = st.x; d.pos = st.pos; d.nwords = st.nwords;
+        d.words = reinterpret_cast<const uint32_t *>(lane_ptr[sidx]);
+        d.w_next = d.pos < d.nwords ? __ldg(d.words + d.pos) : 0u;
+        krow = ksi + (size_t)r * ld_ksi;
+        sc = *reinterpret_cast<const float4 *>(krow);
+        mu = *reinterpret_cast<const float4 *>(krow + M);
+    }
+    const int nvec = (total + 64 * 257 + 7) >> 3;          // 16-byte units (the allocation is padded accordingly)
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) dec_smem[i] = reinterpret_cast<const uint4 *>(cdf16)[i];
+    int *s_off = reinterpret_cast<int *>(dec_smem + nvec);
+    int *s_len = s_off + 64, *s_offs = s_len + 64;
+    float *s_tab = reinterpret_cast<float *>(s_offs + 64);
+    if (threadIdx.x < 64) {
+        s_off[threadIdx.x] = off16[threadIdx.x];
+        s_len[threadIdx.x] = cdf_len[threadIdx.x];
+        s_offs[threadIdx.x] = offs[threadIdx.x];
+        s_tab[threadIdx.x] = scale_tab[threadIdx.x];
+    }
+    __syncthreads();
+    if (!active) return;
+    const uint16_t *s_cdf = reinterpret_cast<const uint16_t *>(dec_smem);
+    const uint16_t *s_lut = s_cdf + total;
+    const size_t o = (((size_t)img * sd.Hb + v) * sd.Wb + h) * M;
+    const ScaleHint hint = scale_hint(s_tab);
+    for (int c0 = 0; c0 < M; c0 += 4) {
+        const float scs[4] = {sc.x, sc.y, sc.z, sc.w};
+        const float mus[4] = {mu.x, mu.y, mu.z, mu.w};
+        if (c0 + 4 < M) {                       // next four channels' entropy parameters, one iteration ahead
+            sc = *reinterpret_cast<const float4 *>(krow + c0 + 4);
+            mu = *reinterpret_cast<const float4 *>(krow + M + c0 + 4);
+        }
+        int sym[4];
+        h16 hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float sj = fmaxf(scs[j], LBIC_SCALES_MIN);
+            bool ok;
+            int ci = scale_to_index_hinted(sj, s_tab, hint, &ok);
+            if (!ok) ci = scale_to_index_bisect(sj, s_tab);
+            sym[j] = dec_symbol_thread(d, s_cdf + s_off[ci], s_lut + ci * 257, s_len[ci], s_offs[ci]);
+            split_h16((float)sym[j] + mus[j], hi[j], lo[j]);
+        }
+        uint2 uh, ul;
+        uh.x = (uint32_t)__half_as_ushort(hi[0]) | ((uint32_t)__half_as_ushort(hi[1]) << 16);
+        uh.y = (uint32_t)__half_as_ushort(hi[2]) | ((uint32_t)__half_as_ushort(hi[3]) << 16);
+        ul.x = (uint32_t)__half_as_ushort(lo[0]) | ((uint32_t)__half_as_ushort(lo[1]) << 16);
+        ul.y = (uint32_t)__half_as_ushort(lo[2]) | ((uint32_t)__half_as_ushort(lo[3]) << 16);
+        *reinterpret_cast<uint2 *>(yq_hi + (size_t)r * ld_yq + c0) = uh;
+        *reinterpret_cast<uint2 *>(yq_lo + (size_t)r * ld_yq + c0) = ul;
+        if (sym_out) *reinterpret_cast<int4 *>(sym_out + o + c0) = make_int4(sym[0], sym[1], sym[2], sym[3]);
+    }
+    RansStreamState st;
+    st.x = d.x; st.pos = d.pos; st.nwords = d.nwords;
+    states[sidx] = st;
+}
+
 // Closed-loop validation without entropy coding (AGENT:491-549 validate_recu_reco_fast): the rate is estimated as
 // -log2 of the Gaussian-conditional likelihood of each quantised latent (ENT:615-647, eval mode: values = |sym|,
 // scales lower-bounded at 0.11, likelihood lower-bounded at 1e-9).  One thread per (row, channel) of the step.
@@ -459,11 +598,29 @@ int launch_rans_dec_init(const uint8_t *streams, const uint32_t *stream_len, siz
     return 0;
 }
 
+static int g_dec_thread_min_rows = 4096;
+void rans_set_dec_thread_min_rows(int rows) { g_dec_thread_min_rows = rows < 1 ? 1 : rows; }
+
 int launch_rans_dec_step(const Tables &T, RansStreamState *states, const uint8_t *const *lane_ptr, int lanes,
                          const StepDesc &s, int R, int M, const float *ksi, int ld_ksi, h16 *yq_hi, h16 *yq_lo,
                          int ld_yq, int32_t *sym_out, cudaStream_t st) {
     if (R <= 0) return 0;
     if (M > 256) return lbic_fail(LBIC_ERR_INVALID, "M > 256 unsupported by the decode step");
+    // many streams: one thread per stream with the tables in shared memory; few (single images): one warp per stream
+    if (T.cdf16_total > 0 && R >= g_dec_thread_min_rows && M % 4 == 0 && ld_ksi % 4 == 0 && ld_yq % 4 == 0) {
+        const size_t smem = 16 * (((size_t)T.cdf16_total + 64 * 257 + 7) / 8) + 4 * 64 * 4;
+        static bool attr_set = false;
+        if (!attr_set) {
+            LBIC_CUDA(cudaFuncSetAttribute(rans_dec_step_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        rans_dec_step_thread_kernel<<<(R + DEC_T_THREADS - 1) / DEC_T_THREADS, DEC_T_THREADS, smem, st>>>(
+            T.cdf16, T.cdf16_off, T.cdf16_total, T.cdf_length, T.offset, T.d_scale_table, states, lane_ptr, lanes, s, R, M,
+            ksi, ld_ksi, yq_hi, yq_lo, ld_yq, sym_out);
+        count_launch(1);
+        LBIC_CUDA(cudaGetLastError());
+        return 0;
+    }
     const int warps_per_block = 4;
     rans_dec_step_kernel<<<(R + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
         T.cdf, T.stride, T.cdf_length, T.offset, T.d_scale_table, states, lane_ptr, lanes, s, R, M, ksi, ld_ksi, yq_hi, yq_lo,

@@ -132,7 +132,66 @@ double neg_norm_ppf(double q) {
     return z;
 }
 
+// One CTA per level: 16-bit copy of the row (without its final 65536) and the 256-bucket search table.
+__global__ void __launch_bounds__(THREADS) compact_cdf_kernel(const int32_t *__restrict__ cdf, int stride,
+                                                              const int32_t *__restrict__ cdf_len,
+                                                              const int32_t *__restrict__ off16, int total,
+                                                              uint16_t *__restrict__ out) {
+    const int l = blockIdx.x;
+    const int32_t *row = cdf + (size_t)l * stride;
+    const int len = cdf_len[l];
+    uint16_t *dst = out + off16[l];
+    for (int k = threadIdx.x; k < len - 1; k += blockDim.x) dst[k] = (uint16_t)row[k];
+    uint16_t *lut = out + total + (size_t)l * 257;
+    for (int b = threadIdx.x; b <= 256; b += blockDim.x) {
+        int lo = 0, hi = len - 1;                 // first k with row[k] > 256 b; row[len-1] = 65536 always qualifies
+        if (b < 256) {
+            const int32_t t = 256 * b;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (row[mid] > t) hi = mid; else lo = mid + 1;
+            }
+        } else {
+            lo = len - 1;
+        }
+        lut[b] = (uint16_t)lo;
+    }
+}
+
 }  // namespace
+
+void tables_free(Tables &T) {
+    if (T.cdf) { cudaFree(T.cdf); cudaFree(T.cdf_length); cudaFree(T.offset); T.cdf = nullptr; }
+    if (T.cdf16) { cudaFree(T.cdf16); cudaFree(T.cdf16_off); T.cdf16 = nullptr; T.cdf16_off = nullptr; }
+    T.cdf16_total = 0;
+}
+
+int tables_compact(Tables &T, cudaStream_t st) {
+    if (T.cdf16) { cudaFree(T.cdf16); cudaFree(T.cdf16_off); T.cdf16 = nullptr; T.cdf16_off = nullptr; }
+    T.cdf16_total = 0;
+    if (!T.cdf || T.n_levels != 64) return 0;
+    int32_t len[64], off[65];
+    LBIC_CUDA(cudaMemcpyAsync(len, T.cdf_length, sizeof(int32_t) * 64, cudaMemcpyDeviceToHost, st));
+    LBIC_CUDA(cudaStreamSynchronize(st));
+    int total = 0;
+    for (int i = 0; i < 64; ++i) {
+        if (len[i] < 3 || len[i] > T.stride) return 0;   // not a table this kernel understands: keep the warp kernel
+        off[i] = total;
+        total += len[i] - 1;
+    }
+    off[64] = total;
+    total = (total + 1) & ~1;                            // keep the bucket tables 4-byte aligned
+    if (total > 60000) return 0;                         // 2 B each + 33 KB of bucket tables must fit shared memory
+    LBIC_CUDA(cudaMalloc(&T.cdf16, sizeof(uint16_t) * ((size_t)total + 64 * 257 + 8)));   // + padding: copied in 16-byte units
+    LBIC_CUDA(cudaMalloc(&T.cdf16_off, sizeof(int32_t) * 65));
+    LBIC_CUDA(cudaMemcpyAsync(T.cdf16_off, off, sizeof(int32_t) * 65, cudaMemcpyHostToDevice, st));
+    compact_cdf_kernel<<<64, THREADS, 0, st>>>(T.cdf, T.stride, T.cdf_length, T.cdf16_off, total, T.cdf16);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    LBIC_CUDA(cudaStreamSynchronize(st));                // off[] is a stack buffer; once per table update
+    T.cdf16_total = total;
+    return 0;
+}
 
 int tables_build(Tables &T, const float *scale_table_host, int n_levels, double tail_mass, cudaStream_t st) {
     if (n_levels <= 0 || n_levels > 64) return lbic_fail(LBIC_ERR_INVALID, "n_levels must be in 1..64");
@@ -145,7 +204,7 @@ int tables_build(Tables &T, const float *scale_table_host, int n_levels, double 
     }
     const int stride = max_len + 2;
     if (stride > MAX_CDF) return lbic_fail(LBIC_ERR_INVALID, "cdf length %d exceeds the kernel's capacity", stride);
-    if (T.cdf) { cudaFree(T.cdf); cudaFree(T.cdf_length); cudaFree(T.offset); T.cdf = nullptr; }
+    tables_free(T);
     LBIC_CUDA(cudaMalloc(&T.cdf, sizeof(int32_t) * (size_t)n_levels * stride));
     LBIC_CUDA(cudaMalloc(&T.cdf_length, sizeof(int32_t) * 64));
     LBIC_CUDA(cudaMalloc(&T.offset, sizeof(int32_t) * 64));
@@ -166,5 +225,5 @@ int tables_build(Tables &T, const float *scale_table_host, int n_levels, double 
     for (int i = 0; i < 64; ++i) T.scale_table[i] = i < n_levels ? scale_table_host[i] : 3.0e38f;
     if (!T.d_scale_table) LBIC_CUDA(cudaMalloc(&T.d_scale_table, sizeof(float) * 64));
     LBIC_CUDA(cudaMemcpy(T.d_scale_table, T.scale_table, sizeof(float) * 64, cudaMemcpyHostToDevice));
-    return 0;
+    return tables_compact(T, st);
 }

@@ -208,6 +208,34 @@ def test_decode_roundtrip(dev, case, lanes):
         assert float((zref.cpu() - torch.from_numpy(c["zhat_dec"])).abs().max()) < tol
 
 
+@pytest.mark.parametrize("cfgname", ["B8_lowrate", "B4_highrate", "B16_lowrate"])
+def test_thread_per_stream_decode_equals_warp_per_stream(dev, cfgname):
+    """rans_dec_step_thread_kernel (one stream per thread, compact CDFs + bucket table in shared memory) must decode
+    exactly what the warp-per-stream kernel decodes, for the lane container and the reference container; the harsh
+    weights make escape (bypass) symbols occur."""
+    from lbic_b200.layout import arrange_block_pixels_to_channel_dim
+    for harsh in (False, True):
+        m = get_model(cfgname, 1337, harsh, dev)
+        B = m.B
+        img = weights.synth_images(40, 5 * B, 9 * B, seed0=311, kind="noise" if harsh else "smooth")
+        x = arrange_block_pixels_to_channel_dim((img - 0.5).to(dev), B)
+        try:
+            for lanes in (0, 1):
+                strings, zhat, sym, _ = m.compress_batch(x, lanes=lanes, return_symbols=True)
+                out = {}
+                for rows in (1 << 30, 1):          # never / always the thread kernel
+                    m.set_option("dec_thread_rows", rows)
+                    enc_dev = m.encode_device(x, lanes=lanes)
+                    z, s = m.decode_device(enc_dev.streams, enc_dev.lens, x.shape[0], x.shape[2], x.shape[3], lanes=lanes,
+                                           want_symbols=True)
+                    out[rows] = (z, s)
+                assert torch.equal(out[1][1], out[1 << 30][1]), "symbols differ between the two decode kernels"
+                assert torch.equal(out[1][0], out[1 << 30][0])
+                assert torch.equal(out[1][1], sym) and torch.equal(out[1][0], zhat)
+        finally:
+            m.set_option("dec_thread_rows", 4096)
+
+
 def test_batch_invariance_and_ragged_grids(dev):
     """A block's result must not depend on batch size / tile placement: encode 5 images together and one
     by one; odd grids (1xW, Hx1, 1x1) exercise the wavefront edges."""
