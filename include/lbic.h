@@ -64,6 +64,7 @@ typedef struct {
 #define LBIC_OPT_CLUSTER 5     /* tuning hook: force the chain kernel's cluster size (1,2,3,4,6,8); 0 = cost model */
 #define LBIC_OPT_PAIR 8        /* 1 (default) = CTA-pair (cta_group::2) form of the persistent kernel: 256-row tiles, half the weight traffic per SM */
 #define LBIC_OPT_DEC_THREAD_ROWS 9 /* decode steps with >= this many block rows (default 4096) decode one stream per thread, fewer: one per warp (process-wide) */
+#define LBIC_OPT_ENC_THREAD_STREAMS 10 /* entropy-encode calls with >= this many streams (default 4096) encode one stream per thread, fewer: one per warp (process-wide) */
 #define LBIC_OPT_WS 6          /* 1 (default) = persistent warp-specialised kernel for steps with >= 2 tiles per SM */
 #define LBIC_OPT_PDL 7         /* 1 (default) = programmatic dependent launch between consecutive GEMM kernels (process-wide) */
 #define LBIC_OPT_FORCE_BN 3    /* tuning hook: force the GEMM tile width (multiple of 16, <= 256); 0 = automatic */

@@ -29,6 +29,7 @@ LBIC_OPT_CLUSTER = 5
 LBIC_OPT_WS = 6
 LBIC_OPT_PAIR = 8
 LBIC_OPT_DEC_THREAD_ROWS = 9
+LBIC_OPT_ENC_THREAD_STREAMS = 10
 LBIC_OPT_PDL = 7
 
 # every symbol include/lbic.h declares: (restype, argtypes)

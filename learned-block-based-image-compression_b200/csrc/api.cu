@@ -790,6 +790,9 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
     case LBIC_OPT_DEC_THREAD_ROWS:
         rans_set_dec_thread_min_rows(value);
         return 0;
+    case LBIC_OPT_ENC_THREAD_STREAMS:
+        rans_set_enc_thread_min_streams(value);
+        return 0;
     case LBIC_OPT_PAIR:
         m->use_pair = value < 0 ? 0 : (value > 3 ? 3 : value);   // 2 = narrow (<= 192) tiles only, 3 = wide (<= 256) in the microbench
         return 0;

@@ -164,6 +164,92 @@ __global__ void rans_encode_kernel(const int32_t *__restrict__ cdf, int cdf_stri
     }
 }
 
+// ---- thread-per-stream form of the encoder --------------------------------------------------------
+// A batch holds tens of thousands of independent streams (one per block row per image in the lane container), so
+// one THREAD per stream keeps every lane busy where the warp kernel above replays its serial chain on 32 lanes.
+// The table lookups hit the compact 16-bit rows in shared memory (Tables::cdf16); the division is the plain 64-bit
+// one (its ~100 instructions are cheap next to a warp per stream).  Same arithmetic as enc_put / the warp kernel,
+// hence the same words.
+constexpr int ENC_T_THREADS = 128;
+
+__device__ __forceinline__ void enc_symbol_thread(EncCursor &c, int symbol, int ci, const uint16_t *__restrict__ s_cdf,
+                                                  const int *__restrict__ s_off, const int *__restrict__ s_len,
+                                                  const int *__restrict__ s_offs) {
+    const uint16_t *row = s_cdf + s_off[ci];
+    const int len = s_len[ci];
+    const int max_value = len - 2;
+    int value = symbol - s_offs[ci];
+    uint32_t raw = 0;
+    if (value < 0) {
+        raw = (uint32_t)(-2 * value - 1);
+        value = max_value;
+    } else if (value >= max_value) {
+        raw = (uint32_t)(2 * (value - max_value));
+        value = max_value;
+    }
+    const uint32_t start = row[value];
+    const uint32_t range = ((value + 1 == len - 1) ? 65536u : (uint32_t)row[value + 1]) - start;
+    if (value == max_value) {
+        // escape: pushed order is main, count (15,15,...,rem), nibbles LSB first -> popped in reverse
+        int nb = 0;
+        while (nb < 8 && (raw >> (nb * BYPASS)) != 0) ++nb;
+        for (int q = nb - 1; q >= 0; --q) enc_put_bits(c, (raw >> (q * BYPASS)) & MAX_BYPASS);
+        const int qn = nb / MAX_BYPASS, rem = nb - qn * MAX_BYPASS;
+        for (int q = 0; q <= qn; ++q) enc_put_bits(c, (uint32_t)(q == 0 ? rem : MAX_BYPASS));
+    }
+    enc_put(c, start, range);
+}
+
+__global__ void __launch_bounds__(ENC_T_THREADS)
+rans_encode_thread_kernel(const uint16_t *__restrict__ cdf16, const int32_t *__restrict__ off16, int total,
+                          const int32_t *__restrict__ cdf_len, const int32_t *__restrict__ offs,
+                          const int32_t *__restrict__ sym, const uint8_t *__restrict__ idx, int n_streams, long n_sym,
+                          long stream_stride, uint32_t *__restrict__ scratch, long scratch_words,
+                          uint32_t *__restrict__ start_word, uint32_t *__restrict__ n_words, int *__restrict__ err) {
+    extern __shared__ uint4 enc_smem[];
+    const int nvec = (total + 7) >> 3;
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) enc_smem[i] = reinterpret_cast<const uint4 *>(cdf16)[i];
+    int *s_off = reinterpret_cast<int *>(enc_smem + nvec);
+    int *s_len = s_off + 64, *s_offs = s_len + 64;
+    if (threadIdx.x < 64) {
+        s_off[threadIdx.x] = off16[threadIdx.x];
+        s_len[threadIdx.x] = cdf_len[threadIdx.x];
+        s_offs[threadIdx.x] = offs[threadIdx.x];
+    }
+    __syncthreads();
+    const uint16_t *s_cdf = reinterpret_cast<const uint16_t *>(enc_smem);
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    EncCursor c;
+    c.x = RANS_L;
+    c.base = scratch + (size_t)s * scratch_words;
+    c.pos = scratch_words;
+    c.overflow = false;
+    const int32_t *ps = sym + (size_t)s * stream_stride;
+    const uint8_t *pi = idx + (size_t)s * stream_stride;
+    // the coder walks the symbols backwards, four at a time (n_sym and stream_stride are multiples of 4)
+    for (long k = n_sym - 4; k >= 0; k -= 4) {
+        const int4 v = *reinterpret_cast<const int4 *>(ps + k);
+        const uchar4 ci = *reinterpret_cast<const uchar4 *>(pi + k);
+        enc_symbol_thread(c, v.w, ci.w, s_cdf, s_off, s_len, s_offs);
+        enc_symbol_thread(c, v.z, ci.z, s_cdf, s_off, s_len, s_offs);
+        enc_symbol_thread(c, v.y, ci.y, s_cdf, s_off, s_len, s_offs);
+        enc_symbol_thread(c, v.x, ci.x, s_cdf, s_off, s_len, s_offs);
+    }
+    // Rans64EncFlush: two words, low half first in memory
+    if (c.pos < 2) c.overflow = true;
+    if (!c.overflow) {
+        c.base[--c.pos] = (uint32_t)(c.x >> 32);
+        c.base[--c.pos] = (uint32_t)(c.x);
+        start_word[s] = (uint32_t)c.pos;
+        n_words[s] = (uint32_t)(scratch_words - c.pos);
+    } else {
+        atomicExch(err, 1);
+        start_word[s] = 0;
+        n_words[s] = 0xFFFFFFFFu;
+    }
+}
+
 // move each stream's words to the front of its output slot (coalesced, one CTA per stream)
 __global__ void rans_compact_kernel(const uint32_t *__restrict__ scratch, long scratch_words,
                                     const uint32_t *__restrict__ start_word, const uint32_t *__restrict__ n_words,
@@ -554,6 +640,8 @@ __global__ void rans_decode_full_kernel(const int32_t *__restrict__ cdf, int cdf
 
 }  // namespace
 
+static int g_enc_thread_min_streams = 4096;
+
 // scratch layout: [n_streams * scratch_words] words, then start_word[n_streams], n_words[n_streams]
 int launch_rans_encode(const Tables &T, const int32_t *sym, const uint8_t *idx, int n_streams, int64_t n_sym,
                        int64_t stream_stride, uint32_t *scratch, size_t scratch_words, uint8_t *out, size_t out_stride,
@@ -561,10 +649,26 @@ int launch_rans_encode(const Tables &T, const int32_t *sym, const uint8_t *idx, 
     if (!T.cdf) return lbic_fail(LBIC_ERR_STATE, "Uninitialized CDFs. Run update() first");
     uint32_t *start_word = scratch + (size_t)n_streams * scratch_words;
     uint32_t *n_words = start_word + n_streams;
+    // many streams: one thread per stream with the tables in shared memory; few (single images): one warp per stream
+    const bool thread_form = T.cdf16_total > 0 && n_streams >= g_enc_thread_min_streams && n_sym % 4 == 0 &&
+                             stream_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(sym) & 15) == 0 &&
+                             (reinterpret_cast<uintptr_t>(idx) & 3) == 0;
+    if (thread_form) {
+        const size_t smem = 16 * (((size_t)T.cdf16_total + 7) / 8) + 3 * 64 * 4;
+        static bool attr_set = false;
+        if (!attr_set) {
+            LBIC_CUDA(cudaFuncSetAttribute(rans_encode_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        rans_encode_thread_kernel<<<(n_streams + ENC_T_THREADS - 1) / ENC_T_THREADS, ENC_T_THREADS, smem, st>>>(
+            T.cdf16, T.cdf16_off, T.cdf16_total, T.cdf_length, T.offset, sym, idx, n_streams, (long)n_sym,
+            (long)stream_stride, scratch, (long)scratch_words, start_word, n_words, err_flag);
+    } else {
     const int warps_per_block = 4;
     rans_encode_kernel<<<(n_streams + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
         T.cdf, T.stride, T.cdf_length, T.offset, sym, idx, n_streams, (long)n_sym, (long)stream_stride, scratch,
         (long)scratch_words, start_word, n_words, err_flag);
+    }
     count_launch(1);
     LBIC_CUDA(cudaGetLastError());
     if (out) {
@@ -600,6 +704,7 @@ int launch_rans_dec_init(const uint8_t *streams, const uint32_t *stream_len, siz
 
 static int g_dec_thread_min_rows = 4096;
 void rans_set_dec_thread_min_rows(int rows) { g_dec_thread_min_rows = rows < 1 ? 1 : rows; }
+void rans_set_enc_thread_min_streams(int n) { g_enc_thread_min_streams = n < 1 ? 1 : n; }
 
 int launch_rans_dec_step(const Tables &T, RansStreamState *states, const uint8_t *const *lane_ptr, int lanes,
                          const StepDesc &s, int R, int M, const float *ksi, int ld_ksi, h16 *yq_hi, h16 *yq_lo,

@@ -124,10 +124,13 @@ def _rand_symbols(tabs, n, seed, escapes=True):
     return sym, idx
 
 
-@pytest.mark.parametrize("n_streams,n_sym", [(1, 5000), (7, 1234), (64, 96)])
-def test_rans_bit_exact_vs_oracle(dev, n_streams, n_sym):
-    """K5/K6: GPU rANS bytes == oracle bytes for identical symbols/indexes/tables; GPU decode inverts."""
+@pytest.mark.parametrize("n_streams,n_sym,thread_form", [(1, 5000, 0), (7, 1234, 0), (64, 96, 0), (7, 1236, 1),
+                                                         (300, 96, 1)])
+def test_rans_bit_exact_vs_oracle(dev, n_streams, n_sym, thread_form):
+    """K5/K6: GPU rANS bytes == oracle bytes for identical symbols/indexes/tables; GPU decode inverts.
+    thread_form forces the thread-per-stream encoder (the default for >= 4096 streams)."""
     m = get_model("B8_lowrate", 1337, False, dev)
+    m.set_option("enc_thread_streams", 1 if thread_form else 1 << 30)
     tabs = load_tables()
     g = m.conditional_gaussian_model
     T = onative.Tables(g.quantized_cdf.numpy(), g.cdf_length.numpy(), g.offset.numpy())
@@ -150,6 +153,7 @@ def test_rans_bit_exact_vs_oracle(dev, n_streams, n_sym):
     _lib.check(_lib.lib().lbic_rans_decode(m._need(), out.data_ptr(), lens.data_ptr(), cap, idx_d.data_ptr(),
                                            n_streams, n_sym, dec.data_ptr(), None))
     torch.cuda.synchronize()
+    m.set_option("enc_thread_streams", 4096)
     assert np.array_equal(dec.cpu().numpy(), sym)
 
 
@@ -223,9 +227,12 @@ def test_thread_per_stream_decode_equals_warp_per_stream(dev, cfgname):
             for lanes in (0, 1):
                 strings, zhat, sym, _ = m.compress_batch(x, lanes=lanes, return_symbols=True)
                 out = {}
-                for rows in (1 << 30, 1):          # never / always the thread kernel
+                for rows in (1 << 30, 1):          # never / always the thread-per-stream kernels (decoder and encoder)
                     m.set_option("dec_thread_rows", rows)
+                    m.set_option("enc_thread_streams", rows)
                     enc_dev = m.encode_device(x, lanes=lanes)
+                    got = m._gather_streams(enc_dev)
+                    assert got == strings, "bitstreams differ between the two encoder kernels"
                     z, s = m.decode_device(enc_dev.streams, enc_dev.lens, x.shape[0], x.shape[2], x.shape[3], lanes=lanes,
                                            want_symbols=True)
                     out[rows] = (z, s)
@@ -234,6 +241,7 @@ def test_thread_per_stream_decode_equals_warp_per_stream(dev, cfgname):
                 assert torch.equal(out[1][1], sym) and torch.equal(out[1][0], zhat)
         finally:
             m.set_option("dec_thread_rows", 4096)
+            m.set_option("enc_thread_streams", 4096)
 
 
 def test_batch_invariance_and_ragged_grids(dev):
