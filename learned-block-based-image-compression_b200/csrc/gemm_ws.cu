@@ -33,14 +33,18 @@ constexpr int WS_EPI_THREADS = 256;
 constexpr int WS_MAX_BN = 192;
 constexpr int WS_ACC_STRIDE = 256;          // TMEM columns between the two accumulators
 constexpr int GC = 32;                      // columns per staged group
-constexpr int WF_STRIDE = GC * 4 + 16;      // 144 B
-constexpr int WH_STRIDE = GC * 2 + 16;      // 80 B
-constexpr int WI_STRIDE = GC + 16;          // 48 B
-constexpr int WF_OFF = 0;
-constexpr int WH_OFF = WF_OFF + BM * WF_STRIDE;
-constexpr int WL_OFF = WH_OFF + BM * WH_STRIDE;
-constexpr int WI_OFF = WL_OFF + BM * WH_STRIDE;
-constexpr int WSTG_BYTES = WI_OFF + BM * WI_STRIDE;   // 45,056 B
+// One staging region, reused by two passes per group so that it stays small and the operand ring gets the space
+// (the kernel is bound by L2 -> SM bandwidth; a third 64 KiB stage for the 256-wide pair tiles is worth more than a
+// barrier):  pass F  = the fp32 plane (128 B per row),  pass HL = hi | lo | CDF-index planes (64 + 64 + 32 B per row).
+constexpr int WF_STRIDE = GC * 4 + 16;      // 144 B: rows 16 B apart modulo 128 -> conflict-free 16-byte accesses
+constexpr int WHL_STRIDE = 176;             // 128 + 48: 3 * 16 B apart modulo 128, also conflict-free
+constexpr int WHL_LO = 64, WHL_IDX = 128;   // byte offsets of the lo / index planes within a pass-HL row
+constexpr int WSTG_BYTES = BM * WHL_STRIDE; // 22,528 B
+// GDN modes: pass HL needs no index plane (row stride 144 B) and the group's pre-activations (fp32, 128 x 128 B) get
+// two cp.async buffers behind it, XOR-swizzled in 16-byte chunks instead of padded.
+constexpr int WGDN_STRIDE = 144;
+constexpr int WAUX_BUF = BM * GC * 4;       // 16,384 B
+constexpr int WGDN_BYTES = BM * WGDN_STRIDE + 2 * WAUX_BUF;   // 51,200 B
 constexpr int WS_BAR_BLOCK = 128;           // full[4] empty[4] acc_full[2] acc_empty[2] tmem slot
 constexpr int WS_TAIL = WS_BAR_BLOCK + 2 * 1024 + ROWTAB_BYTES + STAB_BYTES;   // barriers, two bias slices, row table, scale table
 
@@ -48,7 +52,7 @@ struct WsParams {
     int kb[2];
     int bn, ntiles_n, total_tiles;
     int stages;
-    uint32_t slot_bytes, ring_bytes;
+    uint32_t slot_bytes, ring_bytes, stg_bytes;   // stg_bytes: staging region (+ the GDN pre-activation buffer), multiple of 128
     uint32_t idesc;
     EpiParams ep;
 };
@@ -114,7 +118,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t ring = (raw + 1023u) & ~1023u;
     const uint32_t stg = ring + p.ring_bytes;                 // dedicated epilogue staging (1024-aligned)
-    const uint32_t bars = stg + ((WSTG_BYTES + 127) / 128) * 128;
+    const uint32_t bars = stg + p.stg_bytes;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (MAX_STAGES + s); };
     auto acc_full = [&](int a) { return bars + 8u * (2 * MAX_STAGES + a); };
@@ -259,64 +263,71 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
                 rt->idx[rl] = reinterpret_cast<unsigned long long>(mode == EPI_QUANT && ep.idx ? ep.idx + d.blk * ep.M + n0 : nullptr);
             }
             epi_bar();
-            mbar_wait(acc_full(a), (ti >> 1) & 1u);
-            tc_fence_after();
             const uint32_t lane_base = tmem_base + a * WS_ACC_STRIDE + ((uint32_t)(q * 32) << 16);
             const int ngroups = (p.bn + GC - 1) / GC;   // the last group may hold a single 16-column chunk
             // Software pipeline over the 32-column groups: the TMEM load of group g+1 is issued before group g is
-            // finished, and (GDN modes) the pre-activations of group g+1 are fetched from global memory while group g
-            // is being stored, then dropped into the fp32 staging plane, which those modes do not use for output.
+            // finished; in the GDN modes each thread also requests its own row's pre-activations of group g+1 (64
+            // contiguous bytes) one group ahead, so that global-load latency hides behind a whole group of work.
             const int rsub = lane >> 3, c16 = lane & 7;
+            const bool has_f32 = epi_has_f32(mode) && (mode != EPI_QUANT || ep.sym);
+            const bool has_hilo = epi_has_hilo(mode);
             auto group_valid = [&](int g) {
                 int nv = ep.cout - (n0 + g * GC);
                 nv = nv < 0 ? 0 : (nv > GC ? GC : nv);
                 return nv > p.bn - g * GC ? p.bn - g * GC : nv;
             };
-            auto aux_load = [&](int g, uint4 (&v)[4]) {
-                const int nv = group_valid(g);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int row = ew * 16 + j * 4 + rsub;
-                    v[j] = (row < rows_valid && c16 * 4 < nv)
-                               ? *reinterpret_cast<const uint4 *>(ep.aux + (size_t)(m0 + row) * ep.ld_aux + n0 + g * GC + c16 * 4)
-                               : make_uint4(0u, 0u, 0u, 0u);
-                }
+            auto chunk_ok = [&](int g) {
+                return row_ok && (n0 + g * GC + sub * 16) < ep.cout && (g * GC + sub * 16) < p.bn;
             };
-            auto aux_store = [&](const uint4 (&v)[4]) {
+            // GDN modes: the group's pre-activations arrive by cp.async with coalesced 16-byte lanes (4 rows x 128 B per
+            // warp instruction; a row-per-thread read costs four times the L1 tag lookups and was measurably slower),
+            // two groups ahead, into two swizzled buffers behind the staging region: under a saturated L2 a load
+            // takes longer than one group of epilogue work.
+            const int hl_stride = gdn ? WGDN_STRIDE : WHL_STRIDE;
+            const uint32_t aux_base = stg + BM * WGDN_STRIDE;
+            auto aux_issue = [&](int g) {
+                const int nv = group_valid(g);
+                const uint32_t buf = aux_base + (uint32_t)(g & 1) * WAUX_BUF;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int row = ew * 16 + j * 4 + rsub;
-                    sts128(stg + WF_OFF + row * WF_STRIDE + c16 * 16, v[j].x, v[j].y, v[j].z, v[j].w);
+                    const bool valid = row < rows_valid && c16 * 4 < nv;
+                    const float *src = valid ? ep.aux + (size_t)(m0 + row) * ep.ld_aux + n0 + g * GC + c16 * 4 : ep.aux;
+                    const uint32_t dst = buf + row * 128 + ((uint32_t)(c16 ^ (row & 7)) << 4);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
                 }
+                asm volatile("cp.async.commit_group;" ::: "memory");
             };
             uint32_t accA[16], accB[16];
-            tmem_ld_issue(lane_base + (uint32_t)(sub * 16), accA);
-            if (gdn) {
-                uint4 v[4];
-                aux_load(0, v);
-                aux_store(v);
+            if (gdn) {                                       // overlaps the wait for the accumulator
+                aux_issue(0);
+                if (ngroups > 1) {
+                    aux_issue(1);
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                } else {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                }
                 epi_bar();
             }
+            mbar_wait(acc_full(a), (ti >> 1) & 1u);
+            tc_fence_after();
+            tmem_ld_issue(lane_base + (uint32_t)(sub * 16), accA);
             for (int g = 0; g < ngroups; ++g) {
                 const int g0 = g * GC;
                 const int nvalid = group_valid(g);
                 const bool even = (g & 1) == 0;
-                // GDN modes: the next group's pre-activations are requested now and land in shared memory after this
-                // group's stores, so the global-load latency hides behind a whole group of work
-                uint4 nxt[4];
-                const bool fetch_next = gdn && g + 1 < ngroups;
-                if (fetch_next) aux_load(g + 1, nxt);
+                const bool ok = chunk_ok(g);
+                EpiOut<16> o;
                 // phase A: this warp's 16-column chunk of the group
                 {
                     const int c = n0 + g0 + sub * 16;
                     EpiPre<16> pre;
-                    const bool ok = row_ok && c < ep.cout && (g0 + sub * 16) < p.bn;
                     if (ok) {
                         if (gdn) {
-                            const uint32_t src = stg + WF_OFF + rl * WF_STRIDE + sub * 64;
+                            const uint32_t src = aux_base + (uint32_t)(g & 1) * WAUX_BUF + rl * 128;
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const uint4 v = lds128(src + i * 16);
+                                const uint4 v = lds128(src + ((uint32_t)((sub * 4 + i) ^ (rl & 7)) << 4));
                                 pre.a[4 * i] = __uint_as_float(v.x); pre.a[4 * i + 1] = __uint_as_float(v.y);
                                 pre.a[4 * i + 2] = __uint_as_float(v.z); pre.a[4 * i + 3] = __uint_as_float(v.w);
                             }
@@ -341,74 +352,81 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
                         float v[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(even ? accA[i] : accB[i]);
-                        EpiOut<16> o;
                         epi_compute<16>(ep, sb + g0 + sub * 16, v, pre, o, stab);
-                        const int gc = sub * 16;
-                        if (epi_has_f32(mode)) {
-                            const uint32_t d = stg + WF_OFF + rl * WF_STRIDE + gc * 4;
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4)
-                                sts128(d + i * 4, __float_as_uint(o.f[i]), __float_as_uint(o.f[i + 1]),
-                                       __float_as_uint(o.f[i + 2]), __float_as_uint(o.f[i + 3]));
-                        }
-                        if (epi_has_hilo(mode)) {
-                            const uint32_t h = stg + WH_OFF + rl * WH_STRIDE + gc * 2;
-                            const uint32_t l = stg + WL_OFF + rl * WH_STRIDE + gc * 2;
-                            sts128(h, o.hi[0], o.hi[1], o.hi[2], o.hi[3]);
-                            sts128(h + 16, o.hi[4], o.hi[5], o.hi[6], o.hi[7]);
-                            sts128(l, o.lo[0], o.lo[1], o.lo[2], o.lo[3]);
-                            sts128(l + 16, o.lo[4], o.lo[5], o.lo[6], o.lo[7]);
-                        }
-                        if (mode == EPI_QUANT)
-                            sts128(stg + WI_OFF + rl * WI_STRIDE + gc, o.idx[0], o.idx[1], o.idx[2], o.idx[3]);
                     }
                 }
-                epi_bar();                       // group staged (and, GDN: every thread has read its pre-activations)
-                // phase B: coalesced stores, 4 rows per warp instruction
-                if (nvalid > 0) {
-                    if (epi_has_f32(mode) && (mode != EPI_QUANT || ep.sym)) {
-                        if (c16 * 4 < nvalid) {
+                const int gc = sub * 16;
+                auto stage_hl = [&]() {
+                    const uint32_t hrow = stg + rl * hl_stride + gc * 2;
+                    sts128(hrow, o.hi[0], o.hi[1], o.hi[2], o.hi[3]);
+                    sts128(hrow + 16, o.hi[4], o.hi[5], o.hi[6], o.hi[7]);
+                    sts128(hrow + WHL_LO, o.lo[0], o.lo[1], o.lo[2], o.lo[3]);
+                    sts128(hrow + WHL_LO + 16, o.lo[4], o.lo[5], o.lo[6], o.lo[7]);
+                    if (mode == EPI_QUANT) sts128(stg + rl * WHL_STRIDE + WHL_IDX + gc, o.idx[0], o.idx[1], o.idx[2], o.idx[3]);
+                };
+                auto store_hl = [&]() {
+                    const int c8 = lane & 3;                 // 16-byte chunk within the 64-byte plane row
+                    const bool is_lo = (lane >> 2) & 1;
+                    if (c8 * 8 < nvalid) {
+                        h16 *base = (is_lo ? ep.out_lo : ep.out_hi) + g0 + c8 * 8;
+                        const uint32_t src = stg + (is_lo ? WHL_LO : 0) + c8 * 16;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int row = ew * 16 + j * 4 + rsub;
-                                if (row < rows_valid) {
-                                    const uint4 v = lds128(stg + WF_OFF + row * WF_STRIDE + c16 * 16);
-                                    float *dst = reinterpret_cast<float *>(rt->f32[row]) + g0 + c16 * 4;
-                                    *reinterpret_cast<uint4 *>(dst) = v;
-                                }
+                        for (int j = 0; j < 4; ++j) {
+                            const int row = ew * 16 + j * 4 + rsub;
+                            if (row < rows_valid) {
+                                const uint4 v = lds128(src + row * hl_stride);
+                                *reinterpret_cast<uint4 *>(base + rt->hilo[row]) = v;
                             }
                         }
                     }
-                    if (epi_has_hilo(mode)) {
-                        const int c8 = lane & 3;                 // 16-byte chunk within the 64-byte plane row
-                        const bool is_lo = (lane >> 2) & 1;
-                        if (c8 * 8 < nvalid) {
-                            h16 *base = (is_lo ? ep.out_lo : ep.out_hi) + g0 + c8 * 8;
-                            const uint32_t src = stg + (is_lo ? WL_OFF : WH_OFF) + c8 * 16;
+                    if (mode == EPI_QUANT && ep.idx && c16 < 2 && c16 * 16 < nvalid) {      // 2 x 16 B per row
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int row = ew * 16 + j * 4 + rsub;
-                                if (row < rows_valid) {
-                                    const uint4 v = lds128(src + row * WH_STRIDE);
-                                    *reinterpret_cast<uint4 *>(base + rt->hilo[row]) = v;
-                                }
+                        for (int j = 0; j < 4; ++j) {
+                            const int row = ew * 16 + j * 4 + rsub;
+                            if (row < rows_valid) {
+                                const uint4 v = lds128(stg + row * WHL_STRIDE + WHL_IDX + c16 * 16);
+                                *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(rt->idx[row]) + g0 + c16 * 16) = v;
                             }
                         }
                     }
-                    if (mode == EPI_QUANT && ep.idx) {
-                        if (c16 < 2 && c16 * 16 < nvalid) {      // 2 x 16 B per row
+                };
+                if (has_f32) {
+                    // pass F: stage the fp32 plane, then coalesced stores, 4 rows (128 B each) per warp instruction
+                    if (ok) {
+                        const uint32_t d = stg + rl * WF_STRIDE + gc * 4;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int row = ew * 16 + j * 4 + rsub;
-                                if (row < rows_valid) {
-                                    const uint4 v = lds128(stg + WI_OFF + row * WI_STRIDE + c16 * 16);
-                                    *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(rt->idx[row]) + g0 + c16 * 16) = v;
-                                }
+                        for (int i = 0; i < 16; i += 4)
+                            sts128(d + i * 4, __float_as_uint(o.f[i]), __float_as_uint(o.f[i + 1]),
+                                   __float_as_uint(o.f[i + 2]), __float_as_uint(o.f[i + 3]));
+                    }
+                    epi_bar();
+                    if (c16 * 4 < nvalid) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int row = ew * 16 + j * 4 + rsub;
+                            if (row < rows_valid) {
+                                const uint4 v = lds128(stg + row * WF_STRIDE + c16 * 16);
+                                float *dst = reinterpret_cast<float *>(rt->f32[row]) + g0 + c16 * 4;
+                                *reinterpret_cast<uint4 *>(dst) = v;
                             }
                         }
+                    }
+                    if (has_hilo) {
+                        epi_bar();               // the fp32 stores have read the staging area
+                        if (ok) stage_hl();
+                        epi_bar();
+                        if (nvalid > 0) store_hl();
+                    }
+                } else {
+                    if (ok) stage_hl();
+                    epi_bar();                   // (GDN: every thread has also read its pre-activations of this group)
+                    if (gdn && g + 2 < ngroups) aux_issue(g + 2);   // into the buffer this group has just released
+                    if (nvalid > 0) store_hl();
+                    if (gdn && g + 1 < ngroups) {                   // this thread's share of group g+1 has landed
+                        if (g + 2 < ngroups) asm volatile("cp.async.wait_group 1;" ::: "memory");
+                        else asm volatile("cp.async.wait_group 0;" ::: "memory");
                     }
                 }
-                if (fetch_next) aux_store(nxt);
                 if (g + 1 < ngroups) epi_bar();   // stores have read the staging area; next pre-activations visible
             }
         }
@@ -451,7 +469,9 @@ int gemm_ws_launch(const GemmCall &g, cudaStream_t st, int pair) {
     p.ntiles_n = (g.cout + g.bn - 1) / g.bn;
     p.total_tiles = ((g.R + tile_rows - 1) / tile_rows) * p.ntiles_n;
     p.slot_bytes = 2 * A_PLANE + 2 * (uint32_t)w_rows * BK * 2;
-    const int avail = SMEM_LIMIT - 1024 - WSTG_BYTES - 128 - WS_TAIL;
+    const bool gdn_mode = g.ep.mode == EPI_GDN || g.ep.mode == EPI_IGDN;
+    p.stg_bytes = (uint32_t)(gdn_mode ? WGDN_BYTES : WSTG_BYTES);
+    const int avail = SMEM_LIMIT - 1024 - (int)p.stg_bytes - 128 - WS_TAIL;
     int stages = avail / (int)p.slot_bytes;
     stages = stages > MAX_STAGES ? MAX_STAGES : stages;
     {
@@ -473,7 +493,7 @@ int gemm_ws_launch(const GemmCall &g, cudaStream_t st, int pair) {
     int grid = p.total_tiles < n_sm ? p.total_tiles : n_sm;
     if (pair) grid = 2 * (p.total_tiles < n_sm / 2 ? p.total_tiles : n_sm / 2);
     const int s1 = g.nseg > 1 ? 1 : 0;
-    const size_t smem = 1024 + (size_t)p.ring_bytes + ((WSTG_BYTES + 127) / 128) * 128 + WS_TAIL;
+    const size_t smem = 1024 + (size_t)p.ring_bytes + p.stg_bytes + WS_TAIL;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid, 1, 1);
