@@ -179,7 +179,7 @@ __device__ __forceinline__ void epi_compute(const EpiParams &p, const float *__r
         // GDNF:73-78: x * rsqrt(norm) (forward) or x * sqrt(norm) (inverse).  rsqrtf is the 2-ulp hardware
         // approximation (the IEEE sqrt + divide sequences cost ~50 instructions per element and made these
         // epilogues 3x longer, profiles/r1_chain_trace.md); its error (2^-22) is far below the h16 hi/lo operand
-        // split (2^-17) and it is the same instruction in encoder and decoder.
+        // split (2^-22 per operand, more after K accumulation) and it is the same instruction in encoder and decoder.
         const bool inv = (p.mode == EPI_IGDN);
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
