@@ -264,15 +264,16 @@ def main():
     ms_dec = timed(lambda: m.decode_device(enc_out.streams, enc_out.lens, n, Hb, Wb, lanes=args.lanes), args.steps)
     bytes_total = int(enc_out.lens.sum().item())
 
-    # roofline of the dominant kernel (gemm_tc_kernel): one more encode with per-launch CUDA events
+    # roofline of the dominant kernel (gemm_ws_kernel): one more encode with per-launch CUDA events
     m.set_profiling(True)
     m.encode_device(x, lanes=args.lanes, out=enc_out)
     prof = m.get_profile()
+    layers = m.get_layer_profile()
     m.set_profiling(False)
     peaks = load_peaks()
     ach = prof["gemm_flops"] / (prof["gemm_ms"] * 1e-3) / 1e12 if prof["gemm_ms"] > 0 else 0.0
     macs = macs_per_block(cfg)
-    roofline = dict(bound="tensor", kernel="gemm_ws_kernel + gemm_tc_kernel (tcgen05 kind::f16, fp16 hi/lo operand split, 3 MMAs per product, fp32 TMEM accumulate)",
+    roofline = dict(bound="tensor", kernel="gemm_ws_kernel<PAIR> (cta_group::2) + gemm_tc_kernel (tcgen05 kind::f16, fp16 hi/lo operand split, 3 MMAs per product, fp32 TMEM accumulate)",
                     achieved=ach, peak=peaks["tf_sustained"], unit="TFLOP/s", frac=ach / peaks["tf_sustained"],
                     passes=3, frac_pass_adjusted=3 * ach / peaks["tf_sustained"], peak_source=peaks["source"] + " sustained",
                     launches=prof["gemm_launches"], avg_launch_us=1e3 * prof["gemm_ms"] / max(1, prof["gemm_launches"]),
@@ -280,7 +281,10 @@ def main():
                     algorithmic_flop_per_pixel=dict(encode=2 * macs["encode"] / (B * B), decode=2 * macs["decode"] / (B * B)),
                     traffic=None,
                     traffic_note="ncu dram bytes per launch for the dominant shapes are in profiles/r1_gemm_ws.md "
-                                 "(196 MB measured vs 229 MB algorithmic for a 24k x 768 x 768 PREGDN launch)")
+                                 "(196 MB measured vs 229 MB algorithmic for a 24k x 768 x 768 PREGDN launch)",
+                    binding_resource="L2 -> SM bandwidth (~43 B/clk/SM chip-wide): launch time tracks the operand + output "
+                                     "bytes through L2, see profiles/r1_l2_bound.md; the tensor peak is the contract's denominator",
+                    layers_tflops={k: round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) for k, v in layers.items() if v["ms"] > 0})
 
     # the reference's own container (one rANS stream per image, NET:359-360): its decode is serial in raster order,
     # so it is reported beside the headline instead of inside it
