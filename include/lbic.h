@@ -125,6 +125,17 @@ int lbic_decode(lbic_model *m, const uint8_t *streams, const uint32_t *stream_le
 int lbic_validate(lbic_model *m, const float *x, int n_img, int Hb, int Wb, float *zhat_out, float *selfinfo_out,
                   void *stream);
 
+/* model.forward(zhat, x) in eval mode -- NET:90-106, the open-loop pass ACL training-set regeneration runs over
+ * every patch (AGENT:643-684): all blocks are independent given the context zhat_in.
+ *   zhat_in, x    device, (n_img, 3B^2, Hb, Wb) fp32 (context reconstruction, original)
+ *   xhat_out      device, same shape; clamp != 0 applies the caller's clamp_(-0.5, 0.5) (AGENT:667), 0 returns it raw
+ *   selfinfo_out  device or NULL, (n_img, M, Hb, Wb) fp32 = -log2 pmf of every quantised latent
+ *   sym_out       device or NULL, (n_img, Hb, Wb, M) int32 = round(y - means)
+ * Convolutions are zero padded per layer as in the reference's whole-image forward, which for KS[1] = 3 differs from
+ * the codec path's block windows at the image border. */
+int lbic_forward(lbic_model *m, const float *zhat_in, const float *x, int n_img, int Hb, int Wb, float *xhat_out,
+                 float *selfinfo_out, int32_t *sym_out, int clamp, void *stream);
+
 /* Same two calls with HOST buffers (pageable or pinned): the copies are part of the call and the
  * call returns after the results are in host memory.  This is what a reference-side binding
  *  calls from eval_model (AGENT:591-599). */

@@ -60,6 +60,7 @@ PROTOTYPES = {
     "lbic_set_profiling": (_i, [_vp, _i]),
     "lbic_get_profile": (_i, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_double),
                               ctypes.POINTER(ctypes.c_double)]),
+    "lbic_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "lbic_get_layer_profile": (_i, [_vp, _i, ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_double),
                                     ctypes.POINTER(ctypes.c_double)]),
 }

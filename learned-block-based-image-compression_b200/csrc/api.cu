@@ -121,6 +121,8 @@ struct lbic_model {
     int use_ws = 1;        // warp-specialised persistent kernel for large steps
     int use_pair = 1;      // CTA-pair (cta_group::2) form of the persistent kernel
     float *selfinfo_cl = nullptr;   // set by lbic_validate for the duration of the call: (n,Hb,Wb,M) self-information
+    float *recon_cl = nullptr;      // set by lbic_forward: the decoder net writes here instead of the zhat feedback buffer
+    int recon_no_clamp = 0;
     int64_t launches[2] = {0, 0};
     int *err_flag = nullptr;
     // host-call staging
@@ -661,7 +663,8 @@ int run_dec(lbic_model *m, const StepDesc &sd, int R, cudaStream_t st) {
     LBIC_TRY(run_gemm(m, L_D2, R, &ws.vU[1], nullptr, epi_pregdn(m, sd), st));
     LBIC_TRY(run_gdn(m, L_IG2, 2, true, sd, R, st));
     EpiParams e = epi(EPI_RECON, sd);
-    e.zhat = ws.zhat_cl;
+    e.zhat = m->recon_cl ? m->recon_cl : ws.zhat_cl;
+    e.no_clamp = m->recon_no_clamp;
     LBIC_TRY(run_gemm(m, L_D3, R, &ws.vU[2], nullptr, e, st));
     return 0;
 }
@@ -972,6 +975,76 @@ extern "C" int lbic_validate(lbic_model *m, const float *x, int n_img, int Hb, i
     Active act2(m);
     if (rc == 0) rc = launch_cl_to_nchw(cl, selfinfo_out, n_img, m->M, Hb * Wb, st);   // -> (n, M, Hb, Wb) as AGENT:509
     cudaStreamSynchronize(st);
+    free_all(tmp);
+    return rc;
+}
+
+// Open-loop forward = the reference's model.forward(zhat, x) in eval mode (NET:90-106): every block of the batch is
+// independent given the context zhat, so the whole batch is processed as raster chunks of up to R_cap rows through the
+// same gather / GEMM / epilogue kernels (no wavefront).  KS[1] = 3: the second entropy layer is zero padded in this
+// whole-image form, so the hidden-map ring is zero here (the codec path computes it); the hidden map
+// of ALL blocks is produced first, then the rest of the nets.
+extern "C" int lbic_forward(lbic_model *m, const float *zhat_in, const float *x, int n_img, int Hb, int Wb,
+                            float *xhat_out, float *selfinfo_out, int32_t *sym_out, int clamp, void *stream) {
+    LBIC_TRY(check_ready(m, false));
+    if (!zhat_in || !x || !xhat_out || n_img < 1 || Hb < 1 || Wb < 1) return lbic_fail(LBIC_ERR_INVALID, "bad arguments");
+    if (m->use_chain) return lbic_fail(LBIC_ERR_INVALID, "lbic_forward runs on the per-layer path (LBIC_OPT_CHAIN = 0)");
+    Active act(m);
+    cudaStream_t st = (cudaStream_t)stream;
+    LBIC_TRY(ensure_workspace(m, n_img, Hb, Wb));
+    Workspace &ws = m->ws;
+    const int HW = Hb * Wb;
+    const long nblk = (long)n_img * HW;
+    std::vector<void *> tmp;
+    float *xhat_cl = nullptr, *info_cl = nullptr;
+    int rc = 0;
+    do {
+#define P(call) if ((rc = (call)) != 0) break
+        P(dev_alloc(tmp, (void **)&xhat_cl, sizeof(float) * (size_t)nblk * m->Cin));
+        if (selfinfo_out) P(dev_alloc(tmp, (void **)&info_cl, sizeof(float) * (size_t)nblk * m->M));
+        P(launch_nchw_to_cl(x, ws.x_cl, n_img, m->Cin, HW, st));
+        P(launch_nchw_to_cl(zhat_in, ws.zhat_cl, n_img, m->Cin, HW, st));
+        const int chunk = ws.R_cap;
+        if (m->k1 == 3) {
+            const size_t npos = (size_t)n_img * (Hb + 1) * (Wb + 2);
+            if (cudaMemsetAsync(ws.G0.hi, 0, sizeof(h16) * npos * m->E1, st) != cudaSuccess ||
+                cudaMemsetAsync(ws.G0.lo, 0, sizeof(h16) * npos * m->E1, st) != cudaSuccess) {
+                rc = lbic_fail(LBIC_ERR_CUDA, "memset failed");
+                break;
+            }
+            for (long r0 = 0; r0 < nblk && rc == 0; r0 += chunk) {
+                const int R = (int)(nblk - r0 < chunk ? nblk - r0 : chunk);
+                const StepDesc sd{n_img, 0, 0, (int)r0, Hb, Wb};
+                P(launch_gather(nullptr, ws.zhat_cl, m->Cin, sd, R, nullptr, nullptr, 0, ws.T.hi, ws.T.lo, ws.T.ld, st));
+                EpiParams e = epi_hilo(EPI_LRELU, sd, ws.G0);
+                e.out_pos = 1;
+                P(run_gemm(m, L_E0, R, &ws.vT, nullptr, e, st));
+            }
+            if (rc) break;
+        }
+        m->recon_cl = xhat_cl;
+        m->recon_no_clamp = clamp ? 0 : 1;
+        for (long r0 = 0; r0 < nblk && rc == 0; r0 += chunk) {
+            const int R = (int)(nblk - r0 < chunk ? nblk - r0 : chunk);
+            const StepDesc sd{n_img, 0, 0, (int)r0, Hb, Wb};
+            P(launch_gather(ws.x_cl, ws.zhat_cl, m->Cin, sd, R, ws.X.hi, ws.X.lo, ws.X.ld, ws.T.hi, ws.T.lo, ws.T.ld, st));
+            P(run_ent(m, sd, R, st));
+            P(run_enc(m, sd, R, ws.sym, ws.idx, st));
+            P(run_dec(m, sd, R, st));
+            if (info_cl) P(launch_selfinfo_step(sd, R, m->M, ws.KSI, ws.ldKSI, ws.sym, info_cl, st));
+        }
+        m->recon_cl = nullptr;
+        m->recon_no_clamp = 0;
+        if (rc) break;
+        P(launch_cl_to_nchw(xhat_cl, xhat_out, n_img, m->Cin, HW, st));
+        if (info_cl) P(launch_cl_to_nchw(info_cl, selfinfo_out, n_img, m->M, HW, st));
+        if (sym_out && cudaMemcpyAsync(sym_out, ws.sym, sizeof(int32_t) * (size_t)nblk * m->M, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+            rc = lbic_fail(LBIC_ERR_CUDA, "copy failed");
+#undef P
+    } while (0);
+    m->recon_cl = nullptr;
+    m->recon_no_clamp = 0;
+    cudaStreamSynchronize(st);   // the temporaries are freed below
     free_all(tmp);
     return rc;
 }

@@ -217,7 +217,7 @@ __device__ __forceinline__ void epi_compute(const EpiParams &p, const float *__r
     } break;
     case EPI_RECON: {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) o.f[i] = fminf(fmaxf(v[i], -0.5f), 0.5f);   // clamp_(-0.5, 0.5) NET:357
+        for (int i = 0; i < NV; ++i) o.f[i] = p.no_clamp ? v[i] : fminf(fmaxf(v[i], -0.5f), 0.5f);   // clamp_(-0.5, 0.5) NET:357
     } break;
     default: break;
     }

@@ -46,7 +46,18 @@ __host__ __device__ inline size_t g0_pos_index(int img, int v, int h, int Hb, in
     return ((size_t)img * (Hb + 1) + (v + 1)) * (Wb + 2) + (h + 1);
 }
 
+// nv == 0 marks a RASTER chunk (open-loop forward, lbic_forward): row r is block number t + r of the batch in
+// (img, v, h) raster order; otherwise the rows are the blocks of wavefront step t (h + 2v = t) of every image.
 __host__ __device__ inline void step_row_to_block(const StepDesc &s, int r, int &img, int &v, int &h) {
+    if (s.nv == 0) {
+        const int hw = s.Hb * s.Wb;
+        const int g = s.t + r;
+        img = g / hw;
+        const int q = g - img * hw;
+        v = q / s.Wb;
+        h = q - v * s.Wb;
+        return;
+    }
     img = r / s.nv;
     v = s.vmin + (r - img * s.nv);
     h = s.t - 2 * v;
@@ -75,6 +86,7 @@ struct EpiParams {
     h16 *out_hi, *out_lo;
     int ld_out;
     int out_pos;        // 1: hi/lo output row = position in the ring-extended g0 store (KS[1]=3), see g0_pos_index
+    int no_clamp;       // RECON: 1 = leave the reconstruction unclamped (model.forward returns it so, NET:104-106)
     float *out_f32;
     int ld_f32;
     const float *aux;   // pre-GDN activations (GDN modes) or ksi (QUANT)

@@ -284,6 +284,28 @@ class BlockBasedImgCompLossyNetv9:
                                                 self._stream()))
         return zhat, info
 
+    def forward(self, zhat, x, clamp: bool = False, return_symbols: bool = False):
+        """model.forward(zhat, x) of the reference in eval mode (NET:90-106): open-loop pass over every block given
+        the context reconstruction zhat.  Both (n, 3B^2, Hb, Wb) CUDA fp32 -> (xhat, self_informations (n, M, Hb, Wb))
+        [+ symbols (n, Hb, Wb, M)].  xhat is returned unclamped like the reference's; clamp=True applies the caller's
+        clamp_(-0.5, 0.5) (AGENT:667) in the kernel."""
+        h = self._need()
+        if not (x.is_cuda and zhat.is_cuda and x.dtype == torch.float32 and zhat.dtype == torch.float32
+                and x.dim() == 4 and x.shape[1] == self.Cin and zhat.shape == x.shape):
+            raise ValueError(f"zhat and x must be CUDA fp32 tensors of the same shape (n, {self.Cin}, Hb, Wb)")
+        x, zhat = x.contiguous(), zhat.contiguous()
+        n, _, Hb, Wb = x.shape
+        xhat = torch.empty_like(x)
+        info = torch.empty(n, self.M, Hb, Wb, dtype=torch.float32, device=x.device)
+        sym = torch.empty(n, Hb, Wb, self.M, dtype=torch.int32, device=x.device) if return_symbols else None
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().lbic_forward(h, zhat.data_ptr(), x.data_ptr(), n, Hb, Wb, xhat.data_ptr(),
+                                               info.data_ptr(), sym.data_ptr() if sym is not None else None,
+                                               1 if clamp else 0, self._stream()))
+        return (xhat, info, sym) if return_symbols else (xhat, info)
+
+    __call__ = forward
+
     def decode_device(self, streams, lens, n, Hb, Wb, lanes: int = 1, want_symbols: bool = False):
         """streams (n, cap) uint8 CUDA, lens (n,) int32 CUDA -> zhat (n,3B^2,Hb,Wb) [, sym]."""
         h = self._need()

@@ -274,6 +274,45 @@ def whole_image_eval(P, x, zhat, dtype=torch.float32):
     return (sym.permute(0, 2, 3, 1).contiguous(), idx.permute(0, 2, 3, 1).contiguous(), xhat, y, ksi)
 
 
+@torch.no_grad()
+def forward_open_loop(P, zhat, x, dtype=torch.float32):
+    """The reference's model.forward(zhat, x) in eval mode (NET:90-106): ONE whole-image pass of the three nets with
+    every masked conv zero-padded by k//2 (NET:266-302), i.e. no closed loop -- zhat is whatever context the caller
+    supplies (ACL training-set regeneration feeds the previous iteration's reconstructions, AGENT:643-684).
+    Differs from whole_image_eval only for KS[1] = 3: there the second entropy layer sees ZEROS outside the image,
+    not the hidden-map ring the windowed codec path produces.
+    Returns xhat (n,3B^2,Hb,Wb) NOT clamped, self_informations (n,M,Hb,Wb), symbols (n,Hb,Wb,M) int32."""
+    cv = lambda t: t.to(dtype)
+    x, zhat = cv(x), cv(zhat)
+
+    def conv(t, p):
+        k = p[0].shape[-1]
+        return F.conv2d(t, cv(p[0]), cv(p[1]), padding=k // 2)
+
+    def gdn(t, p, inverse):
+        beta, gamma = cv(p[0]), cv(p[1])
+        C = t.shape[1]
+        norm = F.conv2d(t ** 2, gamma.reshape(C, C, 1, 1), beta)
+        return t * (torch.sqrt(norm) if inverse else torch.rsqrt(norm))
+
+    def chain(t, layers, inverse):
+        for i, p in enumerate(layers):
+            t = gdn(t, p, inverse) if i % 2 == 0 else conv(t, p)
+        return t
+
+    y = chain(conv(x, P.f1) + conv(zhat, P.f2), P.f3, False)
+    z = F.leaky_relu(conv(zhat, P.e[0]))
+    z = F.leaky_relu(conv(z, P.e[1]))
+    z = F.leaky_relu(conv(z, P.e[2]))
+    ksi = conv(z, P.e[3])
+    scales, means = ksi.chunk(2, dim=1)
+    sym = torch.round(y - means)
+    y_qnt = sym + means
+    xhat = chain(conv(y_qnt, P.i1) + conv(zhat, P.i2), P.i3, True)
+    info = self_information(sym.int(), scales)
+    return xhat, info, sym.int().permute(0, 2, 3, 1).contiguous()
+
+
 def self_information(sym, scales, likelihood_bound: float = 1e-9):
     """-log2 likelihood of quantised latents: ENT:615-647 (eval mode: values = |round(y - mean)|, scales lower-bounded
     at 0.11, likelihood lower-bounded), as summed by validate_recu_reco_fast (AGENT:509-519)."""

@@ -75,6 +75,20 @@ def _py_pmf_to_cdf(pmf, precision=16):
     return cdf
 
 
+@pytest.mark.parametrize("case", golden_cases())
+def test_oracle_forward_reproduces_reference_forward(case):
+    """forward_<case>.npz = the UNMODIFIED reference's model.forward(zhat, x) (tests/golden/make_golden_forward.py)."""
+    import os
+    from conftest import GOLDEN
+    c = load_case(case)
+    f = np.load(os.path.join(GOLDEN, f"forward_{case}.npz"))
+    cfg, P = _setup(c)
+    xhat, info, sym = nets.forward_open_loop(P, torch.from_numpy(c["zhat"]), torch.from_numpy(c["x"]))
+    assert np.array_equal(sym[0].numpy(), f["symbols"].astype(np.int32))
+    assert float((xhat - torch.from_numpy(f["xhat"])).abs().max()) <= 1e-5 * max(1.0, float(np.abs(f["xhat"]).max()))
+    assert float((info - torch.from_numpy(f["selfinfo"])).abs().max()) < 1e-3
+
+
 def test_pmf_to_quantized_cdf_against_python_transcription():
     rng = np.random.default_rng(0)
     for n in (3, 17, 200):
