@@ -4,6 +4,7 @@
 #include <cmath>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -93,6 +94,8 @@ struct Workspace {
     const uint8_t **lane_ptr = nullptr;
     std::vector<ChainLayer> h_chain;   // host copy of the per-layer chain descriptors (indexed by LayerId)
     ChainLayer *d_chain = nullptr;
+    int *flow_counters = nullptr;      // (layer, 256-row block) completion counters of the dataflow launch
+    size_t flow_counters_cap = 0;
     std::vector<void *> allocs;
 };
 
@@ -120,6 +123,9 @@ struct lbic_model {
     int force_cluster = 0;
     int use_ws = 1;        // warp-specialised persistent kernel for large steps
     int use_pair = 1;      // CTA-pair (cta_group::2) form of the persistent kernel
+    int use_flow = 1;      // dataflow launch of a whole layer range per step (1 = steps with >= flow_min_rows rows, 2 = always)
+    int flow_min_rows = 8192;
+    int flow_max_rows = 1 << 30;
     float *selfinfo_cl = nullptr;   // set by lbic_validate for the duration of the call: (n,Hb,Wb,M) self-information
     float *recon_cl = nullptr;      // set by lbic_forward: the decoder net writes here instead of the zhat feedback buffer
     int recon_no_clamp = 0;
@@ -406,6 +412,8 @@ int ensure_workspace(lbic_model *m, int n_img, int Hb, int Wb) {
     LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.dec_states, sizeof(RansStreamState) * (size_t)n_img * Hb));
     LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.lane_ptr, sizeof(void *) * (size_t)n_img * Hb));
     LBIC_TRY(build_chain(m));
+    ws.flow_counters_cap = (size_t)L_COUNT * ((ws.R_cap + 255) / 256 + 1);
+    LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.flow_counters, sizeof(int) * ws.flow_counters_cap, true));
     return 0;
 }
 
@@ -490,6 +498,38 @@ int run_chain(lbic_model *m, int l0, int l1, const StepDesc &sd, int R, cudaStre
         cudaEventRecord(rec.a, st);
     }
     const int rc = gemm_chain_launch(ws.d_chain, ws.h_chain.data(), l0, l1, R, sd, m->force_cluster, st);
+    if (m->profiling) {
+        cudaEventRecord(rec.b, st);
+        m->prof.push_back(rec);
+    }
+    return rc;
+}
+
+// which layers each layer reads from (operands and epilogue side inputs), by LayerId; -1 = inputs of the step
+const int FLOW_DEP[L_COUNT][2] = {
+    {-1, -1}, {L_E0, -1}, {L_E1, -1}, {L_E2, -1},                                              // E0..E3
+    {-1, -1}, {L_F0, -1}, {L_G0, -1}, {L_F1, -1}, {L_G1, -1}, {L_F2, -1}, {L_G2, L_E3},          // F0 G0 F1 G1 F2 G2 F3 (ksi)
+    {L_F3, -1}, {L_D0, -1}, {L_IG0, -1}, {L_D1, -1}, {L_IG1, -1}, {L_D2, -1}, {L_IG2, -1}};     // D0 IG0 D1 IG1 D2 IG2 D3
+
+bool flow_applies(const lbic_model *m, int R) {
+    return m->gemm_core == 0 && !m->use_chain && m->use_pair && m->use_flow && !m->force_bn &&
+           (m->use_flow == 2 || (R >= m->flow_min_rows && R <= m->flow_max_rows));
+}
+
+int run_flow(lbic_model *m, int l0, int l1, const StepDesc &sd, int R, cudaStream_t st) {
+    Workspace &ws = m->ws;
+    ProfRec rec;
+    if (m->profiling) {
+        double fl = 0;
+        for (int l = l0; l < l1; ++l)
+            for (int s = 0; s < m->L[l].nseg; ++s) fl += 2.0 * R * (double)m->L[l].seg[s].K * m->L[l].cout;
+        cudaEventCreate(&rec.a); cudaEventCreate(&rec.b);
+        rec.flops = fl;
+        rec.layer = -1;
+        cudaEventRecord(rec.a, st);
+    }
+    const int rc = gemm_flow_launch(ws.d_chain, ws.h_chain.data(), l0, l1, FLOW_DEP, R, sd, ws.flow_counters,
+                                    ws.flow_counters_cap, st);
     if (m->profiling) {
         cudaEventRecord(rec.b, st);
         m->prof.push_back(rec);
@@ -729,6 +769,10 @@ extern "C" int lbic_create(const lbic_config *cfg, int device, lbic_model **out)
                          cfg->block_size, cfg->n, cfg->m);
     LBIC_CUDA(cudaSetDevice(device));
     lbic_model *m = new lbic_model();
+    // tuning hooks for benchmarking without code changes (the same switches as lbic_set_option)
+    if (const char *e = getenv("LBIC_FLOW")) m->use_flow = atoi(e) < 0 ? 0 : (atoi(e) > 2 ? 2 : atoi(e));
+    if (const char *e = getenv("LBIC_FLOW_MIN_ROWS")) m->flow_min_rows = atoi(e) < 1 ? 1 : atoi(e);
+    if (const char *e = getenv("LBIC_FLOW_MAX_ROWS")) m->flow_max_rows = atoi(e) < 1 ? 1 : atoi(e);
     m->cfg = *cfg;
     m->device = device;
     m->Cin = 3 * cfg->block_size * cfg->block_size;
@@ -795,6 +839,12 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
         return 0;
     case LBIC_OPT_ENC_THREAD_STREAMS:
         rans_set_enc_thread_min_streams(value);
+        return 0;
+    case LBIC_OPT_FLOW:
+        m->use_flow = value < 0 ? 0 : (value > 2 ? 2 : value);
+        return 0;
+    case LBIC_OPT_FLOW_MIN_ROWS:
+        m->flow_min_rows = value < 1 ? 1 : value;
         return 0;
     case LBIC_OPT_PAIR:
         m->use_pair = value < 0 ? 0 : (value > 3 ? 3 : value);   // 2 = narrow (<= 192) tiles only, 3 = wide (<= 256) in the microbench
@@ -934,6 +984,10 @@ extern "C" int lbic_encode(lbic_model *m, const float *x, int n_img, int Hb, int
             // the whole step (entropy net, encoder net + quantisation, decoder net) in one persistent launch
             if (m->k1 == 3) LBIC_TRY(launch_gather5(ws.G0.hi, ws.G0.lo, m->E1, sd, R, ws.H1x5.hi, ws.H1x5.lo, ws.H1x5.ld, st));
             LBIC_TRY(run_chain(m, m->k1 == 3 ? L_E1 : L_E0, L_COUNT, sd, R, st));
+        } else if (flow_applies(m, R) && !m->recon_cl) {
+            // the whole step (entropy net, encoder net + quantisation, decoder net) as one dataflow launch
+            if (m->k1 == 3) LBIC_TRY(launch_gather5(ws.G0.hi, ws.G0.lo, m->E1, sd, R, ws.H1x5.hi, ws.H1x5.lo, ws.H1x5.ld, st));
+            LBIC_TRY(run_flow(m, m->k1 == 3 ? L_E1 : L_E0, L_COUNT, sd, R, st));
         } else {
             LBIC_TRY(run_ent(m, sd, R, st));
             LBIC_TRY(run_enc(m, sd, R, want_syms ? ws.sym : nullptr, want_syms ? ws.idx : nullptr, st));
@@ -1068,15 +1122,34 @@ extern "C" int lbic_decode(lbic_model *m, const uint8_t *streams, const uint32_t
     auto one_step = [&](const StepDesc &sd, int R) -> int {
         LBIC_TRY(launch_gather(nullptr, ws.zhat_cl, m->Cin, sd, R, nullptr, nullptr, 0, ws.T.hi, ws.T.lo, ws.T.ld, st));
         const bool chain = m->use_chain && m->gemm_core == 0;
-        if (chain) {
+        const bool flow = flow_applies(m, R);
+        if (chain || flow) {
             if (m->k1 == 3) LBIC_TRY(launch_gather5(ws.G0.hi, ws.G0.lo, m->E1, sd, R, ws.H1x5.hi, ws.H1x5.lo, ws.H1x5.ld, st));
-            LBIC_TRY(run_chain(m, m->k1 == 3 ? L_E1 : L_E0, L_F0, sd, R, st));
+            if (chain) LBIC_TRY(run_chain(m, m->k1 == 3 ? L_E1 : L_E0, L_F0, sd, R, st));
+            else LBIC_TRY(run_flow(m, m->k1 == 3 ? L_E1 : L_E0, L_F0, sd, R, st));
         } else {
             LBIC_TRY(run_ent(m, sd, R, st));
         }
         LBIC_TRY(launch_rans_dec_step(m->tables, ws.dec_states, ws.lane_ptr, L, sd, R, m->M, ws.KSI, ws.ldKSI, ws.YQ.hi,
                                       ws.YQ.lo, ws.YQ.ld, sym_out ? ws.sym : nullptr, st));
-        if (chain) LBIC_TRY(run_chain(m, L_D0, L_COUNT, sd, R, st)); else LBIC_TRY(run_dec(m, sd, R, st));
+        static const int dbg_part = getenv("LBIC_FLOW_PART") ? atoi(getenv("LBIC_FLOW_PART")) : 0;   // debugging aid
+        if (chain) LBIC_TRY(run_chain(m, L_D0, L_COUNT, sd, R, st));
+        else if (flow && dbg_part == 1) LBIC_TRY(run_dec(m, sd, R, st));
+        else if (flow && dbg_part >= 10) {
+            // layers D0 .. D0+k-1 through the dataflow launch, the rest one by one
+            const int k = dbg_part - 10;
+            LBIC_TRY(run_flow(m, L_D0, L_D0 + k, sd, R, st));
+            static const int ids[7] = {L_D0, L_IG0, L_D1, L_IG1, L_D2, L_IG2, L_D3};
+            for (int j = k; j < 7; ++j) {
+                const int id = ids[j];
+                if (id == L_D0) LBIC_TRY(run_gemm(m, L_D0, R, &ws.vYQ, &ws.vT, epi_pregdn(m, sd), st));
+                else if (id == L_D3) { EpiParams e = epi(EPI_RECON, sd); e.zhat = ws.zhat_cl; LBIC_TRY(run_gemm(m, L_D3, R, &ws.vU[2], nullptr, e, st)); }
+                else if (id == L_IG0 || id == L_IG1 || id == L_IG2) LBIC_TRY(run_gdn(m, id, (id - L_IG0) / 2, true, sd, R, st));
+                else LBIC_TRY(run_gemm(m, id, R, &ws.vU[(id - L_D1) / 2], nullptr, epi_pregdn(m, sd), st));
+            }
+        }
+        else if (flow) LBIC_TRY(run_flow(m, L_D0, L_COUNT, sd, R, st));
+        else LBIC_TRY(run_dec(m, sd, R, st));
         return 0;
     };
     if (m->k1 == 3) LBIC_TRY(launch_fill_g0_top(m->L[L_E0].bias, m->E1, n_img, Hb, Wb, ws.G0.hi, ws.G0.lo, st));

@@ -107,6 +107,232 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
         ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Epilogue of one 128 x bn tile by the eight epilogue warps (warps 2..9 of the CTA): per-tile setup (bias slice, row
+// table) while the tile's mainloop is still running, then the accumulator is drained in 32-column groups.
+struct EpiCtx {
+    uint32_t stg;             // staging region (shared address)
+    uint32_t acc_full_bar, acc_empty_bar, full_phase;
+    uint32_t tmem_acc;        // TMEM address of this tile's accumulator (column base)
+    float *sb;                // this tile's bias slice buffer
+    RowTab *rt;
+    const float *stab;
+    uint32_t rank;
+    // dataflow launch only: the epilogue's own side input (GDN pre-activations) is written by another layer of the same
+    // launch; it may be fetched once *dep_cnt >= dep_target (the epilogue warps run ahead of the TMA producer)
+    const int *dep_cnt;
+    int dep_target;
+};
+
+template <bool PAIR>
+__device__ __forceinline__ void ws_tile_epilogue(const EpiParams &ep, int bn, int m0, int n0, const EpiCtx &cx) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ew = warp - 2;                 // 0..7
+    const int q = warp & 3;                  // TMEM lane quarter (warp id % 4)
+    const int sub = ew >> 2;                 // which 16-column chunk of a 32-column group
+    const int et = threadIdx.x - 64;         // 0..255
+    const int rl = q * 32 + lane;
+    const int mode = ep.mode;
+    const bool gdn = (mode == EPI_GDN || mode == EPI_IGDN);
+    const uint32_t stg = cx.stg;
+    const int r = m0 + rl;
+    const bool row_ok = r < ep.R;
+    const int rows_valid = (ep.R - m0) < BM ? (ep.R - m0) : BM;
+    float *sb = cx.sb;
+    // per-tile setup (overlaps the mainloop of this tile): bias slice, row table
+    epi_bar();                           // previous tile's stores have finished reading rt / sbias
+    if (mode != EPI_RAW)
+        for (int i = et; i < bn; i += WS_EPI_THREADS) sb[i] = (n0 + i < ep.cout) ? ep.bias[n0 + i] : 0.0f;
+    if (sub == 0 && row_ok) {
+        const EpiRowDst d = epi_row_dst(ep, r);
+        cx.rt->f32[rl] = reinterpret_cast<unsigned long long>(epi_f32_ptr(ep, d, n0));
+        cx.rt->hilo[rl] = (unsigned long long)(d.hilo + n0);
+        cx.rt->idx[rl] = reinterpret_cast<unsigned long long>(mode == EPI_QUANT && ep.idx ? ep.idx + d.blk * ep.M + n0 : nullptr);
+    }
+    epi_bar();
+    const uint32_t lane_base = cx.tmem_acc + ((uint32_t)(q * 32) << 16);
+    const int ngroups = (bn + GC - 1) / GC;   // the last group may hold a single 16-column chunk
+    // Software pipeline over the 32-column groups: the TMEM load of group g+1 is issued before group g is
+    // finished; in the GDN modes each thread also requests its own row's pre-activations of group g+1 (64
+    // contiguous bytes) one group ahead, so that global-load latency hides behind a whole group of work.
+    const int rsub = lane >> 3, c16 = lane & 7;
+    const bool has_f32 = epi_has_f32(mode) && (mode != EPI_QUANT || ep.sym);
+    const bool has_hilo = epi_has_hilo(mode);
+    auto group_valid = [&](int g) {
+        int nv = ep.cout - (n0 + g * GC);
+        nv = nv < 0 ? 0 : (nv > GC ? GC : nv);
+        return nv > bn - g * GC ? bn - g * GC : nv;
+    };
+    auto chunk_ok = [&](int g) {
+        return row_ok && (n0 + g * GC + sub * 16) < ep.cout && (g * GC + sub * 16) < bn;
+    };
+    // GDN modes: the group's pre-activations arrive by cp.async with coalesced 16-byte lanes (4 rows x 128 B per
+    // warp instruction; a row-per-thread read costs four times the L1 tag lookups and was measurably slower),
+    // two groups ahead, into two swizzled buffers behind the staging region: under a saturated L2 a load
+    // takes longer than one group of epilogue work.
+    const int hl_stride = gdn ? WGDN_STRIDE : WHL_STRIDE;
+    const uint32_t aux_base = stg + BM * WGDN_STRIDE;
+    auto aux_issue = [&](int g) {
+        const int nv = group_valid(g);
+        const uint32_t buf = aux_base + (uint32_t)(g & 1) * WAUX_BUF;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int row = ew * 16 + j * 4 + rsub;
+            const bool valid = row < rows_valid && c16 * 4 < nv;
+            const float *src = valid ? ep.aux + (size_t)(m0 + row) * ep.ld_aux + n0 + g * GC + c16 * 4 : ep.aux;
+            const uint32_t dst = buf + row * 128 + ((uint32_t)(c16 ^ (row & 7)) << 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    uint32_t accA[16], accB[16];
+    if (gdn) {                                       // overlaps the wait for the accumulator
+        if (cx.dep_cnt) {
+            if (et == 0) {
+                uint32_t spins = 0;
+                while (ld_acquire_gpu(cx.dep_cnt) < cx.dep_target) {
+                    __nanosleep(64);
+                    if (++spins > (1u << 24)) __trap();
+                }
+            }
+            epi_bar();
+        }
+        aux_issue(0);
+        if (ngroups > 1) {
+            aux_issue(1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        epi_bar();
+    }
+    mbar_wait(cx.acc_full_bar, cx.full_phase);
+    tc_fence_after();
+    tmem_ld_issue(lane_base + (uint32_t)(sub * 16), accA);
+    for (int g = 0; g < ngroups; ++g) {
+        const int g0 = g * GC;
+        const int nvalid = group_valid(g);
+        const bool even = (g & 1) == 0;
+        const bool ok = chunk_ok(g);
+        EpiOut<16> o;
+        // phase A: this warp's 16-column chunk of the group
+        {
+            const int c = n0 + g0 + sub * 16;
+            EpiPre<16> pre;
+            if (ok) {
+                if (gdn) {
+                    const uint32_t src = aux_base + (uint32_t)(g & 1) * WAUX_BUF + rl * 128;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint4 v = lds128(src + ((uint32_t)((sub * 4 + i) ^ (rl & 7)) << 4));
+                        pre.a[4 * i] = __uint_as_float(v.x); pre.a[4 * i + 1] = __uint_as_float(v.y);
+                        pre.a[4 * i + 2] = __uint_as_float(v.z); pre.a[4 * i + 3] = __uint_as_float(v.w);
+                    }
+                } else {
+                    epi_prefetch<16>(ep, r, c, pre);
+                }
+            }
+            if (even) tmem_ld_wait(accA); else tmem_ld_wait(accB);
+            if (g + 1 < ngroups) {
+                if (even) tmem_ld_issue(lane_base + (uint32_t)(g0 + GC + sub * 16), accB);
+                else tmem_ld_issue(lane_base + (uint32_t)(g0 + GC + sub * 16), accA);
+            } else {
+                // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_remote(cx.acc_empty_bar, 0);
+                    else mbar_arrive(cx.acc_empty_bar);
+                }
+            }
+            if (ok) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(even ? accA[i] : accB[i]);
+                epi_compute<16>(ep, sb + g0 + sub * 16, v, pre, o, cx.stab);
+            }
+        }
+        const int gc = sub * 16;
+        auto stage_hl = [&]() {
+            const uint32_t hrow = stg + rl * hl_stride + gc * 2;
+            sts128(hrow, o.hi[0], o.hi[1], o.hi[2], o.hi[3]);
+            sts128(hrow + 16, o.hi[4], o.hi[5], o.hi[6], o.hi[7]);
+            sts128(hrow + WHL_LO, o.lo[0], o.lo[1], o.lo[2], o.lo[3]);
+            sts128(hrow + WHL_LO + 16, o.lo[4], o.lo[5], o.lo[6], o.lo[7]);
+            if (mode == EPI_QUANT) sts128(stg + rl * WHL_STRIDE + WHL_IDX + gc, o.idx[0], o.idx[1], o.idx[2], o.idx[3]);
+        };
+        auto store_hl = [&]() {
+            const int c8 = lane & 3;                 // 16-byte chunk within the 64-byte plane row
+            const bool is_lo = (lane >> 2) & 1;
+            if (c8 * 8 < nvalid) {
+                h16 *base = (is_lo ? ep.out_lo : ep.out_hi) + g0 + c8 * 8;
+                const uint32_t src = stg + (is_lo ? WHL_LO : 0) + c8 * 16;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int row = ew * 16 + j * 4 + rsub;
+                    if (row < rows_valid) {
+                        const uint4 v = lds128(src + row * hl_stride);
+                        *reinterpret_cast<uint4 *>(base + cx.rt->hilo[row]) = v;
+                    }
+                }
+            }
+            if (mode == EPI_QUANT && ep.idx && c16 < 2 && c16 * 16 < nvalid) {      // 2 x 16 B per row
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int row = ew * 16 + j * 4 + rsub;
+                    if (row < rows_valid) {
+                        const uint4 v = lds128(stg + row * WHL_STRIDE + WHL_IDX + c16 * 16);
+                        *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(cx.rt->idx[row]) + g0 + c16 * 16) = v;
+                    }
+                }
+            }
+        };
+        if (has_f32) {
+            // pass F: stage the fp32 plane, then coalesced stores, 4 rows (128 B each) per warp instruction
+            if (ok) {
+                const uint32_t d = stg + rl * WF_STRIDE + gc * 4;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4)
+                    sts128(d + i * 4, __float_as_uint(o.f[i]), __float_as_uint(o.f[i + 1]),
+                           __float_as_uint(o.f[i + 2]), __float_as_uint(o.f[i + 3]));
+            }
+            epi_bar();
+            if (c16 * 4 < nvalid) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int row = ew * 16 + j * 4 + rsub;
+                    if (row < rows_valid) {
+                        const uint4 v = lds128(stg + row * WF_STRIDE + c16 * 16);
+                        float *dst = reinterpret_cast<float *>(cx.rt->f32[row]) + g0 + c16 * 4;
+                        *reinterpret_cast<uint4 *>(dst) = v;
+                    }
+                }
+            }
+            if (has_hilo) {
+                epi_bar();               // the fp32 stores have read the staging area
+                if (ok) stage_hl();
+                epi_bar();
+                if (nvalid > 0) store_hl();
+            }
+        } else {
+            if (ok) stage_hl();
+            epi_bar();                   // (GDN: every thread has also read its pre-activations of this group)
+            if (gdn && g + 2 < ngroups) aux_issue(g + 2);   // into the buffer this group has just released
+            if (nvalid > 0) store_hl();
+            if (gdn && g + 1 < ngroups) {                   // this thread's share of group g+1 has landed
+                if (g + 2 < ngroups) asm volatile("cp.async.wait_group 1;" ::: "memory");
+                else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+        }
+        if (g + 1 < ngroups) epi_bar();   // stores have read the staging area; next pre-activations visible
+    }
+}
+
 template <bool PAIR>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant__ CUtensorMap tmA0l,
@@ -236,199 +462,15 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
         }
     } else {
         // ---- epilogue warps 2..9 ----------------------------------------------------------------------
-        const int ew = warp - 2;                 // 0..7
-        const int q = warp & 3;                  // TMEM lane quarter (warp id % 4)
-        const int sub = ew >> 2;                 // which 16-column chunk of a 32-column group
-        const int et = threadIdx.x - 64;         // 0..255
-        const int rl = q * 32 + lane;
-        const EpiParams &ep = p.ep;
-        const int mode = ep.mode;
-        const bool gdn = (mode == EPI_GDN || mode == EPI_IGDN);
         uint32_t ti = 0;
         for (int t = tile_first; t < p.total_tiles; t += tile_stride, ++ti) {
             const uint32_t a = ti & 1u;
             const int m0 = (t / p.ntiles_n) * tile_rows + (int)rank * BM, n0 = (t % p.ntiles_n) * p.bn;
-            const int r = m0 + rl;
-            const bool row_ok = r < ep.R;
-            const int rows_valid = (ep.R - m0) < BM ? (ep.R - m0) : BM;
-            float *sb = sbias + a * 256;
-            // per-tile setup (overlaps the mainloop of this tile): bias slice, row table
-            epi_bar();                           // previous tile's stores have finished reading rt / sbias
-            if (mode != EPI_RAW)
-                for (int i = et; i < p.bn; i += WS_EPI_THREADS) sb[i] = (n0 + i < ep.cout) ? ep.bias[n0 + i] : 0.0f;
-            if (sub == 0 && row_ok) {
-                const EpiRowDst d = epi_row_dst(ep, r);
-                rt->f32[rl] = reinterpret_cast<unsigned long long>(epi_f32_ptr(ep, d, n0));
-                rt->hilo[rl] = (unsigned long long)(d.hilo + n0);
-                rt->idx[rl] = reinterpret_cast<unsigned long long>(mode == EPI_QUANT && ep.idx ? ep.idx + d.blk * ep.M + n0 : nullptr);
-            }
-            epi_bar();
-            const uint32_t lane_base = tmem_base + a * WS_ACC_STRIDE + ((uint32_t)(q * 32) << 16);
-            const int ngroups = (p.bn + GC - 1) / GC;   // the last group may hold a single 16-column chunk
-            // Software pipeline over the 32-column groups: the TMEM load of group g+1 is issued before group g is
-            // finished; in the GDN modes each thread also requests its own row's pre-activations of group g+1 (64
-            // contiguous bytes) one group ahead, so that global-load latency hides behind a whole group of work.
-            const int rsub = lane >> 3, c16 = lane & 7;
-            const bool has_f32 = epi_has_f32(mode) && (mode != EPI_QUANT || ep.sym);
-            const bool has_hilo = epi_has_hilo(mode);
-            auto group_valid = [&](int g) {
-                int nv = ep.cout - (n0 + g * GC);
-                nv = nv < 0 ? 0 : (nv > GC ? GC : nv);
-                return nv > p.bn - g * GC ? p.bn - g * GC : nv;
-            };
-            auto chunk_ok = [&](int g) {
-                return row_ok && (n0 + g * GC + sub * 16) < ep.cout && (g * GC + sub * 16) < p.bn;
-            };
-            // GDN modes: the group's pre-activations arrive by cp.async with coalesced 16-byte lanes (4 rows x 128 B per
-            // warp instruction; a row-per-thread read costs four times the L1 tag lookups and was measurably slower),
-            // two groups ahead, into two swizzled buffers behind the staging region: under a saturated L2 a load
-            // takes longer than one group of epilogue work.
-            const int hl_stride = gdn ? WGDN_STRIDE : WHL_STRIDE;
-            const uint32_t aux_base = stg + BM * WGDN_STRIDE;
-            auto aux_issue = [&](int g) {
-                const int nv = group_valid(g);
-                const uint32_t buf = aux_base + (uint32_t)(g & 1) * WAUX_BUF;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int row = ew * 16 + j * 4 + rsub;
-                    const bool valid = row < rows_valid && c16 * 4 < nv;
-                    const float *src = valid ? ep.aux + (size_t)(m0 + row) * ep.ld_aux + n0 + g * GC + c16 * 4 : ep.aux;
-                    const uint32_t dst = buf + row * 128 + ((uint32_t)(c16 ^ (row & 7)) << 4);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-            };
-            uint32_t accA[16], accB[16];
-            if (gdn) {                                       // overlaps the wait for the accumulator
-                aux_issue(0);
-                if (ngroups > 1) {
-                    aux_issue(1);
-                    asm volatile("cp.async.wait_group 1;" ::: "memory");
-                } else {
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
-                }
-                epi_bar();
-            }
-            mbar_wait(acc_full(a), (ti >> 1) & 1u);
-            tc_fence_after();
-            tmem_ld_issue(lane_base + (uint32_t)(sub * 16), accA);
-            for (int g = 0; g < ngroups; ++g) {
-                const int g0 = g * GC;
-                const int nvalid = group_valid(g);
-                const bool even = (g & 1) == 0;
-                const bool ok = chunk_ok(g);
-                EpiOut<16> o;
-                // phase A: this warp's 16-column chunk of the group
-                {
-                    const int c = n0 + g0 + sub * 16;
-                    EpiPre<16> pre;
-                    if (ok) {
-                        if (gdn) {
-                            const uint32_t src = aux_base + (uint32_t)(g & 1) * WAUX_BUF + rl * 128;
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const uint4 v = lds128(src + ((uint32_t)((sub * 4 + i) ^ (rl & 7)) << 4));
-                                pre.a[4 * i] = __uint_as_float(v.x); pre.a[4 * i + 1] = __uint_as_float(v.y);
-                                pre.a[4 * i + 2] = __uint_as_float(v.z); pre.a[4 * i + 3] = __uint_as_float(v.w);
-                            }
-                        } else {
-                            epi_prefetch<16>(ep, r, c, pre);
-                        }
-                    }
-                    if (even) tmem_ld_wait(accA); else tmem_ld_wait(accB);
-                    if (g + 1 < ngroups) {
-                        if (even) tmem_ld_issue(lane_base + (uint32_t)(g0 + GC + sub * 16), accB);
-                        else tmem_ld_issue(lane_base + (uint32_t)(g0 + GC + sub * 16), accA);
-                    } else {
-                        // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) {
-                            if (PAIR) mbar_arrive_remote(acc_empty(a), 0);
-                            else mbar_arrive(acc_empty(a));
-                        }
-                    }
-                    if (ok) {
-                        float v[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(even ? accA[i] : accB[i]);
-                        epi_compute<16>(ep, sb + g0 + sub * 16, v, pre, o, stab);
-                    }
-                }
-                const int gc = sub * 16;
-                auto stage_hl = [&]() {
-                    const uint32_t hrow = stg + rl * hl_stride + gc * 2;
-                    sts128(hrow, o.hi[0], o.hi[1], o.hi[2], o.hi[3]);
-                    sts128(hrow + 16, o.hi[4], o.hi[5], o.hi[6], o.hi[7]);
-                    sts128(hrow + WHL_LO, o.lo[0], o.lo[1], o.lo[2], o.lo[3]);
-                    sts128(hrow + WHL_LO + 16, o.lo[4], o.lo[5], o.lo[6], o.lo[7]);
-                    if (mode == EPI_QUANT) sts128(stg + rl * WHL_STRIDE + WHL_IDX + gc, o.idx[0], o.idx[1], o.idx[2], o.idx[3]);
-                };
-                auto store_hl = [&]() {
-                    const int c8 = lane & 3;                 // 16-byte chunk within the 64-byte plane row
-                    const bool is_lo = (lane >> 2) & 1;
-                    if (c8 * 8 < nvalid) {
-                        h16 *base = (is_lo ? ep.out_lo : ep.out_hi) + g0 + c8 * 8;
-                        const uint32_t src = stg + (is_lo ? WHL_LO : 0) + c8 * 16;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int row = ew * 16 + j * 4 + rsub;
-                            if (row < rows_valid) {
-                                const uint4 v = lds128(src + row * hl_stride);
-                                *reinterpret_cast<uint4 *>(base + rt->hilo[row]) = v;
-                            }
-                        }
-                    }
-                    if (mode == EPI_QUANT && ep.idx && c16 < 2 && c16 * 16 < nvalid) {      // 2 x 16 B per row
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int row = ew * 16 + j * 4 + rsub;
-                            if (row < rows_valid) {
-                                const uint4 v = lds128(stg + row * WHL_STRIDE + WHL_IDX + c16 * 16);
-                                *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(rt->idx[row]) + g0 + c16 * 16) = v;
-                            }
-                        }
-                    }
-                };
-                if (has_f32) {
-                    // pass F: stage the fp32 plane, then coalesced stores, 4 rows (128 B each) per warp instruction
-                    if (ok) {
-                        const uint32_t d = stg + rl * WF_STRIDE + gc * 4;
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4)
-                            sts128(d + i * 4, __float_as_uint(o.f[i]), __float_as_uint(o.f[i + 1]),
-                                   __float_as_uint(o.f[i + 2]), __float_as_uint(o.f[i + 3]));
-                    }
-                    epi_bar();
-                    if (c16 * 4 < nvalid) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int row = ew * 16 + j * 4 + rsub;
-                            if (row < rows_valid) {
-                                const uint4 v = lds128(stg + row * WF_STRIDE + c16 * 16);
-                                float *dst = reinterpret_cast<float *>(rt->f32[row]) + g0 + c16 * 4;
-                                *reinterpret_cast<uint4 *>(dst) = v;
-                            }
-                        }
-                    }
-                    if (has_hilo) {
-                        epi_bar();               // the fp32 stores have read the staging area
-                        if (ok) stage_hl();
-                        epi_bar();
-                        if (nvalid > 0) store_hl();
-                    }
-                } else {
-                    if (ok) stage_hl();
-                    epi_bar();                   // (GDN: every thread has also read its pre-activations of this group)
-                    if (gdn && g + 2 < ngroups) aux_issue(g + 2);   // into the buffer this group has just released
-                    if (nvalid > 0) store_hl();
-                    if (gdn && g + 1 < ngroups) {                   // this thread's share of group g+1 has landed
-                        if (g + 2 < ngroups) asm volatile("cp.async.wait_group 1;" ::: "memory");
-                        else asm volatile("cp.async.wait_group 0;" ::: "memory");
-                    }
-                }
-                if (g + 1 < ngroups) epi_bar();   // stores have read the staging area; next pre-activations visible
-            }
+            EpiCtx c;
+            c.stg = stg; c.acc_full_bar = acc_full(a); c.acc_empty_bar = acc_empty(a); c.full_phase = (ti >> 1) & 1u;
+            c.tmem_acc = tmem_base + a * WS_ACC_STRIDE; c.sb = sbias + a * 256; c.rt = rt; c.stab = stab; c.rank = rank;
+            c.dep_cnt = nullptr; c.dep_target = 0;
+            ws_tile_epilogue<PAIR>(p.ep, p.bn, m0, n0, c);
         }
     }
     tc_fence_before();
@@ -440,6 +482,227 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
             asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Dataflow form: ONE launch runs a whole range of layers of a wavefront step.
+//
+// With one launch per layer every launch ends with the epilogue of its last wave of tiles running alone (~12 us of
+// a ~70 us launch), pays a prologue, and rounds its tile count up to whole waves of 74 CTA pairs.  Here the tiles of all
+// layers form one list in layer order, the persistent CTA pairs walk it round-robin, and the only synchronisation
+// between layers is per 256-row block: a tile of layer l may load its operands once every tile of the layers it reads
+// from has been stored for the same row block (a counter per (layer, row block), bumped by each CTA after its stores
+// and a __threadfence, polled with ld.acquire by the TMA producer).  A pair only ever waits for tiles with a smaller
+// index, and every pair walks the list in order, so the scheme cannot deadlock.  Same tiles, same arithmetic, same
+// results as the per-layer launches.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int FLOW_MAX_LAYERS = 18;
+constexpr int FLOW_SLOT = 2 * A_PLANE + 2 * (WS_MAX_BN / 2) * BK * 2;   // 56 KiB: 128 activation rows + 96 weight rows, hi + lo
+constexpr int FLOW_STAGES = 3;
+constexpr int FLOW_TAIL = WS_TAIL + 256;    // + the current layer's EpiParams
+constexpr int FLOW_THREADS = WS_THREADS + 32;   // + one warp that publishes finished tiles (the gpu-scope release
+                                                // waits for the tile's stores to drain; the epilogue warps do not)
+
+struct FlowParams {
+    const ChainLayer *layers;     // device table indexed by absolute layer id
+    int *counters;                // [n_layers][n_rb], zero at launch
+    int l0, n_layers, n_rb, R, variant, total_tiles;
+    StepDesc step;
+    int tile_begin[FLOW_MAX_LAYERS + 1];
+    int ntn[FLOW_MAX_LAYERS];     // column tiles per layer
+    int dep[FLOW_MAX_LAYERS][2];  // relative layer indices this layer reads from, -1 = none
+};
+
+__global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowParams p) {
+    static_assert(sizeof(EpiParams) <= 256, "EpiParams must fit its shared-memory slot");
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t ring = (raw + 1023u) & ~1023u;
+    const uint32_t stg = ring + FLOW_STAGES * FLOW_SLOT;
+    const uint32_t bars = stg + WGDN_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (MAX_STAGES + s); };
+    auto acc_full = [&](int a) { return bars + 8u * (2 * MAX_STAGES + a); };
+    auto acc_empty = [&](int a) { return bars + 8u * (2 * MAX_STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * MAX_STAGES + 4);
+    auto tile_done = [&](int a) { return bars + 8u * (2 * MAX_STAGES + 6 + a); };
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - raw));
+    float *sbias = reinterpret_cast<float *>(smem_raw + (bars + WS_BAR_BLOCK - raw));        // [2][256]
+    RowTab *rt = reinterpret_cast<RowTab *>(smem_raw + (bars + WS_BAR_BLOCK + 2048 - raw));
+    float *stab = reinterpret_cast<float *>(rt + 1);
+    EpiParams *s_ep = reinterpret_cast<EpiParams *>(stab + 64);
+    {
+        const float *gtab = p.layers[p.l0].ep.scale_tab;
+        if (gtab && threadIdx.x < 64) stab[threadIdx.x] = gtab[threadIdx.x];
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int tile_first = (int)(blockIdx.x >> 1), tile_stride = (int)(gridDim.x >> 1);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < FLOW_STAGES; ++s) {
+            mbar_init(full_bar(s), 2);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(acc_full(a), 1);
+            mbar_init(acc_empty(a), 2 * (WS_EPI_THREADS / 32));
+            mbar_init(tile_done(a), WS_EPI_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            int li = 0;
+            for (int t = tile_first; t < p.total_tiles; t += tile_stride) {
+                while (t >= p.tile_begin[li + 1]) ++li;
+                const ChainLayer &Lr = p.layers[p.l0 + li];
+                const int bn = Lr.bn_v[p.variant], ntn = p.ntn[li], w_rows = bn / 2;
+                const int lt = t - p.tile_begin[li];
+                const int rb = lt / ntn;
+                const int m0 = rb * (2 * BM) + (int)rank * BM;
+                const int n0 = (lt - rb * ntn) * bn + (int)rank * w_rows;
+                // wait until the layers this one reads from have stored this row block (both CTAs of every pair)
+                for (int d = 0; d < 2; ++d) {
+                    const int dl = p.dep[li][d];
+                    if (dl < 0) continue;
+                    const int *cnt = p.counters + (size_t)dl * p.n_rb + rb;
+                    const int target = 2 * p.ntn[dl];
+                    uint32_t spins = 0;
+                    while (ld_acquire_gpu(cnt) < target) {
+                        __nanosleep(64);
+                        if (++spins > (1u << 24)) __trap();     // a broken dependency must fail the launch, not hang
+                    }
+                }
+                asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores of other CTAs -> our TMA reads
+                const int kb0 = Lr.kb[0], nkb = kb0 + (Lr.nseg > 1 ? Lr.kb[1] : 0);
+                const uint32_t w_plane = (uint32_t)w_rows * (BK * 2);
+                const uint32_t stage_tx = (2 * A_PLANE + 2 * w_plane) * 2u;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % FLOW_STAGES;
+                    const uint32_t ph = (it / FLOW_STAGES) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t sa = ring + s * FLOW_SLOT;
+                    const int seg = kb >= kb0 ? 1 : 0;
+                    const int kk = (seg ? kb - kb0 : kb) * BK;
+                    if (rank == 0) mbar_expect_tx(full_bar(s), stage_tx);
+                    else mbar_arrive_remote(full_bar(s), 0);
+                    tma_load_2d_pair(sa, &Lr.tmA[seg][0], full_bar(s), kk, m0);
+                    tma_load_2d_pair(sa + A_PLANE, &Lr.tmA[seg][1], full_bar(s), kk, m0);
+                    tma_load_2d_pair(sa + 2 * A_PLANE, &Lr.tmW[p.variant][seg][0], full_bar(s), kk, n0);
+                    tma_load_2d_pair(sa + 2 * A_PLANE + w_plane, &Lr.tmW[p.variant][seg][1], full_bar(s), kk, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            uint32_t it = 0, ti = 0;
+            int li = 0;
+            for (int t = tile_first; t < p.total_tiles; t += tile_stride, ++ti) {
+                while (t >= p.tile_begin[li + 1]) ++li;
+                const ChainLayer &Lr = p.layers[p.l0 + li];
+                const int bn = Lr.bn_v[p.variant];
+                const int nkb = Lr.kb[0] + (Lr.nseg > 1 ? Lr.kb[1] : 0);
+                const uint32_t w_plane = (uint32_t)(bn / 2) * (BK * 2);
+                const uint32_t idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+                const uint32_t a = ti & 1u;
+                mbar_wait(acc_empty(a), ((ti >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_acc = tmem_base + a * WS_ACC_STRIDE;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % FLOW_STAGES;
+                    const uint32_t ph = (it / FLOW_STAGES) & 1u;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = ring + s * FLOW_SLOT;
+                    const uint64_t a_hi = make_smem_desc(sa);
+                    const uint64_t a_lo = make_smem_desc(sa + A_PLANE);
+                    const uint64_t w_hi = make_smem_desc(sa + 2 * A_PLANE);
+                    const uint64_t w_lo = make_smem_desc(sa + 2 * A_PLANE + w_plane);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) umma_f16_pair(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) umma_f16_pair(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) umma_f16_pair(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
+                    umma_commit_pair(empty_bar(s));
+                }
+                umma_commit_pair(acc_full(a));
+            }
+        }
+    } else if (warp == 10) {
+        // ---- publisher: tile (layer, row block) of this CTA is stored -> bump its counter with gpu-scope release ----
+        if (lane == 0) {
+            uint32_t ti = 0;
+            int li = 0;
+            for (int t = tile_first; t < p.total_tiles; t += tile_stride, ++ti) {
+                while (t >= p.tile_begin[li + 1]) ++li;
+                const int rb = (t - p.tile_begin[li]) / p.ntn[li];
+                mbar_wait(tile_done(ti & 1u), (ti >> 1) & 1u);       // all eight epilogue warps have issued their stores
+                asm volatile("fence.proxy.async;" ::: "memory");
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.counters + (size_t)li * p.n_rb + rb) : "memory");
+            }
+        }
+    } else {
+        // ---- epilogue warps 2..9 ----------------------------------------------------------------------
+        const int et = threadIdx.x - 64;
+        uint32_t ti = 0;
+        int li = 0, cur = -1;
+        for (int t = tile_first; t < p.total_tiles; t += tile_stride, ++ti) {
+            while (t >= p.tile_begin[li + 1]) ++li;
+            const ChainLayer &Lr = p.layers[p.l0 + li];
+            const int bn = Lr.bn_v[p.variant], ntn = p.ntn[li];
+            const int lt = t - p.tile_begin[li];
+            const int rb = lt / ntn;
+            const int m0 = rb * (2 * BM) + (int)rank * BM, n0 = (lt - rb * ntn) * bn;
+            if (li != cur) {
+                // a new layer: its epilogue description, with this launch's row count and step, into shared memory
+                if (cur >= 0) epi_bar();     // every epilogue thread is past the previous tile (which read the old copy)
+                constexpr int NW = (int)(sizeof(EpiParams) / 4);
+                constexpr int OFF_R = (int)(offsetof(EpiParams, R) / 4), OFF_STEP = (int)(offsetof(EpiParams, step) / 4);
+                constexpr int NSTEP = (int)(sizeof(StepDesc) / 4);
+                const uint32_t *g = reinterpret_cast<const uint32_t *>(&Lr.ep);
+                const uint32_t *sw = reinterpret_cast<const uint32_t *>(&p.step);
+                if (et < NW) {
+                    uint32_t w = g[et];
+                    if (et == OFF_R) w = (uint32_t)p.R;
+                    else if (et >= OFF_STEP && et < OFF_STEP + NSTEP) w = sw[et - OFF_STEP];
+                    reinterpret_cast<uint32_t *>(s_ep)[et] = w;
+                }
+                cur = li;
+                epi_bar();
+            }
+            const uint32_t a = ti & 1u;
+            EpiCtx c;
+            c.stg = stg; c.acc_full_bar = acc_full(a); c.acc_empty_bar = acc_empty(a); c.full_phase = (ti >> 1) & 1u;
+            c.tmem_acc = tmem_base + a * WS_ACC_STRIDE; c.sb = sbias + a * 256; c.rt = rt; c.stab = stab; c.rank = rank;
+            const int dl = p.dep[li][0];
+            c.dep_cnt = dl >= 0 ? p.counters + (size_t)dl * p.n_rb + rb : nullptr;
+            c.dep_target = dl >= 0 ? 2 * p.ntn[dl] : 0;
+            ws_tile_epilogue<true>(*s_ep, bn, m0, n0, c);
+            // this CTA's part of tile (layer, row block) is stored: hand it to the publisher warp
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tile_done(a));
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+bool g_flow_attr = false;
 
 bool g_ws_attr[2] = {false, false};
 
@@ -520,6 +783,69 @@ int gemm_ws_launch(const GemmCall &g, cudaStream_t st, int pair) {
     else
         LBIC_CUDA(cudaLaunchKernelEx(&cfg, gemm_ws_kernel<false>, *g.A[0].tm_hi, *g.A[0].tm_lo, *g.W[0].tm_hi, *g.W[0].tm_lo,
                                      *g.A[s1].tm_hi, *g.A[s1].tm_lo, *g.W[s1].tm_hi, *g.W[s1].tm_lo, p));
+    count_launch(0);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Layers [l0, l1) of one wavefront step in a single dataflow launch.  dep: for every absolute layer id the (up to two)
+// layer ids it reads from (-1 = none); layers outside [l0, l1) count as already complete.
+int gemm_flow_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int l0, int l1, const int (*dep)[2], int R,
+                     const StepDesc &step, int *d_counters, size_t counters_cap, cudaStream_t st) {
+    if (R <= 0 || l1 <= l0) return 0;
+    LBIC_TRY(gemm_tc_init());
+    const int nl = l1 - l0;
+    if (nl > FLOW_MAX_LAYERS) return lbic_fail(LBIC_ERR_INVALID, "flow kernel: too many layers");
+    if (!g_flow_attr) {
+        LBIC_CUDA(cudaFuncSetAttribute(gemm_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        g_flow_attr = true;
+    }
+    FlowParams p;
+    memset(&p, 0, sizeof(p));
+    p.layers = d_layers; p.counters = d_counters; p.l0 = l0; p.n_layers = nl; p.R = R; p.step = step;
+    p.variant = LBIC_PAIR_VARIANT;
+    p.n_rb = (R + 2 * BM - 1) / (2 * BM);
+    if ((size_t)nl * p.n_rb > counters_cap) return lbic_fail(LBIC_ERR_INVALID, "flow kernel: counter buffer too small");
+    int total = 0;
+    for (int i = 0; i < nl; ++i) {
+        const ChainLayer &L = h_layers[l0 + i];
+        const int bn = L.bn_v[LBIC_PAIR_VARIANT];
+        if (bn % 16 || bn < 16 || bn > WS_MAX_BN) return lbic_fail(LBIC_ERR_INVALID, "flow kernel: bad tile N %d", bn);
+        p.ntn[i] = (L.cout + bn - 1) / bn;
+        p.tile_begin[i] = total;
+        total += p.n_rb * p.ntn[i];
+        for (int d = 0; d < 2; ++d) {
+            const int a = dep[l0 + i][d];
+            p.dep[i][d] = (a >= l0 && a < l0 + i) ? a - l0 : -1;
+        }
+    }
+    p.tile_begin[nl] = total;
+    p.total_tiles = total;
+    LBIC_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(int) * (size_t)nl * p.n_rb, st));
+    int n_sm = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int grid = 2 * (total < n_sm / 2 ? total : n_sm / 2);
+    const size_t smem = 1024 + (size_t)FLOW_STAGES * FLOW_SLOT + WGDN_BYTES + FLOW_TAIL;
+    if (smem > (size_t)SMEM_LIMIT) return lbic_fail(LBIC_ERR_INVALID, "flow kernel: shared memory budget exceeded");
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(FLOW_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+    // no programmatic dependent launch here: the counters are zeroed by a memset node right before the kernel
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    LBIC_CUDA(cudaLaunchKernelEx(&cfg, gemm_flow_kernel, p));
     count_launch(0);
     LBIC_CUDA(cudaGetLastError());
     return 0;

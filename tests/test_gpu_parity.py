@@ -286,7 +286,7 @@ def test_chain_kernel_equals_per_layer_launches(dev, cfgname):
             zdec = m.decompress_batch(got[0], x.shape, lanes=0)
             assert torch.equal(zdec, zdec_ref) and torch.equal(zdec, got[1])
     finally:
-        m.set_option("chain", 1)
+        m.set_option("chain", 0)
         m.set_option("cluster", 0)
 
 
@@ -313,6 +313,31 @@ def test_warp_specialised_kernel_equals_per_tile_kernel(dev, cfgname):
     finally:
         m.set_option("ws", 1)
         m.set_option("pair", 1)
+
+
+@pytest.mark.parametrize("cfgname", ["B8_lowrate", "B4_highrate", "B16_lowrate"])
+def test_dataflow_launch_equals_per_layer_launches(dev, cfgname):
+    """gemm_flow_kernel (all layers of a step in one launch, row-block dependency counters instead of kernel boundaries)
+    must be bit-identical to one launch per layer, encode and decode, including ragged last row blocks."""
+    m = get_model(cfgname, 1337, False, dev)
+    B = m.B
+    from lbic_b200.layout import arrange_block_pixels_to_channel_dim
+    img = weights.synth_images(37, 7 * B, 12 * B, seed0=57)
+    x = arrange_block_pixels_to_channel_dim((img - 0.5).to(dev), B)
+    try:
+        m.set_option("flow", 0)
+        ref = m.compress_batch(x, lanes=0, return_symbols=True)
+        zref = m.decompress_batch(ref[0], x.shape, lanes=0)
+        m.set_option("flow", 2)
+        got = m.compress_batch(x, lanes=0, return_symbols=True)
+        assert got[0] == ref[0], "bitstreams differ"
+        assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2]) and torch.equal(got[3], ref[3])
+        zdec = m.decompress_batch(got[0], x.shape, lanes=0)
+        assert torch.equal(zdec, zref) and torch.equal(zdec, got[1])
+        zv, iv = m.validate_recu_reco(x)
+        assert torch.equal(zv, got[1])
+    finally:
+        m.set_option("flow", 1)
 
 
 @pytest.mark.parametrize("cfgname,H,W", [("B8_lowrate", 512, 768), ("B4_highrate", 128, 192), ("B16_lowrate", 256, 256)])
