@@ -845,6 +845,18 @@ int gemm_flow_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int
     // no programmatic dependent launch here: the counters are zeroed by a memset node right before the kernel
     cfg.attrs = attr;
     cfg.numAttrs = na;
+    {
+        // every CTA pair must be resident at once (a pair waits for tiles owned by the others): checked once
+        static int max_clusters = -1;
+        if (max_clusters < 0) {
+            int nc = 0;
+            if (cudaOccupancyMaxActiveClusters(&nc, gemm_flow_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); nc = 0; }
+            max_clusters = nc;
+        }
+        if (max_clusters * 2 < grid)
+            return lbic_fail(LBIC_ERR_INVALID, "flow kernel: only %d CTA pairs can be co-resident, %d needed (set LBIC_OPT_FLOW to 0)",
+                             max_clusters, grid / 2);
+    }
     LBIC_CUDA(cudaLaunchKernelEx(&cfg, gemm_flow_kernel, p));
     count_launch(0);
     LBIC_CUDA(cudaGetLastError());
