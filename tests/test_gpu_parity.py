@@ -480,6 +480,45 @@ def test_open_loop_forward_matches_reference_golden(dev, case):
     assert torch.equal(xb[2], xhat[0]) and torch.equal(ib[1], info[0])
 
 
+@pytest.mark.parametrize("lanes", [1, 0])
+def test_image_codec_roundtrip_on_ragged_size(dev, lanes, tmp_path):
+    """whole-image encode / decode through the self-describing container on an image whose size is
+    not a multiple of the block size (replicate padding AGENT:583-586, crop after depth->space), plus PNG in / out."""
+    from lbic_b200.codec import ImageCodec, unpack_container
+    m = get_model("B8_lowrate", 1337, False, dev)
+    codec = ImageCodec(m, lanes=lanes)
+    H, W = 203, 261                                             # 26 x 33 blocks after padding to 208 x 264
+    img = weights.synth_images(1, H, W, seed0=5)[0]
+    blob = codec.encode(img)
+    meta, payload = unpack_container(blob)
+    assert (meta["H"], meta["W"], meta["B"], meta["lanes"]) == (H, W, 8, lanes)
+    rec = codec.decode(blob)
+    assert rec.shape == (1, 3, H, W) and float(rec.min()) >= 0.0 and float(rec.max()) <= 1.0
+    # the same numbers as driving the model by hand the way eval_model does
+    from lbic_b200.codec import pad_to_blocks
+    x = lbic_b200.arrange_block_pixels_to_channel_dim(pad_to_blocks(img[None].to(dev) - 0.5, 8), 8)
+    if lanes == 1:
+        stream, zhat = m.compress(x, [1, 1, 1], m.M)
+        assert stream == payload
+    else:
+        zhat = m.compress_batch(x, lanes=0)[1]
+    want = (lbic_b200.arrange_channel_dim_to_block_pixels(zhat, 8)[:, :, :H, :W] + 0.5).clamp(0, 1)
+    assert torch.equal(rec, want)
+    ev = codec.evaluate(img)
+    assert ev["bytes"] == len(payload) and abs(ev["bpp"] - 8.0 * len(payload) / (H * W)) < 1e-12
+    assert "msssim" in ev and 0.0 < ev["msssim"] <= 1.0
+    # files
+    from PIL import Image
+    src = tmp_path / "in.png"
+    Image.fromarray((img * 255).round().to(torch.uint8).permute(1, 2, 0).numpy(), "RGB").save(src)
+    blob2 = codec.encode_file(str(src))
+    codec.decode_to_file(blob2, str(tmp_path / "out.png"))
+    with Image.open(tmp_path / "out.png") as im:
+        assert im.size == (W, H)
+    with pytest.raises(ValueError):
+        ImageCodec(get_model("B16_lowrate", 1337, False, dev)).decode(blob)
+
+
 def test_layout_kernels_match_reference_definition(dev):
     from lbic_b200.layout import arrange_block_pixels_to_channel_dim, arrange_channel_dim_to_block_pixels
     from oracle import nets
