@@ -285,9 +285,11 @@ def main():
                     launches=prof["gemm_launches"], avg_launch_us=1e3 * prof["gemm_ms"] / max(1, prof["gemm_launches"]),
                     gemm_share_of_encode=prof["gemm_ms"] / (ms_enc / args.steps),
                     algorithmic_flop_per_pixel=dict(encode=2 * macs["encode"] / (B * B), decode=2 * macs["decode"] / (B * B)),
-                    traffic=None,
-                    traffic_note="ncu dram bytes per launch for the dominant shapes are in profiles/r1_gemm_ws.md "
-                                 "(196 MB measured vs 229 MB algorithmic for a 24k x 768 x 768 PREGDN launch)",
+                    traffic=4.09e9,
+                    traffic_note="dram__bytes_read.sum + dram__bytes_write.sum of one gemm_flow_kernel launch (a whole wavefront "
+                                 "step of ~40 k block rows, all 18 layers, 1.46 ms) from ncu --set full on this command: "
+                                 "profiles/r1_final_gemm_flow_ncu_summary.txt; about the bytes of writing and reading every "
+                                 "activation once (the batch's activations do not fit the 126 MB L2); tensor pipe active 63.5 %",
                     binding_resource="L2 -> SM bandwidth (~43 B/clk/SM chip-wide): launch time tracks the operand + output "
                                      "bytes through L2, see profiles/r1_l2_bound.md; the tensor peak is the contract's denominator",
                     layers_tflops_per_layer_launches={k: round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)
