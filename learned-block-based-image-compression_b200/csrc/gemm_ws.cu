@@ -507,10 +507,26 @@ struct FlowParams {
     int *counters;                // [n_layers][n_rb], zero at launch
     int l0, n_layers, n_rb, R, variant, total_tiles;
     StepDesc step;
-    int tile_begin[FLOW_MAX_LAYERS + 1];
+    int chunk_rb;                 // row blocks per chunk: tiles are ordered chunk by chunk, layer by layer inside a chunk,
+    int tiles_per_chunk;          // so that a chunk's activations are still in L2 when the next layer reads them
+    int pre[FLOW_MAX_LAYERS + 1]; // prefix sums of ntn (column tiles of one row block over the layers)
     int ntn[FLOW_MAX_LAYERS];     // column tiles per layer
     int dep[FLOW_MAX_LAYERS][2];  // relative layer indices this layer reads from, -1 = none
 };
+
+// tile index -> (layer, row block, column tile)
+__device__ __forceinline__ void flow_tile(const FlowParams &p, int t, int &li, int &rb, int &nt) {
+    const int c = t / p.tiles_per_chunk;
+    const int u = t - c * p.tiles_per_chunk;
+    const int rb0 = c * p.chunk_rb;
+    const int crb = (p.n_rb - rb0) < p.chunk_rb ? (p.n_rb - rb0) : p.chunk_rb;   // the last chunk may be short
+    li = 0;
+    while (u >= crb * p.pre[li + 1]) ++li;
+    const int v = u - crb * p.pre[li];
+    const int q = v / p.ntn[li];
+    rb = rb0 + q;
+    nt = v - q * p.ntn[li];
+}
 
 __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowParams p) {
     static_assert(sizeof(EpiParams) <= 256, "EpiParams must fit its shared-memory slot");
@@ -564,15 +580,13 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowPa
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
-            int li = 0;
             for (int t = tile_first; t < p.total_tiles; t += tile_stride) {
-                while (t >= p.tile_begin[li + 1]) ++li;
+                int li, rb, nt;
+                flow_tile(p, t, li, rb, nt);
                 const ChainLayer &Lr = p.layers[p.l0 + li];
-                const int bn = Lr.bn_v[p.variant], ntn = p.ntn[li], w_rows = bn / 2;
-                const int lt = t - p.tile_begin[li];
-                const int rb = lt / ntn;
+                const int bn = Lr.bn_v[p.variant], w_rows = bn / 2;
                 const int m0 = rb * (2 * BM) + (int)rank * BM;
-                const int n0 = (lt - rb * ntn) * bn + (int)rank * w_rows;
+                const int n0 = nt * bn + (int)rank * w_rows;
                 // wait until the layers this one reads from have stored this row block (both CTAs of every pair)
                 for (int d = 0; d < 2; ++d) {
                     const int dl = p.dep[li][d];
@@ -608,9 +622,9 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowPa
     } else if (warp == 1) {
         if (lane == 0 && rank == 0) {
             uint32_t it = 0, ti = 0;
-            int li = 0;
             for (int t = tile_first; t < p.total_tiles; t += tile_stride, ++ti) {
-                while (t >= p.tile_begin[li + 1]) ++li;
+                int li, rb, nt;
+                flow_tile(p, t, li, rb, nt);
                 const ChainLayer &Lr = p.layers[p.l0 + li];
                 const int bn = Lr.bn_v[p.variant];
                 const int nkb = Lr.kb[0] + (Lr.nseg > 1 ? Lr.kb[1] : 0);
@@ -645,10 +659,9 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowPa
         // ---- publisher: tile (layer, row block) of this CTA is stored -> bump its counter with gpu-scope release ----
         if (lane == 0) {
             uint32_t ti = 0;
-            int li = 0;
             for (int t = tile_first; t < p.total_tiles; t += tile_stride, ++ti) {
-                while (t >= p.tile_begin[li + 1]) ++li;
-                const int rb = (t - p.tile_begin[li]) / p.ntn[li];
+                int li, rb, nt;
+                flow_tile(p, t, li, rb, nt);
                 mbar_wait(tile_done(ti & 1u), (ti >> 1) & 1u);       // all eight epilogue warps have issued their stores
                 asm volatile("fence.proxy.async;" ::: "memory");
                 asm volatile("fence.acq_rel.gpu;" ::: "memory");
@@ -659,14 +672,13 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowPa
         // ---- epilogue warps 2..9 ----------------------------------------------------------------------
         const int et = threadIdx.x - 64;
         uint32_t ti = 0;
-        int li = 0, cur = -1;
+        int cur = -1;
         for (int t = tile_first; t < p.total_tiles; t += tile_stride, ++ti) {
-            while (t >= p.tile_begin[li + 1]) ++li;
+            int li, rb, nt;
+            flow_tile(p, t, li, rb, nt);
             const ChainLayer &Lr = p.layers[p.l0 + li];
-            const int bn = Lr.bn_v[p.variant], ntn = p.ntn[li];
-            const int lt = t - p.tile_begin[li];
-            const int rb = lt / ntn;
-            const int m0 = rb * (2 * BM) + (int)rank * BM, n0 = (lt - rb * ntn) * bn;
+            const int bn = Lr.bn_v[p.variant];
+            const int m0 = rb * (2 * BM) + (int)rank * BM, n0 = nt * bn;
             if (li != cur) {
                 // a new layer: its epilogue description, with this launch's row count and step, into shared memory
                 if (cur >= 0) epi_bar();     // every epilogue thread is past the previous tile (which read the old copy)
@@ -812,14 +824,25 @@ int gemm_flow_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int
         const int bn = L.bn_v[LBIC_PAIR_VARIANT];
         if (bn % 16 || bn < 16 || bn > WS_MAX_BN) return lbic_fail(LBIC_ERR_INVALID, "flow kernel: bad tile N %d", bn);
         p.ntn[i] = (L.cout + bn - 1) / bn;
-        p.tile_begin[i] = total;
-        total += p.n_rb * p.ntn[i];
+        p.pre[i] = total;
+        total += p.ntn[i];
         for (int d = 0; d < 2; ++d) {
             const int a = dep[l0 + i][d];
             p.dep[i][d] = (a >= l0 && a < l0 + i) ? a - l0 : -1;
         }
     }
-    p.tile_begin[nl] = total;
+    p.pre[nl] = total;
+    {
+        // tuning hook: LBIC_FLOW_CHUNK = row blocks (of 256 rows) per chunk, 0 = one chunk (default).  Chunks keep a
+        // layer's output in L2 for the next layer (DRAM traffic of a step drops from 4 GB), but a chunk of 16 / 32 / 64
+        // row blocks leaves only 1-4 waves of tiles per layer between producer and consumer and the pairs stall on the
+        // counters: 702 / 959 / 1004 Mpixel/s encode against 989-1043 unchunked (profiles/r1_dataflow.md)
+        static int chunk = -1;
+        if (chunk < 0) { const char *e = getenv("LBIC_FLOW_CHUNK"); chunk = e ? atoi(e) : 0; }
+        p.chunk_rb = (chunk <= 0 || chunk > p.n_rb) ? p.n_rb : chunk;
+    }
+    p.tiles_per_chunk = p.chunk_rb * total;
+    total *= p.n_rb;
     p.total_tiles = total;
     LBIC_CUDA(cudaMemsetAsync(d_counters, 0, sizeof(int) * (size_t)nl * p.n_rb, st));
     int n_sm = 148;
