@@ -1132,22 +1132,7 @@ extern "C" int lbic_decode(lbic_model *m, const uint8_t *streams, const uint32_t
         }
         LBIC_TRY(launch_rans_dec_step(m->tables, ws.dec_states, ws.lane_ptr, L, sd, R, m->M, ws.KSI, ws.ldKSI, ws.YQ.hi,
                                       ws.YQ.lo, ws.YQ.ld, sym_out ? ws.sym : nullptr, st));
-        static const int dbg_part = getenv("LBIC_FLOW_PART") ? atoi(getenv("LBIC_FLOW_PART")) : 0;   // debugging aid
         if (chain) LBIC_TRY(run_chain(m, L_D0, L_COUNT, sd, R, st));
-        else if (flow && dbg_part == 1) LBIC_TRY(run_dec(m, sd, R, st));
-        else if (flow && dbg_part >= 10) {
-            // layers D0 .. D0+k-1 through the dataflow launch, the rest one by one
-            const int k = dbg_part - 10;
-            LBIC_TRY(run_flow(m, L_D0, L_D0 + k, sd, R, st));
-            static const int ids[7] = {L_D0, L_IG0, L_D1, L_IG1, L_D2, L_IG2, L_D3};
-            for (int j = k; j < 7; ++j) {
-                const int id = ids[j];
-                if (id == L_D0) LBIC_TRY(run_gemm(m, L_D0, R, &ws.vYQ, &ws.vT, epi_pregdn(m, sd), st));
-                else if (id == L_D3) { EpiParams e = epi(EPI_RECON, sd); e.zhat = ws.zhat_cl; LBIC_TRY(run_gemm(m, L_D3, R, &ws.vU[2], nullptr, e, st)); }
-                else if (id == L_IG0 || id == L_IG1 || id == L_IG2) LBIC_TRY(run_gdn(m, id, (id - L_IG0) / 2, true, sd, R, st));
-                else LBIC_TRY(run_gemm(m, id, R, &ws.vU[(id - L_D1) / 2], nullptr, epi_pregdn(m, sd), st));
-            }
-        }
         else if (flow) LBIC_TRY(run_flow(m, L_D0, L_COUNT, sd, R, st));
         else LBIC_TRY(run_dec(m, sd, R, st));
         return 0;

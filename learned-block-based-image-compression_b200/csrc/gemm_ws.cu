@@ -10,7 +10,7 @@
 //   warps 2..9      epilogue of tile i-1 from the other TMEM buffer, in 32-column groups staged through a small
 //                   dedicated shared-memory area (so the ring keeps streaming), then coalesced row stores
 //
-// Tiles are 128 x bn with bn <= 192 (2 stages of 80 KiB + 44 KiB staging fit the 227 KiB of shared memory).  Same
+// Single-CTA tiles are 128 x bn with bn <= 192 (2 stages of 80 KiB + 22 KiB staging, 51 KiB in the GDN modes).  Same
 // operand planes, same k order and same epilogue arithmetic as gemm_tc_kernel: results are bit-identical.
 //
 // PAIR = true is the CTA-pair form (cluster of 2, tcgen05 cta_group::2).  The single-CTA kernel turned out to be bound
@@ -19,7 +19,10 @@
 // tile: each CTA loads its own 128 activation rows but only HALF of the weight tile, and the tensor cores of both SMs
 // read both halves, which cuts the bytes per flop by 30 %.  The leader CTA (rank 0) issues every MMA; full barriers live
 // in the leader, empty / acc_full barriers are signalled in both CTAs by multicast commits, and both epilogues report
-// to the leader's acc_empty barrier.
+// to the leader's acc_empty barrier.  Pair tiles are up to 256 wide with 3 stages of 56-64 KiB.
+//
+// gemm_flow_kernel (further down) is the same machinery with the layer boundaries removed: one launch per wavefront
+// step, the tiles of all layers in one list, layers ordered per 256-row block by global counters.
 #include "tc_common.cuh"
 
 #include <cstdio>
