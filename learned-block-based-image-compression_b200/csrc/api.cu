@@ -513,7 +513,7 @@ const int FLOW_DEP[L_COUNT][2] = {
 
 bool flow_applies(const lbic_model *m, int R) {
     return m->gemm_core == 0 && !m->use_chain && m->use_pair && m->use_flow && !m->force_bn &&
-           (m->use_flow == 2 || (R >= m->flow_min_rows && R <= m->flow_max_rows));
+           (m->use_flow == 2 || (R >= m->flow_min_rows && R <= m->flow_max_rows)) && gemm_flow_supported();
 }
 
 int run_flow(lbic_model *m, int l0, int l1, const StepDesc &sd, int R, cudaStream_t st) {

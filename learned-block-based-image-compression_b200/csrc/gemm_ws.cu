@@ -803,6 +803,37 @@ int gemm_ws_launch(const GemmCall &g, cudaStream_t st, int pair) {
     return 0;
 }
 
+// Every CTA pair of the dataflow launch must be resident at once (a pair waits for tiles owned by the others): true on a
+// whole B200, not necessarily on a partitioned or shared one.  Checked once; callers fall back to per-layer launches.
+int gemm_flow_supported() {
+    static int ok = -1;
+    if (ok >= 0) return ok;
+    ok = 0;
+    if (gemm_tc_init() != 0) return ok;
+    if (cudaFuncSetAttribute(gemm_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
+        cudaGetLastError();
+        return ok;
+    }
+    g_flow_attr = true;
+    int dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(n_sm / 2 * 2, 1, 1);
+    cfg.blockDim = dim3(FLOW_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = 1024 + (size_t)FLOW_STAGES * FLOW_SLOT + WGDN_BYTES + FLOW_TAIL;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, gemm_flow_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); nc = 0; }
+    ok = (nc * 2 >= n_sm / 2 * 2) ? 1 : 0;
+    return ok;
+}
+
 // Layers [l0, l1) of one wavefront step in a single dataflow launch.  dep: for every absolute layer id the (up to two)
 // layer ids it reads from (-1 = none); layers outside [l0, l1) count as already complete.
 int gemm_flow_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int l0, int l1, const int (*dep)[2], int R,
@@ -871,18 +902,6 @@ int gemm_flow_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int
     // no programmatic dependent launch here: the counters are zeroed by a memset node right before the kernel
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    {
-        // every CTA pair must be resident at once (a pair waits for tiles owned by the others): checked once
-        static int max_clusters = -1;
-        if (max_clusters < 0) {
-            int nc = 0;
-            if (cudaOccupancyMaxActiveClusters(&nc, gemm_flow_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); nc = 0; }
-            max_clusters = nc;
-        }
-        if (max_clusters * 2 < grid)
-            return lbic_fail(LBIC_ERR_INVALID, "flow kernel: only %d CTA pairs can be co-resident, %d needed (set LBIC_OPT_FLOW to 0)",
-                             max_clusters, grid / 2);
-    }
     LBIC_CUDA(cudaLaunchKernelEx(&cfg, gemm_flow_kernel, p));
     count_launch(0);
     LBIC_CUDA(cudaGetLastError());

@@ -138,6 +138,7 @@ int gemm_chain_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, in
 int gemm_ws_launch(const GemmCall &g, cudaStream_t st, int pair = 0);   // persistent warp-specialised kernel (gemm_ws.cu)
 int gemm_flow_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int l0, int l1, const int (*dep)[2], int R,
                      const StepDesc &step, int *d_counters, size_t counters_cap, cudaStream_t st);
+int gemm_flow_supported();   // 1 if all CTA pairs of the dataflow launch can be co-resident on this device
 int gemm_ws_max_bn();
 int gemm_pair_max_bn();
 void gemm_set_pdl(int on);   // programmatic dependent launch between consecutive GEMM kernels (default on)
