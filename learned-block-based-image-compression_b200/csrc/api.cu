@@ -127,6 +127,9 @@ struct lbic_model {
     int flow_min_rows = 8192;
     int flow_max_rows = 1 << 30;
     float *selfinfo_cl = nullptr;   // set by lbic_validate for the duration of the call: (n,Hb,Wb,M) self-information
+    int keep_err_flag = 0;          // host wrappers: the second half of a split batch must not clear the first half's error
+    cudaStream_t hs[3] = {nullptr, nullptr, nullptr};   // host-call pipeline: copies in, compute, copies out
+    cudaEvent_t hev[4] = {nullptr, nullptr, nullptr, nullptr};
     float *recon_cl = nullptr;      // set by lbic_forward: the decoder net writes here instead of the zhat feedback buffer
     int recon_no_clamp = 0;
     int64_t launches[2] = {0, 0};
@@ -806,6 +809,8 @@ extern "C" void lbic_destroy(lbic_model *m) {
     if (m->tables.d_scale_table) cudaFree(m->tables.d_scale_table);
     if (m->err_flag) cudaFree(m->err_flag);
     if (m->io_dev) cudaFree(m->io_dev);
+    for (auto &h : m->hs) if (h) cudaStreamDestroy(h);
+    for (auto &ev : m->hev) if (ev) cudaEventDestroy(ev);
     for (auto &r : m->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     delete m;
 }
@@ -968,7 +973,7 @@ extern "C" int lbic_encode(lbic_model *m, const float *x, int n_img, int Hb, int
     Workspace &ws = m->ws;
     const int HW = Hb * Wb;
     const size_t nblk = (size_t)n_img * HW;
-    LBIC_CUDA(cudaMemsetAsync(m->err_flag, 0, sizeof(int), st));
+    if (!m->keep_err_flag) LBIC_CUDA(cudaMemsetAsync(m->err_flag, 0, sizeof(int), st));
     LBIC_TRY(launch_nchw_to_cl(x, ws.x_cl, n_img, m->Cin, HW, st));
     LBIC_CUDA(cudaMemsetAsync(ws.zhat_cl, 0, sizeof(float) * nblk * m->Cin, st));   // NET:336
     const bool want_syms = sym_out || idx_out || stream_out || m->selfinfo_cl;
@@ -1116,7 +1121,7 @@ extern "C" int lbic_decode(lbic_model *m, const uint8_t *streams, const uint32_t
     const int HW = Hb * Wb;
     const size_t nblk = (size_t)n_img * HW;
     const int L = lanes == 1 ? 1 : Hb;
-    LBIC_CUDA(cudaMemsetAsync(m->err_flag, 0, sizeof(int), st));
+    if (!m->keep_err_flag) LBIC_CUDA(cudaMemsetAsync(m->err_flag, 0, sizeof(int), st));
     LBIC_CUDA(cudaMemsetAsync(ws.zhat_cl, 0, sizeof(float) * nblk * m->Cin, st));   // NET:417
     LBIC_TRY(launch_rans_dec_init(streams, stream_len, stream_cap, n_img, L, ws.dec_states, ws.lane_ptr, m->err_flag, st));
     auto one_step = [&](const StepDesc &sd, int R) -> int {
@@ -1192,54 +1197,123 @@ int check_async(lbic_model *m) {
 }
 }  // namespace
 
+namespace {
+// Host-buffer calls split a large batch in two halves and pipeline them over three streams, so that the second half's
+// input copy runs under the first half's compute and the first half's output copy under the second half's compute
+// (images are independent; the halves share the workspace and therefore compute one after the other).  Below
+// HOST_SPLIT_MIN images the loss in GEMM efficiency of a smaller batch outweighs the hidden copies.
+constexpr int HOST_SPLIT_MIN = 512;
+
+int host_pipeline_init(lbic_model *m) {
+    if (m->hs[0]) return 0;
+    for (int i = 0; i < 3; ++i) LBIC_CUDA(cudaStreamCreateWithFlags(&m->hs[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) LBIC_CUDA(cudaEventCreateWithFlags(&m->hev[i], cudaEventDisableTiming));
+    return 0;
+}
+}  // namespace
+
 extern "C" int lbic_encode_host(lbic_model *m, const float *x, int n_img, int Hb, int Wb, float *zhat_out,
                                 uint8_t *stream_out, size_t stream_cap, uint32_t *stream_len, int lanes) {
     LBIC_TRY(check_ready(m, stream_out != nullptr));
-    if (!x) return lbic_fail(LBIC_ERR_INVALID, "null input");
+    if (!x || n_img < 1) return lbic_fail(LBIC_ERR_INVALID, "null input");
     Active act(m);
-    const size_t nx = sizeof(float) * (size_t)n_img * m->Cin * Hb * Wb;
+    LBIC_TRY(host_pipeline_init(m));
+    LBIC_CUDA(cudaDeviceSynchronize());   // the pipeline streams do not order against earlier work on the caller's streams
+    const size_t per = sizeof(float) * (size_t)m->Cin * Hb * Wb;
+    const size_t nx = per * n_img;
     const size_t o_x = 0, o_z = align256(nx), o_len = o_z + align256(nx), o_s = o_len + align256(4 * (size_t)n_img);
     LBIC_TRY(ensure_io(m, o_s + (stream_out ? (size_t)n_img * stream_cap : 0)));
+    LBIC_TRY(ensure_workspace(m, n_img, Hb, Wb));     // sized once for the whole batch, shared by the halves
     uint8_t *io = (uint8_t *)m->io_dev;
-    cudaStream_t st = 0;
-    LBIC_CUDA(cudaMemcpyAsync(io + o_x, x, nx, cudaMemcpyHostToDevice, st));
-    LBIC_TRY(lbic_encode(m, (const float *)(io + o_x), n_img, Hb, Wb, zhat_out ? (float *)(io + o_z) : nullptr, nullptr,
-                         nullptr, stream_out ? io + o_s : nullptr, stream_cap, (uint32_t *)(io + o_len), lanes, st));
+    cudaStream_t s_in = m->hs[0], s_cmp = m->hs[1], s_out = m->hs[2];
+    const int parts = n_img >= HOST_SPLIT_MIN ? 2 : 1;
+    const int cut[3] = {0, parts == 2 ? n_img / 2 : n_img, n_img};
+    for (int c = 0; c < parts; ++c) {
+        LBIC_CUDA(cudaMemcpyAsync(io + o_x + per * cut[c], (const uint8_t *)x + per * cut[c], per * (cut[c + 1] - cut[c]),
+                                  cudaMemcpyHostToDevice, s_in));
+        LBIC_CUDA(cudaEventRecord(m->hev[c], s_in));
+    }
+    int rc = 0;
+    for (int c = 0; c < parts && rc == 0; ++c) {
+        const int n_c = cut[c + 1] - cut[c];
+        LBIC_CUDA(cudaStreamWaitEvent(s_cmp, m->hev[c], 0));
+        m->keep_err_flag = c > 0;
+        rc = lbic_encode(m, (const float *)(io + o_x + per * cut[c]), n_c, Hb, Wb,
+                         zhat_out ? (float *)(io + o_z + per * cut[c]) : nullptr, nullptr, nullptr,
+                         stream_out ? io + o_s + (size_t)cut[c] * stream_cap : nullptr, stream_cap,
+                         (uint32_t *)(io + o_len) + cut[c], lanes, s_cmp);
+        m->keep_err_flag = 0;
+        if (rc) break;
+        Active again(m);
+        LBIC_CUDA(cudaEventRecord(m->hev[2 + c], s_cmp));
+        LBIC_CUDA(cudaStreamWaitEvent(s_out, m->hev[2 + c], 0));
+        if (zhat_out)
+            LBIC_CUDA(cudaMemcpyAsync((uint8_t *)zhat_out + per * cut[c], io + o_z + per * cut[c], per * n_c,
+                                      cudaMemcpyDeviceToHost, s_out));
+        if (stream_out)
+            LBIC_CUDA(cudaMemcpyAsync(stream_len + cut[c], (uint32_t *)(io + o_len) + cut[c], 4 * (size_t)n_c,
+                                      cudaMemcpyDeviceToHost, s_out));
+    }
     Active act2(m);
-    if (zhat_out) LBIC_CUDA(cudaMemcpyAsync(zhat_out, io + o_z, nx, cudaMemcpyDeviceToHost, st));
+    cudaError_t e1 = cudaStreamSynchronize(s_cmp), e2 = cudaStreamSynchronize(s_out);
+    if (rc) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+        return lbic_fail(LBIC_ERR_CUDA, "encode failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     if (stream_out) {
-        LBIC_CUDA(cudaMemcpyAsync(stream_len, io + o_len, 4 * (size_t)n_img, cudaMemcpyDeviceToHost, st));
-        LBIC_CUDA(cudaStreamSynchronize(st));
         LBIC_TRY(check_async(m));
         for (int i = 0; i < n_img; ++i)
             LBIC_CUDA(cudaMemcpyAsync(stream_out + (size_t)i * stream_cap, io + o_s + (size_t)i * stream_cap,
-                                      stream_len[i], cudaMemcpyDeviceToHost, st));
+                                      stream_len[i], cudaMemcpyDeviceToHost, s_out));
+        LBIC_CUDA(cudaStreamSynchronize(s_out));
     }
-    LBIC_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
 
 extern "C" int lbic_decode_host(lbic_model *m, const uint8_t *streams, const uint32_t *stream_len, size_t stream_cap,
                                 int n_img, int Hb, int Wb, float *zhat_out, int lanes) {
     LBIC_TRY(check_ready(m, true));
-    if (!streams || !stream_len || !zhat_out) return lbic_fail(LBIC_ERR_INVALID, "null argument");
+    if (!streams || !stream_len || !zhat_out || n_img < 1) return lbic_fail(LBIC_ERR_INVALID, "null argument");
     Active act(m);
-    const size_t nx = sizeof(float) * (size_t)n_img * m->Cin * Hb * Wb;
+    LBIC_TRY(host_pipeline_init(m));
+    LBIC_CUDA(cudaDeviceSynchronize());   // the pipeline streams do not order against earlier work on the caller's streams
+    const size_t per = sizeof(float) * (size_t)m->Cin * Hb * Wb;
+    const size_t nx = per * n_img;
     const size_t o_z = 0, o_len = align256(nx), o_s = o_len + align256(4 * (size_t)n_img);
     LBIC_TRY(ensure_io(m, o_s + (size_t)n_img * stream_cap));
+    LBIC_TRY(ensure_workspace(m, n_img, Hb, Wb));
     uint8_t *io = (uint8_t *)m->io_dev;
-    cudaStream_t st = 0;
-    LBIC_CUDA(cudaMemcpyAsync(io + o_len, stream_len, 4 * (size_t)n_img, cudaMemcpyHostToDevice, st));
-    for (int i = 0; i < n_img; ++i) {
+    cudaStream_t s_in = m->hs[0], s_cmp = m->hs[1], s_out = m->hs[2];
+    const int parts = n_img >= HOST_SPLIT_MIN ? 2 : 1;
+    const int cut[3] = {0, parts == 2 ? n_img / 2 : n_img, n_img};
+    for (int i = 0; i < n_img; ++i)
         if (stream_len[i] > stream_cap) return lbic_fail(LBIC_ERR_INVALID, "stream %d longer than stream_cap", i);
-        LBIC_CUDA(cudaMemcpyAsync(io + o_s + (size_t)i * stream_cap, streams + (size_t)i * stream_cap, stream_len[i],
-                                  cudaMemcpyHostToDevice, st));
+    LBIC_CUDA(cudaMemcpyAsync(io + o_len, stream_len, 4 * (size_t)n_img, cudaMemcpyHostToDevice, s_in));
+    for (int c = 0; c < parts; ++c) {
+        for (int i = cut[c]; i < cut[c + 1]; ++i)
+            LBIC_CUDA(cudaMemcpyAsync(io + o_s + (size_t)i * stream_cap, streams + (size_t)i * stream_cap, stream_len[i],
+                                      cudaMemcpyHostToDevice, s_in));
+        LBIC_CUDA(cudaEventRecord(m->hev[c], s_in));
     }
-    LBIC_TRY(lbic_decode(m, io + o_s, (const uint32_t *)(io + o_len), stream_cap, n_img, Hb, Wb, (float *)(io + o_z),
-                         nullptr, lanes, st));
+    int rc = 0;
+    for (int c = 0; c < parts && rc == 0; ++c) {
+        const int n_c = cut[c + 1] - cut[c];
+        LBIC_CUDA(cudaStreamWaitEvent(s_cmp, m->hev[c], 0));
+        m->keep_err_flag = c > 0;
+        rc = lbic_decode(m, io + o_s + (size_t)cut[c] * stream_cap, (const uint32_t *)(io + o_len) + cut[c], stream_cap, n_c,
+                         Hb, Wb, (float *)(io + o_z + per * cut[c]), nullptr, lanes, s_cmp);
+        m->keep_err_flag = 0;
+        if (rc) break;
+        Active again(m);
+        LBIC_CUDA(cudaEventRecord(m->hev[2 + c], s_cmp));
+        LBIC_CUDA(cudaStreamWaitEvent(s_out, m->hev[2 + c], 0));
+        LBIC_CUDA(cudaMemcpyAsync((uint8_t *)zhat_out + per * cut[c], io + o_z + per * cut[c], per * n_c,
+                                  cudaMemcpyDeviceToHost, s_out));
+    }
     Active act2(m);
-    LBIC_CUDA(cudaMemcpyAsync(zhat_out, io + o_z, nx, cudaMemcpyDeviceToHost, st));
-    LBIC_CUDA(cudaStreamSynchronize(st));
+    cudaError_t e1 = cudaStreamSynchronize(s_cmp), e2 = cudaStreamSynchronize(s_out);
+    if (rc) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+        return lbic_fail(LBIC_ERR_CUDA, "decode failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     LBIC_TRY(check_async(m));
     return 0;
 }
