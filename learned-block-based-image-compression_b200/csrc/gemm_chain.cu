@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_chain_kernel(const ChainP
     }
 }
 
-bool g_chain_attr_set = false;
+unsigned long long g_chain_attr_mask = 0;
 
 // per-tile time model (us) used only to pick the cluster size; from profiles/r1_gemm_sweep_v2_staged_epilogue.log
 double tile_us(int kblocks, int bn) {
@@ -233,10 +233,9 @@ int gemm_chain_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, in
                       const StepDesc &step, int force_S, cudaStream_t st) {
     if (R <= 0 || l1 <= l0) return 0;
     LBIC_TRY(gemm_tc_init());
-    if (!g_chain_attr_set) {
+    if (lbic_first_use_on_device(g_chain_attr_mask)) {
         LBIC_CUDA(cudaFuncSetAttribute(gemm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         LBIC_CUDA(cudaFuncSetAttribute(gemm_chain_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
-        g_chain_attr_set = true;
     }
     int n_sm = 148;
     {

@@ -152,6 +152,9 @@ void gemm_set_pdl(int on) { g_use_pdl = on != 0; }
 int gemm_get_pdl() { return g_use_pdl ? 1 : 0; }
 
 int gemm_tc_init() {
+    static unsigned long long attr_mask = 0;
+    if (lbic_first_use_on_device(attr_mask))
+        LBIC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     if (g_encode_tiled) return 0;
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -159,7 +162,6 @@ int gemm_tc_init() {
     if (!fn || qres != cudaDriverEntryPointSuccess)
         return lbic_fail(LBIC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
-    LBIC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     return 0;
 }
 

@@ -717,9 +717,9 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowPa
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
-bool g_flow_attr = false;
+unsigned long long g_flow_attr_mask = 0;
 
-bool g_ws_attr[2] = {false, false};
+unsigned long long g_ws_attr_mask[2] = {0, 0};
 
 }  // namespace
 
@@ -733,10 +733,9 @@ int gemm_ws_launch(const GemmCall &g, cudaStream_t st, int pair) {
     pair = pair ? 1 : 0;
     if (g.bn % 16 || g.bn < 16 || g.bn > (pair ? WS_ACC_STRIDE : WS_MAX_BN))
         return lbic_fail(LBIC_ERR_INVALID, "ws kernel: bad tile N %d", g.bn);
-    if (!g_ws_attr[pair]) {
+    if (lbic_first_use_on_device(g_ws_attr_mask[pair])) {
         if (pair) LBIC_CUDA(cudaFuncSetAttribute(gemm_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         else LBIC_CUDA(cudaFuncSetAttribute(gemm_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        g_ws_attr[pair] = true;
     }
     WsParams p;
     const int tile_rows = pair ? 2 * BM : BM;
@@ -806,15 +805,20 @@ int gemm_ws_launch(const GemmCall &g, cudaStream_t st, int pair) {
 // Every CTA pair of the dataflow launch must be resident at once (a pair waits for tiles owned by the others): true on a
 // whole B200, not necessarily on a partitioned or shared one.  Checked once; callers fall back to per-layer launches.
 int gemm_flow_supported() {
-    static int ok = -1;
+    static int cache[64];
+    static bool cache_init = false;
+    if (!cache_init) { for (int &c : cache) c = -1; cache_init = true; }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    int &ok = cache[cur & 63];
     if (ok >= 0) return ok;
     ok = 0;
     if (gemm_tc_init() != 0) return ok;
-    if (cudaFuncSetAttribute(gemm_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
+    if (lbic_first_use_on_device(g_flow_attr_mask) &&
+        cudaFuncSetAttribute(gemm_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
         cudaGetLastError();
         return ok;
     }
-    g_flow_attr = true;
     int dev = 0, n_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -842,10 +846,8 @@ int gemm_flow_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int
     LBIC_TRY(gemm_tc_init());
     const int nl = l1 - l0;
     if (nl > FLOW_MAX_LAYERS) return lbic_fail(LBIC_ERR_INVALID, "flow kernel: too many layers");
-    if (!g_flow_attr) {
+    if (lbic_first_use_on_device(g_flow_attr_mask))
         LBIC_CUDA(cudaFuncSetAttribute(gemm_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        g_flow_attr = true;
-    }
     FlowParams p;
     memset(&p, 0, sizeof(p));
     p.layers = d_layers; p.counters = d_counters; p.l0 = l0; p.n_layers = nl; p.R = R; p.step = step;

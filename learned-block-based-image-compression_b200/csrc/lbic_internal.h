@@ -226,4 +226,14 @@ int launch_rans_decode_full(const Tables &T, const uint8_t *streams, const uint3
 
 // launch bookkeeping
 void count_launch(int family);   // 0 = gemm, 1 = other
+
+// Function attributes (opt-in shared memory) are per device: true the first time it is called for (mask, current device).
+inline bool lbic_first_use_on_device(unsigned long long &mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
 extern thread_local int64_t *g_launch_counter;   // points into the active model

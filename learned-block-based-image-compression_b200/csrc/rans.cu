@@ -655,11 +655,9 @@ int launch_rans_encode(const Tables &T, const int32_t *sym, const uint8_t *idx, 
                              (reinterpret_cast<uintptr_t>(idx) & 3) == 0;
     if (thread_form) {
         const size_t smem = 16 * (((size_t)T.cdf16_total + 7) / 8) + 3 * 64 * 4;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static unsigned long long attr_mask = 0;
+        if (lbic_first_use_on_device(attr_mask))
             LBIC_CUDA(cudaFuncSetAttribute(rans_encode_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
-        }
         rans_encode_thread_kernel<<<(n_streams + ENC_T_THREADS - 1) / ENC_T_THREADS, ENC_T_THREADS, smem, st>>>(
             T.cdf16, T.cdf16_off, T.cdf16_total, T.cdf_length, T.offset, sym, idx, n_streams, (long)n_sym,
             (long)stream_stride, scratch, (long)scratch_words, start_word, n_words, err_flag);
@@ -714,11 +712,9 @@ int launch_rans_dec_step(const Tables &T, RansStreamState *states, const uint8_t
     // many streams: one thread per stream with the tables in shared memory; few (single images): one warp per stream
     if (T.cdf16_total > 0 && R >= g_dec_thread_min_rows && M % 4 == 0 && ld_ksi % 4 == 0 && ld_yq % 4 == 0) {
         const size_t smem = 16 * (((size_t)T.cdf16_total + 64 * 257 + 7) / 8) + 4 * 64 * 4;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static unsigned long long attr_mask = 0;
+        if (lbic_first_use_on_device(attr_mask))
             LBIC_CUDA(cudaFuncSetAttribute(rans_dec_step_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_set = true;
-        }
         rans_dec_step_thread_kernel<<<(R + DEC_T_THREADS - 1) / DEC_T_THREADS, DEC_T_THREADS, smem, st>>>(
             T.cdf16, T.cdf16_off, T.cdf16_total, T.cdf_length, T.offset, T.d_scale_table, states, lane_ptr, lanes, s, R, M,
             ksi, ld_ksi, yq_hi, yq_lo, ld_yq, sym_out);

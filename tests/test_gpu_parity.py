@@ -519,6 +519,33 @@ def test_image_codec_roundtrip_on_ragged_size(dev, lanes, tmp_path):
         ImageCodec(get_model("B16_lowrate", 1337, False, dev)).decode(blob)
 
 
+def test_two_devices_in_one_process(dev):
+    """One model per device inside ONE process (function attributes, tensor maps and workspaces are per device)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from lbic_b200.layout import arrange_block_pixels_to_channel_dim
+    cfg = lbic_b200.load_config("B8_lowrate")
+    sd = weights.synth_state_dict(cfg, 1337)
+    img = weights.synth_images(70, 64, 96, seed0=3)
+    outs = []
+    for d in (1, 0):                                   # the second device first: nothing may be cached from device 0
+        devd = torch.device("cuda", d)
+        m = BlockBasedImgCompLossyNetv9(cfg, device=devd)
+        m.load_state_dict(sd)
+        m.update(force=True)
+        m.set_option("flow", 2)
+        m.set_option("enc_thread_streams", 1)
+        m.set_option("dec_thread_rows", 1)
+        x = arrange_block_pixels_to_channel_dim((img - 0.5).to(devd), 8)
+        strings, zhat = m.compress_batch(x, lanes=0)
+        zdec = m.decompress_batch(strings, x.shape, lanes=0)
+        assert torch.equal(zdec, zhat)
+        outs.append((strings, zhat.cpu()))
+        m.set_option("enc_thread_streams", 4096)
+        m.set_option("dec_thread_rows", 4096)
+    assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_layout_kernels_match_reference_definition(dev):
     from lbic_b200.layout import arrange_block_pixels_to_channel_dim, arrange_channel_dim_to_block_pixels
     from oracle import nets
