@@ -59,7 +59,7 @@ typedef struct {
  *   0 = tcgen05/TMEM/TMA tensor-core tiles, fp16 hi/lo operand split, 3 MMAs per product (product path)
  *   1 = fp32 SIMT evaluation of the same split operands (bring-up / cross-check twin)      */
 #define LBIC_OPT_GEMM_CORE 1
-#define LBIC_OPT_USE_GRAPH 2   /* 1 = replay the per-(n,Hb,Wb) step sequence as a CUDA graph */
+#define LBIC_OPT_USE_GRAPH 2   /* reserved: accepted and ignored (host launch time is hidden behind the GPU in every measured configuration; the dataflow launch removed 17 of 18 launches per step instead) */
 #define LBIC_OPT_CHAIN 4       /* 1 = one persistent chain kernel per wavefront step (experimental); 0 (default) = one launch per layer */
 #define LBIC_OPT_CLUSTER 5     /* tuning hook: force the chain kernel's cluster size (1,2,3,4,6,8); 0 = cost model */
 #define LBIC_OPT_PAIR 8        /* 1 (default) = CTA-pair (cta_group::2) form of the persistent kernel: 256-row tiles, half the weight traffic per SM */
