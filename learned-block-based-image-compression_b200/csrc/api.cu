@@ -125,6 +125,8 @@ struct lbic_model {
     int use_pair = 1;      // CTA-pair (cta_group::2) form of the persistent kernel
     int use_flow = 1;      // dataflow launch of a whole layer range per step (1 = steps with >= flow_min_rows rows, 2 = always)
     int flow_min_rows = 8192;
+    int flow_small = 0;    // steps below flow_min_rows: 1 = single-CTA dataflow launch with 96-wide tiles, 0 = one launch per
+                           // layer (default: the counter hand-off costs as much as a PDL-chained launch, profiles/r1_dataflow.md)
     int flow_max_rows = 1 << 30;
     float *selfinfo_cl = nullptr;   // set by lbic_validate for the duration of the call: (n,Hb,Wb,M) self-information
     int keep_err_flag = 0;          // host wrappers: the second half of a split batch must not clear the first half's error
@@ -170,8 +172,8 @@ void free_all(std::vector<void *> &list) {
 // tile-width variants of a layer, one per split factor (lbic_split): widest first
 int bn_variants(int cout, int *out) {
     for (int i = 0; i < NBN; ++i) {
-        if (i == LBIC_WS_VARIANT || i == LBIC_PAIR_VARIANT || i == LBIC_PAIR_WIDE) {
-            const int wmax = i == LBIC_PAIR_WIDE ? gemm_pair_max_bn() : gemm_ws_max_bn();
+        if (i == LBIC_WS_VARIANT || i == LBIC_PAIR_VARIANT || i == LBIC_PAIR_WIDE || i == LBIC_SMALL_VARIANT) {
+            const int wmax = i == LBIC_PAIR_WIDE ? gemm_pair_max_bn() : (i == LBIC_SMALL_VARIANT ? gemm_ws_max_bn() / 2 : gemm_ws_max_bn());
             const int nt = (cout + wmax - 1) / wmax;
             out[i] = ((cout + nt - 1) / nt + 15) / 16 * 16;
             continue;
@@ -415,7 +417,7 @@ int ensure_workspace(lbic_model *m, int n_img, int Hb, int Wb) {
     LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.dec_states, sizeof(RansStreamState) * (size_t)n_img * Hb));
     LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.lane_ptr, sizeof(void *) * (size_t)n_img * Hb));
     LBIC_TRY(build_chain(m));
-    ws.flow_counters_cap = (size_t)L_COUNT * ((ws.R_cap + 255) / 256 + 1);
+    ws.flow_counters_cap = (size_t)L_COUNT * ((ws.R_cap + 127) / 128 + 1);
     LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.flow_counters, sizeof(int) * ws.flow_counters_cap, true));
     return 0;
 }
@@ -514,9 +516,11 @@ const int FLOW_DEP[L_COUNT][2] = {
     {-1, -1}, {L_F0, -1}, {L_G0, -1}, {L_F1, -1}, {L_G1, -1}, {L_F2, -1}, {L_G2, L_E3},          // F0 G0 F1 G1 F2 G2 F3 (ksi)
     {L_F3, -1}, {L_D0, -1}, {L_IG0, -1}, {L_D1, -1}, {L_IG1, -1}, {L_D2, -1}, {L_IG2, -1}};     // D0 IG0 D1 IG1 D2 IG2 D3
 
-bool flow_applies(const lbic_model *m, int R) {
-    return m->gemm_core == 0 && !m->use_chain && m->use_pair && m->use_flow && !m->force_bn &&
-           (m->use_flow == 2 || (R >= m->flow_min_rows && R <= m->flow_max_rows)) && gemm_flow_supported();
+// 0: one launch per layer; 1: dataflow launch on CTA pairs (large steps); 2: dataflow launch on single CTAs (small steps)
+int flow_applies(const lbic_model *m, int R) {
+    if (m->gemm_core != 0 || m->use_chain || !m->use_pair || !m->use_flow || m->force_bn || !gemm_flow_supported()) return 0;
+    if (m->use_flow == 2 || (R >= m->flow_min_rows && R <= m->flow_max_rows)) return 1;
+    return (m->flow_small && R < m->flow_min_rows) ? 2 : 0;
 }
 
 int run_flow(lbic_model *m, int l0, int l1, const StepDesc &sd, int R, cudaStream_t st) {
@@ -532,7 +536,7 @@ int run_flow(lbic_model *m, int l0, int l1, const StepDesc &sd, int R, cudaStrea
         cudaEventRecord(rec.a, st);
     }
     const int rc = gemm_flow_launch(ws.d_chain, ws.h_chain.data(), l0, l1, FLOW_DEP, R, sd, ws.flow_counters,
-                                    ws.flow_counters_cap, st);
+                                    ws.flow_counters_cap, st, flow_applies(m, R) == 1);
     if (m->profiling) {
         cudaEventRecord(rec.b, st);
         m->prof.push_back(rec);
@@ -776,6 +780,7 @@ extern "C" int lbic_create(const lbic_config *cfg, int device, lbic_model **out)
     if (const char *e = getenv("LBIC_FLOW")) m->use_flow = atoi(e) < 0 ? 0 : (atoi(e) > 2 ? 2 : atoi(e));
     if (const char *e = getenv("LBIC_FLOW_MIN_ROWS")) m->flow_min_rows = atoi(e) < 1 ? 1 : atoi(e);
     if (const char *e = getenv("LBIC_FLOW_MAX_ROWS")) m->flow_max_rows = atoi(e) < 1 ? 1 : atoi(e);
+    if (const char *e = getenv("LBIC_FLOW_SMALL")) m->flow_small = atoi(e) ? 1 : 0;
     m->cfg = *cfg;
     m->device = device;
     m->Cin = 3 * cfg->block_size * cfg->block_size;
@@ -850,6 +855,9 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
         return 0;
     case LBIC_OPT_FLOW_MIN_ROWS:
         m->flow_min_rows = value < 1 ? 1 : value;
+        return 0;
+    case LBIC_OPT_FLOW_SMALL:
+        m->flow_small = value ? 1 : 0;
         return 0;
     case LBIC_OPT_PAIR:
         m->use_pair = value < 0 ? 0 : (value > 3 ? 3 : value);   // 2 = narrow (<= 192) tiles only, 3 = wide (<= 256) in the microbench
@@ -1127,7 +1135,7 @@ extern "C" int lbic_decode(lbic_model *m, const uint8_t *streams, const uint32_t
     auto one_step = [&](const StepDesc &sd, int R) -> int {
         LBIC_TRY(launch_gather(nullptr, ws.zhat_cl, m->Cin, sd, R, nullptr, nullptr, 0, ws.T.hi, ws.T.lo, ws.T.ld, st));
         const bool chain = m->use_chain && m->gemm_core == 0;
-        const bool flow = flow_applies(m, R);
+        const bool flow = flow_applies(m, R) != 0;
         if (chain || flow) {
             if (m->k1 == 3) LBIC_TRY(launch_gather5(ws.G0.hi, ws.G0.lo, m->E1, sd, R, ws.H1x5.hi, ws.H1x5.lo, ws.H1x5.ld, st));
             if (chain) LBIC_TRY(run_chain(m, m->k1 == 3 ? L_E1 : L_E0, L_F0, sd, R, st));

@@ -531,6 +531,9 @@ __device__ __forceinline__ void flow_tile(const FlowParams &p, int t, int &li, i
     nt = v - q * p.ntn[li];
 }
 
+// PAIR = true: 256-row tiles on CTA pairs (large steps).  PAIR = false: 128 x (<= 96) tiles on single CTAs for small
+// steps, where a layer has a handful of tiles and what matters is the latency from one layer to the next.
+template <bool PAIR>
 __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowParams p) {
     static_assert(sizeof(EpiParams) <= 256, "EpiParams must fit its shared-memory slot");
     extern __shared__ uint8_t smem_raw[];
@@ -554,27 +557,35 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowPa
         if (gtab && threadIdx.x < 64) stab[threadIdx.x] = gtab[threadIdx.x];
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int tile_first = (int)(blockIdx.x >> 1), tile_stride = (int)(gridDim.x >> 1);
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    constexpr int TILE_ROWS = PAIR ? 2 * BM : BM;
+    constexpr int CTAS = PAIR ? 2 : 1;          // CTAs that store (and publish) each tile
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < FLOW_STAGES; ++s) {
-            mbar_init(full_bar(s), 2);
+            mbar_init(full_bar(s), CTAS);
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(acc_full(a), 1);
-            mbar_init(acc_empty(a), 2 * (WS_EPI_THREADS / 32));
+            mbar_init(acc_empty(a), CTAS * (WS_EPI_THREADS / 32));
             mbar_init(tile_done(a), WS_EPI_THREADS / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    cluster_sync_all();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -587,15 +598,15 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowPa
                 int li, rb, nt;
                 flow_tile(p, t, li, rb, nt);
                 const ChainLayer &Lr = p.layers[p.l0 + li];
-                const int bn = Lr.bn_v[p.variant], w_rows = bn / 2;
-                const int m0 = rb * (2 * BM) + (int)rank * BM;
+                const int bn = Lr.bn_v[p.variant], w_rows = PAIR ? bn / 2 : bn;
+                const int m0 = rb * TILE_ROWS + (int)rank * BM;
                 const int n0 = nt * bn + (int)rank * w_rows;
                 // wait until the layers this one reads from have stored this row block (both CTAs of every pair)
                 for (int d = 0; d < 2; ++d) {
                     const int dl = p.dep[li][d];
                     if (dl < 0) continue;
                     const int *cnt = p.counters + (size_t)dl * p.n_rb + rb;
-                    const int target = 2 * p.ntn[dl];
+                    const int target = CTAS * p.ntn[dl];
                     uint32_t spins = 0;
                     while (ld_acquire_gpu(cnt) < target) {
                         __nanosleep(64);
@@ -605,7 +616,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowPa
                 asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores of other CTAs -> our TMA reads
                 const int kb0 = Lr.kb[0], nkb = kb0 + (Lr.nseg > 1 ? Lr.kb[1] : 0);
                 const uint32_t w_plane = (uint32_t)w_rows * (BK * 2);
-                const uint32_t stage_tx = (2 * A_PLANE + 2 * w_plane) * 2u;
+                const uint32_t stage_tx = (2 * A_PLANE + 2 * w_plane) * (uint32_t)CTAS;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % FLOW_STAGES;
                     const uint32_t ph = (it / FLOW_STAGES) & 1u;
@@ -613,12 +624,20 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowPa
                     const uint32_t sa = ring + s * FLOW_SLOT;
                     const int seg = kb >= kb0 ? 1 : 0;
                     const int kk = (seg ? kb - kb0 : kb) * BK;
-                    if (rank == 0) mbar_expect_tx(full_bar(s), stage_tx);
-                    else mbar_arrive_remote(full_bar(s), 0);
-                    tma_load_2d_pair(sa, &Lr.tmA[seg][0], full_bar(s), kk, m0);
-                    tma_load_2d_pair(sa + A_PLANE, &Lr.tmA[seg][1], full_bar(s), kk, m0);
-                    tma_load_2d_pair(sa + 2 * A_PLANE, &Lr.tmW[p.variant][seg][0], full_bar(s), kk, n0);
-                    tma_load_2d_pair(sa + 2 * A_PLANE + w_plane, &Lr.tmW[p.variant][seg][1], full_bar(s), kk, n0);
+                    if (PAIR) {
+                        if (rank == 0) mbar_expect_tx(full_bar(s), stage_tx);
+                        else mbar_arrive_remote(full_bar(s), 0);
+                        tma_load_2d_pair(sa, &Lr.tmA[seg][0], full_bar(s), kk, m0);
+                        tma_load_2d_pair(sa + A_PLANE, &Lr.tmA[seg][1], full_bar(s), kk, m0);
+                        tma_load_2d_pair(sa + 2 * A_PLANE, &Lr.tmW[p.variant][seg][0], full_bar(s), kk, n0);
+                        tma_load_2d_pair(sa + 2 * A_PLANE + w_plane, &Lr.tmW[p.variant][seg][1], full_bar(s), kk, n0);
+                    } else {
+                        mbar_expect_tx(full_bar(s), stage_tx);
+                        tma_load_2d(sa, &Lr.tmA[seg][0], full_bar(s), kk, m0);
+                        tma_load_2d(sa + A_PLANE, &Lr.tmA[seg][1], full_bar(s), kk, m0);
+                        tma_load_2d(sa + 2 * A_PLANE, &Lr.tmW[p.variant][seg][0], full_bar(s), kk, n0);
+                        tma_load_2d(sa + 2 * A_PLANE + w_plane, &Lr.tmW[p.variant][seg][1], full_bar(s), kk, n0);
+                    }
                 }
             }
         }
@@ -631,8 +650,8 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowPa
                 const ChainLayer &Lr = p.layers[p.l0 + li];
                 const int bn = Lr.bn_v[p.variant];
                 const int nkb = Lr.kb[0] + (Lr.nseg > 1 ? Lr.kb[1] : 0);
-                const uint32_t w_plane = (uint32_t)(bn / 2) * (BK * 2);
-                const uint32_t idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+                const uint32_t w_plane = (uint32_t)(PAIR ? bn / 2 : bn) * (BK * 2);
+                const uint32_t idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24);
                 const uint32_t a = ti & 1u;
                 mbar_wait(acc_empty(a), ((ti >> 1) & 1u) ^ 1u);
                 tc_fence_after();
@@ -647,15 +666,19 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowPa
                     const uint64_t a_lo = make_smem_desc(sa + A_PLANE);
                     const uint64_t w_hi = make_smem_desc(sa + 2 * A_PLANE);
                     const uint64_t w_lo = make_smem_desc(sa + 2 * A_PLANE + w_plane);
+                    auto mma = [&](uint64_t ad, uint64_t wd, uint32_t acc) {
+                        if (PAIR) umma_f16_pair(tmem_acc, ad, wd, idesc, acc);
+                        else umma_f16(tmem_acc, ad, wd, idesc, acc);
+                    };
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) umma_f16_pair(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BK / 16; ++k) mma(a_hi + 2 * k, w_hi + 2 * k, (kb | k) != 0 ? 1u : 0u);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) umma_f16_pair(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
+                    for (int k = 0; k < BK / 16; ++k) mma(a_hi + 2 * k, w_lo + 2 * k, 1u);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) umma_f16_pair(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
-                    umma_commit_pair(empty_bar(s));
+                    for (int k = 0; k < BK / 16; ++k) mma(a_lo + 2 * k, w_hi + 2 * k, 1u);
+                    if (PAIR) umma_commit_pair(empty_bar(s)); else umma_commit(empty_bar(s));
                 }
-                umma_commit_pair(acc_full(a));
+                if (PAIR) umma_commit_pair(acc_full(a)); else umma_commit(acc_full(a));
             }
         }
     } else if (warp == 10) {
@@ -681,7 +704,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowPa
             flow_tile(p, t, li, rb, nt);
             const ChainLayer &Lr = p.layers[p.l0 + li];
             const int bn = Lr.bn_v[p.variant];
-            const int m0 = rb * (2 * BM) + (int)rank * BM, n0 = nt * bn;
+            const int m0 = rb * TILE_ROWS + (int)rank * BM, n0 = nt * bn;
             if (li != cur) {
                 // a new layer: its epilogue description, with this launch's row count and step, into shared memory
                 if (cur >= 0) epi_bar();     // every epilogue thread is past the previous tile (which read the old copy)
@@ -705,19 +728,22 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowPa
             c.tmem_acc = tmem_base + a * WS_ACC_STRIDE; c.sb = sbias + a * 256; c.rt = rt; c.stab = stab; c.rank = rank;
             const int dl = p.dep[li][0];
             c.dep_cnt = dl >= 0 ? p.counters + (size_t)dl * p.n_rb + rb : nullptr;
-            c.dep_target = dl >= 0 ? 2 * p.ntn[dl] : 0;
-            ws_tile_epilogue<true>(*s_ep, bn, m0, n0, c);
+            c.dep_target = dl >= 0 ? CTAS * p.ntn[dl] : 0;
+            ws_tile_epilogue<PAIR>(*s_ep, bn, m0, n0, c);
             // this CTA's part of tile (layer, row block) is stored: hand it to the publisher warp
             __syncwarp();
             if (lane == 0) mbar_arrive(tile_done(a));
         }
     }
     tc_fence_before();
-    cluster_sync_all();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (PAIR) cluster_sync_all(); else __syncthreads();
+    if (warp == 1) {
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
 }
 
-unsigned long long g_flow_attr_mask = 0;
+unsigned long long g_flow_attr_mask[2] = {0, 0};
 
 unsigned long long g_ws_attr_mask[2] = {0, 0};
 
@@ -814,8 +840,8 @@ int gemm_flow_supported() {
     if (ok >= 0) return ok;
     ok = 0;
     if (gemm_tc_init() != 0) return ok;
-    if (lbic_first_use_on_device(g_flow_attr_mask) &&
-        cudaFuncSetAttribute(gemm_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
+    if (lbic_first_use_on_device(g_flow_attr_mask[1]) &&
+        cudaFuncSetAttribute(gemm_flow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
         cudaGetLastError();
         return ok;
     }
@@ -833,7 +859,7 @@ int gemm_flow_supported() {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, gemm_flow_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); nc = 0; }
+    if (cudaOccupancyMaxActiveClusters(&nc, gemm_flow_kernel<true>, &cfg) != cudaSuccess) { cudaGetLastError(); nc = 0; }
     ok = (nc * 2 >= n_sm / 2 * 2) ? 1 : 0;
     return ok;
 }
@@ -841,24 +867,30 @@ int gemm_flow_supported() {
 // Layers [l0, l1) of one wavefront step in a single dataflow launch.  dep: for every absolute layer id the (up to two)
 // layer ids it reads from (-1 = none); layers outside [l0, l1) count as already complete.
 int gemm_flow_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int l0, int l1, const int (*dep)[2], int R,
-                     const StepDesc &step, int *d_counters, size_t counters_cap, cudaStream_t st) {
+                     const StepDesc &step, int *d_counters, size_t counters_cap, cudaStream_t st, int pair) {
     if (R <= 0 || l1 <= l0) return 0;
     LBIC_TRY(gemm_tc_init());
     const int nl = l1 - l0;
     if (nl > FLOW_MAX_LAYERS) return lbic_fail(LBIC_ERR_INVALID, "flow kernel: too many layers");
-    if (lbic_first_use_on_device(g_flow_attr_mask))
-        LBIC_CUDA(cudaFuncSetAttribute(gemm_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    pair = pair ? 1 : 0;
+    if (lbic_first_use_on_device(g_flow_attr_mask[pair])) {
+        if (pair) LBIC_CUDA(cudaFuncSetAttribute(gemm_flow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        else LBIC_CUDA(cudaFuncSetAttribute(gemm_flow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    }
+    const int variant = pair ? LBIC_PAIR_VARIANT : LBIC_SMALL_VARIANT;
+    const int tile_rows = pair ? 2 * BM : BM;
+    const int max_bn = pair ? WS_MAX_BN : WS_MAX_BN / 2;     // both fill a 56 KiB stage: 2 x 96 weight rows or 1 x 96
     FlowParams p;
     memset(&p, 0, sizeof(p));
     p.layers = d_layers; p.counters = d_counters; p.l0 = l0; p.n_layers = nl; p.R = R; p.step = step;
-    p.variant = LBIC_PAIR_VARIANT;
-    p.n_rb = (R + 2 * BM - 1) / (2 * BM);
+    p.variant = variant;
+    p.n_rb = (R + tile_rows - 1) / tile_rows;
     if ((size_t)nl * p.n_rb > counters_cap) return lbic_fail(LBIC_ERR_INVALID, "flow kernel: counter buffer too small");
     int total = 0;
     for (int i = 0; i < nl; ++i) {
         const ChainLayer &L = h_layers[l0 + i];
-        const int bn = L.bn_v[LBIC_PAIR_VARIANT];
-        if (bn % 16 || bn < 16 || bn > WS_MAX_BN) return lbic_fail(LBIC_ERR_INVALID, "flow kernel: bad tile N %d", bn);
+        const int bn = L.bn_v[variant];
+        if (bn % 16 || bn < 16 || bn > max_bn) return lbic_fail(LBIC_ERR_INVALID, "flow kernel: bad tile N %d", bn);
         p.ntn[i] = (L.cout + bn - 1) / bn;
         p.pre[i] = total;
         total += p.ntn[i];
@@ -887,7 +919,7 @@ int gemm_flow_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int grid = 2 * (total < n_sm / 2 ? total : n_sm / 2);
+    const int grid = pair ? 2 * (total < n_sm / 2 ? total : n_sm / 2) : (total < n_sm ? total : n_sm);
     const size_t smem = 1024 + (size_t)FLOW_STAGES * FLOW_SLOT + WGDN_BYTES + FLOW_TAIL;
     if (smem > (size_t)SMEM_LIMIT) return lbic_fail(LBIC_ERR_INVALID, "flow kernel: shared memory budget exceeded");
     cudaLaunchConfig_t cfg;
@@ -898,13 +930,16 @@ int gemm_flow_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     int na = 0;
-    attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
-    ++na;
+    if (pair) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
     // no programmatic dependent launch here: the counters are zeroed by a memset node right before the kernel
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    LBIC_CUDA(cudaLaunchKernelEx(&cfg, gemm_flow_kernel, p));
+    if (pair) LBIC_CUDA(cudaLaunchKernelEx(&cfg, gemm_flow_kernel<true>, p));
+    else LBIC_CUDA(cudaLaunchKernelEx(&cfg, gemm_flow_kernel<false>, p));
     count_launch(0);
     LBIC_CUDA(cudaGetLastError());
     return 0;

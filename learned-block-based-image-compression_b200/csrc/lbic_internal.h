@@ -117,9 +117,10 @@ struct GemmCall {
 // One layer of a persistent chain launch (gemm_chain.cu), resident in device memory.
 // Tile-width variants per layer, indexed by "split factor" f: the layer's Cout is cut into f * ceil(Cout / (256 f))
 // equal tiles (width rounded up to 16), so a cluster of f CTAs gets the same number of tiles per CTA.
-constexpr int LBIC_NBN = 9;          // 6 split factors + the warp-specialised kernel's tiling (width <= 192) + its CTA-pair form
+constexpr int LBIC_NBN = 10;          // 6 split factors + the warp-specialised kernel's tiling (width <= 192) + its CTA-pair form
 constexpr int LBIC_WS_VARIANT = 6;
 constexpr int LBIC_PAIR_WIDE = 8;     // CTA-pair form with tiles up to 256 wide (2 pipeline stages instead of 3)
+constexpr int LBIC_SMALL_VARIANT = 9;  // tiles of at most 96 columns for the single-CTA dataflow launch of small steps
 constexpr int LBIC_PAIR_VARIANT = 7;  // same tile width as LBIC_WS_VARIANT; weight TMA box = half the tile (one half per CTA)
 __host__ __device__ inline int lbic_split(int i) { return i == 0 ? 1 : i == 1 ? 2 : i == 2 ? 3 : i == 3 ? 4 : i == 4 ? 6 : 8; }
 struct alignas(64) ChainLayer {
@@ -137,7 +138,7 @@ int gemm_chain_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, in
 
 int gemm_ws_launch(const GemmCall &g, cudaStream_t st, int pair = 0);   // persistent warp-specialised kernel (gemm_ws.cu)
 int gemm_flow_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int l0, int l1, const int (*dep)[2], int R,
-                     const StepDesc &step, int *d_counters, size_t counters_cap, cudaStream_t st);
+                     const StepDesc &step, int *d_counters, size_t counters_cap, cudaStream_t st, int pair = 1);
 int gemm_flow_supported();   // 1 if all CTA pairs of the dataflow launch can be co-resident on this device
 int gemm_ws_max_bn();
 int gemm_pair_max_bn();

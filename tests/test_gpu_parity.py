@@ -336,8 +336,15 @@ def test_dataflow_launch_equals_per_layer_launches(dev, cfgname):
         assert torch.equal(zdec, zref) and torch.equal(zdec, got[1])
         zv, iv = m.validate_recu_reco(x)
         assert torch.equal(zv, got[1])
+        # the single-CTA form for small steps (128 x 96 tiles, off by default)
+        m.set_option("flow", 1)
+        m.set_option("flow_small", 1)
+        small = m.compress_batch(x, lanes=0, return_symbols=True)
+        assert small[0] == ref[0] and torch.equal(small[1], ref[1]) and torch.equal(small[2], ref[2])
+        assert torch.equal(m.decompress_batch(small[0], x.shape, lanes=0), zref)
     finally:
         m.set_option("flow", 1)
+        m.set_option("flow_small", 0)
 
 
 @pytest.mark.parametrize("cfgname,H,W", [("B8_lowrate", 512, 768), ("B4_highrate", 128, 192), ("B16_lowrate", 256, 256)])
