@@ -176,7 +176,7 @@ def main():
     ap.add_argument("--width", type=int, default=768)
     ap.add_argument("--lanes", type=int, default=0, help="1 = reference container, 0 = lane container")
     ap.add_argument("--ref-blocks", type=int, default=1536, help="blocks per step of the CPU reference arm")
-    ap.add_argument("--cpu-blocks", type=int, default=3072, help="blocks of the cpu_baseline sample")
+    ap.add_argument("--cpu-blocks", type=int, default=6144, help="blocks of the cpu_baseline sample (6144 = one whole 768x512 B8 image, ~10 s)")
     ap.add_argument("--core", default="tcgen05", choices=["tcgen05", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
