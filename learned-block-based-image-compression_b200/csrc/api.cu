@@ -124,7 +124,7 @@ struct lbic_model {
     int use_ws = 1;        // warp-specialised persistent kernel for large steps
     int use_pair = 1;      // CTA-pair (cta_group::2) form of the persistent kernel
     int use_flow = 1;      // dataflow launch of a whole layer range per step (1 = steps with >= flow_min_rows rows, 2 = always)
-    int flow_min_rows = 8192;
+    int flow_min_rows = 4096;
     int flow_small = 0;    // steps below flow_min_rows: 1 = single-CTA dataflow launch with 96-wide tiles, 0 = one launch per
                            // layer (default: the counter hand-off costs as much as a PDL-chained launch, profiles/r1_dataflow.md)
     int flow_max_rows = 1 << 30;
