@@ -1210,7 +1210,7 @@ namespace {
 // input copy runs under the first half's compute and the first half's output copy under the second half's compute
 // (images are independent; the halves share the workspace and therefore compute one after the other).  Below
 // HOST_SPLIT_MIN images the loss in GEMM efficiency of a smaller batch outweighs the hidden copies.
-constexpr int HOST_SPLIT_MIN = 512;
+constexpr int HOST_SPLIT_MIN = 1024;
 
 int host_pipeline_init(lbic_model *m) {
     if (m->hs[0]) return 0;
