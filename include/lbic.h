@@ -68,6 +68,7 @@ typedef struct {
 #define LBIC_OPT_FLOW 11         /* 1 (default) = run each large wavefront step's layers as ONE dataflow launch (row-block dependencies instead of kernel boundaries); 2 = always; 0 = one launch per layer */
 #define LBIC_OPT_FLOW_MIN_ROWS 12 /* steps with at least this many block rows take the dataflow launch (default 4096) */
 #define LBIC_OPT_FLOW_SMALL 13    /* 1 = steps below LBIC_OPT_FLOW_MIN_ROWS also run as one dataflow launch, on single CTAs with 128 x 96 tiles; 0 (default) = one launch per layer there */
+#define LBIC_OPT_HOST_SPLIT_MIN 14 /* lbic_encode_host / lbic_decode_host pipeline batches of at least this many images as two halves over copy-in / compute / copy-out streams (default 1024) */
 #define LBIC_OPT_WS 6          /* 1 (default) = persistent warp-specialised kernel for steps with >= 2 tiles per SM */
 #define LBIC_OPT_PDL 7         /* 1 (default) = programmatic dependent launch between consecutive GEMM kernels (process-wide) */
 #define LBIC_OPT_FORCE_BN 3    /* tuning hook: force the GEMM tile width (multiple of 16, <= 256); 0 = automatic */

@@ -33,6 +33,7 @@ LBIC_OPT_ENC_THREAD_STREAMS = 10
 LBIC_OPT_FLOW = 11
 LBIC_OPT_FLOW_MIN_ROWS = 12
 LBIC_OPT_FLOW_SMALL = 13
+LBIC_OPT_HOST_SPLIT_MIN = 14
 LBIC_OPT_PDL = 7
 
 # every symbol include/lbic.h declares: (restype, argtypes)

@@ -129,6 +129,7 @@ struct lbic_model {
                            // layer (default: the counter hand-off costs as much as a PDL-chained launch, profiles/r1_dataflow.md)
     int flow_max_rows = 1 << 30;
     float *selfinfo_cl = nullptr;   // set by lbic_validate for the duration of the call: (n,Hb,Wb,M) self-information
+    int host_split_min = 1024;      // host-buffer calls split batches of at least this many images in two pipelined halves
     int keep_err_flag = 0;          // host wrappers: the second half of a split batch must not clear the first half's error
     cudaStream_t hs[3] = {nullptr, nullptr, nullptr};   // host-call pipeline: copies in, compute, copies out
     cudaEvent_t hev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -856,6 +857,9 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
     case LBIC_OPT_FLOW_MIN_ROWS:
         m->flow_min_rows = value < 1 ? 1 : value;
         return 0;
+    case LBIC_OPT_HOST_SPLIT_MIN:
+        m->host_split_min = value < 2 ? 2 : value;
+        return 0;
     case LBIC_OPT_FLOW_SMALL:
         m->flow_small = value ? 1 : 0;
         return 0;
@@ -1209,8 +1213,8 @@ namespace {
 // Host-buffer calls split a large batch in two halves and pipeline them over three streams, so that the second half's
 // input copy runs under the first half's compute and the first half's output copy under the second half's compute
 // (images are independent; the halves share the workspace and therefore compute one after the other).  Below
-// HOST_SPLIT_MIN images the loss in GEMM efficiency of a smaller batch outweighs the hidden copies.
-constexpr int HOST_SPLIT_MIN = 1024;
+// lbic_model::host_split_min images (1024; LBIC_OPT_HOST_SPLIT_MIN) the loss in GEMM efficiency of a smaller batch outweighs
+// the hidden copies: halves of 512 images run 6 % slower than 1024 at once, halves of 256 17 %.
 
 int host_pipeline_init(lbic_model *m) {
     if (m->hs[0]) return 0;
@@ -1234,7 +1238,7 @@ extern "C" int lbic_encode_host(lbic_model *m, const float *x, int n_img, int Hb
     LBIC_TRY(ensure_workspace(m, n_img, Hb, Wb));     // sized once for the whole batch, shared by the halves
     uint8_t *io = (uint8_t *)m->io_dev;
     cudaStream_t s_in = m->hs[0], s_cmp = m->hs[1], s_out = m->hs[2];
-    const int parts = n_img >= HOST_SPLIT_MIN ? 2 : 1;
+    const int parts = (n_img >= m->host_split_min && n_img >= 2) ? 2 : 1;
     const int cut[3] = {0, parts == 2 ? n_img / 2 : n_img, n_img};
     for (int c = 0; c < parts; ++c) {
         LBIC_CUDA(cudaMemcpyAsync(io + o_x + per * cut[c], (const uint8_t *)x + per * cut[c], per * (cut[c + 1] - cut[c]),
@@ -1291,7 +1295,7 @@ extern "C" int lbic_decode_host(lbic_model *m, const uint8_t *streams, const uin
     LBIC_TRY(ensure_workspace(m, n_img, Hb, Wb));
     uint8_t *io = (uint8_t *)m->io_dev;
     cudaStream_t s_in = m->hs[0], s_cmp = m->hs[1], s_out = m->hs[2];
-    const int parts = n_img >= HOST_SPLIT_MIN ? 2 : 1;
+    const int parts = (n_img >= m->host_split_min && n_img >= 2) ? 2 : 1;
     const int cut[3] = {0, parts == 2 ? n_img / 2 : n_img, n_img};
     for (int i = 0; i < n_img; ++i)
         if (stream_len[i] > stream_cap) return lbic_fail(LBIC_ERR_INVALID, "stream %d longer than stream_cap", i);

@@ -119,7 +119,7 @@ class BlockBasedImgCompLossyNetv9:
                "graph": _lib.LBIC_OPT_USE_GRAPH, "ws": _lib.LBIC_OPT_WS, "pdl": _lib.LBIC_OPT_PDL,
                "pair": _lib.LBIC_OPT_PAIR, "dec_thread_rows": _lib.LBIC_OPT_DEC_THREAD_ROWS,
                "enc_thread_streams": _lib.LBIC_OPT_ENC_THREAD_STREAMS, "flow": _lib.LBIC_OPT_FLOW,
-               "flow_min_rows": _lib.LBIC_OPT_FLOW_MIN_ROWS, "flow_small": _lib.LBIC_OPT_FLOW_SMALL}[name]
+               "flow_min_rows": _lib.LBIC_OPT_FLOW_MIN_ROWS, "flow_small": _lib.LBIC_OPT_FLOW_SMALL, "host_split_min": _lib.LBIC_OPT_HOST_SPLIT_MIN}[name]
         _lib.check(_lib.lib().lbic_set_option(self._need(), opt, int(value)))
 
     # ---- state_dict ----------------------------------------------------------------------------

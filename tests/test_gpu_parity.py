@@ -553,6 +553,38 @@ def test_two_devices_in_one_process(dev):
     assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1])
 
 
+def test_host_calls_pipelined_halves_equal_single_pass(dev):
+    """lbic_encode_host / lbic_decode_host with the batch split in two halves pipelined over three streams (the default
+    from 1024 images on) must return exactly what the unsplit calls return; odd batch size, both containers."""
+    import ctypes
+    from lbic_b200 import _lib
+    from lbic_b200.layout import arrange_block_pixels_to_channel_dim
+    m = get_model("B8_lowrate", 1337, False, dev)
+    L = _lib.lib()
+    n, Hb, Wb = 11, 5, 9
+    img = weights.synth_images(n, Hb * 8, Wb * 8, seed0=77)
+    xh = arrange_block_pixels_to_channel_dim((img - 0.5).to(dev), 8).cpu().contiguous()
+    try:
+        for lanes in (0, 1):
+            cap = (m.stream_bound(Hb, Wb, lanes) + 3) // 4 * 4
+            res = {}
+            for split in (1 << 30, 2):
+                m.set_option("host_split_min", split)
+                zenc, zdec = torch.empty_like(xh), torch.empty_like(xh)
+                streams = np.zeros((n, cap), np.uint8)
+                lens = np.zeros(n, np.uint32)
+                _lib.check(L.lbic_encode_host(m._need(), xh.data_ptr(), n, Hb, Wb, zenc.data_ptr(), streams.ctypes.data, cap,
+                                              lens.ctypes.data, lanes))
+                _lib.check(L.lbic_decode_host(m._need(), streams.ctypes.data, lens.ctypes.data, cap, n, Hb, Wb,
+                                              zdec.data_ptr(), lanes))
+                assert torch.equal(zenc, zdec)
+                res[split] = ([streams[i, :lens[i]].tobytes() for i in range(n)], zenc.clone())
+            assert res[2][0] == res[1 << 30][0], f"bitstreams differ (lanes={lanes})"
+            assert torch.equal(res[2][1], res[1 << 30][1])
+    finally:
+        m.set_option("host_split_min", 1024)
+
+
 def test_layout_kernels_match_reference_definition(dev):
     from lbic_b200.layout import arrange_block_pixels_to_channel_dim, arrange_channel_dim_to_block_pixels
     from oracle import nets
