@@ -59,7 +59,6 @@ typedef struct {
  *   0 = tcgen05/TMEM/TMA tensor-core tiles, fp16 hi/lo operand split, 3 MMAs per product (product path)
  *   1 = fp32 SIMT evaluation of the same split operands (bring-up / cross-check twin)      */
 #define LBIC_OPT_GEMM_CORE 1
-#define LBIC_OPT_USE_GRAPH 2   /* reserved: accepted and ignored (host launch time is hidden behind the GPU in every measured configuration; the dataflow launch removed 17 of 18 launches per step instead) */
 #define LBIC_OPT_CHAIN 4       /* 1 = one persistent chain kernel per wavefront step (experimental); 0 (default) = one launch per layer */
 #define LBIC_OPT_CLUSTER 5     /* tuning hook: force the chain kernel's cluster size (1,2,3,4,6,8); 0 = cost model */
 #define LBIC_OPT_PAIR 8        /* 1 (default) = CTA-pair (cta_group::2) form of the persistent kernel: 256-row tiles, half the weight traffic per SM */
@@ -68,7 +67,7 @@ typedef struct {
 #define LBIC_OPT_FLOW 11         /* 1 (default) = run each large wavefront step's layers as ONE dataflow launch (row-block dependencies instead of kernel boundaries); 2 = always; 0 = one launch per layer */
 #define LBIC_OPT_FLOW_MIN_ROWS 12 /* steps with at least this many block rows take the dataflow launch (default 4096) */
 #define LBIC_OPT_FLOW_SMALL 13    /* 1 = steps below LBIC_OPT_FLOW_MIN_ROWS also run as one dataflow launch, on single CTAs with 128 x 96 tiles; 0 (default) = one launch per layer there */
-#define LBIC_OPT_HOST_SPLIT_MIN 14 /* lbic_encode_host / lbic_decode_host pipeline batches of at least this many images as two halves over copy-in / compute / copy-out streams (default 1024) */
+#define LBIC_OPT_HOST_BANDS 14     /* the *_host entry points move a batch in / out in this many bands of block rows, overlapped with the wavefront (1..16, default 16; 1 = copy, compute, copy) */
 #define LBIC_OPT_WS 6          /* 1 (default) = persistent warp-specialised kernel for steps with >= 2 tiles per SM */
 #define LBIC_OPT_PDL 7         /* 1 (default) = programmatic dependent launch between consecutive GEMM kernels (process-wide) */
 #define LBIC_OPT_FORCE_BN 3    /* tuning hook: force the GEMM tile width (multiple of 16, <= 256); 0 = automatic */
@@ -140,15 +139,36 @@ int lbic_validate(lbic_model *m, const float *x, int n_img, int Hb, int Wb, floa
 int lbic_forward(lbic_model *m, const float *zhat_in, const float *x, int n_img, int Hb, int Wb, float *xhat_out,
                  float *selfinfo_out, int32_t *sym_out, int clamp, void *stream);
 
+/* Kernels cannot return errors: a bitstream buffer that was too small (encode) or a malformed lane container (decode) is
+ * flagged on the device; the affected image's stream_len is 0xFFFFFFFF / its lanes decode as empty streams.  This call
+ * synchronises `stream` and returns LBIC_ERR_OVERFLOW / LBIC_ERR_INVALID if the last lbic_encode / lbic_decode enqueued on
+ * it flagged anything (the *_host entry points below do this themselves). */
+int lbic_check_errors(lbic_model *m, void *stream);
+
 /* Same two calls with HOST buffers (pageable or pinned): the copies are part of the call and the
  * call returns after the results are in host memory.  This is what a reference-side binding
- *  calls from eval_model (AGENT:591-599). */
+ *  calls from eval_model (AGENT:591-599).  The batch moves over PCIe in bands of block rows while
+ * the wavefront runs (LBIC_OPT_HOST_BANDS), so only the first input band and the last output band are exposed. */
 int lbic_encode_host(lbic_model *m, const float *x, int n_img, int Hb, int Wb, float *zhat_out,
                      uint8_t *stream_out, size_t stream_cap, uint32_t *stream_len, int lanes);
 int lbic_decode_host(lbic_model *m, const uint8_t *streams, const uint32_t *stream_len,
                      size_t stream_cap, int n_img, int Hb, int Wb, float *zhat_out, int lanes);
 
-/* Upper bound on one image's bitstream size in bytes for the given grid. */
+/* The per-image body of eval_model for a batch of 8-bit RGB images of identical size (host memory, (n_img, 3, H, W)):
+ *   encode: ToTensor (u8 / 255), x - 0.5 (AGENT:581), replicate padding to a multiple of B (AGENT:583-586),
+ *           arrange_block_pixels_to_channel_dim (AGENT:588-589) and model.compress (AGENT:592); recon_out (nullable)
+ *           receives the encoder-side reconstruction as the reference would save it: arrange_channel_dim_to_block_pixels,
+ *           crop, + 0.5 and torchvision save_image's 8-bit quantisation (AGENT:610, 628);
+ *   decode: model.decompress (AGENT:598) and the same conversion of the decoder's reconstruction.
+ * Same streams as lbic_encode_host on the float tensors eval_model would build from these images. */
+int lbic_encode_images_u8_host(lbic_model *m, const uint8_t *img, int n_img, int H, int W, uint8_t *recon_out,
+                               uint8_t *stream_out, size_t stream_cap, uint32_t *stream_len, int lanes);
+int lbic_decode_images_u8_host(lbic_model *m, const uint8_t *streams, const uint32_t *stream_len, size_t stream_cap,
+                               int n_img, int H, int W, uint8_t *img_out, int lanes);
+
+/* Worst-case size in bytes of one image's bitstream for the given grid (8 bytes per symbol + 64 per rANS stream + the
+ * lane-container header): a buffer of this size cannot overflow, whatever the symbols.  Typical streams are far smaller;
+ * callers that size stream_cap from experience must check stream_len / lbic_check_errors. */
 size_t lbic_stream_bound(const lbic_model *m, int Hb, int Wb, int lanes);
 
 /* arrange_block_pixels_to_channel_dim / arrange_channel_dim_to_block_pixels -- AGENT:853-873.

@@ -22,7 +22,6 @@ class LbicTensorDesc(ctypes.Structure):
 
 
 LBIC_OPT_GEMM_CORE = 1
-LBIC_OPT_USE_GRAPH = 2
 LBIC_OPT_FORCE_BN = 3
 LBIC_OPT_CHAIN = 4
 LBIC_OPT_CLUSTER = 5
@@ -33,7 +32,7 @@ LBIC_OPT_ENC_THREAD_STREAMS = 10
 LBIC_OPT_FLOW = 11
 LBIC_OPT_FLOW_MIN_ROWS = 12
 LBIC_OPT_FLOW_SMALL = 13
-LBIC_OPT_HOST_SPLIT_MIN = 14
+LBIC_OPT_HOST_BANDS = 14
 LBIC_OPT_PDL = 7
 
 # every symbol include/lbic.h declares: (restype, argtypes)
@@ -53,6 +52,9 @@ PROTOTYPES = {
     "lbic_validate": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "lbic_encode_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp, _i]),
     "lbic_decode_host": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _vp, _i]),
+    "lbic_check_errors": (_i, [_vp, _vp]),
+    "lbic_encode_images_u8_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp, _i]),
+    "lbic_decode_images_u8_host": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _vp, _i]),
     "lbic_stream_bound": (_sz, [_vp, _i, _i, _i]),
     "lbic_space_to_depth": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "lbic_depth_to_space": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -99,6 +99,8 @@ struct Workspace {
     std::vector<void *> allocs;
 };
 
+constexpr int LBIC_MAX_BANDS = 16;   // host calls move images in at most this many bands of block rows
+
 struct ProfRec {
     cudaEvent_t a, b;
     double flops;
@@ -117,7 +119,6 @@ struct lbic_model {
     Tables tables;
     Workspace ws;
     int gemm_core = 0;
-    int use_graph = 0;
     int force_bn = 0;
     int use_chain = 0;     // 1: persistent chain kernel per step (experimental; the per-layer path is faster today)
     int force_cluster = 0;
@@ -129,14 +130,20 @@ struct lbic_model {
                            // layer (default: the counter hand-off costs as much as a PDL-chained launch, profiles/r1_dataflow.md)
     int flow_max_rows = 1 << 30;
     float *selfinfo_cl = nullptr;   // set by lbic_validate for the duration of the call: (n,Hb,Wb,M) self-information
-    int host_split_min = 1024;      // host-buffer calls split batches of at least this many images in two pipelined halves
-    int keep_err_flag = 0;          // host wrappers: the second half of a split batch must not clear the first half's error
     cudaStream_t hs[3] = {nullptr, nullptr, nullptr};   // host-call pipeline: copies in, compute, copies out
-    cudaEvent_t hev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t hev[2 * LBIC_MAX_BANDS] = {};            // band b copied in / band b ready to copy out
+    // grow-only device temporaries of lbic_validate / lbic_forward (channel-last self-information, reconstruction)
+    float *aux[2] = {nullptr, nullptr};
+    size_t aux_bytes[2] = {0, 0};
+    int host_bands = LBIC_MAX_BANDS;   // host calls: bands of block rows per batch (copy / compute overlap granularity)
     float *recon_cl = nullptr;      // set by lbic_forward: the decoder net writes here instead of the zhat feedback buffer
     int recon_no_clamp = 0;
     int64_t launches[2] = {0, 0};
     int *err_flag = nullptr;
+    // the workspace is shared by all calls on this model: a call on another stream than the previous one waits for it
+    cudaEvent_t ws_event = nullptr;
+    cudaStream_t ws_stream = nullptr;
+    bool ws_used = false;
     // host-call staging
     void *io_dev = nullptr;
     size_t io_bytes = 0;
@@ -747,10 +754,53 @@ int check_ready(lbic_model *m, bool need_tables) {
     return 0;
 }
 
-size_t stream_bound(const lbic_model *m, int Hb, int Wb, int lanes) {
-    if (lanes == 1) return 4 * ((size_t)Hb * Wb * m->M) + 64;
-    return 8 + 4 * (size_t)Hb + (size_t)Hb * (4 * ((size_t)Wb * m->M) + 64);
+// Worst case of one rANS64 stream of n_sym symbols: a table symbol costs at most 16 bits, an escaped one at most
+// 16 (tail bin) + 4 (nibble count) + 32 (eight 4-bit nibbles of the 32-bit raw value) = 52 bits, plus the 64-bit final
+// state and one word of renormalisation slack: 8 bytes per symbol + 64 can never overflow.  (CompressAI's flush() sizes
+// its buffer as one 32-bit word per PUSHED entry, bypass nibbles included; this is the same bound per worst-case symbol.)
+size_t lane_bound(size_t n_sym) { return 8 * n_sym + 64; }
+
+// is_lane_container: 'LBML' | lanes | len[lanes] | payloads  (one lane per block row), else the raw reference stream
+size_t stream_bound(const lbic_model *m, int Hb, int Wb, bool is_lane_container) {
+    if (!is_lane_container) return lane_bound((size_t)Hb * Wb * m->M);
+    return 8 + 4 * (size_t)Hb + (size_t)Hb * lane_bound((size_t)Wb * m->M);
 }
+
+// Host-side callbacks of the wavefront drivers: the *_host entry points use them to move the batch in and out in bands
+// of block rows while the wavefront is running (block row v is first read by step 2v and final after step Wb-1+2v).
+struct RowHooks {
+    void *ctx = nullptr;
+    int (*need_rows)(void *ctx, int v_hi, cudaStream_t st) = nullptr;    // x_cl block rows [0, v_hi] are read by what is enqueued next
+    int (*rows_done)(void *ctx, int v_done, cudaStream_t st) = nullptr;  // zhat_cl block rows [0, v_done) are final after what has been enqueued
+};
+
+int ws_acquire(lbic_model *m, cudaStream_t st) {
+    if (m->ws_used && st != m->ws_stream) LBIC_CUDA(cudaStreamWaitEvent(st, m->ws_event, 0));
+    return 0;
+}
+int ws_release(lbic_model *m, cudaStream_t st) {
+    LBIC_CUDA(cudaEventRecord(m->ws_event, st));
+    m->ws_stream = st;
+    m->ws_used = true;
+    return 0;
+}
+
+int ensure_aux(lbic_model *m, int which, size_t bytes, float **out) {
+    if (m->aux_bytes[which] < bytes) {
+        if (m->aux[which]) { LBIC_CUDA(cudaDeviceSynchronize()); cudaFree(m->aux[which]); m->aux[which] = nullptr; m->aux_bytes[which] = 0; }
+        cudaError_t e = cudaMalloc(&m->aux[which], bytes);
+        if (e != cudaSuccess) return lbic_fail(LBIC_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        m->aux_bytes[which] = bytes;
+    }
+    *out = m->aux[which];
+    return 0;
+}
+
+int encode_impl(lbic_model *m, const float *x, int n_img, int Hb, int Wb, float *zhat_out, int32_t *sym_out,
+                uint8_t *idx_out, uint8_t *stream_out, size_t stream_cap, uint32_t *stream_len, int lanes,
+                cudaStream_t st, const RowHooks *hk);
+int decode_impl(lbic_model *m, const uint8_t *streams, const uint32_t *stream_len, size_t stream_cap, int n_img, int Hb,
+                int Wb, float *zhat_out, int32_t *sym_out, int lanes, cudaStream_t st, const RowHooks *hk);
 
 }  // namespace
 
@@ -799,6 +849,11 @@ extern "C" int lbic_create(const lbic_config *cfg, int device, lbic_model **out)
         return lbic_fail(LBIC_ERR_NOMEM, "cudaMalloc failed");
     }
     cudaMemset(m->err_flag, 0, sizeof(int));
+    if (cudaEventCreateWithFlags(&m->ws_event, cudaEventDisableTiming) != cudaSuccess) {
+        cudaFree(m->err_flag);
+        delete m;
+        return lbic_fail(LBIC_ERR_CUDA, "cudaEventCreate failed");
+    }
     const char *core = getenv("LBIC_GEMM_CORE");
     if (core && !strcmp(core, "simt")) m->gemm_core = 1;
     *out = m;
@@ -814,7 +869,9 @@ extern "C" void lbic_destroy(lbic_model *m) {
     tables_free(m->tables);
     if (m->tables.d_scale_table) cudaFree(m->tables.d_scale_table);
     if (m->err_flag) cudaFree(m->err_flag);
+    if (m->ws_event) cudaEventDestroy(m->ws_event);
     if (m->io_dev) cudaFree(m->io_dev);
+    for (auto &a : m->aux) if (a) cudaFree(a);
     for (auto &h : m->hs) if (h) cudaStreamDestroy(h);
     for (auto &ev : m->hev) if (ev) cudaEventDestroy(ev);
     for (auto &r : m->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -827,9 +884,6 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
     case LBIC_OPT_GEMM_CORE:
         if (value != 0 && value != 1) return lbic_fail(LBIC_ERR_INVALID, "gemm core must be 0 or 1");
         m->gemm_core = value;
-        return 0;
-    case LBIC_OPT_USE_GRAPH:
-        m->use_graph = value ? 1 : 0;
         return 0;
     case LBIC_OPT_CHAIN:
         m->use_chain = value ? 1 : 0;
@@ -857,8 +911,8 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
     case LBIC_OPT_FLOW_MIN_ROWS:
         m->flow_min_rows = value < 1 ? 1 : value;
         return 0;
-    case LBIC_OPT_HOST_SPLIT_MIN:
-        m->host_split_min = value < 2 ? 2 : value;
+    case LBIC_OPT_HOST_BANDS:
+        m->host_bands = value < 1 ? 1 : (value > LBIC_MAX_BANDS ? LBIC_MAX_BANDS : value);
         return 0;
     case LBIC_OPT_FLOW_SMALL:
         m->flow_small = value ? 1 : 0;
@@ -968,25 +1022,56 @@ extern "C" int lbic_get_tables(lbic_model *m, int *n_levels, int *cdf_stride, in
 }
 
 extern "C" size_t lbic_stream_bound(const lbic_model *m, int Hb, int Wb, int lanes) {
-    if (!m) return 0;
-    return stream_bound(m, Hb, Wb, lanes == 1 ? 1 : Hb);
+    if (!m || Hb < 1 || Wb < 1) return 0;
+    return stream_bound(m, Hb, Wb, lanes != 1);
 }
 
 extern "C" int lbic_encode(lbic_model *m, const float *x, int n_img, int Hb, int Wb, float *zhat_out,
                            int32_t *sym_out, uint8_t *idx_out, uint8_t *stream_out, size_t stream_cap,
                            uint32_t *stream_len, int lanes, void *stream) {
+    if (!x) return lbic_fail(LBIC_ERR_INVALID, "bad arguments");
+    return encode_impl(m, x, n_img, Hb, Wb, zhat_out, sym_out, idx_out, stream_out, stream_cap, stream_len, lanes,
+                       (cudaStream_t)stream, nullptr);
+}
+
+namespace {
+// One encode-side wavefront step: entropy net, encoder net + quantisation, decoder net for the R rows of `sd`
+// (NET:363-377 for every block of the diagonal at once).  The gather of the step's operands has been enqueued.
+int encode_step(lbic_model *m, const StepDesc &sd, int R, bool want_syms, cudaStream_t st) {
+    Workspace &ws = m->ws;
+    if (m->use_chain && m->gemm_core == 0) {
+        // the whole step in one persistent chain launch (experimental)
+        if (m->k1 == 3) LBIC_TRY(launch_gather5(ws.G0.hi, ws.G0.lo, m->E1, sd, R, ws.H1x5.hi, ws.H1x5.lo, ws.H1x5.ld, st));
+        return run_chain(m, m->k1 == 3 ? L_E1 : L_E0, L_COUNT, sd, R, st);
+    }
+    if (flow_applies(m, R) && !m->recon_cl) {
+        // the whole step as one dataflow launch; if the launch itself is refused (no co-residency: a shared or
+        // partitioned GPU) the per-layer path below takes over for good
+        if (m->k1 == 3) LBIC_TRY(launch_gather5(ws.G0.hi, ws.G0.lo, m->E1, sd, R, ws.H1x5.hi, ws.H1x5.lo, ws.H1x5.ld, st));
+        const int rc = run_flow(m, m->k1 == 3 ? L_E1 : L_E0, L_COUNT, sd, R, st);
+        if (rc != LBIC_FLOW_REFUSED) return rc;
+        m->use_flow = 0;
+    }
+    LBIC_TRY(run_ent(m, sd, R, st));
+    LBIC_TRY(run_enc(m, sd, R, want_syms ? ws.sym : nullptr, want_syms ? ws.idx : nullptr, st));
+    return run_dec(m, sd, R, st);
+}
+
+int encode_impl(lbic_model *m, const float *x, int n_img, int Hb, int Wb, float *zhat_out, int32_t *sym_out,
+                uint8_t *idx_out, uint8_t *stream_out, size_t stream_cap, uint32_t *stream_len, int lanes,
+                cudaStream_t st, const RowHooks *hk) {
     LBIC_TRY(check_ready(m, stream_out != nullptr));
-    if (!x || n_img < 1 || Hb < 1 || Wb < 1) return lbic_fail(LBIC_ERR_INVALID, "bad arguments");
+    if ((!x && !(hk && hk->need_rows)) || n_img < 1 || Hb < 1 || Wb < 1) return lbic_fail(LBIC_ERR_INVALID, "bad arguments");
     if (lanes != 0 && lanes != 1) return lbic_fail(LBIC_ERR_INVALID, "lanes must be 1 (reference) or 0 (per block row)");
     if (stream_out && (!stream_len || stream_cap % 4)) return lbic_fail(LBIC_ERR_INVALID, "stream_cap must be a multiple of 4");
     Active act(m);
-    cudaStream_t st = (cudaStream_t)stream;
     LBIC_TRY(ensure_workspace(m, n_img, Hb, Wb));
     Workspace &ws = m->ws;
     const int HW = Hb * Wb;
     const size_t nblk = (size_t)n_img * HW;
-    if (!m->keep_err_flag) LBIC_CUDA(cudaMemsetAsync(m->err_flag, 0, sizeof(int), st));
-    LBIC_TRY(launch_nchw_to_cl(x, ws.x_cl, n_img, m->Cin, HW, st));
+    LBIC_TRY(ws_acquire(m, st));
+    LBIC_CUDA(cudaMemsetAsync(m->err_flag, 0, sizeof(int), st));
+    if (x) LBIC_TRY(launch_nchw_to_cl(x, ws.x_cl, n_img, m->Cin, HW, st));
     LBIC_CUDA(cudaMemsetAsync(ws.zhat_cl, 0, sizeof(float) * nblk * m->Cin, st));   // NET:336
     const bool want_syms = sym_out || idx_out || stream_out || m->selfinfo_cl;
     const int T_steps = Wb + 2 * (Hb - 1);
@@ -996,22 +1081,15 @@ extern "C" int lbic_encode(lbic_model *m, const float *x, int n_img, int Hb, int
         if (m->k1 == 3 && wave_step_ext(t, n_img, Hb, Wb, ext)) LBIC_TRY(run_g0(m, ext, n_img * ext.nv, st));
         if (!wave_step(t, n_img, Hb, Wb, sd)) continue;
         const int R = n_img * sd.nv;
+        if (hk && hk->need_rows) LBIC_TRY(hk->need_rows(hk->ctx, sd.vmin + sd.nv - 1, st));
         LBIC_TRY(launch_gather(ws.x_cl, ws.zhat_cl, m->Cin, sd, R, ws.X.hi, ws.X.lo, ws.X.ld, ws.T.hi, ws.T.lo, ws.T.ld, st));
-        if (m->use_chain && m->gemm_core == 0) {
-            // the whole step (entropy net, encoder net + quantisation, decoder net) in one persistent launch
-            if (m->k1 == 3) LBIC_TRY(launch_gather5(ws.G0.hi, ws.G0.lo, m->E1, sd, R, ws.H1x5.hi, ws.H1x5.lo, ws.H1x5.ld, st));
-            LBIC_TRY(run_chain(m, m->k1 == 3 ? L_E1 : L_E0, L_COUNT, sd, R, st));
-        } else if (flow_applies(m, R) && !m->recon_cl) {
-            // the whole step (entropy net, encoder net + quantisation, decoder net) as one dataflow launch
-            if (m->k1 == 3) LBIC_TRY(launch_gather5(ws.G0.hi, ws.G0.lo, m->E1, sd, R, ws.H1x5.hi, ws.H1x5.lo, ws.H1x5.ld, st));
-            LBIC_TRY(run_flow(m, m->k1 == 3 ? L_E1 : L_E0, L_COUNT, sd, R, st));
-        } else {
-            LBIC_TRY(run_ent(m, sd, R, st));
-            LBIC_TRY(run_enc(m, sd, R, want_syms ? ws.sym : nullptr, want_syms ? ws.idx : nullptr, st));
-            LBIC_TRY(run_dec(m, sd, R, st));
-        }
+        LBIC_TRY(encode_step(m, sd, R, want_syms, st));
         if (m->selfinfo_cl)
             LBIC_TRY(launch_selfinfo_step(sd, R, m->M, ws.KSI, ws.ldKSI, ws.sym, m->selfinfo_cl, st));
+        if (hk && hk->rows_done && t >= Wb - 1) {
+            const int done = (t - (Wb - 1)) / 2 + 1;
+            LBIC_TRY(hk->rows_done(hk->ctx, done < Hb ? done : Hb, st));
+        }
     }
     if (zhat_out) LBIC_TRY(launch_cl_to_nchw(ws.zhat_cl, zhat_out, n_img, m->Cin, HW, st));
     if (sym_out) LBIC_CUDA(cudaMemcpyAsync(sym_out, ws.sym, sizeof(int32_t) * nblk * m->M, cudaMemcpyDeviceToDevice, st));
@@ -1020,15 +1098,18 @@ extern "C" int lbic_encode(lbic_model *m, const float *x, int n_img, int Hb, int
         const int L = lanes == 1 ? 1 : Hb;
         const int n_streams = n_img * L;
         const int64_t n_sym = (int64_t)HW * m->M / L;
-        const size_t per = (lanes == 1 ? stream_cap : (4 * (size_t)n_sym + 64)) / 4;   // scratch words per stream
+        // scratch words per stream: the reference container is coded straight into the caller's slot size; a lane gets
+        // its worst case (lane_bound), so only the caller's stream_cap can ever be the limit
+        const size_t per = (lanes == 1 ? stream_cap : lane_bound((size_t)n_sym)) / 4;
         LBIC_TRY(ensure_rans_scratch(m, (size_t)n_streams * per + 2 * (size_t)n_streams));
         LBIC_TRY(launch_rans_encode(m->tables, ws.sym, ws.idx, n_streams, n_sym, n_sym, ws.rans_scratch, per,
                                     lanes == 1 ? stream_out : nullptr, stream_cap, stream_len, m->err_flag, st));
         if (lanes != 1)
             LBIC_TRY(launch_lane_pack(ws.rans_scratch, per, n_img, L, stream_out, stream_cap, stream_len, m->err_flag, st));
     }
-    return 0;
+    return ws_release(m, st);
 }
+}  // namespace
 
 extern "C" int lbic_validate(lbic_model *m, const float *x, int n_img, int Hb, int Wb, float *zhat_out,
                              float *selfinfo_out, void *stream) {
@@ -1038,15 +1119,13 @@ extern "C" int lbic_validate(lbic_model *m, const float *x, int n_img, int Hb, i
     cudaStream_t st = (cudaStream_t)stream;
     LBIC_TRY(ensure_workspace(m, n_img, Hb, Wb));
     float *cl = nullptr;
-    std::vector<void *> tmp;
-    LBIC_TRY(dev_alloc(tmp, (void **)&cl, sizeof(float) * (size_t)n_img * Hb * Wb * m->M));
+    LBIC_TRY(ensure_aux(m, 0, sizeof(float) * (size_t)n_img * Hb * Wb * m->M, &cl));
     m->selfinfo_cl = cl;
     int rc = lbic_encode(m, x, n_img, Hb, Wb, zhat_out, nullptr, nullptr, nullptr, 0, nullptr, 1, stream);
     m->selfinfo_cl = nullptr;
     Active act2(m);
     if (rc == 0) rc = launch_cl_to_nchw(cl, selfinfo_out, n_img, m->M, Hb * Wb, st);   // -> (n, M, Hb, Wb) as AGENT:509
-    cudaStreamSynchronize(st);
-    free_all(tmp);
+    if (rc == 0) rc = ws_release(m, st);
     return rc;
 }
 
@@ -1066,13 +1145,13 @@ extern "C" int lbic_forward(lbic_model *m, const float *zhat_in, const float *x,
     Workspace &ws = m->ws;
     const int HW = Hb * Wb;
     const long nblk = (long)n_img * HW;
-    std::vector<void *> tmp;
     float *xhat_cl = nullptr, *info_cl = nullptr;
     int rc = 0;
     do {
 #define P(call) if ((rc = (call)) != 0) break
-        P(dev_alloc(tmp, (void **)&xhat_cl, sizeof(float) * (size_t)nblk * m->Cin));
-        if (selfinfo_out) P(dev_alloc(tmp, (void **)&info_cl, sizeof(float) * (size_t)nblk * m->M));
+        P(ws_acquire(m, st));
+        P(ensure_aux(m, 1, sizeof(float) * (size_t)nblk * m->Cin, &xhat_cl));
+        if (selfinfo_out) P(ensure_aux(m, 0, sizeof(float) * (size_t)nblk * m->M, &info_cl));
         P(launch_nchw_to_cl(x, ws.x_cl, n_img, m->Cin, HW, st));
         P(launch_nchw_to_cl(zhat_in, ws.zhat_cl, n_img, m->Cin, HW, st));
         const int chunk = ws.R_cap;
@@ -1111,53 +1190,86 @@ extern "C" int lbic_forward(lbic_model *m, const float *zhat_in, const float *x,
         if (info_cl) P(launch_cl_to_nchw(info_cl, selfinfo_out, n_img, m->M, HW, st));
         if (sym_out && cudaMemcpyAsync(sym_out, ws.sym, sizeof(int32_t) * (size_t)nblk * m->M, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
             rc = lbic_fail(LBIC_ERR_CUDA, "copy failed");
+        if (rc == 0) rc = ws_release(m, st);
 #undef P
     } while (0);
     m->recon_cl = nullptr;
     m->recon_no_clamp = 0;
-    cudaStreamSynchronize(st);   // the temporaries are freed below
-    free_all(tmp);
     return rc;
 }
 
 extern "C" int lbic_decode(lbic_model *m, const uint8_t *streams, const uint32_t *stream_len, size_t stream_cap,
                            int n_img, int Hb, int Wb, float *zhat_out, int32_t *sym_out, int lanes, void *stream) {
+    return decode_impl(m, streams, stream_len, stream_cap, n_img, Hb, Wb, zhat_out, sym_out, lanes, (cudaStream_t)stream,
+                       nullptr);
+}
+
+// Synchronises `stream` and reports what the kernels enqueued on it flagged since the last encode / decode started:
+// a stream buffer that was too small (LBIC_ERR_OVERFLOW) or a malformed lane container (LBIC_ERR_INVALID).
+extern "C" int lbic_check_errors(lbic_model *m, void *stream) {
+    if (!m) return lbic_fail(LBIC_ERR_INVALID, "null model");
+    Active act(m);
+    LBIC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    int flag = 0;
+    LBIC_CUDA(cudaMemcpy(&flag, m->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+        cudaMemset(m->err_flag, 0, sizeof(int));
+        return lbic_fail(flag == 1 ? LBIC_ERR_OVERFLOW : LBIC_ERR_INVALID,
+                         flag == 1 ? "bitstream buffer too small (stream_cap)" : "malformed lane container");
+    }
+    return 0;
+}
+
+namespace {
+int decode_impl(lbic_model *m, const uint8_t *streams, const uint32_t *stream_len, size_t stream_cap, int n_img, int Hb,
+                int Wb, float *zhat_out, int32_t *sym_out, int lanes, cudaStream_t st, const RowHooks *hk) {
     LBIC_TRY(check_ready(m, true));
     if (!streams || !stream_len || n_img < 1 || Hb < 1 || Wb < 1) return lbic_fail(LBIC_ERR_INVALID, "bad arguments");
     if (lanes != 0 && lanes != 1) return lbic_fail(LBIC_ERR_INVALID, "lanes must be 1 (reference) or 0 (per block row)");
     if (stream_cap % 4) return lbic_fail(LBIC_ERR_INVALID, "stream_cap must be a multiple of 4");
     Active act(m);
-    cudaStream_t st = (cudaStream_t)stream;
     LBIC_TRY(ensure_workspace(m, n_img, Hb, Wb));
     Workspace &ws = m->ws;
     const int HW = Hb * Wb;
     const size_t nblk = (size_t)n_img * HW;
     const int L = lanes == 1 ? 1 : Hb;
-    if (!m->keep_err_flag) LBIC_CUDA(cudaMemsetAsync(m->err_flag, 0, sizeof(int), st));
+    LBIC_TRY(ws_acquire(m, st));
+    LBIC_CUDA(cudaMemsetAsync(m->err_flag, 0, sizeof(int), st));
     LBIC_CUDA(cudaMemsetAsync(ws.zhat_cl, 0, sizeof(float) * nblk * m->Cin, st));   // NET:417
-    LBIC_TRY(launch_rans_dec_init(streams, stream_len, stream_cap, n_img, L, ws.dec_states, ws.lane_ptr, m->err_flag, st));
+    LBIC_TRY(launch_rans_dec_init(streams, stream_len, stream_cap, n_img, L, lanes != 1, ws.dec_states, ws.lane_ptr,
+                                  m->err_flag, st));
     auto one_step = [&](const StepDesc &sd, int R) -> int {
         LBIC_TRY(launch_gather(nullptr, ws.zhat_cl, m->Cin, sd, R, nullptr, nullptr, 0, ws.T.hi, ws.T.lo, ws.T.ld, st));
         const bool chain = m->use_chain && m->gemm_core == 0;
-        const bool flow = flow_applies(m, R) != 0;
+        bool flow = !chain && flow_applies(m, R) != 0;
+        bool ent_done = false;
         if (chain || flow) {
             if (m->k1 == 3) LBIC_TRY(launch_gather5(ws.G0.hi, ws.G0.lo, m->E1, sd, R, ws.H1x5.hi, ws.H1x5.lo, ws.H1x5.ld, st));
-            if (chain) LBIC_TRY(run_chain(m, m->k1 == 3 ? L_E1 : L_E0, L_F0, sd, R, st));
-            else LBIC_TRY(run_flow(m, m->k1 == 3 ? L_E1 : L_E0, L_F0, sd, R, st));
-        } else {
-            LBIC_TRY(run_ent(m, sd, R, st));
+            if (chain) {
+                LBIC_TRY(run_chain(m, m->k1 == 3 ? L_E1 : L_E0, L_F0, sd, R, st));
+                ent_done = true;
+            } else {
+                const int rc = run_flow(m, m->k1 == 3 ? L_E1 : L_E0, L_F0, sd, R, st);
+                if (rc == LBIC_FLOW_REFUSED) { m->use_flow = 0; flow = false; }
+                else if (rc) return rc;
+                else ent_done = true;
+            }
         }
+        if (!ent_done) LBIC_TRY(run_ent(m, sd, R, st));
         LBIC_TRY(launch_rans_dec_step(m->tables, ws.dec_states, ws.lane_ptr, L, sd, R, m->M, ws.KSI, ws.ldKSI, ws.YQ.hi,
                                       ws.YQ.lo, ws.YQ.ld, sym_out ? ws.sym : nullptr, st));
-        if (chain) LBIC_TRY(run_chain(m, L_D0, L_COUNT, sd, R, st));
-        else if (flow) LBIC_TRY(run_flow(m, L_D0, L_COUNT, sd, R, st));
-        else LBIC_TRY(run_dec(m, sd, R, st));
-        return 0;
+        if (chain) return run_chain(m, L_D0, L_COUNT, sd, R, st);
+        if (flow) {
+            const int rc = run_flow(m, L_D0, L_COUNT, sd, R, st);
+            if (rc != LBIC_FLOW_REFUSED) return rc;
+            m->use_flow = 0;
+        }
+        return run_dec(m, sd, R, st);
     };
     if (m->k1 == 3) LBIC_TRY(launch_fill_g0_top(m->L[L_E0].bias, m->E1, n_img, Hb, Wb, ws.G0.hi, ws.G0.lo, st));
-    if (L == 1) {
+    if (L == 1 && lanes == 1) {
         // reference container: the rANS state threads through the blocks in raster order (NET:420-450)
-        for (int v = 0; v < Hb; ++v)
+        for (int v = 0; v < Hb; ++v) {
             for (int h = 0; h < Wb; ++h) {
                 if (m->k1 == 3) {
                     // hidden-map positions that become computable now: the ring columns of the row start, then (v,h)
@@ -1172,6 +1284,8 @@ extern "C" int lbic_decode(lbic_model *m, const uint8_t *streams, const uint32_t
                 StepDesc sd{n_img, 1, v, h + 2 * v, Hb, Wb};
                 LBIC_TRY(one_step(sd, n_img));
             }
+            if (hk && hk->rows_done) LBIC_TRY(hk->rows_done(hk->ctx, v + 1, st));
+        }
     } else {
         const int T_steps = Wb + 2 * (Hb - 1);
         for (int t = (m->k1 == 3 ? -1 : 0); t < T_steps; ++t) {
@@ -1179,14 +1293,17 @@ extern "C" int lbic_decode(lbic_model *m, const uint8_t *streams, const uint32_t
             if (m->k1 == 3 && wave_step_ext(t, n_img, Hb, Wb, ext)) LBIC_TRY(run_g0(m, ext, n_img * ext.nv, st));
             if (!wave_step(t, n_img, Hb, Wb, sd)) continue;
             LBIC_TRY(one_step(sd, n_img * sd.nv));
+            if (hk && hk->rows_done && t >= Wb - 1) {
+                const int done = (t - (Wb - 1)) / 2 + 1;
+                LBIC_TRY(hk->rows_done(hk->ctx, done < Hb ? done : Hb, st));
+            }
         }
     }
     if (zhat_out) LBIC_TRY(launch_cl_to_nchw(ws.zhat_cl, zhat_out, n_img, m->Cin, HW, st));
     if (sym_out) LBIC_CUDA(cudaMemcpyAsync(sym_out, ws.sym, sizeof(int32_t) * nblk * m->M, cudaMemcpyDeviceToDevice, st));
-    return 0;
+    return ws_release(m, st);
 }
 
-namespace {
 int ensure_io(lbic_model *m, size_t bytes) {
     if (m->io_bytes >= bytes) return 0;
     if (m->io_dev) { cudaDeviceSynchronize(); cudaFree(m->io_dev); m->io_dev = nullptr; m->io_bytes = 0; }
@@ -1207,127 +1324,196 @@ int check_async(lbic_model *m) {
     }
     return 0;
 }
-}  // namespace
 
-namespace {
-// Host-buffer calls split a large batch in two halves and pipeline them over three streams, so that the second half's
-// input copy runs under the first half's compute and the first half's output copy under the second half's compute
-// (images are independent; the halves share the workspace and therefore compute one after the other).  Below
-// lbic_model::host_split_min images (1024; LBIC_OPT_HOST_SPLIT_MIN) the loss in GEMM efficiency of a smaller batch outweighs
-// the hidden copies: halves of 512 images run 6 % slower than 1024 at once, halves of 256 17 %.
-
+// ---- host-buffer calls -----------------------------------------------------------------------------------------
+// The wavefront reads block row v of the input for the first time at step 2v and writes block row v of the
+// reconstruction for the last time at step Wb-1+2v, so a host call moves the batch in BANDS of block rows: all input
+// bands are queued on a copy stream up front and the compute stream waits for band b only right before the first step
+// that touches it (converting it to the channel-last working layout then); every finished band of the reconstruction is
+// converted and handed to a second copy stream at once.  The whole batch stays ONE batch for the GEMMs, and all but the
+// first input band and the last output band of the PCIe time hides behind the wavefront.
 int host_pipeline_init(lbic_model *m) {
     if (m->hs[0]) return 0;
     for (int i = 0; i < 3; ++i) LBIC_CUDA(cudaStreamCreateWithFlags(&m->hs[i], cudaStreamNonBlocking));
-    for (int i = 0; i < 4; ++i) LBIC_CUDA(cudaEventCreateWithFlags(&m->hev[i], cudaEventDisableTiming));
+    for (auto &ev : m->hev) LBIC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     return 0;
 }
-}  // namespace
 
-extern "C" int lbic_encode_host(lbic_model *m, const float *x, int n_img, int Hb, int Wb, float *zhat_out,
-                                uint8_t *stream_out, size_t stream_cap, uint32_t *stream_len, int lanes) {
-    LBIC_TRY(check_ready(m, stream_out != nullptr));
-    if (!x || n_img < 1) return lbic_fail(LBIC_ERR_INVALID, "null input");
-    Active act(m);
-    LBIC_TRY(host_pipeline_init(m));
-    LBIC_CUDA(cudaDeviceSynchronize());   // the pipeline streams do not order against earlier work on the caller's streams
-    const size_t per = sizeof(float) * (size_t)m->Cin * Hb * Wb;
-    const size_t nx = per * n_img;
-    const size_t o_x = 0, o_z = align256(nx), o_len = o_z + align256(nx), o_s = o_len + align256(4 * (size_t)n_img);
-    LBIC_TRY(ensure_io(m, o_s + (stream_out ? (size_t)n_img * stream_cap : 0)));
-    LBIC_TRY(ensure_workspace(m, n_img, Hb, Wb));     // sized once for the whole batch, shared by the halves
-    uint8_t *io = (uint8_t *)m->io_dev;
-    cudaStream_t s_in = m->hs[0], s_cmp = m->hs[1], s_out = m->hs[2];
-    const int parts = (n_img >= m->host_split_min && n_img >= 2) ? 2 : 1;
-    const int cut[3] = {0, parts == 2 ? n_img / 2 : n_img, n_img};
-    for (int c = 0; c < parts; ++c) {
-        LBIC_CUDA(cudaMemcpyAsync(io + o_x + per * cut[c], (const uint8_t *)x + per * cut[c], per * (cut[c + 1] - cut[c]),
-                                  cudaMemcpyHostToDevice, s_in));
-        LBIC_CUDA(cudaEventRecord(m->hev[c], s_in));
-    }
+struct BandPipe {
+    lbic_model *m = nullptr;
+    int n = 0, Hb = 0, Wb = 0;
+    int nb = 0, vb[LBIC_MAX_BANDS + 1] = {};      // band b = block rows [vb[b], vb[b+1])
+    int next_in = 0, next_out = 0;
+    int fmt = 0;                                  // 0: fp32 (n, Cin, Hb, Wb) block tensors, 1: u8 (n, 3, H, W) images
+    int H = 0, W = 0, B = 0;                      // fmt 1
+    const uint8_t *h_in = nullptr; uint8_t *d_in = nullptr;
+    uint8_t *h_out = nullptr; uint8_t *d_out = nullptr;
     int rc = 0;
-    for (int c = 0; c < parts && rc == 0; ++c) {
-        const int n_c = cut[c + 1] - cut[c];
-        LBIC_CUDA(cudaStreamWaitEvent(s_cmp, m->hev[c], 0));
-        m->keep_err_flag = c > 0;
-        rc = lbic_encode(m, (const float *)(io + o_x + per * cut[c]), n_c, Hb, Wb,
-                         zhat_out ? (float *)(io + o_z + per * cut[c]) : nullptr, nullptr, nullptr,
-                         stream_out ? io + o_s + (size_t)cut[c] * stream_cap : nullptr, stream_cap,
-                         (uint32_t *)(io + o_len) + cut[c], lanes, s_cmp);
-        m->keep_err_flag = 0;
-        if (rc) break;
-        Active again(m);
-        LBIC_CUDA(cudaEventRecord(m->hev[2 + c], s_cmp));
-        LBIC_CUDA(cudaStreamWaitEvent(s_out, m->hev[2 + c], 0));
-        if (zhat_out)
-            LBIC_CUDA(cudaMemcpyAsync((uint8_t *)zhat_out + per * cut[c], io + o_z + per * cut[c], per * n_c,
-                                      cudaMemcpyDeviceToHost, s_out));
-        if (stream_out)
-            LBIC_CUDA(cudaMemcpyAsync(stream_len + cut[c], (uint32_t *)(io + o_len) + cut[c], 4 * (size_t)n_c,
-                                      cudaMemcpyDeviceToHost, s_out));
-    }
-    Active act2(m);
-    cudaError_t e1 = cudaStreamSynchronize(s_cmp), e2 = cudaStreamSynchronize(s_out);
-    if (rc) return rc;
-    if (e1 != cudaSuccess || e2 != cudaSuccess)
-        return lbic_fail(LBIC_ERR_CUDA, "encode failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-    if (stream_out) {
-        LBIC_TRY(check_async(m));
-        for (int i = 0; i < n_img; ++i)
-            LBIC_CUDA(cudaMemcpyAsync(stream_out + (size_t)i * stream_cap, io + o_s + (size_t)i * stream_cap,
-                                      stream_len[i], cudaMemcpyDeviceToHost, s_out));
-        LBIC_CUDA(cudaStreamSynchronize(s_out));
-    }
-    return 0;
-}
 
-extern "C" int lbic_decode_host(lbic_model *m, const uint8_t *streams, const uint32_t *stream_len, size_t stream_cap,
-                                int n_img, int Hb, int Wb, float *zhat_out, int lanes) {
-    LBIC_TRY(check_ready(m, true));
-    if (!streams || !stream_len || !zhat_out || n_img < 1) return lbic_fail(LBIC_ERR_INVALID, "null argument");
+    void plan(lbic_model *model, int n_img, int hb, int wb) {
+        m = model; n = n_img; Hb = hb; Wb = wb;
+        nb = hb < m->host_bands ? hb : m->host_bands;
+        for (int b = 0; b <= nb; ++b) vb[b] = (int)((long)hb * b / nb);
+    }
+    // plane geometry of a band for the 2-D copies: `planes` rows of `pitch` bytes, the band is bytes [off, off + width)
+    void geom(int b, size_t &planes, size_t &pitch, size_t &off, size_t &width) const {
+        if (fmt == 0) {
+            planes = (size_t)n * m->Cin; pitch = sizeof(float) * (size_t)Hb * Wb;
+            off = sizeof(float) * (size_t)vb[b] * Wb; width = sizeof(float) * (size_t)(vb[b + 1] - vb[b]) * Wb;
+        } else {
+            const int y0 = vb[b] * B, y1 = vb[b + 1] * B < H ? vb[b + 1] * B : H;
+            planes = (size_t)n * 3; pitch = (size_t)H * W;
+            off = (size_t)y0 * W; width = y1 > y0 ? (size_t)(y1 - y0) * W : 0;
+        }
+    }
+    int queue_inputs() {
+        for (int b = 0; b < nb; ++b) {
+            size_t planes, pitch, off, width;
+            geom(b, planes, pitch, off, width);
+            if (width) LBIC_CUDA(cudaMemcpy2DAsync(d_in + off, pitch, h_in + off, pitch, width, planes, cudaMemcpyHostToDevice, m->hs[0]));
+            LBIC_CUDA(cudaEventRecord(m->hev[b], m->hs[0]));
+        }
+        return 0;
+    }
+    static int need_rows(void *ctx, int v_hi, cudaStream_t st) {
+        BandPipe *p = (BandPipe *)ctx;
+        while (p->next_in < p->nb && p->vb[p->next_in] <= v_hi) {
+            const int b = p->next_in++;
+            LBIC_CUDA(cudaStreamWaitEvent(st, p->m->hev[b], 0));
+            if (p->fmt == 0)
+                LBIC_TRY(launch_nchw_to_cl_band((const float *)p->d_in, p->m->ws.x_cl, p->n, p->m->Cin, p->Hb, p->Wb, p->vb[b], p->vb[b + 1], st));
+            else
+                LBIC_TRY(launch_u8_to_xcl(p->d_in, p->m->ws.x_cl, p->n, p->H, p->W, p->Hb, p->Wb, p->B, p->vb[b], p->vb[b + 1], st));
+        }
+        return 0;
+    }
+    static int rows_done(void *ctx, int v_done, cudaStream_t st) {
+        BandPipe *p = (BandPipe *)ctx;
+        while (p->next_out < p->nb && p->vb[p->next_out + 1] <= v_done) {
+            const int b = p->next_out++;
+            if (p->fmt == 0)
+                LBIC_TRY(launch_cl_to_nchw_band(p->m->ws.zhat_cl, (float *)p->d_out, p->n, p->m->Cin, p->Hb, p->Wb, p->vb[b], p->vb[b + 1], st));
+            else
+                LBIC_TRY(launch_zcl_to_u8(p->m->ws.zhat_cl, p->d_out, p->n, p->H, p->W, p->Hb, p->Wb, p->B, p->vb[b], p->vb[b + 1], st));
+            LBIC_CUDA(cudaEventRecord(p->m->hev[LBIC_MAX_BANDS + b], st));
+            LBIC_CUDA(cudaStreamWaitEvent(p->m->hs[2], p->m->hev[LBIC_MAX_BANDS + b], 0));
+            size_t planes, pitch, off, width;
+            p->geom(b, planes, pitch, off, width);
+            if (width) LBIC_CUDA(cudaMemcpy2DAsync(p->h_out + off, pitch, p->d_out + off, pitch, width, planes, cudaMemcpyDeviceToHost, p->m->hs[2]));
+        }
+        return 0;
+    }
+};
+
+// fmt 0: x / zhat are fp32 (n, 3B^2, Hb, Wb) block tensors; fmt 1: 8-bit (n, 3, H, W) images (pad / crop fused)
+int encode_host_impl(lbic_model *m, int fmt, const void *in, int n_img, int H, int W, int Hb, int Wb, void *recon_out,
+                     uint8_t *stream_out, size_t stream_cap, uint32_t *stream_len, int lanes) {
+    LBIC_TRY(check_ready(m, stream_out != nullptr));
+    if (!in || n_img < 1 || Hb < 1 || Wb < 1) return lbic_fail(LBIC_ERR_INVALID, "bad arguments");
+    if (stream_out && (!stream_len || stream_cap % 4)) return lbic_fail(LBIC_ERR_INVALID, "stream_cap must be a multiple of 4");
     Active act(m);
     LBIC_TRY(host_pipeline_init(m));
-    LBIC_CUDA(cudaDeviceSynchronize());   // the pipeline streams do not order against earlier work on the caller's streams
-    const size_t per = sizeof(float) * (size_t)m->Cin * Hb * Wb;
-    const size_t nx = per * n_img;
-    const size_t o_z = 0, o_len = align256(nx), o_s = o_len + align256(4 * (size_t)n_img);
+    const size_t nin = fmt == 0 ? sizeof(float) * (size_t)m->Cin * Hb * Wb * n_img : (size_t)n_img * 3 * H * W;
+    const size_t o_in = 0, o_out = align256(nin), o_len = o_out + (recon_out ? align256(nin) : 0),
+                 o_s = o_len + align256(4 * (size_t)n_img);
+    LBIC_TRY(ensure_io(m, o_s + (stream_out ? (size_t)n_img * stream_cap : 0)));
+    LBIC_TRY(ensure_workspace(m, n_img, Hb, Wb));
+    uint8_t *io = (uint8_t *)m->io_dev;
+    cudaStream_t s_cmp = m->hs[1], s_out = m->hs[2];
+    BandPipe bp;
+    bp.plan(m, n_img, Hb, Wb);
+    bp.fmt = fmt; bp.H = H; bp.W = W; bp.B = m->cfg.block_size;
+    bp.h_in = (const uint8_t *)in; bp.d_in = io + o_in;
+    bp.h_out = (uint8_t *)recon_out; bp.d_out = io + o_out;
+    LBIC_TRY(bp.queue_inputs());
+    RowHooks hk;
+    hk.ctx = &bp; hk.need_rows = BandPipe::need_rows; hk.rows_done = recon_out ? BandPipe::rows_done : nullptr;
+    int rc = encode_impl(m, nullptr, n_img, Hb, Wb, nullptr, nullptr, nullptr, stream_out ? io + o_s : nullptr, stream_cap,
+                         (uint32_t *)(io + o_len), lanes, s_cmp, &hk);
+    Active act2(m);
+    if (rc == 0 && stream_out && cudaMemcpyAsync(stream_len, io + o_len, 4 * (size_t)n_img, cudaMemcpyDeviceToHost, s_cmp) != cudaSuccess)
+        rc = lbic_fail(LBIC_ERR_CUDA, "copy failed");
+    cudaError_t e0 = cudaStreamSynchronize(m->hs[0]), e1 = cudaStreamSynchronize(s_cmp);
+    if (rc == 0 && (e0 != cudaSuccess || e1 != cudaSuccess))
+        rc = lbic_fail(LBIC_ERR_CUDA, "encode failed: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+    if (rc == 0 && stream_out) rc = check_async(m);
+    if (rc == 0 && stream_out) {
+        // one strided copy for all bitstreams: every image's slot up to the longest stream of the batch
+        size_t longest = 0;
+        for (int i = 0; i < n_img; ++i) longest = stream_len[i] > longest ? stream_len[i] : longest;
+        if (longest > stream_cap) rc = lbic_fail(LBIC_ERR_OVERFLOW, "bitstream buffer too small (stream_cap)");
+        else if (longest && cudaMemcpy2DAsync(stream_out, stream_cap, io + o_s, stream_cap, longest, n_img, cudaMemcpyDeviceToHost, s_cmp) != cudaSuccess)
+            rc = lbic_fail(LBIC_ERR_CUDA, "copy failed");
+        if (cudaStreamSynchronize(s_cmp) != cudaSuccess && rc == 0) rc = lbic_fail(LBIC_ERR_CUDA, "stream copy failed");
+    }
+    cudaError_t e2 = cudaStreamSynchronize(s_out);
+    if (rc == 0 && e2 != cudaSuccess) rc = lbic_fail(LBIC_ERR_CUDA, "encode failed: %s", cudaGetErrorString(e2));
+    return rc;
+}
+
+int decode_host_impl(lbic_model *m, int fmt, const uint8_t *streams, const uint32_t *stream_len, size_t stream_cap,
+                     int n_img, int H, int W, int Hb, int Wb, void *out, int lanes) {
+    LBIC_TRY(check_ready(m, true));
+    if (!streams || !stream_len || !out || n_img < 1 || Hb < 1 || Wb < 1) return lbic_fail(LBIC_ERR_INVALID, "null argument");
+    if (stream_cap % 4) return lbic_fail(LBIC_ERR_INVALID, "stream_cap must be a multiple of 4");
+    Active act(m);
+    LBIC_TRY(host_pipeline_init(m));
+    const size_t nout = fmt == 0 ? sizeof(float) * (size_t)m->Cin * Hb * Wb * n_img : (size_t)n_img * 3 * H * W;
+    const size_t o_out = 0, o_len = align256(nout), o_s = o_len + align256(4 * (size_t)n_img);
     LBIC_TRY(ensure_io(m, o_s + (size_t)n_img * stream_cap));
     LBIC_TRY(ensure_workspace(m, n_img, Hb, Wb));
     uint8_t *io = (uint8_t *)m->io_dev;
-    cudaStream_t s_in = m->hs[0], s_cmp = m->hs[1], s_out = m->hs[2];
-    const int parts = (n_img >= m->host_split_min && n_img >= 2) ? 2 : 1;
-    const int cut[3] = {0, parts == 2 ? n_img / 2 : n_img, n_img};
-    for (int i = 0; i < n_img; ++i)
+    cudaStream_t s_cmp = m->hs[1], s_out = m->hs[2];
+    size_t longest = 0;
+    for (int i = 0; i < n_img; ++i) {
         if (stream_len[i] > stream_cap) return lbic_fail(LBIC_ERR_INVALID, "stream %d longer than stream_cap", i);
-    LBIC_CUDA(cudaMemcpyAsync(io + o_len, stream_len, 4 * (size_t)n_img, cudaMemcpyHostToDevice, s_in));
-    for (int c = 0; c < parts; ++c) {
-        for (int i = cut[c]; i < cut[c + 1]; ++i)
-            LBIC_CUDA(cudaMemcpyAsync(io + o_s + (size_t)i * stream_cap, streams + (size_t)i * stream_cap, stream_len[i],
-                                      cudaMemcpyHostToDevice, s_in));
-        LBIC_CUDA(cudaEventRecord(m->hev[c], s_in));
+        longest = stream_len[i] > longest ? stream_len[i] : longest;
     }
-    int rc = 0;
-    for (int c = 0; c < parts && rc == 0; ++c) {
-        const int n_c = cut[c + 1] - cut[c];
-        LBIC_CUDA(cudaStreamWaitEvent(s_cmp, m->hev[c], 0));
-        m->keep_err_flag = c > 0;
-        rc = lbic_decode(m, io + o_s + (size_t)cut[c] * stream_cap, (const uint32_t *)(io + o_len) + cut[c], stream_cap, n_c,
-                         Hb, Wb, (float *)(io + o_z + per * cut[c]), nullptr, lanes, s_cmp);
-        m->keep_err_flag = 0;
-        if (rc) break;
-        Active again(m);
-        LBIC_CUDA(cudaEventRecord(m->hev[2 + c], s_cmp));
-        LBIC_CUDA(cudaStreamWaitEvent(s_out, m->hev[2 + c], 0));
-        LBIC_CUDA(cudaMemcpyAsync((uint8_t *)zhat_out + per * cut[c], io + o_z + per * cut[c], per * n_c,
-                                  cudaMemcpyDeviceToHost, s_out));
-    }
+    LBIC_CUDA(cudaMemcpyAsync(io + o_len, stream_len, 4 * (size_t)n_img, cudaMemcpyHostToDevice, s_cmp));
+    if (longest) LBIC_CUDA(cudaMemcpy2DAsync(io + o_s, stream_cap, streams, stream_cap, longest, n_img, cudaMemcpyHostToDevice, s_cmp));
+    BandPipe bp;
+    bp.plan(m, n_img, Hb, Wb);
+    bp.fmt = fmt; bp.H = H; bp.W = W; bp.B = m->cfg.block_size;
+    bp.h_out = (uint8_t *)out; bp.d_out = io + o_out;
+    RowHooks hk;
+    hk.ctx = &bp; hk.rows_done = BandPipe::rows_done;
+    int rc = decode_impl(m, io + o_s, (const uint32_t *)(io + o_len), stream_cap, n_img, Hb, Wb, nullptr, nullptr, lanes,
+                         s_cmp, &hk);
     Active act2(m);
     cudaError_t e1 = cudaStreamSynchronize(s_cmp), e2 = cudaStreamSynchronize(s_out);
     if (rc) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess)
         return lbic_fail(LBIC_ERR_CUDA, "decode failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-    LBIC_TRY(check_async(m));
-    return 0;
+    return check_async(m);
+}
+}  // namespace
+
+extern "C" int lbic_encode_host(lbic_model *m, const float *x, int n_img, int Hb, int Wb, float *zhat_out,
+                                uint8_t *stream_out, size_t stream_cap, uint32_t *stream_len, int lanes) {
+    return encode_host_impl(m, 0, x, n_img, 0, 0, Hb, Wb, zhat_out, stream_out, stream_cap, stream_len, lanes);
+}
+
+extern "C" int lbic_decode_host(lbic_model *m, const uint8_t *streams, const uint32_t *stream_len, size_t stream_cap,
+                                int n_img, int Hb, int Wb, float *zhat_out, int lanes) {
+    return decode_host_impl(m, 0, streams, stream_len, stream_cap, n_img, 0, 0, Hb, Wb, zhat_out, lanes);
+}
+
+extern "C" int lbic_encode_images_u8_host(lbic_model *m, const uint8_t *img, int n_img, int H, int W, uint8_t *recon_out,
+                                          uint8_t *stream_out, size_t stream_cap, uint32_t *stream_len, int lanes) {
+    if (!m) return lbic_fail(LBIC_ERR_INVALID, "null model");
+    if (H < 1 || W < 1) return lbic_fail(LBIC_ERR_INVALID, "bad image size");
+    const int B = m->cfg.block_size;
+    return encode_host_impl(m, 1, img, n_img, H, W, (H + B - 1) / B, (W + B - 1) / B, recon_out, stream_out, stream_cap,
+                            stream_len, lanes);
+}
+
+extern "C" int lbic_decode_images_u8_host(lbic_model *m, const uint8_t *streams, const uint32_t *stream_len,
+                                          size_t stream_cap, int n_img, int H, int W, uint8_t *img_out, int lanes) {
+    if (!m) return lbic_fail(LBIC_ERR_INVALID, "null model");
+    if (H < 1 || W < 1) return lbic_fail(LBIC_ERR_INVALID, "bad image size");
+    const int B = m->cfg.block_size;
+    return decode_host_impl(m, 1, streams, stream_len, stream_cap, n_img, H, W, (H + B - 1) / B, (W + B - 1) / B, img_out,
+                            lanes);
 }
 
 extern "C" int lbic_space_to_depth(const float *img, float *blk, int n, int C, int Hb, int Wb, int B, void *stream) {

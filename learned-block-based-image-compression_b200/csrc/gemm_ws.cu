@@ -935,12 +935,31 @@ int gemm_flow_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int
         attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
         ++na;
     }
-    // no programmatic dependent launch here: the counters are zeroed by a memset node right before the kernel
-    cfg.attrs = attr;
-    cfg.numAttrs = na;
-    if (pair) LBIC_CUDA(cudaLaunchKernelEx(&cfg, gemm_flow_kernel<true>, p));
-    else LBIC_CUDA(cudaLaunchKernelEx(&cfg, gemm_flow_kernel<false>, p));
-    count_launch(0);
-    LBIC_CUDA(cudaGetLastError());
-    return 0;
+    // Every CTA (pair) waits for tiles owned by the others, so all of them must be resident at once.  A cooperative
+    // launch makes the driver guarantee that or refuse the launch (another kernel holding SMs, MPS / MIG sharing);
+    // the occupancy query of gemm_flow_supported() alone cannot see what else is running.  A refused launch is
+    // reported as LBIC_FLOW_REFUSED and the caller runs one launch per layer instead.
+    // (no programmatic dependent launch here: the counters are zeroed by a memset node right before the kernel)
+    static int use_coop = 1;   // 0 after a driver that rejects cooperative + cluster launches outright
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        int n_attr = na;
+        if (use_coop) {
+            attr[n_attr].id = cudaLaunchAttributeCooperative;
+            attr[n_attr].val.cooperative = 1;
+            ++n_attr;
+        }
+        cfg.attrs = attr;
+        cfg.numAttrs = n_attr;
+        const cudaError_t e = pair ? cudaLaunchKernelEx(&cfg, gemm_flow_kernel<true>, p)
+                                   : cudaLaunchKernelEx(&cfg, gemm_flow_kernel<false>, p);
+        if (e == cudaSuccess) {
+            count_launch(0);
+            return 0;
+        }
+        cudaGetLastError();
+        if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) return LBIC_FLOW_REFUSED;
+        if (!use_coop) return lbic_fail(LBIC_ERR_CUDA, "dataflow launch failed: %s", cudaGetErrorString(e));
+        use_coop = 0;          // e.g. cudaErrorNotSupported / invalid value for the attribute combination: plain launch
+    }
+    return LBIC_FLOW_REFUSED;
 }

@@ -42,6 +42,112 @@ __global__ void space_depth_kernel(const float *__restrict__ src, float *__restr
     }
 }
 
+// ---- 8-bit image <-> channel-last block tensors (eval_model's per-image body, AGENT:581-589 and 610-628) ---------
+// Block rows [v0, v1) of every image of the batch, so that the host wrappers can convert band by band while the rest
+// of the batch is still in flight over PCIe.
+//   x_cl[(img, v, h)][(bv*B + bh)*3 + c] = img[c][min(v*B+bv, H-1)][min(h*B+bh, W-1)] / 255 - 0.5
+// = ToTensor() (u8 / 255 in fp32), `x - 0.5` (AGENT:581), replicate padding to a multiple of B (AGENT:583-586) and
+// arrange_block_pixels_to_channel_dim (AGENT:853-860) in one pass.  One thread per padded pixel, bh fastest.
+__global__ void u8_to_xcl_kernel(const uint8_t *__restrict__ img, float *__restrict__ x_cl, int n, int H, int W, int Hb,
+                                 int Wb, int B, int v0, int v1) {
+    const int Wp = Wb * B;
+    const size_t per_img = (size_t)(v1 - v0) * B * Wp;
+    const size_t total = (size_t)n * per_img;
+    const int Cin = 3 * B * B;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / per_img);
+        const size_t q = i - (size_t)b * per_img;
+        const int yy = (int)(q / Wp), x = (int)(q - (size_t)yy * Wp);
+        const int y = v0 * B + yy;
+        const int v = y / B, bv = y - v * B, h = x / B, bh = x - h * B;
+        const int ys = y < H ? y : H - 1, xs = x < W ? x : W - 1;
+        const uint8_t *src = img + ((size_t)b * 3 * H + ys) * W + xs;
+        float *dst = x_cl + (((size_t)b * Hb + v) * Wb + h) * Cin + (bv * B + bh) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            dst[c] = __fsub_rn(__fdiv_rn((float)src[(size_t)c * H * W], 255.0f), 0.5f);
+    }
+}
+
+// out[c][y][x] = uint8(clamp((z + 0.5) * 255 + 0.5, 0, 255)) for y < H, x < W: arrange_channel_dim_to_block_pixels
+// (AGENT:863-873), the crop of the padding, `+ 0.5` (AGENT:628) and torchvision's save_image quantisation
+// (mul(255).add_(0.5).clamp_(0, 255).to(uint8)) in one pass.  One thread per 4 horizontally adjacent pixels.
+__global__ void zcl_to_u8_kernel(const float *__restrict__ z_cl, uint8_t *__restrict__ out, int n, int H, int W, int Hb,
+                                 int Wb, int B, int v0, int v1) {
+    const int y0 = v0 * B, y1 = (v1 * B < H) ? v1 * B : H;
+    if (y1 <= y0) return;
+    const int W4 = (W + 3) >> 2;
+    const size_t per_img = (size_t)(y1 - y0) * W4;
+    const size_t total = (size_t)n * per_img;
+    const int Cin = 3 * B * B;
+    const bool vec = (W & 3) == 0 && (B & 3) == 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / per_img);
+        const size_t q = i - (size_t)b * per_img;
+        const int yy = (int)(q / W4), x4 = (int)(q - (size_t)yy * W4) << 2;
+        const int y = y0 + yy, v = y / B, bv = y - v * B;
+        uint8_t px[3][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = x4 + j < W ? x4 + j : W - 1;
+            const int h = x / B, bh = x - h * B;
+            const float *src = z_cl + (((size_t)b * Hb + v) * Wb + h) * Cin + (bv * B + bh) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float t = __fadd_rn(__fmul_rn(__fadd_rn(src[c], 0.5f), 255.0f), 0.5f);
+                t = fminf(fmaxf(t, 0.0f), 255.0f);
+                px[c][j] = (uint8_t)t;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            uint8_t *dst = out + (((size_t)b * 3 + c) * H + y) * W + x4;
+            if (vec) {
+                *reinterpret_cast<uchar4 *>(dst) = make_uchar4(px[c][0], px[c][1], px[c][2], px[c][3]);
+            } else {
+                for (int j = 0; j < 4 && x4 + j < W; ++j) dst[j] = px[c][j];
+            }
+        }
+    }
+}
+
+// (n, C, Hb, Wb) fp32 -> channel-last, block rows [v0, v1) only (band-wise form of transpose_kernel for the host calls)
+__global__ void nchw_to_cl_band_kernel(const float *__restrict__ src, float *__restrict__ dst, int C, int Hb, int Wb,
+                                       int v0, int v1) {
+    __shared__ float tile[32][33];
+    const int HW = Hb * Wb, p0 = v0 * Wb, np = (v1 - v0) * Wb;
+    const size_t base = (size_t)blockIdx.z * C * HW;
+    const int p = blockIdx.x * 32 + threadIdx.x;         // position within the band
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c = blockIdx.y * 32 + j;
+        if (c < C && p < np) tile[j][threadIdx.x] = src[base + (size_t)c * HW + p0 + p];
+    }
+    __syncthreads();
+    const int c2 = blockIdx.y * 32 + threadIdx.x;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int p2 = blockIdx.x * 32 + j;
+        if (c2 < C && p2 < np) dst[base + (size_t)(p0 + p2) * C + c2] = tile[threadIdx.x][j];
+    }
+}
+
+__global__ void cl_to_nchw_band_kernel(const float *__restrict__ src, float *__restrict__ dst, int C, int Hb, int Wb,
+                                       int v0, int v1) {
+    __shared__ float tile[32][33];
+    const int HW = Hb * Wb, p0 = v0 * Wb, np = (v1 - v0) * Wb;
+    const size_t base = (size_t)blockIdx.z * C * HW;
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int p = blockIdx.y * 32 + j;
+        if (c < C && p < np) tile[j][threadIdx.x] = src[base + (size_t)(p0 + p) * C + c];
+    }
+    __syncthreads();
+    const int p2 = blockIdx.y * 32 + threadIdx.x;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c2 = blockIdx.x * 32 + j;
+        if (c2 < C && p2 < np) dst[base + (size_t)c2 * HW + p0 + p2] = tile[threadIdx.x][j];
+    }
+}
+
 __global__ void split_kernel(const float *__restrict__ src, h16 *__restrict__ hi, h16 *__restrict__ lo, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         h16 h, l;
@@ -202,6 +308,44 @@ int launch_nchw_to_cl(const float *src, float *dst, int n, int C, int HW, cudaSt
 int launch_cl_to_nchw(const float *src, float *dst, int n, int C, int HW, cudaStream_t st) {
     dim3 grid((C + 31) / 32, (HW + 31) / 32, n), block(32, 8);
     transpose_kernel<<<grid, block, 0, st>>>(src, dst, HW, C);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_u8_to_xcl(const uint8_t *img, float *x_cl, int n, int H, int W, int Hb, int Wb, int B, int v0, int v1,
+                     cudaStream_t st) {
+    if (v1 <= v0) return 0;
+    const size_t total = (size_t)n * (v1 - v0) * B * Wb * B;
+    u8_to_xcl_kernel<<<grid_for(total, 256), 256, 0, st>>>(img, x_cl, n, H, W, Hb, Wb, B, v0, v1);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_zcl_to_u8(const float *z_cl, uint8_t *img, int n, int H, int W, int Hb, int Wb, int B, int v0, int v1,
+                     cudaStream_t st) {
+    if (v1 <= v0 || v0 * B >= H) return 0;
+    const size_t total = (size_t)n * ((size_t)(v1 - v0) * B) * ((W + 3) / 4);
+    zcl_to_u8_kernel<<<grid_for(total, 256), 256, 0, st>>>(z_cl, img, n, H, W, Hb, Wb, B, v0, v1);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_nchw_to_cl_band(const float *src, float *dst, int n, int C, int Hb, int Wb, int v0, int v1, cudaStream_t st) {
+    if (v1 <= v0) return 0;
+    dim3 grid(((v1 - v0) * Wb + 31) / 32, (C + 31) / 32, n), block(32, 8);
+    nchw_to_cl_band_kernel<<<grid, block, 0, st>>>(src, dst, C, Hb, Wb, v0, v1);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_cl_to_nchw_band(const float *src, float *dst, int n, int C, int Hb, int Wb, int v0, int v1, cudaStream_t st) {
+    if (v1 <= v0) return 0;
+    dim3 grid((C + 31) / 32, ((v1 - v0) * Wb + 31) / 32, n), block(32, 8);
+    cl_to_nchw_band_kernel<<<grid, block, 0, st>>>(src, dst, C, Hb, Wb, v0, v1);
     count_launch(1);
     LBIC_CUDA(cudaGetLastError());
     return 0;

@@ -139,6 +139,7 @@ int gemm_chain_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, in
 int gemm_ws_launch(const GemmCall &g, cudaStream_t st, int pair = 0);   // persistent warp-specialised kernel (gemm_ws.cu)
 int gemm_flow_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int l0, int l1, const int (*dep)[2], int R,
                      const StepDesc &step, int *d_counters, size_t counters_cap, cudaStream_t st, int pair = 1);
+constexpr int LBIC_FLOW_REFUSED = 1000;   // gemm_flow_launch: the (cooperative) launch was refused; use the per-layer path
 int gemm_flow_supported();   // 1 if all CTA pairs of the dataflow launch can be co-resident on this device
 int gemm_ws_max_bn();
 int gemm_pair_max_bn();
@@ -155,6 +156,14 @@ int make_tmap_2d(CUtensorMap *tm, const void *base, uint64_t inner, uint64_t out
 // ------------------------------------------------------------------------------------------------
 int launch_nchw_to_cl(const float *src, float *dst, int n, int C, int HW, cudaStream_t st);
 int launch_cl_to_nchw(const float *src, float *dst, int n, int C, int HW, cudaStream_t st);
+// band-wise forms (block rows [v0, v1) of every image): the host calls convert while later bands are still in flight
+int launch_nchw_to_cl_band(const float *src, float *dst, int n, int C, int Hb, int Wb, int v0, int v1, cudaStream_t st);
+int launch_cl_to_nchw_band(const float *src, float *dst, int n, int C, int Hb, int Wb, int v0, int v1, cudaStream_t st);
+// 8-bit RGB images (n,3,H,W) <-> channel-last block tensors (pad / crop, +-0.5 and the 8-bit quantisation fused)
+int launch_u8_to_xcl(const uint8_t *img, float *x_cl, int n, int H, int W, int Hb, int Wb, int B, int v0, int v1,
+                     cudaStream_t st);
+int launch_zcl_to_u8(const float *z_cl, uint8_t *img, int n, int H, int W, int Hb, int Wb, int B, int v0, int v1,
+                     cudaStream_t st);
 int launch_space_to_depth(const float *img, float *blk, int n, int C, int Hb, int Wb, int B, cudaStream_t st);
 int launch_depth_to_space(const float *blk, float *img, int n, int C, int Hb, int Wb, int B, cudaStream_t st);
 int launch_split_f32(const float *src, h16 *hi, h16 *lo, int64_t n, cudaStream_t st);
@@ -212,8 +221,10 @@ int launch_rans_encode(const Tables &T, const int32_t *sym, const uint8_t *idx, 
 // lane container: merges `lanes` consecutive single streams per image into header|lengths|payload
 int launch_lane_pack(const uint32_t *scratch, size_t scratch_words, int n_img, int lanes, uint8_t *out,
                      size_t out_stride, uint32_t *out_len, int *err_flag, cudaStream_t st);
+// lanes_container != 0: the streams are 'LBML' lane containers (also when lanes == 1, i.e. a one-block-row image)
 int launch_rans_dec_init(const uint8_t *streams, const uint32_t *stream_len, size_t stream_stride, int n_img,
-                         int lanes, RansStreamState *states, const uint8_t **lane_ptr, int *err_flag, cudaStream_t st);
+                         int lanes, int lanes_container, RansStreamState *states, const uint8_t **lane_ptr, int *err_flag,
+                         cudaStream_t st);
 // decode M symbols for every row of a step; writes yq = sym + mean (hi/lo) and optionally symbols
 void rans_set_enc_thread_min_streams(int n);   // encodes of at least this many streams use the thread-per-stream kernel
 void rans_set_dec_thread_min_rows(int rows);   // steps with at least this many rows use the thread-per-stream kernel

@@ -373,8 +373,9 @@ __device__ __forceinline__ int dec_symbol_warp(DecCursor &d, const int32_t *__re
 
 // Parses the per-image container(s) and initialises one decoder state per lane.
 __global__ void rans_dec_init_kernel(const uint8_t *__restrict__ streams, const uint32_t *__restrict__ stream_len,
-                                     size_t stream_stride, int n_img, int lanes, RansStreamState *__restrict__ states,
-                                     const uint8_t **__restrict__ lane_ptr, int *__restrict__ err) {
+                                     size_t stream_stride, int n_img, int lanes, int lanes_container,
+                                     RansStreamState *__restrict__ states, const uint8_t **__restrict__ lane_ptr,
+                                     int *__restrict__ err) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_img * lanes) return;
     const int img = i / lanes, l = i - img * lanes;
@@ -382,17 +383,33 @@ __global__ void rans_dec_init_kernel(const uint8_t *__restrict__ streams, const 
     const uint32_t total = stream_len[img];
     const uint8_t *p = base;
     uint32_t nbytes = total;
-    if (lanes > 1) {
+    // The container comes from the caller (possibly from an untrusted file): every length is checked in 64-bit
+    // arithmetic against what is left of the image's slot, lane payloads must be whole 32-bit words, and a stream
+    // may not be longer than its slot.  A rejected container decodes as an empty stream (all reads return zero).
+    if ((size_t)total > stream_stride || (total & 3u)) {
+        atomicExch(err, 2);
+        nbytes = 0;
+    } else if (lanes_container) {
         const uint32_t *hdr = reinterpret_cast<const uint32_t *>(base);
-        if (total < 8u + 4u * lanes || hdr[0] != LANE_MAGIC || hdr[1] != (uint32_t)lanes) {
+        const unsigned long long hdr_bytes = 8ull + 4ull * (unsigned long long)lanes;
+        if ((unsigned long long)total < hdr_bytes || hdr[0] != LANE_MAGIC || hdr[1] != (uint32_t)lanes) {
             atomicExch(err, 2);
             nbytes = 0;
         } else {
-            uint32_t o = 8u + 4u * lanes;
-            for (int j = 0; j < l; ++j) o += hdr[2 + j];
-            nbytes = hdr[2 + l];
-            p = base + o;
-            if (o + nbytes > total) { atomicExch(err, 2); nbytes = 0; }
+            unsigned long long o = hdr_bytes;
+            bool ok = true;
+            for (int j = 0; j <= l && ok; ++j) {
+                const uint32_t len_j = hdr[2 + j];
+                ok = !(len_j & 3u) && (unsigned long long)len_j <= (unsigned long long)total - o;
+                if (ok && j < l) o += len_j;
+            }
+            if (ok) {
+                nbytes = hdr[2 + l];
+                p = base + o;
+            } else {
+                atomicExch(err, 2);
+                nbytes = 0;
+            }
         }
     }
     RansStreamState st;
@@ -691,10 +708,11 @@ int launch_lane_pack(const uint32_t *scratch, size_t scratch_words, int n_img, i
 }
 
 int launch_rans_dec_init(const uint8_t *streams, const uint32_t *stream_len, size_t stream_stride, int n_img, int lanes,
-                         RansStreamState *states, const uint8_t **lane_ptr, int *err_flag, cudaStream_t st) {
+                         int lanes_container, RansStreamState *states, const uint8_t **lane_ptr, int *err_flag,
+                         cudaStream_t st) {
     const int n = n_img * lanes;
-    rans_dec_init_kernel<<<(n + 127) / 128, 128, 0, st>>>(streams, stream_len, stream_stride, n_img, lanes, states,
-                                                          lane_ptr, err_flag);
+    rans_dec_init_kernel<<<(n + 127) / 128, 128, 0, st>>>(streams, stream_len, stream_stride, n_img, lanes,
+                                                          lanes_container, states, lane_ptr, err_flag);
     count_launch(1);
     LBIC_CUDA(cudaGetLastError());
     return 0;

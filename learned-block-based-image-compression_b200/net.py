@@ -113,13 +113,14 @@ class BlockBasedImgCompLossyNetv9:
 
     def set_option(self, name: str, value: int):
         """Tuning hooks: 'chain' (1 = persistent chain kernel per step; default 0), 'cluster' (forced cluster size),
-        'force_bn' (forced tile width), 'graph', 'ws' (0 off / 1 auto / 2 always: persistent kernel),
-        'pair' (CTA-pair form of the persistent kernel), 'pdl'."""
+        'force_bn' (forced tile width), 'ws' (0 off / 1 auto / 2 always: persistent kernel),
+        'pair' (CTA-pair form of the persistent kernel), 'pdl', 'host_bands' (bands of block rows of the host calls)."""
         opt = {"chain": _lib.LBIC_OPT_CHAIN, "cluster": _lib.LBIC_OPT_CLUSTER, "force_bn": _lib.LBIC_OPT_FORCE_BN,
-               "graph": _lib.LBIC_OPT_USE_GRAPH, "ws": _lib.LBIC_OPT_WS, "pdl": _lib.LBIC_OPT_PDL,
+               "ws": _lib.LBIC_OPT_WS, "pdl": _lib.LBIC_OPT_PDL,
                "pair": _lib.LBIC_OPT_PAIR, "dec_thread_rows": _lib.LBIC_OPT_DEC_THREAD_ROWS,
                "enc_thread_streams": _lib.LBIC_OPT_ENC_THREAD_STREAMS, "flow": _lib.LBIC_OPT_FLOW,
-               "flow_min_rows": _lib.LBIC_OPT_FLOW_MIN_ROWS, "flow_small": _lib.LBIC_OPT_FLOW_SMALL, "host_split_min": _lib.LBIC_OPT_HOST_SPLIT_MIN}[name]
+               "flow_min_rows": _lib.LBIC_OPT_FLOW_MIN_ROWS, "flow_small": _lib.LBIC_OPT_FLOW_SMALL,
+               "host_bands": _lib.LBIC_OPT_HOST_BANDS}[name]
         _lib.check(_lib.lib().lbic_set_option(self._need(), opt, int(value)))
 
     # ---- state_dict ----------------------------------------------------------------------------
@@ -307,8 +308,15 @@ class BlockBasedImgCompLossyNetv9:
 
     __call__ = forward
 
+    def check_errors(self):
+        """Synchronises the current stream and raises if the last encode / decode enqueued on it flagged an overflowing
+        stream buffer (RuntimeError) or a malformed lane container (RuntimeError, 'malformed')."""
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.lib().lbic_check_errors(self._need(), self._stream()))
+
     def decode_device(self, streams, lens, n, Hb, Wb, lanes: int = 1, want_symbols: bool = False):
-        """streams (n, cap) uint8 CUDA, lens (n,) int32 CUDA -> zhat (n,3B^2,Hb,Wb) [, sym]."""
+        """streams (n, cap) uint8 CUDA, lens (n,) int32 CUDA -> zhat (n,3B^2,Hb,Wb) [, sym].  Asynchronous: a malformed
+        lane container is only flagged on the device; call check_errors() (decompress_batch does)."""
         h = self._need()
         dev = streams.device
         zhat = torch.empty(n, self.Cin, Hb, Wb, dtype=torch.float32, device=dev)
@@ -345,7 +353,45 @@ class BlockBasedImgCompLossyNetv9:
             host[i, : len(s)] = np.frombuffer(s, dtype=np.uint8)
         streams = torch.from_numpy(host).to(dev)
         lens = torch.tensor([len(s) for s in strings], dtype=torch.int32, device=dev)
-        return self.decode_device(streams, lens, n, Hb, Wb, lanes=lanes)
+        zhat = self.decode_device(streams, lens, n, Hb, Wb, lanes=lanes)
+        self.check_errors()
+        return zhat
+
+    # ---- 8-bit images in host memory (eval_model's per-image body for a batch, AGENT:581-599, 610-628) -------------
+    def compress_images_u8(self, images, lanes: int = 1, return_recon: bool = False, stream_cap: int | None = None):
+        """images: (n, 3, H, W) uint8, host (numpy array or CPU tensor; pinned memory makes the copies asynchronous).
+        -> (list[bytes], recon uint8 (n,3,H,W) or None).  ToTensor, -0.5, replicate padding, space-to-depth, compress
+        and (optionally) the 8-bit reconstruction the reference would save, in one call."""
+        h = self._need()
+        a = images.numpy() if isinstance(images, torch.Tensor) else np.ascontiguousarray(images)
+        if a.dtype != np.uint8 or a.ndim != 4 or a.shape[1] != 3:
+            raise ValueError("images must be uint8 of shape (n, 3, H, W)")
+        n, _, H, W = a.shape
+        Hb, Wb = -(-H // self.B), -(-W // self.B)
+        cap = (int(stream_cap or self.stream_bound(Hb, Wb, lanes)) + 3) // 4 * 4
+        streams = np.empty((n, cap), dtype=np.uint8)
+        lens = np.zeros(n, dtype=np.uint32)
+        recon = np.empty_like(a) if return_recon else None
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.lib().lbic_encode_images_u8_host(
+                h, a.ctypes.data, n, H, W, recon.ctypes.data if recon is not None else None, streams.ctypes.data, cap,
+                lens.ctypes.data, lanes))
+        return [streams[i, : lens[i]].tobytes() for i in range(n)], recon
+
+    def decompress_images_u8(self, strings, H: int, W: int, lanes: int = 1):
+        """list[bytes] -> (n, 3, H, W) uint8 numpy array: decompress + depth-to-space + crop + 8-bit quantisation."""
+        h = self._need()
+        n = len(strings)
+        cap = (max(len(s) for s in strings) + 3) // 4 * 4
+        host = np.zeros((n, cap), dtype=np.uint8)
+        for i, s in enumerate(strings):
+            host[i, : len(s)] = np.frombuffer(s, dtype=np.uint8)
+        lens = np.array([len(s) for s in strings], dtype=np.uint32)
+        out = np.empty((n, 3, H, W), dtype=np.uint8)
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.lib().lbic_decode_images_u8_host(h, host.ctypes.data, lens.ctypes.data, cap, n, H, W,
+                                                             out.ctypes.data, lanes))
+        return out
 
     def compress(self, x, LRU=None, chlat=None):
         """NET:319-361: one image (1, 3B^2, Hb, Wb) -> (bitstream bytes, zhat)."""
