@@ -49,6 +49,20 @@ def load_peaks():
     return dict(tf_sustained=1400.0, tf_burst=1590.0, hbm=6650.0, source="fallback")
 
 
+def measured_traffic(args):
+    """roofline.traffic comes from an ncu --set full capture of THIS command (scripts/ncu_traffic.py parses the report
+    into profiles/ncu_traffic.json keyed by workload); it is null when no capture of the workload being run exists."""
+    key = f"{args.config}:{args.images}:{args.width}x{args.height}:lanes{args.lanes}"
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        rec = json.load(open(p)).get(key)
+    except Exception:
+        rec = None
+    if not rec:
+        return dict(traffic=None, traffic_note=f"no ncu --set full capture for workload {key} under profiles/ncu_traffic.json")
+    return dict(traffic=rec["dram_bytes_per_launch"], traffic_note=rec["note"])
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -90,23 +104,26 @@ class ClockSampler:
 
 
 def synth_batch_gpu(n, H, W, seed, dev):
-    """Smooth-plus-noise synthetic images in [0,1], generated on the device."""
+    """Smooth-plus-noise synthetic 8-bit RGB images, generated on the device: (n,3,H,W) uint8."""
     import torch
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
     low = torch.rand(n, 3, max(H // 16, 2), max(W // 16, 2), generator=g, device=dev)
     up = torch.nn.functional.interpolate(low, size=(H, W), mode="bicubic", align_corners=False)
-    return (up + 0.05 * torch.randn(n, 3, H, W, generator=g, device=dev)).clamp_(0, 1)
+    img = (up + 0.05 * torch.randn(n, 3, H, W, generator=g, device=dev)).clamp_(0, 1)
+    return img.mul_(255).round_().to(torch.uint8)
 
 
 def cpu_baseline(cfg, H, W, max_blocks, threads):
     """The oracle port of the reference's compress()/decompress() loops (torch CPU fp32 convs exactly as
-    NET:363-398) timed on a bounded sample: the first `max_blocks` blocks in raster order of one image."""
+    NET:363-398) timed on a bounded sample: the first `max_blocks` blocks in raster order of one image.
+    threads = 1 is the reference's own CPU setting (AGENT:565-566 torch.set_num_threads(1))."""
     import torch
     import lbic_b200
     from lbic_b200 import weights
     from oracle import nets
     torch.set_num_threads(threads)
+    torch.use_deterministic_algorithms(True)      # AGENT:562
     B = int(cfg.block_size)
     sd = weights.synth_state_dict(cfg, 1337)
     P = nets.effective_params(sd, cfg)
@@ -146,7 +163,7 @@ def run_reference(args, cfg, rank):
     sample = (f"first {vals[0]['blocks']} raster-order blocks of one {args.width}x{args.height} image per step, "
               f"compress loop + decompress loop, torch CPU fp32, {threads} threads")
     line = dict(metric="encode+decode Mpixel/s", value=value, unit="Mpixel/s", n_gpus=args.gpus, steps=args.steps,
-                warmup=args.warmup, ms_per_step=1e3 * t / len(vals), higher_is_better=True, scaling="weak",
+                warmup=args.warmup, ms_per_step=1e3 * t / len(vals), higher_is_better=True, scaling=args.scaling,
                 vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
                 config=workload_config(args, cfg),
                 cpu_baseline=dict(value=value, unit="Mpixel/s", cores=threads, kind="port", sample=sample),
@@ -155,8 +172,11 @@ def run_reference(args, cfg, rank):
 
 
 def workload_config(args, cfg):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    split = (f"{args.images} images per GPU (weak scaling)" if args.scaling == "weak" else
+             f"{args.total_images} images in total, image-sharded over {world} GPU(s) = {args.images} per GPU (strong scaling)")
     return dict(workload=f"{args.config} (B{cfg.block_size}, KS{''.join(map(str, cfg.KS))}, N{cfg.N} M{cfg.M}) "
-                         f"compress+decompress of {args.images} synthetic {args.width}x{args.height} RGB images per GPU, "
+                         f"compress+decompress of synthetic {args.width}x{args.height} RGB images, {split}, "
                          f"random-init conditioned weights",
                 images_per_gpu=args.images, height=args.height, width=args.width,
                 container="reference (1 rANS stream per image)" if args.lanes == 1 else "lane (1 rANS stream per block row)",
@@ -171,7 +191,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="B8_lowrate")
-    ap.add_argument("--images", type=int, default=1024, help="images per GPU per step")
+    ap.add_argument("--images", type=int, default=1024, help="images per GPU per step (weak scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: --total-images are image-sharded over the N GPUs (BASELINE config 3)")
+    ap.add_argument("--total-images", type=int, default=1024, help="batch of the whole job under --scaling strong")
     ap.add_argument("--height", type=int, default=512)
     ap.add_argument("--width", type=int, default=768)
     ap.add_argument("--lanes", type=int, default=0, help="1 = reference container, 0 = lane container")
@@ -188,6 +211,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.scaling == "strong":
+        if args.total_images % world:
+            raise SystemExit(f"--total-images {args.total_images} is not divisible by {world} GPUs")
+        args.images = args.total_images // world
 
     if args.impl == "reference":
         run_reference(args, cfg, rank)
@@ -213,9 +240,11 @@ def main():
     m.load_state_dict(weights.synth_state_dict(cfg, 1337))
     m.update(force=True)
     m.set_gemm_core(args.core)
-    img = synth_batch_gpu(n, H, W, 1000 + rank, dev)
-    x = arrange_block_pixels_to_channel_dim(img - 0.5, B)
-    del img
+    img_u8 = synth_batch_gpu(n, H, W, 1000 + rank, dev)
+    # ToTensor (a TRUE division by 255: a tensor divisor, because torch's CUDA kernel for `x / python_scalar` multiplies by
+    # the reciprocal and differs from the reference's CPU division in the last bit), AGENT:581, 588-589
+    x = arrange_block_pixels_to_channel_dim(
+        torch.true_divide(img_u8.float(), torch.full((), 255.0, device=dev)) - 0.5, B)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if x.numel() * 4 < 126e6 else None
 
     def barrier():
@@ -285,11 +314,7 @@ def main():
                     launches=prof["gemm_launches"], avg_launch_us=1e3 * prof["gemm_ms"] / max(1, prof["gemm_launches"]),
                     gemm_share_of_encode=prof["gemm_ms"] / (ms_enc / args.steps),
                     algorithmic_flop_per_pixel=dict(encode=2 * macs["encode"] / (B * B), decode=2 * macs["decode"] / (B * B)),
-                    traffic=4.09e9,
-                    traffic_note="dram__bytes_read.sum + dram__bytes_write.sum of one gemm_flow_kernel launch (a whole wavefront "
-                                 "step of ~40 k block rows, all 18 layers, 1.46 ms) from ncu --set full on this command: "
-                                 "profiles/r1_final_gemm_flow_ncu_summary.txt; about the bytes of writing and reading every "
-                                 "activation once (the batch's activations do not fit the 126 MB L2); tensor pipe active 63.5 %",
+                    **measured_traffic(args),
                     binding_resource="L2 -> SM bandwidth (~43 B/clk/SM chip-wide): launch time tracks the operand + output "
                                      "bytes through L2, see profiles/r1_l2_bound.md; the tensor peak is the contract's denominator",
                     layers_tflops_per_layer_launches={k: round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)
@@ -305,38 +330,44 @@ def main():
         ms_d1 = timed(lambda: m.decode_device(o1.streams, o1.lens, n, Hb, Wb, lanes=1), 1)
         z1 = m.decode_device(o1.streams, o1.lens, n, Hb, Wb, lanes=1)
         refc = dict(container="reference (1 rANS64 stream per image)", images_per_gpu=n,
+                    value=pixels_step / ((ms_e1 + ms_d1) * 1e-3) / 1e6, unit="Mpixel/s (encode+decode round trip)",
                     encode_mpix_s=pixels_step / (ms_e1 * 1e-3) / 1e6, decode_mpix_s=pixels_step / (ms_d1 * 1e-3) / 1e6,
                     enc_dec_identical=bool(torch.equal(z1, o1.zhat)), bpp=8.0 * int(o1.lens.sum().item()) / (n * H * W))
         del o1, z1
 
-    # end to end through the host-buffer C ABI (pinned host memory, H2D + D2H inside the timed region)
+    # end to end through the reference-facing host call: 8-bit images in pinned host memory -> bitstreams in host memory
+    # (ToTensor, -0.5, padding, space-to-depth, compress: AGENT:581-592) -> 8-bit reconstructions in host memory
+    # (decompress, depth-to-space, 8-bit quantisation: AGENT:598, 610, 628); H2D + D2H copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        import ctypes
         import numpy as np
         from lbic_b200 import _lib
         L = _lib.lib()
-        xh = torch.empty(x.shape, dtype=torch.float32).pin_memory()
-        xh.copy_(x)
-        zh = torch.empty(x.shape, dtype=torch.float32).pin_memory()
+        ih = torch.empty(img_u8.shape, dtype=torch.uint8).pin_memory()
+        ih.copy_(img_u8)
+        oh = torch.empty(img_u8.shape, dtype=torch.uint8).pin_memory()
         cap = int(min(enc_out.streams.shape[1], ((int(enc_out.lens.max().item()) * 2 + 4096) + 3) // 4 * 4))
         sh = torch.empty(n, cap, dtype=torch.uint8).pin_memory()
         lh = torch.zeros(n, dtype=torch.int32).pin_memory()
 
         def e2e_step():
-            _lib.check(L.lbic_encode_host(m._need(), xh.data_ptr(), n, Hb, Wb, None, sh.data_ptr(), cap, lh.data_ptr(),
-                                          args.lanes))
-            _lib.check(L.lbic_decode_host(m._need(), sh.data_ptr(), lh.data_ptr(), cap, n, Hb, Wb, zh.data_ptr(),
-                                          args.lanes))
+            _lib.check(L.lbic_encode_images_u8_host(m._need(), ih.data_ptr(), n, H, W, None, sh.data_ptr(), cap,
+                                                    lh.data_ptr(), args.lanes))
+            _lib.check(L.lbic_decode_images_u8_host(m._need(), sh.data_ptr(), lh.data_ptr(), cap, n, H, W, oh.data_ptr(),
+                                                    args.lanes))
         e2e_step()
         ms_e2e = timed(e2e_step, args.steps)
         lens_h = lh.numpy().astype(np.int64)
-        h2d = xh.numel() * 4 + int(lens_h.sum()) + 4 * n
-        d2h = int(lens_h.sum()) + 4 * n + zh.numel() * 4
+        from lbic_b200.layout import arrange_channel_dim_to_block_pixels
+        want = (arrange_channel_dim_to_block_pixels(enc_out.zhat, B) + 0.5).mul_(255).add_(0.5).clamp_(0, 255).to(torch.uint8)
         e2e = dict(value=pixels_step * args.steps / (ms_e2e * 1e-3) / 1e6, unit="Mpixel/s",
-                   h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                   api="lbic_encode_host + lbic_decode_host (pinned host buffers)",
-                   parity=bool(torch.equal(zh.to(dev), enc_out.zhat)))
+                   h2d_bytes_per_step=ih.numel() + int(lens_h.sum()) + 4 * n,
+                   d2h_bytes_per_step=int(lens_h.sum()) + 4 * n + oh.numel(),
+                   api="lbic_encode_images_u8_host + lbic_decode_images_u8_host (8-bit images and bitstreams in pinned host "
+                       "memory; copies overlapped with the wavefront in bands of block rows)",
+                   parity=bool(torch.equal(oh.to(dev), want)), ratio_to_device_value=None)
+        e2e["ratio_to_device_value"] = e2e["value"] / value
+        del ih, oh, sh, want
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:   # reported at N=1 only (host cores are shared by the ranks)
@@ -346,10 +377,14 @@ def main():
                    sample=f"first {r['blocks']} raster-order blocks of one {W}x{H} image: oracle port of the reference "
                           f"compress loop ({r['enc_s']:.1f} s) + decompress loop ({r['dec_s']:.1f} s), torch CPU fp32",
                    encode_mpix_s=r["enc_mpix_s"], decode_mpix_s=r["dec_mpix_s"])
+        # the reference's own CPU setting is ONE thread (AGENT:565-566): a smaller sample of the same loops
+        r1 = cpu_baseline(cfg, H, W, max(16, args.cpu_blocks // 16), 1)
+        cpu["one_thread"] = dict(value=r1["mpix_s"], cores=1, encode_mpix_s=r1["enc_mpix_s"], decode_mpix_s=r1["dec_mpix_s"],
+                                 sample=f"first {r1['blocks']} blocks, torch.set_num_threads(1) as agents/blkbsdimgcomp_agent.py:565-566")
 
     if rank == 0:
         line = dict(metric="encode+decode Mpixel/s", value=value, unit="Mpixel/s", n_gpus=world, steps=args.steps,
-                    warmup=args.warmup, ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak",
+                    warmup=args.warmup, ms_per_step=ms_total / args.steps, higher_is_better=True, scaling=args.scaling,
                     vs_baseline=None, dtype="f16x3->f32", data="synthetic", config=workload_config(args, cfg),
                     encode_mpix_s=pixels_step * args.steps / (ms_enc * 1e-3) / 1e6,
                     decode_mpix_s=pixels_step * args.steps / (ms_dec * 1e-3) / 1e6,

@@ -43,6 +43,42 @@ def get_model(cfgname, seed, harsh, dev, core="tcgen05"):
     return m
 
 
+# Worst distance of a teacher-forced mismatch from its rounding boundary.  The arithmetic noise of y - mean on the B200
+# path is the tensor cores' truncating fp32 accumulation (profiles/r2_gemm_precision.md: 2-3.5e-6 relative at K = 576-960,
+# 1.4e-5 at K = 3840, growing linearly with K; the hi/lo operand split itself contributes 6e-8).  Measured worst distances
+# over 36 full-size images (profiles/r2_parity_sweep.jsonl): 8.8e-5 for the B8 / B4 topologies, 1.7e-4 for B16 (first
+# layers with K = 3840).  The bars are ~2-3x those, an order of magnitude below a 1e-3 arithmetic bug.
+TF_BOUNDARY_TOL = 2e-4
+TF_BOUNDARY_TOL_BY_CONFIG = {"B16_lowrate": 5e-4}
+
+
+def tf_tol(cfgname):
+    return TF_BOUNDARY_TOL_BY_CONFIG.get(str(cfgname), TF_BOUNDARY_TOL)
+
+
+def tf_boundary_report(s2, i2, y2, ksi2, sym_c, idx_c, scale_table):
+    """EVERY teacher-forced mismatch (oracle evaluation on the GPU's own zhat vs the GPU's symbols / indexes) must be a
+    rounding-boundary case: the oracle's y - mean within TF_BOUNDARY_TOL of a .5 boundary AND the two symbols adjacent
+    integers; for an index, the oracle's scale within TF_BOUNDARY_TOL (relative) of a scale-table threshold.
+    Returns the worst distances over all mismatching positions."""
+    M = sym_c.shape[-1]
+    d = (y2 - ksi2[:, M:]).permute(0, 2, 3, 1)                               # (n,Hb,Wb,M) like the symbols
+    frac = (d - torch.floor(d) - 0.5).abs()
+    smis = s2 != sym_c
+    sc = torch.clamp(ksi2[:, :M], min=0.11).permute(0, 2, 3, 1)
+    rel = ((sc[..., None] - scale_table) .abs() / scale_table).min(dim=-1).values
+    imis = i2 != idx_c
+    return dict(tf_worst_symbol_boundary_distance=float(frac[smis].max()) if bool(smis.any()) else 0.0,
+                tf_worst_symbol_step=int((s2 - sym_c).abs().max()),
+                tf_worst_index_boundary_distance=float(rel[imis].max()) if bool(imis.any()) else 0.0,
+                tf_worst_index_step=int((i2 - idx_c).abs().max()))
+
+
+def assert_tf_boundary(rep, tol=TF_BOUNDARY_TOL):
+    assert rep["tf_worst_symbol_boundary_distance"] < tol and rep["tf_worst_symbol_step"] <= 1, rep
+    assert rep["tf_worst_index_boundary_distance"] < tol and rep["tf_worst_index_step"] <= 1, rep
+
+
 def closed_loop_report(cfgname, seed, harsh, x, sym, idx, zhat, ref_sym, ref_idx):
     """Compares a GPU closed-loop result with the reference's.
 
@@ -63,6 +99,7 @@ def closed_loop_report(cfgname, seed, harsh, x, sym, idx, zhat, ref_sym, ref_idx
     rep = dict(symbols=n, tf_symbol_mismatches=int((s2 != sym_c).sum()), tf_index_mismatches=int((i2 != idx_c).sum()),
                closed_loop_symbol_mismatches=int((sym_c != ref_sym).sum()),
                closed_loop_index_mismatches=int((idx_c != ref_idx).sum()), first_mismatch=None)
+    rep.update(tf_boundary_report(s2, i2, y2, ksi2, sym_c, idx_c, P.scale_table))
     bad = ((sym_c != ref_sym) | (idx_c != ref_idx))
     if bool(bad.any()):
         M = sym_c.shape[-1]
@@ -173,10 +210,12 @@ def test_encode_matches_reference_golden(dev, case, core):
     rep = closed_loop_report(str(c["config"]), int(c["seed"]), bool(c["harsh"]), x, sym, idx, zhat, ref_sym, ref_idx)
     n = rep["symbols"]
     assert rep["tf_symbol_mismatches"] <= max(1, n // 10000) and rep["tf_index_mismatches"] <= max(1, n // 10000), rep
+    tol = 1e-3 if bool(c["harsh"]) else tf_tol(c["config"])
+    assert_tf_boundary(rep, tol)
     mism = rep["closed_loop_symbol_mismatches"] + rep["closed_loop_index_mismatches"]
     if mism:
         # accumulation-order noise is ~1e-5 here; anything that is not a boundary case is a real bug
-        assert max(rep["first_mismatch"]["boundary_distance"]) < 2e-3, rep
+        assert max(rep["first_mismatch"]["boundary_distance"]) < tol, rep
     zref = torch.from_numpy(c["zhat"])
     xh = torch.from_numpy(c["x"])
     psnr = lambda z: -10.0 * float(torch.log10(((xh - z) ** 2).mean()))
@@ -214,7 +253,7 @@ def test_decode_roundtrip(dev, case, lanes):
         assert float((zref.cpu() - torch.from_numpy(c["zhat_dec"])).abs().max()) < tol
 
 
-@pytest.mark.parametrize("cfgname", ["B8_lowrate", "B4_highrate", "B16_lowrate"])
+@pytest.mark.parametrize("cfgname", ["B8_lowrate", "B4_highrate", "B16_lowrate", "B8_highrate"])
 def test_thread_per_stream_decode_equals_warp_per_stream(dev, cfgname):
     """rans_dec_step_thread_kernel (one stream per thread, compact CDFs + bucket table in shared memory) must decode
     exactly what the warp-per-stream kernel decodes, for the lane container and the reference container; the harsh
@@ -290,7 +329,7 @@ def test_chain_kernel_equals_per_layer_launches(dev, cfgname):
         m.set_option("cluster", 0)
 
 
-@pytest.mark.parametrize("cfgname", ["B8_lowrate", "B4_highrate", "B16_lowrate"])
+@pytest.mark.parametrize("cfgname", ["B8_lowrate", "B4_highrate", "B16_lowrate", "B8_highrate"])
 def test_warp_specialised_kernel_equals_per_tile_kernel(dev, cfgname):
     """gemm_ws_kernel (persistent, overlapped epilogue, 192-wide tiles), in its single-CTA and CTA-pair (cta_group::2,
     256-row tiles) forms, must be bit-identical to gemm_tc_kernel."""
@@ -315,7 +354,7 @@ def test_warp_specialised_kernel_equals_per_tile_kernel(dev, cfgname):
         m.set_option("pair", 1)
 
 
-@pytest.mark.parametrize("cfgname", ["B8_lowrate", "B4_highrate", "B16_lowrate"])
+@pytest.mark.parametrize("cfgname", ["B8_lowrate", "B4_highrate", "B16_lowrate", "B8_highrate"])
 def test_dataflow_launch_equals_per_layer_launches(dev, cfgname):
     """gemm_flow_kernel (all layers of a step in one launch, row-block dependency counters instead of kernel boundaries)
     must be bit-identical to one launch per layer, encode and decode, including ragged last row blocks."""
@@ -347,8 +386,13 @@ def test_dataflow_launch_equals_per_layer_launches(dev, cfgname):
         m.set_option("flow_small", 0)
 
 
-@pytest.mark.parametrize("cfgname,H,W", [("B8_lowrate", 512, 768), ("B4_highrate", 128, 192), ("B16_lowrate", 256, 256)])
-def test_full_size_fixed_point_vs_oracle(dev, cfgname, H, W):
+# BASELINE.json configs at their own sizes: C1 (B8_lowrate 768x512), C2 (B4_highrate 768x512, batch of 24),
+# C3 (B8_highrate 768x512, enough images that the persistent / CTA-pair / dataflow kernels engage: 96 images x 48 rows
+# = 4608-row steps), C4 (B16_lowrate 2048x2048).  The oracle checks the first `n_chk` images; encode -> decode covers all.
+@pytest.mark.parametrize("cfgname,H,W,n_img,n_chk", [("B8_lowrate", 512, 768, 2, 2), ("B4_highrate", 512, 768, 24, 2),
+                                                     ("B8_highrate", 512, 768, 96, 2), ("B16_lowrate", 2048, 2048, 1, 1),
+                                                     ("B4_highrate", 128, 192, 2, 2), ("B16_lowrate", 256, 256, 2, 2)])
+def test_full_size_fixed_point_vs_oracle(dev, cfgname, H, W, n_img, n_chk):
     """BASELINE-size check through a size-independent property: the closed-loop result is
     the unique fixed point of the open-loop network, so ONE parallel oracle evaluation (torch CPU fp32) on the GPU's
     final zhat must reproduce the GPU's symbols (>= 99.99 %), indexes and reconstruction; and decode(encode) == zhat."""
@@ -358,28 +402,34 @@ def test_full_size_fixed_point_vs_oracle(dev, cfgname, H, W):
     cfg = lbic_b200.load_config(cfgname)
     m = get_model(cfgname, 1337, False, dev)
     B = m.B
-    img = weights.synth_images(2, H, W, seed0=1000)
+    img = weights.synth_images(n_img, H, W, seed0=1000)
     x = arrange_block_pixels_to_channel_dim((img - 0.5).to(dev), B)
-    strings, zhat, sym, idx = m.compress_batch(x, lanes=1, return_symbols=True)
+    lanes = 1 if n_img <= 2 else 0          # the raster-serial reference container on the small batches only
+    strings, zhat, sym, idx = m.compress_batch(x, lanes=lanes, return_symbols=True)
     P = nets.effective_params(weights.synth_state_dict(cfg, 1337), cfg)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    s2, i2, xh2, _, _ = nets.whole_image_eval(P, x.cpu(), zhat.cpu())
-    n = sym.numel()
-    sym_mis = int((s2 != sym.cpu()).sum())
-    idx_mis = int((i2 != idx.cpu().int()).sum())
+    xc, zc, sc, ic = x[:n_chk].cpu(), zhat[:n_chk].cpu(), sym[:n_chk].cpu(), idx[:n_chk].cpu().int()
+    s2, i2, xh2, y2, ksi2 = nets.whole_image_eval(P, xc, zc)
+    n = sc.numel()
+    sym_mis = int((s2 != sc).sum())
+    idx_mis = int((i2 != ic).sum())
+    brep = tf_boundary_report(s2, i2, y2, ksi2, sc, ic, P.scale_table)
     # compare reconstructions only on blocks whose symbols agree (a +-1 symbol flip legitimately moves its block)
-    same_blk = ((s2 == sym.cpu()).all(dim=-1)).unsqueeze(1)                       # (n,1,Hb,Wb)
-    zerr = float(((xh2 - zhat.cpu()).abs() * same_blk).max())
+    same_blk = ((s2 == sc).all(dim=-1)).unsqueeze(1)                              # (n,1,Hb,Wb)
+    zerr = float(((xh2 - zc).abs() * same_blk).max())
     os.makedirs("gpurun_out", exist_ok=True)
     with open(f"gpurun_out/fixed_point_{cfgname}_{W}x{H}.json", "w") as f:
-        json.dump(dict(config=cfgname, H=H, W=W, images=2, symbols=n, symbol_mismatches=sym_mis,
+        json.dump(dict(config=cfgname, H=H, W=W, images=n_img, images_checked=n_chk, symbols=n, symbol_mismatches=sym_mis,
                        index_mismatches=idx_mis, zhat_maxdiff=zerr, sym_std=float(sym.float().std()),
-                       sym_absmax=int(sym.abs().max()), bytes=[len(s) for s in strings]), f)
+                       sym_absmax=int(sym.abs().max()), bytes=[len(s) for s in strings[:4]], **brep), f)
     assert sym_mis <= n // 10000, f"{sym_mis} of {n} symbols differ from the oracle fixed point (> 0.01 %)"
     assert idx_mis <= n // 10000, f"{idx_mis} of {n} indexes differ"
+    assert_tf_boundary(brep, tf_tol(cfgname))
     assert zerr < 5e-4, f"zhat differs from the oracle fixed point by {zerr:.2e}"
-    zdec = m.decompress_batch(strings, x.shape, lanes=1)
+    zdec = m.decompress_batch(strings, x.shape, lanes=lanes)
     assert torch.equal(zdec, zhat)
+    if lanes != 1:
+        return
     # bit-exact entropy stage for the GPU's own symbols, against the oracle coder
     g = m.conditional_gaussian_model
     T = onative.Tables(g.quantized_cdf.numpy(), g.cdf_length.numpy(), g.offset.numpy())
@@ -387,42 +437,62 @@ def test_full_size_fixed_point_vs_oracle(dev, cfgname, H, W):
     assert strings[0] == want
 
 
-def test_full_size_image_vs_reference_closed_loop(dev):
-    """The headline parity number: ONE full 768x512 image (B8 KS3111 N768 M96, 589 824 symbols) against the
-    UNMODIFIED reference's closed loop (tests/golden/make_golden_full.py; ~100 s of CPU there).  north_star bar:
-    symbols identical on >= 99.99 % of positions, bpp within 0.1 %, PSNR within 0.01 dB; if all symbols match, the
-    bitstream must be byte-identical (sha256)."""
+@pytest.mark.parametrize("cfgname,gw,gh", [("B8_lowrate", 768, 512), ("B8_highrate", 768, 512), ("B4_highrate", 768, 512),
+                                           ("B16_lowrate", 2048, 2048)])
+def test_full_size_image_vs_reference_closed_loop(dev, cfgname, gw, gh):
+    """The headline parity number: ONE full-size image per reference topology at the size BASELINE.json names for it
+    (B8 KS3111 N768 M96 768x512: 589 824 symbols; B8 KS3311 N1152 M128: 786 432; B4 KS3311 N512 M96: 2 359 296;
+    B16 KS3111 N1280 M192 2048x2048: 3 145 728) against the UNMODIFIED reference's closed loop
+    (tests/golden/make_golden_full.py).
+
+    north_star bar: symbols identical on >= 99.99 % of positions, bpp within 0.1 %, PSNR within 0.01 dB; if all symbols
+    match, the bitstream must be byte-identical (sha256).  The symbol bar is only meaningful up to the first
+    rounding-boundary flip: the UNMODIFIED reference itself, run with a permuted accumulation order or with ONE symbol
+    forced the other way, differs from its own stock run on 0.1-1.2 % of the image
+    (tests/golden/closed_loop_noise_B8_lowrate_768x512.json, make_closed_loop_noise.py).  So this test asserts
+      * identity with the reference up to the first mismatch, which must be a boundary case (< TF_BOUNDARY_TOL);
+      * EVERY teacher-forced mismatch over the whole image is a boundary case of one step (assert_tf_boundary) and
+        there are <= 100 ppm of them;
+      * after the first flip the fraction of differing symbols stays within what ONE forced flip produces in the
+        reference itself (<= 3 %: the fixture's worst case is 1.2 %);
+      * bpp / PSNR bars; decode(encode) exact."""
     import hashlib, json, os
     from lbic_b200.layout import arrange_block_pixels_to_channel_dim
-    path = os.path.join(os.path.dirname(__file__), "golden", "full_B8_lowrate_768x512.npz")
+    path = os.path.join(os.path.dirname(__file__), "golden", f"full_{cfgname}_{gw}x{gh}.npz")
     if not os.path.exists(path):
         pytest.skip("full-size golden not generated")
     gold = np.load(path)
-    m = get_model("B8_lowrate", 1337, False, dev)
+    m = get_model(cfgname, 1337, False, dev)
     H, W = int(gold["H"]), int(gold["W"])
     x_img = weights.u8_to_model_input(weights.synth_image_u8(H, W, int(gold["image_seed"])))
     x = arrange_block_pixels_to_channel_dim(x_img.to(dev), m.B)
     strings, zhat, sym, idx = m.compress_batch(x, lanes=1, return_symbols=True)
     ref_sym = torch.from_numpy(gold["symbols"].astype(np.int32))[None]
     ref_idx = torch.from_numpy(gold["indexes"].astype(np.int32))[None]
-    rep = closed_loop_report("B8_lowrate", 1337, False, x, sym, idx, zhat, ref_sym, ref_idx)
+    rep = closed_loop_report(cfgname, 1337, False, x, sym, idx, zhat, ref_sym, ref_idx)
     n = rep["symbols"]
     psnr = -10.0 * float(torch.log10(((x - zhat) ** 2).mean()))
     bpp_rel = abs(len(strings[0]) - int(gold["stream_len"])) / int(gold["stream_len"])
     rep.update(bytes=len(strings[0]), ref_bytes=int(gold["stream_len"]), bpp_rel_diff=bpp_rel, psnr=psnr,
                ref_psnr=float(gold["psnr"]), reference_fp32_noise_floor_symbol_mismatches=int(gold["fp32_noise_symbol_mismatches"]),
                stream_identical=hashlib.sha256(strings[0]).hexdigest() == str(gold["stream_sha256"]))
+    if rep["first_mismatch"]:
+        v, h = rep["first_mismatch"]["block"]
+        after = n - (v * sym.shape[2] + h) * sym.shape[3]
+        rep["mismatches_after_first_fraction"] = rep["closed_loop_symbol_mismatches"] / max(1, after)
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/full_size_parity.json", "w") as f:
+    with open(f"gpurun_out/full_size_parity_{cfgname}.json", "w") as f:
         json.dump(rep, f)
     assert rep["tf_symbol_mismatches"] <= n // 10000 and rep["tf_index_mismatches"] <= n // 10000, rep
+    assert_tf_boundary(rep, tf_tol(cfgname))
     if rep["closed_loop_symbol_mismatches"] + rep["closed_loop_index_mismatches"]:
-        assert max(rep["first_mismatch"]["boundary_distance"]) < 2e-3, rep
+        assert max(rep["first_mismatch"]["boundary_distance"]) < tf_tol(cfgname), rep
+        assert rep["mismatches_after_first_fraction"] < 0.03, rep
     else:
         assert rep["stream_identical"], "identical symbols but different bytes"
     assert bpp_rel < 1e-3, f"bpp differs by {100 * bpp_rel:.3f} %"
     assert abs(psnr - float(gold["psnr"])) < 0.01
-    zdec = m.decompress(strings[0], list(get_lru(m.KS)), x.shape, m.M, dev)
+    zdec = m.decompress_batch(strings, x.shape, lanes=1)
     assert torch.equal(zdec, zhat)
 
 
@@ -553,36 +623,72 @@ def test_two_devices_in_one_process(dev):
     assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1])
 
 
-def test_host_calls_pipelined_halves_equal_single_pass(dev):
-    """lbic_encode_host / lbic_decode_host with the batch split in two halves pipelined over three streams (the default
-    from 1024 images on) must return exactly what the unsplit calls return; odd batch size, both containers."""
-    import ctypes
+def test_host_calls_banded_pipeline_equals_device_calls(dev):
+    """lbic_encode_host / lbic_decode_host move the batch over PCIe in bands of block rows overlapped with the wavefront
+    (LBIC_OPT_HOST_BANDS); any band count must return exactly what the device-resident calls return; odd batch size,
+    a grid whose rows do not divide by the band count, both containers, both topologies' first layers."""
     from lbic_b200 import _lib
     from lbic_b200.layout import arrange_block_pixels_to_channel_dim
-    m = get_model("B8_lowrate", 1337, False, dev)
     L = _lib.lib()
-    n, Hb, Wb = 11, 5, 9
-    img = weights.synth_images(n, Hb * 8, Wb * 8, seed0=77)
-    xh = arrange_block_pixels_to_channel_dim((img - 0.5).to(dev), 8).cpu().contiguous()
-    try:
-        for lanes in (0, 1):
-            cap = (m.stream_bound(Hb, Wb, lanes) + 3) // 4 * 4
-            res = {}
-            for split in (1 << 30, 2):
-                m.set_option("host_split_min", split)
-                zenc, zdec = torch.empty_like(xh), torch.empty_like(xh)
-                streams = np.zeros((n, cap), np.uint8)
-                lens = np.zeros(n, np.uint32)
-                _lib.check(L.lbic_encode_host(m._need(), xh.data_ptr(), n, Hb, Wb, zenc.data_ptr(), streams.ctypes.data, cap,
-                                              lens.ctypes.data, lanes))
-                _lib.check(L.lbic_decode_host(m._need(), streams.ctypes.data, lens.ctypes.data, cap, n, Hb, Wb,
-                                              zdec.data_ptr(), lanes))
-                assert torch.equal(zenc, zdec)
-                res[split] = ([streams[i, :lens[i]].tobytes() for i in range(n)], zenc.clone())
-            assert res[2][0] == res[1 << 30][0], f"bitstreams differ (lanes={lanes})"
-            assert torch.equal(res[2][1], res[1 << 30][1])
-    finally:
-        m.set_option("host_split_min", 1024)
+    for cfgname, n, Hb, Wb in (("B8_lowrate", 11, 5, 9), ("B4_highrate", 3, 19, 7)):
+        m = get_model(cfgname, 1337, False, dev)
+        B = m.B
+        img = weights.synth_images(n, Hb * B, Wb * B, seed0=77)
+        x = arrange_block_pixels_to_channel_dim((img - 0.5).to(dev), B)
+        xh = x.cpu().contiguous()
+        try:
+            for lanes in (0, 1):
+                want_s, want_z = m.compress_batch(x, lanes=lanes)
+                cap = (m.stream_bound(Hb, Wb, lanes) + 3) // 4 * 4
+                for bands in (1, 3, 16):
+                    m.set_option("host_bands", bands)
+                    zenc, zdec = torch.full_like(xh, 7.0), torch.full_like(xh, 9.0)
+                    streams = np.zeros((n, cap), np.uint8)
+                    lens = np.zeros(n, np.uint32)
+                    _lib.check(L.lbic_encode_host(m._need(), xh.data_ptr(), n, Hb, Wb, zenc.data_ptr(), streams.ctypes.data,
+                                                  cap, lens.ctypes.data, lanes))
+                    _lib.check(L.lbic_decode_host(m._need(), streams.ctypes.data, lens.ctypes.data, cap, n, Hb, Wb,
+                                                  zdec.data_ptr(), lanes))
+                    got = [streams[i, :lens[i]].tobytes() for i in range(n)]
+                    assert got == want_s, f"bitstreams differ ({cfgname}, lanes={lanes}, bands={bands})"
+                    assert torch.equal(zenc, want_z.cpu()) and torch.equal(zdec, zenc)
+        finally:
+            m.set_option("host_bands", 16)
+
+
+@pytest.mark.parametrize("cfgname,H,W", [("B8_lowrate", 203, 261), ("B8_lowrate", 64, 96), ("B4_highrate", 50, 37),
+                                         ("B16_lowrate", 40, 72)])
+def test_u8_image_entry_points_match_eval_model_steps(dev, cfgname, H, W):
+    """lbic_encode_images_u8_host / lbic_decode_images_u8_host = eval_model's per-image body (AGENT:581-599, 610-628)
+    for a batch: the streams must equal those of compress() on the float tensor eval_model builds (ToTensor, -0.5,
+    replicate padding, space-to-depth: done here with torch ops exactly as the reference does), and the 8-bit images
+    must equal depth-to-space + crop + save_image's quantisation of the reconstruction.  Ragged sizes included."""
+    import torch.nn.functional as F
+    from lbic_b200.layout import arrange_block_pixels_to_channel_dim, arrange_channel_dim_to_block_pixels
+    m = get_model(cfgname, 1337, False, dev)
+    B = m.B
+    n = 5
+    imgs = np.stack([weights.synth_image_u8(H, W, seed=40 + i) for i in range(n)])
+    # ToTensor on the CPU as the reference's loader does (a TRUE division: torch's CUDA kernel for `x / scalar` multiplies
+    # by the reciprocal and differs in the last bit for some pixel values), then AGENT:581
+    x = (torch.from_numpy(imgs).float().div(255) - 0.5).to(dev)
+    Hp, Wp = (H + B - 1) // B * B, (W + B - 1) // B * B
+    xp = F.pad(x, (0, Wp - W, 0, Hp - H), mode="replicate")                           # AGENT:583-586
+    xb = arrange_block_pixels_to_channel_dim(xp, B)                                   # AGENT:588-589
+    for lanes in (1, 0):
+        want_s, zhat = m.compress_batch(xb, lanes=lanes)
+        rec = arrange_channel_dim_to_block_pixels(zhat, B)[:, :, :H, :W] + 0.5         # AGENT:610, 628
+        want_u8 = rec.mul(255).add_(0.5).clamp_(0, 255).to(torch.uint8).cpu().numpy()  # torchvision.utils.save_image
+        for bands in (16, 2):
+            m.set_option("host_bands", bands)
+            got_s, got_rec = m.compress_images_u8(imgs, lanes=lanes, return_recon=True)
+            assert got_s == want_s, f"streams differ (lanes={lanes}, bands={bands})"
+            assert np.array_equal(got_rec, want_u8)
+            dec = m.decompress_images_u8(got_s, H, W, lanes=lanes)
+            assert np.array_equal(dec, want_u8)
+        m.set_option("host_bands", 16)
+        got_s2, none = m.compress_images_u8(torch.from_numpy(imgs), lanes=lanes)
+        assert got_s2 == want_s and none is None
 
 
 def test_layout_kernels_match_reference_definition(dev):
@@ -626,9 +732,33 @@ def test_stream_capacity_and_corrupt_streams(dev):
         m._gather_streams(o)
     lane_strings, _ = m.compress_batch(x, lanes=0)
     bad = bytearray(lane_strings[0]); bad[0] ^= 0xFF               # break the 'LBML' magic
-    zb = m.decompress_batch([bytes(bad), lane_strings[1]], x.shape, lanes=0)
-    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="malformed"):           # rejected, not silently decoded to garbage
+        m.decompress_batch([bytes(bad), lane_strings[1]], x.shape, lanes=0)
+    # a lane length that wraps 32-bit offset arithmetic: offset + 0xFFFFFFF0 overflows to a small number
+    wrap = bytearray(lane_strings[0])
+    wrap[8 + 4:8 + 8] = (0xFFFFFFF0).to_bytes(4, "little")         # length of lane 1
+    with pytest.raises(RuntimeError, match="malformed"):
+        m.decompress_batch([bytes(wrap), lane_strings[1]], x.shape, lanes=0)
+    odd = bytearray(lane_strings[0])
+    odd[8:12] = (int.from_bytes(odd[8:12], "little") + 2).to_bytes(4, "little")   # lane 0 length not a multiple of 4
+    with pytest.raises(RuntimeError, match="malformed"):
+        m.decompress_batch([bytes(odd), lane_strings[1]], x.shape, lanes=0)
+    # the device API flags the error without raising and leaves the intact image of the batch untouched
+    cap = (max(len(bad), len(lane_strings[1])) + 3) // 4 * 4
+    host = np.zeros((2, cap), np.uint8)
+    host[0, :len(bad)] = np.frombuffer(bytes(bad), np.uint8)
+    host[1, :len(lane_strings[1])] = np.frombuffer(lane_strings[1], np.uint8)
+    lens = torch.tensor([len(bad), len(lane_strings[1])], dtype=torch.int32, device=dev)
+    zb = m.decode_device(torch.from_numpy(host).to(dev), lens, 2, x.shape[2], x.shape[3], lanes=0)
+    with pytest.raises(RuntimeError):
+        m.check_errors()
     assert torch.equal(zb[1], zhat[1])                             # the intact image is unaffected
+    m.check_errors()                                               # the flag is cleared by reading it
+    # lane container of a one-block-row image (lanes == 1 row): header must still be parsed as a container
+    x1 = x[:, :, :1].contiguous()
+    s1, z1 = m.compress_batch(x1, lanes=0)
+    assert s1[0][:4] == b"LBML" and torch.equal(m.decompress_batch(s1, x1.shape, lanes=0), z1)
+    assert m.stream_bound(1, 6, 0) >= m.stream_bound(1, 6, 1) + 12
     cut = good[0][: len(good[0]) // 2 // 4 * 4]
     zc = m.decompress_batch([cut, good[1]], x.shape, lanes=1)
     assert bool(torch.isfinite(zc).all()) and torch.equal(zc[1], zhat[1])
