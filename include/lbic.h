@@ -59,14 +59,15 @@ typedef struct {
  *   0 = tcgen05/TMEM/TMA tensor-core tiles, fp16 hi/lo operand split, 3 MMAs per product (product path)
  *   1 = fp32 SIMT evaluation of the same split operands (bring-up / cross-check twin)      */
 #define LBIC_OPT_GEMM_CORE 1
-#define LBIC_OPT_CHAIN 4       /* 1 = one persistent chain kernel per wavefront step (experimental); 0 (default) = one launch per layer */
-#define LBIC_OPT_CLUSTER 5     /* tuning hook: force the chain kernel's cluster size (1,2,3,4,6,8); 0 = cost model */
 #define LBIC_OPT_PAIR 8        /* 1 (default) = CTA-pair (cta_group::2) form of the persistent kernel: 256-row tiles, half the weight traffic per SM */
 #define LBIC_OPT_DEC_THREAD_ROWS 9 /* decode steps with >= this many block rows (default 4096) decode one stream per thread, fewer: one per warp (process-wide) */
 #define LBIC_OPT_ENC_THREAD_STREAMS 10 /* entropy-encode calls with >= this many streams (default 4096) encode one stream per thread, fewer: one per warp (process-wide) */
+#define LBIC_OPT_ENC_BLOCK_STREAMS 17 /* entropy-encode calls with at most this many streams (default 592) encode one stream per CTA: table lookups by seven warps, the serial state chain on one thread (process-wide; 0 = never) */
 #define LBIC_OPT_FLOW 11         /* 1 (default) = run each large wavefront step's layers as ONE dataflow launch (row-block dependencies instead of kernel boundaries); 2 = always; 0 = one launch per layer */
 #define LBIC_OPT_FLOW_MIN_ROWS 12 /* steps with at least this many block rows take the dataflow launch (default 4096) */
 #define LBIC_OPT_FLOW_SMALL 13    /* 1 = steps below LBIC_OPT_FLOW_MIN_ROWS also run as one dataflow launch, on single CTAs with 128 x 96 tiles; 0 (default) = one launch per layer there */
+#define LBIC_OPT_WAVE 15           /* 1 (default) = calls whose wavefront steps have at most LBIC_OPT_WAVE_MAX_ROWS block rows (single images, small batches; KS[1] = 1) run as ONE persistent cooperative launch per call (gemm_wave.cu): gather, all layers and the rANS decode step are tiles of an in-kernel work list; 0 = one launch per layer */
+#define LBIC_OPT_WAVE_MAX_ROWS 16  /* default 2048, at most 4096 */
 #define LBIC_OPT_HOST_BANDS 14     /* the *_host entry points move a batch in / out in this many bands of block rows, overlapped with the wavefront (1..16, default 16; 1 = copy, compute, copy) */
 #define LBIC_OPT_WS 6          /* 1 (default) = persistent warp-specialised kernel for steps with >= 2 tiles per SM */
 #define LBIC_OPT_PDL 7         /* 1 (default) = programmatic dependent launch between consecutive GEMM kernels (process-wide) */

@@ -23,8 +23,6 @@ class LbicTensorDesc(ctypes.Structure):
 
 LBIC_OPT_GEMM_CORE = 1
 LBIC_OPT_FORCE_BN = 3
-LBIC_OPT_CHAIN = 4
-LBIC_OPT_CLUSTER = 5
 LBIC_OPT_WS = 6
 LBIC_OPT_PAIR = 8
 LBIC_OPT_DEC_THREAD_ROWS = 9
@@ -33,6 +31,9 @@ LBIC_OPT_FLOW = 11
 LBIC_OPT_FLOW_MIN_ROWS = 12
 LBIC_OPT_FLOW_SMALL = 13
 LBIC_OPT_HOST_BANDS = 14
+LBIC_OPT_WAVE = 15
+LBIC_OPT_ENC_BLOCK_STREAMS = 17
+LBIC_OPT_WAVE_MAX_ROWS = 16
 LBIC_OPT_PDL = 7
 
 # every symbol include/lbic.h declares: (restype, argtypes)

@@ -57,7 +57,7 @@ struct PackedSeg {
 
 struct PackedLayer {
     int cout = 0, bn = 0, nseg = 0;
-    int bn_v[NBN] = {0, 0, 0, 0, 0, 0, 0};
+    int bn_v[NBN] = {};
     int n_bn = 0;
     PackedSeg seg[2];
     float *bias = nullptr;
@@ -72,7 +72,8 @@ struct ActBuf {
 struct ActView {   // an activation buffer seen as a GEMM A operand of logical width K
     const ActBuf *buf = nullptr;
     int K = 0;
-    CUtensorMap tm_hi, tm_lo;
+    CUtensorMap tm_hi, tm_lo;         // box 64 k x 128 rows
+    CUtensorMap tm_hi64, tm_lo64;     // box 64 k x 64 rows (latency kernel, steps of at most 64 rows)
 };
 
 struct Workspace {
@@ -96,6 +97,8 @@ struct Workspace {
     ChainLayer *d_chain = nullptr;
     int *flow_counters = nullptr;      // (layer, 256-row block) completion counters of the dataflow launch
     size_t flow_counters_cap = 0;
+    int *wave_counters = nullptr;      // (list entry, 128-row block) counters of the persistent wavefront kernel
+    size_t wave_counters_cap = 0;
     std::vector<void *> allocs;
 };
 
@@ -120,8 +123,6 @@ struct lbic_model {
     Workspace ws;
     int gemm_core = 0;
     int force_bn = 0;
-    int use_chain = 0;     // 1: persistent chain kernel per step (experimental; the per-layer path is faster today)
-    int force_cluster = 0;
     int use_ws = 1;        // warp-specialised persistent kernel for large steps
     int use_pair = 1;      // CTA-pair (cta_group::2) form of the persistent kernel
     int use_flow = 1;      // dataflow launch of a whole layer range per step (1 = steps with >= flow_min_rows rows, 2 = always)
@@ -129,6 +130,8 @@ struct lbic_model {
     int flow_small = 0;    // steps below flow_min_rows: 1 = single-CTA dataflow launch with 96-wide tiles, 0 = one launch per
                            // layer (default: the counter hand-off costs as much as a PDL-chained launch, profiles/r1_dataflow.md)
     int flow_max_rows = 1 << 30;
+    int use_wave = 1;      // persistent wavefront (latency) kernel for steps of at most wave_max_rows rows (KS[1] == 1)
+    int wave_max_rows = 2048;
     float *selfinfo_cl = nullptr;   // set by lbic_validate for the duration of the call: (n,Hb,Wb,M) self-information
     cudaStream_t hs[3] = {nullptr, nullptr, nullptr};   // host-call pipeline: copies in, compute, copies out
     cudaEvent_t hev[2 * LBIC_MAX_BANDS] = {};            // band b copied in / band b ready to copy out
@@ -180,8 +183,9 @@ void free_all(std::vector<void *> &list) {
 // tile-width variants of a layer, one per split factor (lbic_split): widest first
 int bn_variants(int cout, int *out) {
     for (int i = 0; i < NBN; ++i) {
-        if (i == LBIC_WS_VARIANT || i == LBIC_PAIR_VARIANT || i == LBIC_PAIR_WIDE || i == LBIC_SMALL_VARIANT) {
-            const int wmax = i == LBIC_PAIR_WIDE ? gemm_pair_max_bn() : (i == LBIC_SMALL_VARIANT ? gemm_ws_max_bn() / 2 : gemm_ws_max_bn());
+        if (i == LBIC_WS_VARIANT || i == LBIC_PAIR_VARIANT || i == LBIC_PAIR_WIDE || i == LBIC_SMALL_VARIANT || i == LBIC_LAT_VARIANT) {
+            const int wmax = i == LBIC_PAIR_WIDE ? gemm_pair_max_bn()
+                             : (i == LBIC_SMALL_VARIANT ? gemm_ws_max_bn() / 2 : (i == LBIC_LAT_VARIANT ? LBIC_LAT_MAX_BN : gemm_ws_max_bn()));
             const int nt = (cout + wmax - 1) / wmax;
             out[i] = ((cout + nt - 1) / nt + 15) / 16 * 16;
             continue;
@@ -361,6 +365,8 @@ int make_view(Workspace &ws, ActView &v, const ActBuf &b, int K) {
     v.K = K;
     LBIC_TRY(make_tmap_2d(&v.tm_hi, b.hi, K, ws.R_cap, b.ld, 64, 128));
     LBIC_TRY(make_tmap_2d(&v.tm_lo, b.lo, K, ws.R_cap, b.ld, 64, 128));
+    LBIC_TRY(make_tmap_2d(&v.tm_hi64, b.hi, K, ws.R_cap, b.ld, 64, 64));
+    LBIC_TRY(make_tmap_2d(&v.tm_lo64, b.lo, K, ws.R_cap, b.ld, 64, 64));
     return 0;
 }
 
@@ -412,6 +418,8 @@ int ensure_workspace(lbic_model *m, int n_img, int Hb, int Wb) {
         ws.vText.buf = &ws.Text; ws.vText.K = 4 * m->Cin;
         LBIC_TRY(make_tmap_2d(&ws.vText.tm_hi, ws.Text.hi, 4 * m->Cin, ws.R_ext_cap, ws.Text.ld, 64, 128));
         LBIC_TRY(make_tmap_2d(&ws.vText.tm_lo, ws.Text.lo, 4 * m->Cin, ws.R_ext_cap, ws.Text.ld, 64, 128));
+        LBIC_TRY(make_tmap_2d(&ws.vText.tm_hi64, ws.Text.hi, 4 * m->Cin, ws.R_ext_cap, ws.Text.ld, 64, 64));
+        LBIC_TRY(make_tmap_2d(&ws.vText.tm_lo64, ws.Text.lo, 4 * m->Cin, ws.R_ext_cap, ws.Text.ld, 64, 64));
     }
     LBIC_TRY(make_view(ws, ws.vH2, ws.H2, m->E2));
     LBIC_TRY(make_view(ws, ws.vH3, ws.H3, m->E3));
@@ -427,6 +435,8 @@ int ensure_workspace(lbic_model *m, int n_img, int Hb, int Wb) {
     LBIC_TRY(build_chain(m));
     ws.flow_counters_cap = (size_t)L_COUNT * ((ws.R_cap + 127) / 128 + 1);
     LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.flow_counters, sizeof(int) * ws.flow_counters_cap, true));
+    ws.wave_counters_cap = 24 * 32;
+    LBIC_TRY(dev_alloc(ws.allocs, (void **)&ws.wave_counters, sizeof(int) * ws.wave_counters_cap, true));
     return 0;
 }
 
@@ -446,6 +456,7 @@ int build_chain(lbic_model *m) {
         for (int s = 0; s < L.nseg; ++s) {
             c.kb[s] = (L.seg[s].K + 63) / 64;
             c.tmA[s][0] = av[s]->tm_hi; c.tmA[s][1] = av[s]->tm_lo;
+            c.tmA64[s][0] = av[s]->tm_hi64; c.tmA64[s][1] = av[s]->tm_lo64;
             for (int v = 0; v < L.n_bn; ++v) { c.tmW[v][s][0] = L.seg[s].tm_hi[v]; c.tmW[v][s][1] = L.seg[s].tm_lo[v]; }
         }
         for (int v = 0; v < L.n_bn; ++v) c.bn_v[v] = L.bn_v[v];
@@ -498,26 +509,6 @@ int build_chain(lbic_model *m) {
     return 0;
 }
 
-int run_chain(lbic_model *m, int l0, int l1, const StepDesc &sd, int R, cudaStream_t st) {
-    Workspace &ws = m->ws;
-    ProfRec rec;
-    if (m->profiling) {
-        double fl = 0;
-        for (int l = l0; l < l1; ++l)
-            for (int s = 0; s < m->L[l].nseg; ++s) fl += 2.0 * R * (double)m->L[l].seg[s].K * m->L[l].cout;
-        cudaEventCreate(&rec.a); cudaEventCreate(&rec.b);
-        rec.flops = fl;
-        rec.layer = -1;
-        cudaEventRecord(rec.a, st);
-    }
-    const int rc = gemm_chain_launch(ws.d_chain, ws.h_chain.data(), l0, l1, R, sd, m->force_cluster, st);
-    if (m->profiling) {
-        cudaEventRecord(rec.b, st);
-        m->prof.push_back(rec);
-    }
-    return rc;
-}
-
 // which layers each layer reads from (operands and epilogue side inputs), by LayerId; -1 = inputs of the step
 const int FLOW_DEP[L_COUNT][2] = {
     {-1, -1}, {L_E0, -1}, {L_E1, -1}, {L_E2, -1},                                              // E0..E3
@@ -526,7 +517,7 @@ const int FLOW_DEP[L_COUNT][2] = {
 
 // 0: one launch per layer; 1: dataflow launch on CTA pairs (large steps); 2: dataflow launch on single CTAs (small steps)
 int flow_applies(const lbic_model *m, int R) {
-    if (m->gemm_core != 0 || m->use_chain || !m->use_pair || !m->use_flow || m->force_bn || !gemm_flow_supported()) return 0;
+    if (m->gemm_core != 0 || !m->use_pair || !m->use_flow || m->force_bn || !gemm_flow_supported()) return 0;
     if (m->use_flow == 2 || (R >= m->flow_min_rows && R <= m->flow_max_rows)) return 1;
     return (m->flow_small && R < m->flow_min_rows) ? 2 : 0;
 }
@@ -772,7 +763,48 @@ struct RowHooks {
     void *ctx = nullptr;
     int (*need_rows)(void *ctx, int v_hi, cudaStream_t st) = nullptr;    // x_cl block rows [0, v_hi] are read by what is enqueued next
     int (*rows_done)(void *ctx, int v_done, cudaStream_t st) = nullptr;  // zhat_cl block rows [0, v_done) are final after what has been enqueued
+    // would the matching call enqueue anything?  (the latency path batches steps into one launch and only cuts the
+    // launch where a hook has work to put between two steps)
+    bool (*will_need)(void *ctx, int v_hi) = nullptr;
+    bool (*will_done)(void *ctx, int v_done) = nullptr;
 };
+
+// The persistent wavefront kernel (gemm_wave.cu) takes over when every step of the call has at most wave_max_rows rows.
+bool wave_applies(const lbic_model *m, int n_img, int Hb, int Wb, bool raster) {
+    if (!m->use_wave || m->gemm_core != 0 || m->force_bn || m->k1 != 1 || m->profiling || m->selfinfo_cl ||
+        m->recon_cl || !gemm_wave_supported())
+        return false;
+    const int max_nv = Hb < (Wb + 1) / 2 ? Hb : (Wb + 1) / 2;
+    const long rows = raster ? n_img : (long)n_img * max_nv;
+    const int cap = m->wave_max_rows < gemm_wave_max_rows() ? m->wave_max_rows : gemm_wave_max_rows();
+    return rows <= cap;
+}
+
+int run_wave(lbic_model *m, bool decode, bool raster, int s_begin, int s_end, int n_img, int Hb, int Wb, int lanes_L,
+             int32_t *sym_out, cudaStream_t st) {
+    Workspace &ws = m->ws;
+    WaveLaunch w;
+    memset(&w, 0, sizeof(w));
+    w.d_layers = ws.d_chain; w.h_layers = ws.h_chain.data();
+    w.decode = decode ? 1 : 0; w.raster = raster ? 1 : 0;
+    w.s_begin = s_begin; w.s_end = s_end; w.n_img = n_img; w.Hb = Hb; w.Wb = Wb;
+    for (int i = 0; i < L_COUNT; ++i) w.ids[i] = i;
+    w.x_cl = ws.x_cl; w.zhat_cl = ws.zhat_cl; w.Cin = m->Cin;
+    w.X_hi = ws.X.hi; w.X_lo = ws.X.lo; w.ldX = ws.X.ld;
+    w.T_hi = ws.T.hi; w.T_lo = ws.T.lo; w.ldT = ws.T.ld;
+    w.scale_tab = m->tables.d_scale_table;
+    if (decode) {
+        const Tables &T = m->tables;
+        w.cdf = T.cdf; w.cdf_stride = T.stride; w.cdf_len = T.cdf_length; w.offs = T.offset;
+        w.states = ws.dec_states; w.lane_ptr = ws.lane_ptr; w.lanes = lanes_L;
+        w.ksi = ws.KSI; w.ld_ksi = ws.ldKSI; w.yq_hi = ws.YQ.hi; w.yq_lo = ws.YQ.lo; w.ld_yq = ws.YQ.ld;
+        w.sym_out = sym_out; w.M = m->M;
+    }
+    w.counters = ws.wave_counters; w.counters_cap = ws.wave_counters_cap;
+    w.err_flag = m->err_flag;
+    return gemm_wave_launch(w, st);
+}
+
 
 int ws_acquire(lbic_model *m, cudaStream_t st) {
     if (m->ws_used && st != m->ws_stream) LBIC_CUDA(cudaStreamWaitEvent(st, m->ws_event, 0));
@@ -832,6 +864,8 @@ extern "C" int lbic_create(const lbic_config *cfg, int device, lbic_model **out)
     if (const char *e = getenv("LBIC_FLOW_MIN_ROWS")) m->flow_min_rows = atoi(e) < 1 ? 1 : atoi(e);
     if (const char *e = getenv("LBIC_FLOW_MAX_ROWS")) m->flow_max_rows = atoi(e) < 1 ? 1 : atoi(e);
     if (const char *e = getenv("LBIC_FLOW_SMALL")) m->flow_small = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("LBIC_WAVE")) m->use_wave = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("LBIC_WAVE_MAX_ROWS")) m->wave_max_rows = atoi(e) < 1 ? 1 : atoi(e);
     m->cfg = *cfg;
     m->device = device;
     m->Cin = 3 * cfg->block_size * cfg->block_size;
@@ -885,14 +919,6 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
         if (value != 0 && value != 1) return lbic_fail(LBIC_ERR_INVALID, "gemm core must be 0 or 1");
         m->gemm_core = value;
         return 0;
-    case LBIC_OPT_CHAIN:
-        m->use_chain = value ? 1 : 0;
-        return 0;
-    case LBIC_OPT_CLUSTER:
-        if (value != 0 && value != 1 && value != 2 && value != 3 && value != 4 && value != 6 && value != 8)
-            return lbic_fail(LBIC_ERR_INVALID, "cluster size must be one of 0 (auto), 1, 2, 3, 4, 6, 8");
-        m->force_cluster = value;
-        return 0;
     case LBIC_OPT_PDL:
         gemm_set_pdl(value);
         return 0;
@@ -905,11 +931,20 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
     case LBIC_OPT_ENC_THREAD_STREAMS:
         rans_set_enc_thread_min_streams(value);
         return 0;
+    case LBIC_OPT_ENC_BLOCK_STREAMS:
+        rans_set_enc_block_max_streams(value);
+        return 0;
     case LBIC_OPT_FLOW:
         m->use_flow = value < 0 ? 0 : (value > 2 ? 2 : value);
         return 0;
     case LBIC_OPT_FLOW_MIN_ROWS:
         m->flow_min_rows = value < 1 ? 1 : value;
+        return 0;
+    case LBIC_OPT_WAVE:
+        m->use_wave = value ? 1 : 0;
+        return 0;
+    case LBIC_OPT_WAVE_MAX_ROWS:
+        m->wave_max_rows = value < 1 ? 1 : (value > gemm_wave_max_rows() ? gemm_wave_max_rows() : value);
         return 0;
     case LBIC_OPT_HOST_BANDS:
         m->host_bands = value < 1 ? 1 : (value > LBIC_MAX_BANDS ? LBIC_MAX_BANDS : value);
@@ -1039,11 +1074,6 @@ namespace {
 // (NET:363-377 for every block of the diagonal at once).  The gather of the step's operands has been enqueued.
 int encode_step(lbic_model *m, const StepDesc &sd, int R, bool want_syms, cudaStream_t st) {
     Workspace &ws = m->ws;
-    if (m->use_chain && m->gemm_core == 0) {
-        // the whole step in one persistent chain launch (experimental)
-        if (m->k1 == 3) LBIC_TRY(launch_gather5(ws.G0.hi, ws.G0.lo, m->E1, sd, R, ws.H1x5.hi, ws.H1x5.lo, ws.H1x5.ld, st));
-        return run_chain(m, m->k1 == 3 ? L_E1 : L_E0, L_COUNT, sd, R, st);
-    }
     if (flow_applies(m, R) && !m->recon_cl) {
         // the whole step as one dataflow launch; if the launch itself is refused (no co-residency: a shared or
         // partitioned GPU) the per-layer path below takes over for good
@@ -1076,21 +1106,58 @@ int encode_impl(lbic_model *m, const float *x, int n_img, int Hb, int Wb, float 
     const bool want_syms = sym_out || idx_out || stream_out || m->selfinfo_cl;
     const int T_steps = Wb + 2 * (Hb - 1);
     if (m->k1 == 3) LBIC_TRY(launch_fill_g0_top(m->L[L_E0].bias, m->E1, n_img, Hb, Wb, ws.G0.hi, ws.G0.lo, st));
-    for (int t = (m->k1 == 3 ? -1 : 0); t < T_steps; ++t) {
+    // one step through the per-layer / dataflow launches
+    auto launch_step = [&](int t) -> int {
         StepDesc sd, ext;
         if (m->k1 == 3 && wave_step_ext(t, n_img, Hb, Wb, ext)) LBIC_TRY(run_g0(m, ext, n_img * ext.nv, st));
-        if (!wave_step(t, n_img, Hb, Wb, sd)) continue;
+        if (!wave_step(t, n_img, Hb, Wb, sd)) return 0;
         const int R = n_img * sd.nv;
-        if (hk && hk->need_rows) LBIC_TRY(hk->need_rows(hk->ctx, sd.vmin + sd.nv - 1, st));
         LBIC_TRY(launch_gather(ws.x_cl, ws.zhat_cl, m->Cin, sd, R, ws.X.hi, ws.X.lo, ws.X.ld, ws.T.hi, ws.T.lo, ws.T.ld, st));
         LBIC_TRY(encode_step(m, sd, R, want_syms, st));
         if (m->selfinfo_cl)
             LBIC_TRY(launch_selfinfo_step(sd, R, m->M, ws.KSI, ws.ldKSI, ws.sym, m->selfinfo_cl, st));
-        if (hk && hk->rows_done && t >= Wb - 1) {
-            const int done = (t - (Wb - 1)) / 2 + 1;
-            LBIC_TRY(hk->rows_done(hk->ctx, done < Hb ? done : Hb, st));
+        return 0;
+    };
+    // Small steps (single images, small batches): consecutive steps are collected into ONE launch of the persistent
+    // wavefront kernel, cut only where a host hook has copies or conversions to put between two steps.
+    bool wave = wave_applies(m, n_img, Hb, Wb, false);
+    int pend = -1;                                   // steps [pend, t) wait to be launched
+    auto flush = [&](int t_end) -> int {
+        if (pend < 0) return 0;
+        const int b = pend;
+        pend = -1;
+        const int rc = run_wave(m, false, false, b, t_end, n_img, Hb, Wb, 0, nullptr, st);
+        if (rc != LBIC_FLOW_REFUSED) return rc;
+        m->use_wave = 0;                             // no co-residency on this device: per-layer launches from now on
+        wave = false;
+        for (int t = b; t < t_end; ++t) LBIC_TRY(launch_step(t));
+        return 0;
+    };
+    for (int t = (m->k1 == 3 ? -1 : 0); t < T_steps; ++t) {
+        StepDesc sd;
+        const bool has = wave_step(t, n_img, Hb, Wb, sd);
+        if (has && hk && hk->need_rows) {
+            const int v_hi = sd.vmin + sd.nv - 1;
+            if (!wave || !hk->will_need || hk->will_need(hk->ctx, v_hi)) {
+                LBIC_TRY(flush(t));
+                LBIC_TRY(hk->need_rows(hk->ctx, v_hi, st));
+            }
+        }
+        if (wave) {
+            if (has && pend < 0) pend = t;
+        } else {
+            LBIC_TRY(launch_step(t));
+        }
+        if (has && hk && hk->rows_done && t >= Wb - 1) {
+            int done = (t - (Wb - 1)) / 2 + 1;
+            done = done < Hb ? done : Hb;
+            if (!wave || !hk->will_done || hk->will_done(hk->ctx, done)) {
+                LBIC_TRY(flush(t + 1));
+                LBIC_TRY(hk->rows_done(hk->ctx, done, st));
+            }
         }
     }
+    LBIC_TRY(flush(T_steps));
     if (zhat_out) LBIC_TRY(launch_cl_to_nchw(ws.zhat_cl, zhat_out, n_img, m->Cin, HW, st));
     if (sym_out) LBIC_CUDA(cudaMemcpyAsync(sym_out, ws.sym, sizeof(int32_t) * nblk * m->M, cudaMemcpyDeviceToDevice, st));
     if (idx_out) LBIC_CUDA(cudaMemcpyAsync(idx_out, ws.idx, nblk * m->M, cudaMemcpyDeviceToDevice, st));
@@ -1138,7 +1205,6 @@ extern "C" int lbic_forward(lbic_model *m, const float *zhat_in, const float *x,
                             float *xhat_out, float *selfinfo_out, int32_t *sym_out, int clamp, void *stream) {
     LBIC_TRY(check_ready(m, false));
     if (!zhat_in || !x || !xhat_out || n_img < 1 || Hb < 1 || Wb < 1) return lbic_fail(LBIC_ERR_INVALID, "bad arguments");
-    if (m->use_chain) return lbic_fail(LBIC_ERR_INVALID, "lbic_forward runs on the per-layer path (LBIC_OPT_CHAIN = 0)");
     Active act(m);
     cudaStream_t st = (cudaStream_t)stream;
     LBIC_TRY(ensure_workspace(m, n_img, Hb, Wb));
@@ -1240,25 +1306,18 @@ int decode_impl(lbic_model *m, const uint8_t *streams, const uint32_t *stream_le
                                   m->err_flag, st));
     auto one_step = [&](const StepDesc &sd, int R) -> int {
         LBIC_TRY(launch_gather(nullptr, ws.zhat_cl, m->Cin, sd, R, nullptr, nullptr, 0, ws.T.hi, ws.T.lo, ws.T.ld, st));
-        const bool chain = m->use_chain && m->gemm_core == 0;
-        bool flow = !chain && flow_applies(m, R) != 0;
+        bool flow = flow_applies(m, R) != 0;
         bool ent_done = false;
-        if (chain || flow) {
+        if (flow) {
             if (m->k1 == 3) LBIC_TRY(launch_gather5(ws.G0.hi, ws.G0.lo, m->E1, sd, R, ws.H1x5.hi, ws.H1x5.lo, ws.H1x5.ld, st));
-            if (chain) {
-                LBIC_TRY(run_chain(m, m->k1 == 3 ? L_E1 : L_E0, L_F0, sd, R, st));
-                ent_done = true;
-            } else {
-                const int rc = run_flow(m, m->k1 == 3 ? L_E1 : L_E0, L_F0, sd, R, st);
-                if (rc == LBIC_FLOW_REFUSED) { m->use_flow = 0; flow = false; }
-                else if (rc) return rc;
-                else ent_done = true;
-            }
+            const int rc = run_flow(m, m->k1 == 3 ? L_E1 : L_E0, L_F0, sd, R, st);
+            if (rc == LBIC_FLOW_REFUSED) { m->use_flow = 0; flow = false; }
+            else if (rc) return rc;
+            else ent_done = true;
         }
         if (!ent_done) LBIC_TRY(run_ent(m, sd, R, st));
         LBIC_TRY(launch_rans_dec_step(m->tables, ws.dec_states, ws.lane_ptr, L, sd, R, m->M, ws.KSI, ws.ldKSI, ws.YQ.hi,
                                       ws.YQ.lo, ws.YQ.ld, sym_out ? ws.sym : nullptr, st));
-        if (chain) return run_chain(m, L_D0, L_COUNT, sd, R, st);
         if (flow) {
             const int rc = run_flow(m, L_D0, L_COUNT, sd, R, st);
             if (rc != LBIC_FLOW_REFUSED) return rc;
@@ -1267,38 +1326,66 @@ int decode_impl(lbic_model *m, const uint8_t *streams, const uint32_t *stream_le
         return run_dec(m, sd, R, st);
     };
     if (m->k1 == 3) LBIC_TRY(launch_fill_g0_top(m->L[L_E0].bias, m->E1, n_img, Hb, Wb, ws.G0.hi, ws.G0.lo, st));
-    if (L == 1 && lanes == 1) {
-        // reference container: the rANS state threads through the blocks in raster order (NET:420-450)
-        for (int v = 0; v < Hb; ++v) {
-            for (int h = 0; h < Wb; ++h) {
-                if (m->k1 == 3) {
-                    // hidden-map positions that become computable now: the ring columns of the row start, then (v,h)
-                    if (h == 0) {
-                        if (v >= 1) { StepDesc e{n_img, 1, v - 1, Wb + 2 * (v - 1), Hb, Wb}; LBIC_TRY(run_g0(m, e, n_img, st)); }
-                        StepDesc e{n_img, 1, v, -1 + 2 * v, Hb, Wb};
-                        LBIC_TRY(run_g0(m, e, n_img, st));
-                    }
-                    StepDesc e{n_img, 1, v, h + 2 * v, Hb, Wb};
+    const bool raster = (L == 1 && lanes == 1);      // reference container: the rANS state threads through the blocks in
+                                                     // raster order (NET:420-450), one block of every image per step
+    // raster step s = v * Wb + h; wavefront step s = t
+    auto launch_step = [&](int s) -> int {
+        if (raster) {
+            const int v = s / Wb, h = s - v * Wb;
+            if (m->k1 == 3) {
+                // hidden-map positions that become computable now: the ring columns of the row start, then (v,h)
+                if (h == 0) {
+                    if (v >= 1) { StepDesc e{n_img, 1, v - 1, Wb + 2 * (v - 1), Hb, Wb}; LBIC_TRY(run_g0(m, e, n_img, st)); }
+                    StepDesc e{n_img, 1, v, -1 + 2 * v, Hb, Wb};
                     LBIC_TRY(run_g0(m, e, n_img, st));
                 }
-                StepDesc sd{n_img, 1, v, h + 2 * v, Hb, Wb};
-                LBIC_TRY(one_step(sd, n_img));
+                StepDesc e{n_img, 1, v, h + 2 * v, Hb, Wb};
+                LBIC_TRY(run_g0(m, e, n_img, st));
             }
-            if (hk && hk->rows_done) LBIC_TRY(hk->rows_done(hk->ctx, v + 1, st));
+            StepDesc sd{n_img, 1, v, h + 2 * v, Hb, Wb};
+            return one_step(sd, n_img);
         }
-    } else {
-        const int T_steps = Wb + 2 * (Hb - 1);
-        for (int t = (m->k1 == 3 ? -1 : 0); t < T_steps; ++t) {
-            StepDesc sd, ext;
-            if (m->k1 == 3 && wave_step_ext(t, n_img, Hb, Wb, ext)) LBIC_TRY(run_g0(m, ext, n_img * ext.nv, st));
-            if (!wave_step(t, n_img, Hb, Wb, sd)) continue;
-            LBIC_TRY(one_step(sd, n_img * sd.nv));
-            if (hk && hk->rows_done && t >= Wb - 1) {
-                const int done = (t - (Wb - 1)) / 2 + 1;
-                LBIC_TRY(hk->rows_done(hk->ctx, done < Hb ? done : Hb, st));
+        StepDesc sd, ext;
+        if (m->k1 == 3 && wave_step_ext(s, n_img, Hb, Wb, ext)) LBIC_TRY(run_g0(m, ext, n_img * ext.nv, st));
+        if (!wave_step(s, n_img, Hb, Wb, sd)) return 0;
+        return one_step(sd, n_img * sd.nv);
+    };
+    bool wave = wave_applies(m, n_img, Hb, Wb, raster);
+    int pend = -1;
+    auto flush = [&](int s_end) -> int {
+        if (pend < 0) return 0;
+        const int b = pend;
+        pend = -1;
+        const int rc = run_wave(m, true, raster, b, s_end, n_img, Hb, Wb, L, sym_out ? ws.sym : nullptr, st);
+        if (rc != LBIC_FLOW_REFUSED) return rc;
+        m->use_wave = 0;
+        wave = false;
+        for (int s = b; s < s_end; ++s) LBIC_TRY(launch_step(s));
+        return 0;
+    };
+    const int s_first = raster ? 0 : (m->k1 == 3 ? -1 : 0);
+    const int s_last = raster ? Hb * Wb : Wb + 2 * (Hb - 1);
+    for (int s = s_first; s < s_last; ++s) {
+        if (wave) {
+            if (pend < 0 && s >= 0) pend = s;
+        } else {
+            LBIC_TRY(launch_step(s));
+        }
+        if (hk && hk->rows_done) {
+            int done = -1;
+            if (raster) {
+                if ((s + 1) % Wb == 0) done = (s + 1) / Wb;
+            } else if (s >= Wb - 1) {
+                done = (s - (Wb - 1)) / 2 + 1;
+                done = done < Hb ? done : Hb;
+            }
+            if (done > 0 && (!wave || !hk->will_done || hk->will_done(hk->ctx, done))) {
+                LBIC_TRY(flush(s + 1));
+                LBIC_TRY(hk->rows_done(hk->ctx, done, st));
             }
         }
     }
+    LBIC_TRY(flush(s_last));
     if (zhat_out) LBIC_TRY(launch_cl_to_nchw(ws.zhat_cl, zhat_out, n_img, m->Cin, HW, st));
     if (sym_out) LBIC_CUDA(cudaMemcpyAsync(sym_out, ws.sym, sizeof(int32_t) * nblk * m->M, cudaMemcpyDeviceToDevice, st));
     return ws_release(m, st);
@@ -1375,6 +1462,14 @@ struct BandPipe {
         }
         return 0;
     }
+    static bool will_need(void *ctx, int v_hi) {
+        const BandPipe *p = (const BandPipe *)ctx;
+        return p->next_in < p->nb && p->vb[p->next_in] <= v_hi;
+    }
+    static bool will_done(void *ctx, int v_done) {
+        const BandPipe *p = (const BandPipe *)ctx;
+        return p->next_out < p->nb && p->vb[p->next_out + 1] <= v_done;
+    }
     static int need_rows(void *ctx, int v_hi, cudaStream_t st) {
         BandPipe *p = (BandPipe *)ctx;
         while (p->next_in < p->nb && p->vb[p->next_in] <= v_hi) {
@@ -1428,6 +1523,7 @@ int encode_host_impl(lbic_model *m, int fmt, const void *in, int n_img, int H, i
     LBIC_TRY(bp.queue_inputs());
     RowHooks hk;
     hk.ctx = &bp; hk.need_rows = BandPipe::need_rows; hk.rows_done = recon_out ? BandPipe::rows_done : nullptr;
+    hk.will_need = BandPipe::will_need; hk.will_done = BandPipe::will_done;
     int rc = encode_impl(m, nullptr, n_img, Hb, Wb, nullptr, nullptr, nullptr, stream_out ? io + o_s : nullptr, stream_cap,
                          (uint32_t *)(io + o_len), lanes, s_cmp, &hk);
     Active act2(m);
@@ -1476,7 +1572,7 @@ int decode_host_impl(lbic_model *m, int fmt, const uint8_t *streams, const uint3
     bp.fmt = fmt; bp.H = H; bp.W = W; bp.B = m->cfg.block_size;
     bp.h_out = (uint8_t *)out; bp.d_out = io + o_out;
     RowHooks hk;
-    hk.ctx = &bp; hk.rows_done = BandPipe::rows_done;
+    hk.ctx = &bp; hk.rows_done = BandPipe::rows_done; hk.will_done = BandPipe::will_done;
     int rc = decode_impl(m, io + o_s, (const uint32_t *)(io + o_len), stream_cap, n_img, Hb, Wb, nullptr, nullptr, lanes,
                          s_cmp, &hk);
     Active act2(m);

@@ -95,6 +95,17 @@ __device__ __forceinline__ void load_f32(const float *__restrict__ p, float (&v)
     }
 }
 
+// Same, bypassing L1 (ld.global.cg): for buffers another CTA of the SAME launch has just written (the persistent
+// dataflow / wavefront kernels reuse the step's compact activation rows launch-long, so an L1 line may be stale).
+template <int NV>
+__device__ __forceinline__ void load_f32_cg(const float *__restrict__ p, float (&v)[NV]) {
+#pragma unroll
+    for (int i = 0; i < NV; i += 4) {
+        const float4 t = __ldcg(reinterpret_cast<const float4 *>(p + i));
+        v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+    }
+}
+
 // Operands an epilogue needs besides the accumulator, fetched ahead of the TMEM load they are combined with
 // (the tcgen05 core software-pipelines: prefetch chunk i+1 while chunk i is being finished).
 template <int NV>
@@ -106,10 +117,10 @@ struct EpiPre {
 template <int NV>
 __device__ __forceinline__ void epi_prefetch(const EpiParams &p, int r, int c, EpiPre<NV> &pre) {
     if (p.mode == EPI_GDN || p.mode == EPI_IGDN) {
-        load_f32<NV>(p.aux + (size_t)r * p.ld_aux + c, pre.a);
+        load_f32_cg<NV>(p.aux + (size_t)r * p.ld_aux + c, pre.a);
     } else if (p.mode == EPI_QUANT) {
-        load_f32<NV>(p.aux + (size_t)r * p.ld_aux + c, pre.a);            // scales = ksi[:, :M]   (NET:369)
-        load_f32<NV>(p.aux + (size_t)r * p.ld_aux + p.M + c, pre.a2);     // means  = ksi[:, M:]
+        load_f32_cg<NV>(p.aux + (size_t)r * p.ld_aux + c, pre.a);            // scales = ksi[:, :M]   (NET:369)
+        load_f32_cg<NV>(p.aux + (size_t)r * p.ld_aux + p.M + c, pre.a2);     // means  = ksi[:, M:]
     }
 }
 

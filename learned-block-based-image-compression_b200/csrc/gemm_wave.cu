@@ -1,0 +1,553 @@
+// The latency kernel: a whole RANGE of wavefront steps of one encode / decode in ONE persistent, cooperative launch.
+//
+// compress / decompress of a single image (what eval_model calls, agents/blkbsdimgcomp_agent.py:578-599) is a chain of
+// dependent small GEMMs: a 768x512 image has 222 wavefront steps (NET:339-357 restated as t = h + 2v) with at most 48
+// block rows each, and every step is 14 dependent layers deep (encoder net -> quantisation -> decoder net; the entropy
+// net runs beside the encoder net).  One launch per layer costs ~11 us per layer whatever the tile does (launch,
+// prologue, TMEM allocation, drain): 48 ms per image, 1 s for the raster-serial reference container.
+//
+// Here the 148 CTAs stay resident for the whole image.  Every step's work is one list of TILES in a fixed order,
+//     GATHER (operand build) | GEMM tiles of every layer, 128 rows x <= 32 columns | RANS (decode only),
+// tile j of the list goes to CTA (offset + j) mod 148, and a tile may start once the tiles it reads from have been
+// published through a monotonic counter per (list entry, 128-row block) -- release by a publisher warp after the
+// tile's stores, acquire by whoever consumes (the TMA producer before its first load, the epilogue warps before a
+// gather / rANS tile or a GDN side input).  Narrow tiles spread a layer over 20-40 SMs so that the tensor time of a
+// layer (K / 16 x 3 MMAs of 128 x 32) is ~1 us; the weights stream from L2 (38 MB of fp16 hi/lo planes do not fit the
+// 33 MB of shared memory of the chip).  A CTA only ever waits for tiles with a smaller list index and all CTAs are
+// co-resident (cooperative launch), so the scheme cannot deadlock; every wait is bounded and traps.
+//
+// Arithmetic is that of gemm_tc_kernel / gemm_ws_kernel: same operand planes, same k order, one TMEM accumulator per
+// output element, same fused epilogues (ws_tile_epilogue) -- results are bit-identical to the per-layer path, which is
+// what lets a stream encoded by one path be decoded by the other.
+#include "rans_device.cuh"
+#include "ws_epilogue.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace {
+
+constexpr int WAVE_MAX_ORD = 20;
+constexpr int WAVE_MAX_RB = 32;                  // 128-row blocks per step
+constexpr int WAVE_STAGES = 4;
+constexpr int WAVE_SLOT = 2 * A_PLANE + 2 * LBIC_LAT_MAX_BN * BK * 2;   // 40 KiB: 128 activation rows + 32 weight rows, hi + lo
+constexpr int WAVE_THREADS = WS_THREADS + 32;    // producer | MMA issuer | 8 epilogue warps | publisher
+constexpr int WAVE_BAR_BLOCK = 256;              // full[4] empty[4] acc_full[2] acc_empty[2] tile_done[2] pub_free[2] tmem slot
+constexpr int WAVE_TAIL = WAVE_BAR_BLOCK + 2 * 1024 + ROWTAB_BYTES + STAB_BYTES + 256;
+constexpr int WAVE_SMEM = 1024 + WAVE_STAGES * WAVE_SLOT + WGDN_BYTES + WAVE_TAIL;
+constexpr int WAVE_RANS_PARTS = 16;              // rANS tiles per 128-row block: 8 rows each, one warp per row
+static_assert(WAVE_SMEM <= SMEM_LIMIT, "wave kernel shared memory");
+
+enum WaveKind { WK_GEMM = 0, WK_GATHER = 1, WK_RANS = 2 };
+
+struct WaveOrd {
+    int kind;
+    int layer;      // ChainLayer index (WK_GEMM)
+    int ntn;        // tiles per 128-row block
+    int bn;         // tile width (WK_GEMM)
+    int dep[2];     // list entries this one reads from, -1 = none
+};
+
+struct WaveParams {
+    const ChainLayer *layers;
+    int *counters;               // [n_ord][WAVE_MAX_RB], zero at launch, never reset: entry (o, rb) counts the tiles of list
+                                 // entry o finished for row block rb over all steps of the launch
+    int n_ord, tiles_per_rb, recon_ord;
+    WaveOrd ord[WAVE_MAX_ORD];
+    int pre[WAVE_MAX_ORD + 1];
+    int mode;                    // 0: wavefront steps t; 1: raster blocks v * Wb + h (reference container decode)
+    int s_begin, s_end;
+    int n_img, Hb, Wb;
+    int variant;
+    const float *x_cl, *zhat_cl;
+    int Cin, gather_first;       // gather tiles cover segments gather_first .. 4 (0 = x, 1..4 = the four zhat taps)
+    h16 *X_hi, *X_lo; int ldX;
+    h16 *T_hi, *T_lo; int ldT;
+    const int32_t *cdf; int cdf_stride; const int32_t *cdf_len, *offs; const float *scale_tab;
+    RansStreamState *states; const uint8_t *const *lane_ptr; int lanes;
+    const float *ksi; int ld_ksi; h16 *yq_hi, *yq_lo; int ld_yq; int32_t *sym_out; int M;
+};
+
+__device__ __forceinline__ bool wave_step_desc(const WaveParams &p, int s, StepDesc &sd) {
+    sd.n_img = p.n_img; sd.Hb = p.Hb; sd.Wb = p.Wb;
+    if (p.mode == 1) {
+        const int v = s / p.Wb, h = s - v * p.Wb;
+        sd.nv = 1; sd.vmin = v; sd.t = h + 2 * v;
+        return true;
+    }
+    const int t = s;
+    const int vmin = t - (p.Wb - 1) <= 0 ? 0 : (t - (p.Wb - 1) + 1) / 2;
+    const int vmax = t / 2 < p.Hb - 1 ? t / 2 : p.Hb - 1;
+    if (t < 0 || vmax < vmin) return false;
+    sd.nv = vmax - vmin + 1; sd.vmin = vmin; sd.t = t;
+    return true;
+}
+
+struct WaveTile {
+    StepDesc sd;
+    int R, n_rb, prev_n_rb;
+    int oi, rb, nt;      // list entry, row block, tile within (entry, row block)
+};
+
+// Every role of a CTA walks the same sequence of tiles: tile j of a step belongs to CTA (off + j) mod gridDim.x, where
+// off is the number of tiles of all earlier steps.  gen[rb] = number of earlier steps of this launch that had row
+// block rb; a dependency on list entry d for row block rb is met once counters[d][rb] >= ord[d].ntn * (gen[rb] + 1).
+template <typename F>
+__device__ __forceinline__ void wave_for_each_tile(const WaveParams &p, F &&f) {
+    int gen[WAVE_MAX_RB];
+#pragma unroll 1
+    for (int i = 0; i < WAVE_MAX_RB; ++i) gen[i] = 0;
+    int off = 0, prev_n_rb = 0;
+    const int G = (int)gridDim.x;
+#pragma unroll 1
+    for (int s = p.s_begin; s < p.s_end; ++s) {
+        WaveTile w;
+        if (!wave_step_desc(p, s, w.sd)) continue;
+        w.R = w.sd.n_img * w.sd.nv;
+        w.n_rb = (w.R + BM - 1) / BM;
+        w.prev_n_rb = prev_n_rb;
+        const int total = w.n_rb * p.tiles_per_rb;
+        int first = (int)blockIdx.x - off;
+        if (first < 0) first += G;
+#pragma unroll 1
+        for (int j = first; j < total; j += G) {
+            int oi = 0;
+            while (j >= w.n_rb * p.pre[oi + 1]) ++oi;
+            const int v = j - w.n_rb * p.pre[oi];
+            w.oi = oi;
+            w.rb = v / p.ord[oi].ntn;
+            w.nt = v - w.rb * p.ord[oi].ntn;
+            f(w, gen);
+        }
+        off = (off + total) % G;
+        for (int rb = 0; rb < w.n_rb; ++rb) gen[rb]++;
+        prev_n_rb = w.n_rb;
+    }
+}
+
+__device__ __forceinline__ void wave_wait(const int *cnt, int target) {
+    uint32_t spins = 0;
+    while (ld_acquire_gpu(cnt) < target) {
+        __nanosleep(20);
+        if (++spins > (1u << 25)) __trap();     // a broken dependency must fail the launch, not hang the GPU
+    }
+}
+
+// waits for the (up to two) list entries a tile reads from, for the tile's row block
+__device__ __forceinline__ void wave_wait_deps(const WaveParams &p, const WaveTile &w, const int *gen) {
+    for (int d = 0; d < 2; ++d) {
+        const int dl = p.ord[w.oi].dep[d];
+        if (dl < 0) continue;
+        wave_wait(p.counters + dl * WAVE_MAX_RB + w.rb, p.ord[dl].ntn * (gen[w.rb] + 1));
+    }
+}
+
+// a gather tile reads zhat blocks of the previous steps: every row block of the previous step's reconstruction layer
+// must be complete (all earlier steps then are, each step ends in that layer)
+__device__ __forceinline__ void wave_wait_prev_step(const WaveParams &p, const WaveTile &w, const int *gen) {
+    for (int rb = 0; rb < w.prev_n_rb; ++rb)
+        wave_wait(p.counters + p.recon_ord * WAVE_MAX_RB + rb, p.ord[p.recon_ord].ntn * gen[rb]);
+}
+
+// ---- GATHER tile: one K segment (x, or one of the four causal zhat taps) of the step's first-layer operands for the
+// rows of one row block; the arithmetic of gather_kernel (kernels_misc.cu), by the 8 epilogue warps.
+__device__ __forceinline__ void wave_gather_tile(const WaveParams &p, const WaveTile &w, int ew, int lane) {
+    const int seg = p.gather_first + w.nt;
+    const int m0 = w.rb * BM;
+    const int rows = (w.R - m0) < BM ? (w.R - m0) : BM;
+    const int c4n = p.Cin >> 2;
+    for (int rl = ew; rl < rows; rl += 8) {
+        const int r = m0 + rl;
+        int img, v, h;
+        step_row_to_block(w.sd, r, img, v, h);
+        const float *src = nullptr;
+        h16 *ph, *pl;
+        if (seg == 0) {
+            src = p.x_cl + (((size_t)img * w.sd.Hb + v) * w.sd.Wb + h) * p.Cin;
+            ph = p.X_hi + (size_t)r * p.ldX;
+            pl = p.X_lo + (size_t)r * p.ldX;
+        } else {
+            const int tap = seg - 1;
+            const int vv = v + ((tap == 3) ? 0 : -1), hh = h + ((tap == 3) ? -1 : tap - 1);
+            if (vv >= 0 && vv < w.sd.Hb && hh >= 0 && hh < w.sd.Wb)
+                src = p.zhat_cl + (((size_t)img * w.sd.Hb + vv) * w.sd.Wb + hh) * p.Cin;
+            ph = p.T_hi + (size_t)r * p.ldT + tap * p.Cin;
+            pl = p.T_lo + (size_t)r * p.ldT + tap * p.Cin;
+        }
+        for (int c4 = lane; c4 < c4n; c4 += 32) {
+            const float4 val = src ? __ldcg(reinterpret_cast<const float4 *>(src) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float f[4] = {val.x, val.y, val.z, val.w};
+            store_hilo<4>(ph + c4 * 4, pl + c4 * 4, f);
+        }
+    }
+}
+
+// ---- RANS tile: 8 rows of a row block, one warp per row: build_indexes, decode M symbols from the row's stream,
+// dequantise -> y_qnt planes (rans_dec_step_kernel of rans.cu; ksi / the stream states were written by other CTAs of
+// this launch, hence the L1-bypassing loads).
+__device__ __forceinline__ void wave_rans_tile(const WaveParams &p, const WaveTile &w, int ew, int lane) {
+    const int r = w.rb * BM + w.nt * 8 + ew;
+    if (r >= w.R) return;
+    int img, v, h;
+    step_row_to_block(w.sd, r, img, v, h);
+    const int sidx = p.lanes > 1 ? img * p.lanes + v : img;
+    DecCursor d;
+    {
+        const uint4 raw = __ldcg(reinterpret_cast<const uint4 *>(p.states + sidx));
+        d.x = (unsigned long long)raw.x | ((unsigned long long)raw.y << 32);
+        d.pos = raw.z; d.nwords = raw.w;
+        d.words = reinterpret_cast<const uint32_t *>(p.lane_ptr[sidx]);
+    }
+    const float *krow = p.ksi + (size_t)r * p.ld_ksi;
+    const int M = p.M;
+    int my_idx[8], my_sym[8];
+    const int per = (M + 31) >> 5;   // M <= 256
+    for (int j = 0; j < per; ++j) {
+        const int c = j * 32 + lane;
+        my_idx[j] = c < M ? scale_to_index(__ldcg(krow + c), p.scale_tab) : 0;
+        my_sym[j] = 0;
+    }
+    for (int c = 0; c < M; ++c) {
+        const int ci = __shfl_sync(0xffffffffu, my_idx[c >> 5], c & 31);
+        const int sym = dec_symbol_warp(d, p.cdf + (size_t)ci * p.cdf_stride, p.cdf_len[ci], p.offs[ci], lane);
+        if (lane == (c & 31)) my_sym[c >> 5] = sym;
+    }
+    if (lane == 0) {
+        uint4 raw;
+        raw.x = (uint32_t)d.x; raw.y = (uint32_t)(d.x >> 32); raw.z = d.pos; raw.w = d.nwords;
+        __stcg(reinterpret_cast<uint4 *>(p.states + sidx), raw);
+    }
+    const size_t o = (((size_t)img * w.sd.Hb + v) * w.sd.Wb + h) * M;
+    for (int j = 0; j < per; ++j) {
+        const int c = j * 32 + lane;
+        if (c < M) {
+            const float yq = (float)my_sym[j] + __ldcg(krow + M + c);
+            h16 hi, lo;
+            split_h16(yq, hi, lo);
+            p.yq_hi[(size_t)r * p.ld_yq + c] = hi;
+            p.yq_lo[(size_t)r * p.ld_yq + c] = lo;
+            if (p.sym_out) p.sym_out[o + c] = my_sym[j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid_constant__ WaveParams p) {
+    static_assert(sizeof(EpiParams) <= 256, "EpiParams must fit its shared-memory slot");
+    static_assert(sizeof(RansStreamState) == 16, "RansStreamState is moved as one 16-byte word");
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t ring = (raw + 1023u) & ~1023u;
+    const uint32_t stg = ring + WAVE_STAGES * WAVE_SLOT;
+    const uint32_t bars = stg + WGDN_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (4 + s); };
+    auto acc_full = [&](int a) { return bars + 8u * (8 + a); };
+    auto acc_empty = [&](int a) { return bars + 8u * (10 + a); };
+    auto tile_done = [&](int a) { return bars + 8u * (12 + a); };
+    auto pub_free = [&](int a) { return bars + 8u * (14 + a); };
+    const uint32_t tmem_slot = bars + 8u * 16;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - raw));
+    float *sbias = reinterpret_cast<float *>(smem_raw + (bars + WAVE_BAR_BLOCK - raw));        // [2][256]
+    RowTab *rt = reinterpret_cast<RowTab *>(smem_raw + (bars + WAVE_BAR_BLOCK + 2048 - raw));
+    float *stab = reinterpret_cast<float *>(rt + 1);
+    EpiParams *s_ep = reinterpret_cast<EpiParams *>(stab + 64);
+    if (p.scale_tab && threadIdx.x < 64) stab[threadIdx.x] = p.scale_tab[threadIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < WAVE_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(acc_full(a), 1);
+            mbar_init(acc_empty(a), WS_EPI_THREADS / 32);
+            mbar_init(tile_done(a), WS_EPI_THREADS / 32);
+            mbar_init(pub_free(a), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ---- TMA producer -------------------------------------------------------------------------------
+        if (lane == 0) {
+            uint32_t it = 0;
+            wave_for_each_tile(p, [&](const WaveTile &w, const int *gen) {
+                const WaveOrd &o = p.ord[w.oi];
+                if (o.kind != WK_GEMM) return;
+                const ChainLayer &Lr = p.layers[o.layer];
+                const int bn = o.bn;
+                const int m0 = w.rb * BM, n0 = w.nt * bn;
+                const bool half = (w.R - m0) <= 64;            // at most 64 valid rows: load half the activation tile
+                wave_wait_deps(p, w, gen);
+                asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores of other CTAs -> our TMA reads
+                const int kb0 = Lr.kb[0], nkb = kb0 + (Lr.nseg > 1 ? Lr.kb[1] : 0);
+                const uint32_t w_plane = (uint32_t)bn * (BK * 2);
+                const uint32_t stage_tx = (half ? A_PLANE : 2 * A_PLANE) + 2 * w_plane;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % WAVE_STAGES;
+                    const uint32_t ph = (it / WAVE_STAGES) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    const uint32_t sa = ring + s * WAVE_SLOT;
+                    const int seg = kb >= kb0 ? 1 : 0;
+                    const int kk = (seg ? kb - kb0 : kb) * BK;
+                    mbar_expect_tx(full_bar(s), stage_tx);
+                    tma_load_2d(sa, half ? &Lr.tmA64[seg][0] : &Lr.tmA[seg][0], full_bar(s), kk, m0);
+                    tma_load_2d(sa + A_PLANE, half ? &Lr.tmA64[seg][1] : &Lr.tmA[seg][1], full_bar(s), kk, m0);
+                    tma_load_2d(sa + 2 * A_PLANE, &Lr.tmW[p.variant][seg][0], full_bar(s), kk, n0);
+                    tma_load_2d(sa + 2 * A_PLANE + w_plane, &Lr.tmW[p.variant][seg][1], full_bar(s), kk, n0);
+                }
+            });
+        }
+    } else if (warp == 1) {
+        // ---- tcgen05.mma issuer ---------------------------------------------------------------------------
+        if (lane == 0) {
+            uint32_t it = 0, gi = 0;
+            wave_for_each_tile(p, [&](const WaveTile &w, const int *) {
+                const WaveOrd &o = p.ord[w.oi];
+                if (o.kind != WK_GEMM) return;
+                const ChainLayer &Lr = p.layers[o.layer];
+                const int bn = o.bn;
+                const int nkb = Lr.kb[0] + (Lr.nseg > 1 ? Lr.kb[1] : 0);
+                const uint32_t w_plane = (uint32_t)bn * (BK * 2);
+                const uint32_t idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                const uint32_t a = gi & 1u;
+                mbar_wait(acc_empty(a), ((gi >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_acc = tmem_base + a * WS_ACC_STRIDE;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % WAVE_STAGES;
+                    const uint32_t ph = (it / WAVE_STAGES) & 1u;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = ring + s * WAVE_SLOT;
+                    const uint64_t a_hi = make_smem_desc(sa);
+                    const uint64_t a_lo = make_smem_desc(sa + A_PLANE);
+                    const uint64_t w_hi = make_smem_desc(sa + 2 * A_PLANE);
+                    const uint64_t w_lo = make_smem_desc(sa + 2 * A_PLANE + w_plane);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(acc_full(a));
+                ++gi;
+            });
+        }
+    } else if (warp == 10) {
+        // ---- publisher: the tile's stores have been issued -> make them visible, bump the tile's counter ----
+        if (lane == 0) {
+            uint32_t di = 0;
+            wave_for_each_tile(p, [&](const WaveTile &w, const int *) {
+                const uint32_t a = di & 1u;
+                mbar_wait(tile_done(a), (di >> 1) & 1u);
+                mbar_arrive(pub_free(a));                           // the epilogue may signal tile di + 2 on this barrier
+                asm volatile("fence.proxy.async;" ::: "memory");
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.counters + w.oi * WAVE_MAX_RB + w.rb) : "memory");
+                ++di;
+            });
+        }
+    } else {
+        // ---- epilogue warps 2..9: GEMM epilogues, gather tiles, rANS tiles ------------------------------------
+        const int et = threadIdx.x - 64;
+        const int ew = warp - 2;
+        uint32_t di = 0, gi = 0;
+        wave_for_each_tile(p, [&](const WaveTile &w, const int *gen) {
+            const WaveOrd &o = p.ord[w.oi];
+            if (o.kind == WK_GEMM) {
+                const ChainLayer &Lr = p.layers[o.layer];
+                const int bn = o.bn;
+                const int m0 = w.rb * BM, n0 = w.nt * bn;
+                // this tile's epilogue description: the layer's, with the step and its row count
+                epi_bar();     // every epilogue thread is past the previous tile (which read the old copy)
+                {
+                    constexpr int NW = (int)(sizeof(EpiParams) / 4);
+                    constexpr int OFF_R = (int)(offsetof(EpiParams, R) / 4), OFF_STEP = (int)(offsetof(EpiParams, step) / 4);
+                    constexpr int NSTEP = (int)(sizeof(StepDesc) / 4);
+                    const uint32_t *g = reinterpret_cast<const uint32_t *>(&Lr.ep);
+                    const uint32_t *sw = reinterpret_cast<const uint32_t *>(&w.sd);
+                    if (et < NW) {
+                        uint32_t wd = g[et];
+                        if (et == OFF_R) wd = (uint32_t)w.R;
+                        else if (et >= OFF_STEP && et < OFF_STEP + NSTEP) wd = sw[et - OFF_STEP];
+                        reinterpret_cast<uint32_t *>(s_ep)[et] = wd;
+                    }
+                }
+                epi_bar();
+                const uint32_t a = gi & 1u;
+                EpiCtx c;
+                c.stg = stg; c.acc_full_bar = acc_full(a); c.acc_empty_bar = acc_empty(a); c.full_phase = (gi >> 1) & 1u;
+                c.tmem_acc = tmem_base + a * WS_ACC_STRIDE; c.sb = sbias + a * 256; c.rt = rt; c.stab = stab; c.rank = 0;
+                const int dl = o.dep[0];
+                c.dep_cnt = dl >= 0 ? p.counters + dl * WAVE_MAX_RB + w.rb : nullptr;
+                c.dep_target = dl >= 0 ? p.ord[dl].ntn * (gen[w.rb] + 1) : 0;
+                const int dl2 = o.dep[1];
+                c.dep2_cnt = dl2 >= 0 ? p.counters + dl2 * WAVE_MAX_RB + w.rb : nullptr;
+                c.dep2_target = dl2 >= 0 ? p.ord[dl2].ntn * (gen[w.rb] + 1) : 0;
+                ws_tile_epilogue<false>(*s_ep, bn, m0, n0, c);
+                ++gi;
+            } else {
+                // non-GEMM tiles: one thread waits for the inputs, then all eight warps work
+                if (et == 0) {
+                    if (o.kind == WK_GATHER) wave_wait_prev_step(p, w, gen);
+                    else wave_wait_deps(p, w, gen);
+                }
+                epi_bar();
+                if (o.kind == WK_GATHER) wave_gather_tile(p, w, ew, lane);
+                else wave_rans_tile(p, w, ew, lane);
+            }
+            // this CTA's tile is stored: hand it to the publisher warp (which must have taken tile di - 2 off this barrier)
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t a = di & 1u;
+                mbar_wait(pub_free(a), ((di >> 1) & 1u) ^ 1u);
+                mbar_arrive(tile_done(a));
+            }
+            ++di;
+        });
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+unsigned long long g_wave_attr_mask = 0;
+
+int wave_prepare() {
+    LBIC_TRY(gemm_tc_init());
+    if (lbic_first_use_on_device(g_wave_attr_mask))
+        LBIC_CUDA(cudaFuncSetAttribute(gemm_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    return 0;
+}
+
+}  // namespace
+
+int gemm_wave_max_rows() { return WAVE_MAX_RB * BM; }
+
+// 1 if one CTA of the wave kernel fits every SM of this device (the launch itself is cooperative, so a busy or shared
+// GPU is refused at launch time, not here)
+int gemm_wave_supported() {
+    static int cache[64];
+    static bool cache_init = false;
+    if (!cache_init) { for (int &c : cache) c = -1; cache_init = true; }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    int &ok = cache[cur & 63];
+    if (ok >= 0) return ok;
+    ok = 0;
+    if (wave_prepare() != 0) return ok;
+    int coop = 0, nb = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cur);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gemm_wave_kernel, WAVE_THREADS, WAVE_SMEM) != cudaSuccess) {
+        cudaGetLastError();
+        nb = 0;
+    }
+    ok = (coop && nb >= 1) ? 1 : 0;
+    return ok;
+}
+
+int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
+    if (w.s_end <= w.s_begin) return 0;
+    LBIC_TRY(wave_prepare());
+    WaveParams p;
+    memset(&p, 0, sizeof(p));
+    p.layers = w.d_layers; p.counters = w.counters;
+    p.mode = w.raster ? 1 : 0; p.s_begin = w.s_begin; p.s_end = w.s_end;
+    p.n_img = w.n_img; p.Hb = w.Hb; p.Wb = w.Wb;
+    p.variant = LBIC_LAT_VARIANT;
+    p.x_cl = w.x_cl; p.zhat_cl = w.zhat_cl; p.Cin = w.Cin;
+    p.X_hi = w.X_hi; p.X_lo = w.X_lo; p.ldX = w.ldX; p.T_hi = w.T_hi; p.T_lo = w.T_lo; p.ldT = w.ldT;
+    p.cdf = w.cdf; p.cdf_stride = w.cdf_stride; p.cdf_len = w.cdf_len; p.offs = w.offs; p.scale_tab = w.scale_tab;
+    p.states = w.states; p.lane_ptr = w.lane_ptr; p.lanes = w.lanes;
+    p.ksi = w.ksi; p.ld_ksi = w.ld_ksi; p.yq_hi = w.yq_hi; p.yq_lo = w.yq_lo; p.ld_yq = w.ld_yq; p.sym_out = w.sym_out; p.M = w.M;
+    const int max_rows = w.raster ? w.n_img : w.n_img * (w.Hb < (w.Wb + 1) / 2 ? w.Hb : (w.Wb + 1) / 2);
+    if (max_rows > WAVE_MAX_RB * BM) return lbic_fail(LBIC_ERR_INVALID, "wave kernel: step of %d rows exceeds %d", max_rows, WAVE_MAX_RB * BM);
+    // the step's list.  ids[0..3] = entropy net, [4..10] = encoder net (F0 G0 F1 G1 F2 G2 F3), [11..17] = decoder net.
+    // The encoder net (the critical path of an encode step) comes first so that its tiles are never queued behind the
+    // entropy net's in a CTA's own list; the entropy net only has to be done when F3 quantises.
+    int n = 0;
+    auto add = [&](int kind, int layer, int ntn, int bn, int d0, int d1) {
+        p.ord[n].kind = kind; p.ord[n].layer = layer; p.ord[n].ntn = ntn; p.ord[n].bn = bn;
+        p.ord[n].dep[0] = d0; p.ord[n].dep[1] = d1;
+        return n++;
+    };
+    auto gemm = [&](int id, int d0, int d1) {
+        const ChainLayer &L = w.h_layers[id];
+        const int bn = L.bn_v[LBIC_LAT_VARIANT];
+        return add(WK_GEMM, id, (L.cout + bn - 1) / bn, bn, d0, d1);
+    };
+    for (int i = 0; i < 18; ++i) {
+        const int bn = w.h_layers[w.ids[i]].bn_v[LBIC_LAT_VARIANT];
+        if (bn % 16 || bn < 16 || bn > LBIC_LAT_MAX_BN) return lbic_fail(LBIC_ERR_INVALID, "wave kernel: bad tile N %d", bn);
+    }
+    const int *E = w.ids, *F = w.ids + 4, *D = w.ids + 11;
+    p.gather_first = w.decode ? 1 : 0;
+    const int g = add(WK_GATHER, -1, w.decode ? 4 : 5, 0, -1, -1);
+    int last_e, last;
+    if (!w.decode) {
+        // interleaved: F0 E0 G0 E1 F1 E2 G1 E3 F2 G2 F3 | D0 .. D3
+        const int f0 = gemm(F[0], g, -1);
+        const int e0 = gemm(E[0], g, -1);
+        const int g0 = gemm(F[1], f0, -1);
+        const int e1 = gemm(E[1], e0, -1);
+        const int f1 = gemm(F[2], g0, -1);
+        const int e2 = gemm(E[2], e1, -1);
+        const int g1 = gemm(F[3], f1, -1);
+        last_e = gemm(E[3], e2, -1);
+        const int f2 = gemm(F[4], g1, -1);
+        const int g2 = gemm(F[5], f2, -1);
+        last = gemm(F[6], g2, last_e);             // QUANT: operand from G2, entropy parameters from E3
+    } else {
+        const int e0 = gemm(E[0], g, -1);
+        const int e1 = gemm(E[1], e0, -1);
+        const int e2 = gemm(E[2], e1, -1);
+        last_e = gemm(E[3], e2, -1);
+        last = add(WK_RANS, -1, WAVE_RANS_PARTS, 0, last_e, -1);
+    }
+    for (int i = 0; i < 7; ++i) last = gemm(D[i], last, -1);   // D0 IG0 D1 IG1 D2 IG2 D3: each reads the one before
+    p.recon_ord = last;
+    p.n_ord = n;
+    int total = 0;
+    for (int i = 0; i < n; ++i) { p.pre[i] = total; total += p.ord[i].ntn; }
+    p.pre[n] = total;
+    p.tiles_per_rb = total;
+    if ((size_t)n * WAVE_MAX_RB > w.counters_cap) return lbic_fail(LBIC_ERR_INVALID, "wave kernel: counter buffer too small");
+    LBIC_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(int) * (size_t)n * WAVE_MAX_RB, st));
+    int n_sm = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(n_sm, 1, 1);
+    cfg.blockDim = dim3(WAVE_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = WAVE_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;     // all CTAs co-resident, or the launch is refused
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_wave_kernel, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources || e == cudaErrorNotSupported)
+            return LBIC_FLOW_REFUSED;
+        return lbic_fail(LBIC_ERR_CUDA, "wave launch failed: %s", cudaGetErrorString(e));
+    }
+    count_launch(0);
+    return 0;
+}

@@ -114,17 +114,20 @@ struct GemmCall {
     EpiParams ep;
 };
 
-// One layer of a persistent chain launch (gemm_chain.cu), resident in device memory.
+// One layer as the persistent multi-layer kernels see it (gemm_flow_kernel, gemm_wave_kernel), resident in device memory.
 // Tile-width variants per layer, indexed by "split factor" f: the layer's Cout is cut into f * ceil(Cout / (256 f))
 // equal tiles (width rounded up to 16), so a cluster of f CTAs gets the same number of tiles per CTA.
-constexpr int LBIC_NBN = 10;          // 6 split factors + the warp-specialised kernel's tiling (width <= 192) + its CTA-pair form
+constexpr int LBIC_NBN = 11;          // 6 split factors + the warp-specialised kernel's tiling (width <= 192) + its CTA-pair forms + small / latency tilings
 constexpr int LBIC_WS_VARIANT = 6;
 constexpr int LBIC_PAIR_WIDE = 8;     // CTA-pair form with tiles up to 256 wide (2 pipeline stages instead of 3)
 constexpr int LBIC_SMALL_VARIANT = 9;  // tiles of at most 96 columns for the single-CTA dataflow launch of small steps
+constexpr int LBIC_LAT_VARIANT = 10;   // tiles of at most 32 columns for the persistent wavefront (latency) kernel, gemm_wave.cu
+constexpr int LBIC_LAT_MAX_BN = 32;
 constexpr int LBIC_PAIR_VARIANT = 7;  // same tile width as LBIC_WS_VARIANT; weight TMA box = half the tile (one half per CTA)
 __host__ __device__ inline int lbic_split(int i) { return i == 0 ? 1 : i == 1 ? 2 : i == 2 ? 3 : i == 3 ? 4 : i == 4 ? 6 : 8; }
 struct alignas(64) ChainLayer {
     CUtensorMap tmA[2][2];              // [segment][hi, lo]   box 64 x 128
+    CUtensorMap tmA64[2][2];            // same operands, box 64 x 64 rows: steps with at most 64 rows load half the bytes
     CUtensorMap tmW[LBIC_NBN][2][2];    // [variant][segment][hi, lo]   box 64 x bn_v[variant]
     int kb[2];                          // 64-wide k-blocks per segment
     int nseg;
@@ -133,14 +136,37 @@ struct alignas(64) ChainLayer {
     int n_bn;
     EpiParams ep;                       // R and step are filled in per launch
 };
-int gemm_chain_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int l0, int l1, int R,
-                      const StepDesc &step, int force_S, cudaStream_t st);
 
 int gemm_ws_launch(const GemmCall &g, cudaStream_t st, int pair = 0);   // persistent warp-specialised kernel (gemm_ws.cu)
 int gemm_flow_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int l0, int l1, const int (*dep)[2], int R,
                      const StepDesc &step, int *d_counters, size_t counters_cap, cudaStream_t st, int pair = 1);
 constexpr int LBIC_FLOW_REFUSED = 1000;   // gemm_flow_launch: the (cooperative) launch was refused; use the per-layer path
 int gemm_flow_supported();   // 1 if all CTA pairs of the dataflow launch can be co-resident on this device
+struct RansStreamState;
+// The latency path (gemm_wave.cu): a range of wavefront steps (or raster blocks) of ONE encode / decode in a single
+// persistent cooperative launch; gather, GEMM layers and (decode) the rANS step are tiles of one in-kernel work list.
+struct WaveLaunch {
+    const ChainLayer *d_layers, *h_layers;
+    int decode;                 // 0: encode step = gather | entropy net | encoder net + quantisation | decoder net
+                                // 1: decode step = gather | entropy net | rANS | decoder net
+    int raster;                 // 1: steps are single blocks in raster order (reference container decode)
+    int s_begin, s_end;         // wavefront: t in [s_begin, s_end); raster: block number v * Wb + h
+    int n_img, Hb, Wb;
+    int ids[20];                // LayerId of E0..E3, F0..F3 (7), D0..D3 (7) in api.cu's LayerId order (18 entries)
+    const float *x_cl, *zhat_cl;
+    int Cin;
+    h16 *X_hi, *X_lo; int ldX;
+    h16 *T_hi, *T_lo; int ldT;
+    // decode only
+    const int32_t *cdf; int cdf_stride; const int32_t *cdf_len, *offs; const float *scale_tab;
+    RansStreamState *states; const uint8_t *const *lane_ptr; int lanes;
+    const float *ksi; int ld_ksi; h16 *yq_hi, *yq_lo; int ld_yq; int32_t *sym_out; int M;
+    int *counters; size_t counters_cap;
+    int *err_flag;
+};
+int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st);   // LBIC_FLOW_REFUSED if the cooperative launch is refused
+int gemm_wave_supported();
+int gemm_wave_max_rows();
 int gemm_ws_max_bn();
 int gemm_pair_max_bn();
 void gemm_set_pdl(int on);   // programmatic dependent launch between consecutive GEMM kernels (default on)
@@ -226,6 +252,7 @@ int launch_rans_dec_init(const uint8_t *streams, const uint32_t *stream_len, siz
                          int lanes, int lanes_container, RansStreamState *states, const uint8_t **lane_ptr, int *err_flag,
                          cudaStream_t st);
 // decode M symbols for every row of a step; writes yq = sym + mean (hi/lo) and optionally symbols
+void rans_set_enc_block_max_streams(int n);    // encodes of at most this many streams use the CTA-per-stream kernel (0 = never)
 void rans_set_enc_thread_min_streams(int n);   // encodes of at least this many streams use the thread-per-stream kernel
 void rans_set_dec_thread_min_rows(int rows);   // steps with at least this many rows use the thread-per-stream kernel
 int launch_rans_dec_step(const Tables &T, RansStreamState *states, const uint8_t *const *lane_ptr, int lanes,

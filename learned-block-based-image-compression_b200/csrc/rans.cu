@@ -10,14 +10,10 @@
 // its decode is serial in raster order.  The lane container (extension) holds one such stream per block row:
 //   u32 'LBML' | u32 lanes | u32 len[lanes] | lane 0 bytes | lane 1 bytes | ...
 // which lets the decoder follow the same slope-2 wavefront as the encoder.
-#include "epilogue.cuh"
+#include "rans_device.cuh"
 
 namespace {
 
-constexpr unsigned long long RANS_L = 1ull << 31;
-constexpr int PREC = 16;
-constexpr int BYPASS = 4;
-constexpr int MAX_BYPASS = 15;
 constexpr uint32_t LANE_MAGIC = 0x4C4D424Cu;   // "LBML"
 
 // ---------------------------------------------------------------------------------------------
@@ -164,6 +160,121 @@ __global__ void rans_encode_kernel(const int32_t *__restrict__ cdf, int cdf_stri
     }
 }
 
+// ---- CTA-per-stream form of the encoder ----------------------------------------------------------------
+// Few, long streams: the reference container of a single image is ONE stream of Hb*Wb*M symbols (589 824 for a
+// 768x512 image), and its state update is a serial chain.  One CTA per stream splits the work by warp: warps 1..7
+// prepare the next chunk of 1024 symbols in parallel (table lookups, escape decision, exact reciprocal of the range,
+// exactly as the warp kernel above) into shared memory while lane 0 of warp 0 replays the previous chunk; the serial
+// chain then consists of one 16-byte shared-memory load (independent of the state, so the unrolled loop keeps several
+// in flight), a compare, a 64-bit mulhi and a few adds per symbol: ~25 ns instead of ~150 ns in the warp kernel,
+// where every lane steps through the chain and the records travel by shuffles.  Same arithmetic, same words.
+constexpr int ENC_B_THREADS = 256;
+constexpr int ENC_B_CHUNK = 1024;
+
+__global__ void __launch_bounds__(ENC_B_THREADS)
+rans_encode_block_kernel(const int32_t *__restrict__ cdf, int cdf_stride, const int32_t *__restrict__ cdf_len,
+                         const int32_t *__restrict__ offs, const int32_t *__restrict__ sym,
+                         const uint8_t *__restrict__ idx, int n_streams, long n_sym, long stream_stride,
+                         uint32_t *__restrict__ scratch, long scratch_words, uint32_t *__restrict__ start_word,
+                         uint32_t *__restrict__ n_words, int *__restrict__ err) {
+    __shared__ uint4 rec[2][ENC_B_CHUNK];        // start | range << 16, escape | shift << 8, rcp lo, rcp hi
+    __shared__ uint32_t raws[2][ENC_B_CHUNK];    // raw value of an escaped symbol
+    const int s = blockIdx.x;
+    if (s >= n_streams) return;
+    const int32_t *ps = sym + (size_t)s * stream_stride;
+    const uint8_t *pi = idx + (size_t)s * stream_stride;
+    const long nchunks = (n_sym + ENC_B_CHUNK - 1) / ENC_B_CHUNK;
+    // element e of chunk c is symbol n_sym - 1 - (c * CHUNK + e): the coder walks the symbols backwards
+    auto prepare = [&](long c, int buf, int first, int stride) {
+        for (int e = first; e < ENC_B_CHUNK; e += stride) {
+            const long k = n_sym - 1 - (c * ENC_B_CHUNK + e);
+            if (k < 0) break;
+            const int ci = pi[k];
+            const int32_t *row = cdf + (size_t)ci * cdf_stride;
+            const int max_value = __ldg(cdf_len + ci) - 2;
+            int value = ps[k] - __ldg(offs + ci);
+            uint32_t raw = 0;
+            if (value < 0) {
+                raw = (uint32_t)(-2 * value - 1);
+                value = max_value;
+            } else if (value >= max_value) {
+                raw = (uint32_t)(2 * (value - max_value));
+                value = max_value;
+            }
+            const uint32_t start = (uint32_t)__ldg(row + value);
+            const uint32_t range = (uint32_t)__ldg(row + value + 1) - start;
+            uint32_t shift = 0;
+            while (range > (1u << shift)) ++shift;
+            unsigned long long rcp = 0;
+            if (range >= 2) {
+                unsigned long long x0 = range - 1;
+                const unsigned long long x1 = 1ull << (shift + 31);
+                const unsigned long long t1 = x1 / range;
+                x0 += (x1 % range) << 32;
+                rcp = x0 / range + (t1 << 32);
+            }
+            rec[buf][e] = make_uint4(start | (range << 16), (value == max_value ? 1u : 0u) | (shift << 8), (uint32_t)rcp,
+                                     (uint32_t)(rcp >> 32));
+            raws[buf][e] = raw;
+        }
+    };
+    prepare(0, 0, threadIdx.x, ENC_B_THREADS);
+    __syncthreads();
+    EncCursor c;
+    c.x = RANS_L;
+    c.base = scratch + (size_t)s * scratch_words;
+    c.pos = scratch_words;
+    c.overflow = false;
+    for (long ch = 0; ch < nchunks; ++ch) {
+        const int buf = (int)(ch & 1);
+        if (threadIdx.x >= 32) {
+            if (ch + 1 < nchunks) prepare(ch + 1, buf ^ 1, threadIdx.x - 32, ENC_B_THREADS - 32);
+        } else if (threadIdx.x == 0) {
+            const long left = n_sym - ch * ENC_B_CHUNK;
+            const int cnt = left < ENC_B_CHUNK ? (int)left : ENC_B_CHUNK;
+#pragma unroll 4
+            for (int e = 0; e < cnt; ++e) {
+                const uint4 r = rec[buf][e];
+                if (r.y & 1u) {
+                    // escape: pushed order is main, count (15,15,...,rem), nibbles LSB first -> popped in reverse
+                    const uint32_t raw = raws[buf][e];
+                    int nb = 0;
+                    while (nb < 8 && (raw >> (nb * BYPASS)) != 0) ++nb;
+                    for (int q = nb - 1; q >= 0; --q) enc_put_bits(c, (raw >> (q * BYPASS)) & MAX_BYPASS);
+                    const int qn = nb / MAX_BYPASS, rem = nb - qn * MAX_BYPASS;
+                    for (int q = 0; q <= qn; ++q) enc_put_bits(c, (uint32_t)(q == 0 ? rem : MAX_BYPASS));
+                }
+                const uint32_t start = r.x & 0xFFFFu, range = r.x >> 16;
+                const unsigned long long x_max = ((RANS_L >> PREC) << 32) * (unsigned long long)range;
+                if (c.x >= x_max) enc_emit(c);
+                unsigned long long q;
+                if (range >= 2) {
+                    const unsigned long long r64 = (unsigned long long)r.z | ((unsigned long long)r.w << 32);
+                    q = __umul64hi(c.x, r64) >> ((r.y >> 8) - 1);
+                } else {
+                    q = c.x;
+                }
+                c.x = (q << PREC) + (c.x - q * range) + start;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        // Rans64EncFlush: two words, low half first in memory
+        if (c.pos < 2) c.overflow = true;
+        if (!c.overflow) {
+            c.base[--c.pos] = (uint32_t)(c.x >> 32);
+            c.base[--c.pos] = (uint32_t)(c.x);
+            start_word[s] = (uint32_t)c.pos;
+            n_words[s] = (uint32_t)(scratch_words - c.pos);
+        } else {
+            atomicExch(err, 1);
+            start_word[s] = 0;
+            n_words[s] = 0xFFFFFFFFu;
+        }
+    }
+}
+
 // ---- thread-per-stream form of the encoder --------------------------------------------------------
 // A batch holds tens of thousands of independent streams (one per block row per image in the lane container), so
 // one THREAD per stream keeps every lane busy where the warp kernel above replays its serial chain on 32 lanes.
@@ -300,75 +411,6 @@ __global__ void lane_pack_kernel(const uint32_t *__restrict__ scratch, long scra
         const uint32_t nw = n_words[s];
         for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) dst[lane_off[l] + i] = src[i];
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// decoder
-// ---------------------------------------------------------------------------------------------
-struct DecCursor {
-    unsigned long long x;
-    const uint32_t *words;
-    uint32_t pos, nwords;
-};
-
-__device__ __forceinline__ uint32_t dec_word(DecCursor &d) {
-    const uint32_t w = d.pos < d.nwords ? __ldg(d.words + d.pos) : 0u;   // a corrupt stream stays finite
-    d.pos++;
-    return w;
-}
-
-__device__ __forceinline__ int dec_bits(DecCursor &d) {
-    const int val = (int)(d.x & MAX_BYPASS);
-    d.x >>= BYPASS;
-    if (d.x < RANS_L) d.x = (d.x << 32) | dec_word(d);
-    return val;
-}
-
-// Decodes one symbol; warp-cooperative CDF search (all 32 lanes hold identical cursor state).
-__device__ __forceinline__ int dec_symbol_warp(DecCursor &d, const int32_t *__restrict__ row, int len, int off,
-                                               int lane) {
-    const uint32_t cf = (uint32_t)(d.x & 0xFFFFu);
-    const int max_value = len - 2;
-    // first k with row[k] > cf, searched in a 32-wide window around the distribution centre (value of symbol 0)
-    int g = -off - 15;
-    g = g < 0 ? 0 : g;
-    g = g > len - 32 ? (len - 32 < 0 ? 0 : len - 32) : g;
-    const int k = g + lane;
-    const bool gt = (k < len) && ((uint32_t)__ldg(row + k) > cf);
-    const unsigned ball = __ballot_sync(0xffffffffu, gt);
-    int s;
-    if ((ball & 1u) == 0 && ball != 0) {
-        s = g + (__ffs(ball) - 1) - 1;
-    } else {
-        // outside the window: upper_bound by bisection (identical result to the reference's linear find_if)
-        int lo = 0, hi = len - 1;   // row[len-1] = 65536 > cf always
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if ((uint32_t)__ldg(row + mid) > cf) hi = mid; else lo = mid + 1;
-        }
-        s = lo - 1;
-    }
-    const uint32_t start = (uint32_t)__ldg(row + s);
-    const uint32_t freq = (uint32_t)__ldg(row + s + 1) - start;
-    d.x = (unsigned long long)freq * (d.x >> PREC) + cf - start;
-    if (d.x < RANS_L) d.x = (d.x << 32) | dec_word(d);
-    int value = s;
-    if (value == max_value) {
-        int val = dec_bits(d);
-        int nb = val;
-        while (val == MAX_BYPASS) {
-            val = dec_bits(d);
-            nb += val;
-        }
-        int raw = 0;
-        for (int j = 0; j < nb; ++j) {
-            val = dec_bits(d);
-            raw |= val << (j * BYPASS);
-        }
-        value = raw >> 1;
-        if (raw & 1) value = -value - 1; else value += max_value;
-    }
-    return value + off;
 }
 
 // Parses the per-image container(s) and initialises one decoder state per lane.
@@ -658,6 +700,7 @@ __global__ void rans_decode_full_kernel(const int32_t *__restrict__ cdf, int cdf
 }  // namespace
 
 static int g_enc_thread_min_streams = 4096;
+static int g_enc_block_max_streams = 592;     // up to 4 CTAs per SM: one CTA per stream; more (and short) streams: one warp each
 
 // scratch layout: [n_streams * scratch_words] words, then start_word[n_streams], n_words[n_streams]
 int launch_rans_encode(const Tables &T, const int32_t *sym, const uint8_t *idx, int n_streams, int64_t n_sym,
@@ -678,11 +721,16 @@ int launch_rans_encode(const Tables &T, const int32_t *sym, const uint8_t *idx, 
         rans_encode_thread_kernel<<<(n_streams + ENC_T_THREADS - 1) / ENC_T_THREADS, ENC_T_THREADS, smem, st>>>(
             T.cdf16, T.cdf16_off, T.cdf16_total, T.cdf_length, T.offset, sym, idx, n_streams, (long)n_sym,
             (long)stream_stride, scratch, (long)scratch_words, start_word, n_words, err_flag);
+    } else if (n_streams <= g_enc_block_max_streams && n_sym >= 256) {
+        // few long streams (single images, the reference container): one CTA per stream, serial chain on one thread
+        rans_encode_block_kernel<<<n_streams, ENC_B_THREADS, 0, st>>>(
+            T.cdf, T.stride, T.cdf_length, T.offset, sym, idx, n_streams, (long)n_sym, (long)stream_stride, scratch,
+            (long)scratch_words, start_word, n_words, err_flag);
     } else {
-    const int warps_per_block = 4;
-    rans_encode_kernel<<<(n_streams + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
-        T.cdf, T.stride, T.cdf_length, T.offset, sym, idx, n_streams, (long)n_sym, (long)stream_stride, scratch,
-        (long)scratch_words, start_word, n_words, err_flag);
+        const int warps_per_block = 4;
+        rans_encode_kernel<<<(n_streams + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+            T.cdf, T.stride, T.cdf_length, T.offset, sym, idx, n_streams, (long)n_sym, (long)stream_stride, scratch,
+            (long)scratch_words, start_word, n_words, err_flag);
     }
     count_launch(1);
     LBIC_CUDA(cudaGetLastError());
@@ -721,6 +769,7 @@ int launch_rans_dec_init(const uint8_t *streams, const uint32_t *stream_len, siz
 static int g_dec_thread_min_rows = 4096;
 void rans_set_dec_thread_min_rows(int rows) { g_dec_thread_min_rows = rows < 1 ? 1 : rows; }
 void rans_set_enc_thread_min_streams(int n) { g_enc_thread_min_streams = n < 1 ? 1 : n; }
+void rans_set_enc_block_max_streams(int n) { g_enc_block_max_streams = n < 0 ? 0 : n; }
 
 int launch_rans_dec_step(const Tables &T, RansStreamState *states, const uint8_t *const *lane_ptr, int lanes,
                          const StepDesc &s, int R, int M, const float *ksi, int ld_ksi, h16 *yq_hi, h16 *yq_lo,

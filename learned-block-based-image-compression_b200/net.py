@@ -112,13 +112,13 @@ class BlockBasedImgCompLossyNetv9:
         _lib.check(_lib.lib().lbic_set_option(self._need(), _lib.LBIC_OPT_GEMM_CORE, {"tcgen05": 0, "simt": 1}[core]))
 
     def set_option(self, name: str, value: int):
-        """Tuning hooks: 'chain' (1 = persistent chain kernel per step; default 0), 'cluster' (forced cluster size),
-        'force_bn' (forced tile width), 'ws' (0 off / 1 auto / 2 always: persistent kernel),
-        'pair' (CTA-pair form of the persistent kernel), 'pdl', 'host_bands' (bands of block rows of the host calls)."""
-        opt = {"chain": _lib.LBIC_OPT_CHAIN, "cluster": _lib.LBIC_OPT_CLUSTER, "force_bn": _lib.LBIC_OPT_FORCE_BN,
+        """Tuning hooks: 'force_bn' (forced tile width), 'ws' (0 off / 1 auto / 2 always: persistent kernel),
+        'pair' (CTA-pair form of the persistent kernel), 'pdl', 'host_bands' (bands of block rows of the host calls),
+        'wave' (persistent wavefront kernel for small steps), 'wave_max_rows'."""
+        opt = {"force_bn": _lib.LBIC_OPT_FORCE_BN, "wave": _lib.LBIC_OPT_WAVE, "wave_max_rows": _lib.LBIC_OPT_WAVE_MAX_ROWS,
                "ws": _lib.LBIC_OPT_WS, "pdl": _lib.LBIC_OPT_PDL,
                "pair": _lib.LBIC_OPT_PAIR, "dec_thread_rows": _lib.LBIC_OPT_DEC_THREAD_ROWS,
-               "enc_thread_streams": _lib.LBIC_OPT_ENC_THREAD_STREAMS, "flow": _lib.LBIC_OPT_FLOW,
+               "enc_thread_streams": _lib.LBIC_OPT_ENC_THREAD_STREAMS, "enc_block_streams": _lib.LBIC_OPT_ENC_BLOCK_STREAMS, "flow": _lib.LBIC_OPT_FLOW,
                "flow_min_rows": _lib.LBIC_OPT_FLOW_MIN_ROWS, "flow_small": _lib.LBIC_OPT_FLOW_SMALL,
                "host_bands": _lib.LBIC_OPT_HOST_BANDS}[name]
         _lib.check(_lib.lib().lbic_set_option(self._need(), opt, int(value)))

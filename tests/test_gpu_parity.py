@@ -265,6 +265,7 @@ def test_thread_per_stream_decode_equals_warp_per_stream(dev, cfgname):
         img = weights.synth_images(40, 5 * B, 9 * B, seed0=311, kind="noise" if harsh else "smooth")
         x = arrange_block_pixels_to_channel_dim((img - 0.5).to(dev), B)
         try:
+            m.set_option("wave", 0)
             for lanes in (0, 1):
                 strings, zhat, sym, _ = m.compress_batch(x, lanes=lanes, return_symbols=True)
                 out = {}
@@ -283,6 +284,7 @@ def test_thread_per_stream_decode_equals_warp_per_stream(dev, cfgname):
         finally:
             m.set_option("dec_thread_rows", 4096)
             m.set_option("enc_thread_streams", 4096)
+            m.set_option("wave", 1)
 
 
 def test_batch_invariance_and_ragged_grids(dev):
@@ -303,30 +305,49 @@ def test_batch_invariance_and_ragged_grids(dev):
         assert torch.equal(zdec, zhat)
 
 
-@pytest.mark.parametrize("cfgname", ["B8_lowrate", "B4_highrate"])
-def test_chain_kernel_equals_per_layer_launches(dev, cfgname):
-    """The persistent chain kernel (any cluster size) and the one-launch-per-layer path run the same tiles in the
-    same k order: symbols, indexes, reconstruction and bytes must be bit-identical."""
+@pytest.mark.parametrize("cfgname,n,Hb,Wb", [("B8_lowrate", 1, 7, 11), ("B8_lowrate", 1, 40, 70), ("B8_lowrate", 6, 9, 13),
+                                             ("B8_lowrate", 5, 30, 64), ("B16_lowrate", 3, 5, 9), ("B8_lowrate", 2, 1, 5),
+                                             ("B8_lowrate", 1, 6, 1)])
+def test_wave_kernel_equals_per_layer_launches(dev, cfgname, n, Hb, Wb):
+    """gemm_wave_kernel (a whole encode / decode of small steps in ONE persistent cooperative launch: gather, every layer
+    and the rANS decode step as tiles of an in-kernel list, 128 x 32 tiles, cross-step dependencies through monotonic
+    counters) must be bit-identical to one launch per layer: symbols, indexes, reconstruction, bytes, for the lane and
+    the reference container, one and several 128-row blocks per step (5 x 30 rows = 150), degenerate grids; and through
+    the host calls, whose band hooks cut the launch into several."""
+    from lbic_b200.layout import arrange_block_pixels_to_channel_dim
     m = get_model(cfgname, 1337, False, dev)
     B = m.B
-    from lbic_b200.layout import arrange_block_pixels_to_channel_dim
-    img = weights.synth_images(6, 7 * B, 11 * B, seed0=77)
+    img = weights.synth_images(n, Hb * B, Wb * B, seed0=131)
     x = arrange_block_pixels_to_channel_dim((img - 0.5).to(dev), B)
-    m.set_option("chain", 0)
-    ref = m.compress_batch(x, lanes=0, return_symbols=True)
-    zdec_ref = m.decompress_batch(ref[0], x.shape, lanes=0)
     try:
-        for S in (0, 1, 2, 3, 4, 6, 8):
-            m.set_option("chain", 1)
-            m.set_option("cluster", S)
-            got = m.compress_batch(x, lanes=0, return_symbols=True)
-            assert got[0] == ref[0], f"cluster {S}: bitstreams differ"
-            assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2]) and torch.equal(got[3], ref[3])
-            zdec = m.decompress_batch(got[0], x.shape, lanes=0)
-            assert torch.equal(zdec, zdec_ref) and torch.equal(zdec, got[1])
+        for lanes in (0, 1):
+            m.set_option("wave", 0)
+            ref = m.compress_batch(x, lanes=lanes, return_symbols=True)
+            zref = m.decompress_batch(ref[0], x.shape, lanes=lanes)
+            l0 = m.launch_count()
+            m.set_option("wave", 1)
+            got = m.compress_batch(x, lanes=lanes, return_symbols=True)
+            assert m.launch_count() - l0 < 12, "the wave path should need a handful of launches per encode"
+            assert torch.equal(got[2], ref[2]), f"symbols differ (lanes={lanes})"
+            assert torch.equal(got[3], ref[3]) and torch.equal(got[1], ref[1])
+            assert got[0] == ref[0], f"bitstreams differ (lanes={lanes})"
+            o = m.encode_device(x, lanes=lanes)
+            zdec, sdec = m.decode_device(o.streams, o.lens, n, Hb, Wb, lanes=lanes, want_symbols=True)
+            assert torch.equal(sdec, ref[2]), f"decoded symbols differ (lanes={lanes})"
+            assert torch.equal(zdec, zref) and torch.equal(zdec, got[1])
+        # host calls: the band hooks cut the wave launch; 8-bit entry points on the same images
+        imgs_u8 = (img * 255).round().to(torch.uint8).numpy()
+        m.set_option("wave", 0)
+        want_s, want_rec = m.compress_images_u8(imgs_u8, lanes=0, return_recon=True)
+        m.set_option("wave", 1)
+        for bands in (16, 3):
+            m.set_option("host_bands", bands)
+            got_s, got_rec = m.compress_images_u8(imgs_u8, lanes=0, return_recon=True)
+            assert got_s == want_s and np.array_equal(got_rec, want_rec)
+            assert np.array_equal(m.decompress_images_u8(got_s, Hb * B, Wb * B, lanes=0), want_rec)
     finally:
-        m.set_option("chain", 0)
-        m.set_option("cluster", 0)
+        m.set_option("wave", 1)
+        m.set_option("host_bands", 16)
 
 
 @pytest.mark.parametrize("cfgname", ["B8_lowrate", "B4_highrate", "B16_lowrate", "B8_highrate"])
@@ -339,6 +360,7 @@ def test_warp_specialised_kernel_equals_per_tile_kernel(dev, cfgname):
     img = weights.synth_images(24, 6 * B, 13 * B, seed0=91)
     x = arrange_block_pixels_to_channel_dim((img - 0.5).to(dev), B)
     try:
+        m.set_option("wave", 0)
         m.set_option("ws", 0)
         ref = m.compress_batch(x, lanes=0, return_symbols=True)
         for pair in (0, 1):
@@ -352,6 +374,7 @@ def test_warp_specialised_kernel_equals_per_tile_kernel(dev, cfgname):
     finally:
         m.set_option("ws", 1)
         m.set_option("pair", 1)
+        m.set_option("wave", 1)
 
 
 @pytest.mark.parametrize("cfgname", ["B8_lowrate", "B4_highrate", "B16_lowrate", "B8_highrate"])
@@ -364,6 +387,7 @@ def test_dataflow_launch_equals_per_layer_launches(dev, cfgname):
     img = weights.synth_images(37, 7 * B, 12 * B, seed0=57)
     x = arrange_block_pixels_to_channel_dim((img - 0.5).to(dev), B)
     try:
+        m.set_option("wave", 0)
         m.set_option("flow", 0)
         ref = m.compress_batch(x, lanes=0, return_symbols=True)
         zref = m.decompress_batch(ref[0], x.shape, lanes=0)
@@ -384,6 +408,7 @@ def test_dataflow_launch_equals_per_layer_launches(dev, cfgname):
     finally:
         m.set_option("flow", 1)
         m.set_option("flow_small", 0)
+        m.set_option("wave", 1)
 
 
 # BASELINE.json configs at their own sizes: C1 (B8_lowrate 768x512), C2 (B4_highrate 768x512, batch of 24),
@@ -611,6 +636,7 @@ def test_two_devices_in_one_process(dev):
         m.load_state_dict(sd)
         m.update(force=True)
         m.set_option("flow", 2)
+        m.set_option("wave", 0)
         m.set_option("enc_thread_streams", 1)
         m.set_option("dec_thread_rows", 1)
         x = arrange_block_pixels_to_channel_dim((img - 0.5).to(devd), 8)
