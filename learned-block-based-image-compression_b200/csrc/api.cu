@@ -73,7 +73,7 @@ struct ActView {   // an activation buffer seen as a GEMM A operand of logical w
     const ActBuf *buf = nullptr;
     int K = 0;
     CUtensorMap tm_hi, tm_lo;         // box 64 k x 128 rows
-    CUtensorMap tm_hi64, tm_lo64;     // box 64 k x 64 rows (latency kernel, steps of at most 64 rows)
+    CUtensorMap tm_small[4][2];       // boxes of 64 k x 16 / 32 / 48 / 64 rows, [class][hi, lo] (latency kernel)
 };
 
 struct Workspace {
@@ -365,8 +365,10 @@ int make_view(Workspace &ws, ActView &v, const ActBuf &b, int K) {
     v.K = K;
     LBIC_TRY(make_tmap_2d(&v.tm_hi, b.hi, K, ws.R_cap, b.ld, 64, 128));
     LBIC_TRY(make_tmap_2d(&v.tm_lo, b.lo, K, ws.R_cap, b.ld, 64, 128));
-    LBIC_TRY(make_tmap_2d(&v.tm_hi64, b.hi, K, ws.R_cap, b.ld, 64, 64));
-    LBIC_TRY(make_tmap_2d(&v.tm_lo64, b.lo, K, ws.R_cap, b.ld, 64, 64));
+    for (int c = 0; c < 4; ++c) {
+        LBIC_TRY(make_tmap_2d(&v.tm_small[c][0], b.hi, K, ws.R_cap, b.ld, 64, lbic_box_rows(c)));
+        LBIC_TRY(make_tmap_2d(&v.tm_small[c][1], b.lo, K, ws.R_cap, b.ld, 64, lbic_box_rows(c)));
+    }
     return 0;
 }
 
@@ -418,8 +420,10 @@ int ensure_workspace(lbic_model *m, int n_img, int Hb, int Wb) {
         ws.vText.buf = &ws.Text; ws.vText.K = 4 * m->Cin;
         LBIC_TRY(make_tmap_2d(&ws.vText.tm_hi, ws.Text.hi, 4 * m->Cin, ws.R_ext_cap, ws.Text.ld, 64, 128));
         LBIC_TRY(make_tmap_2d(&ws.vText.tm_lo, ws.Text.lo, 4 * m->Cin, ws.R_ext_cap, ws.Text.ld, 64, 128));
-        LBIC_TRY(make_tmap_2d(&ws.vText.tm_hi64, ws.Text.hi, 4 * m->Cin, ws.R_ext_cap, ws.Text.ld, 64, 64));
-        LBIC_TRY(make_tmap_2d(&ws.vText.tm_lo64, ws.Text.lo, 4 * m->Cin, ws.R_ext_cap, ws.Text.ld, 64, 64));
+        for (int c = 0; c < 4; ++c) {
+            LBIC_TRY(make_tmap_2d(&ws.vText.tm_small[c][0], ws.Text.hi, 4 * m->Cin, ws.R_ext_cap, ws.Text.ld, 64, lbic_box_rows(c)));
+            LBIC_TRY(make_tmap_2d(&ws.vText.tm_small[c][1], ws.Text.lo, 4 * m->Cin, ws.R_ext_cap, ws.Text.ld, 64, lbic_box_rows(c)));
+        }
     }
     LBIC_TRY(make_view(ws, ws.vH2, ws.H2, m->E2));
     LBIC_TRY(make_view(ws, ws.vH3, ws.H3, m->E3));
@@ -456,7 +460,7 @@ int build_chain(lbic_model *m) {
         for (int s = 0; s < L.nseg; ++s) {
             c.kb[s] = (L.seg[s].K + 63) / 64;
             c.tmA[s][0] = av[s]->tm_hi; c.tmA[s][1] = av[s]->tm_lo;
-            c.tmA64[s][0] = av[s]->tm_hi64; c.tmA64[s][1] = av[s]->tm_lo64;
+            for (int b = 0; b < 4; ++b) { c.tmAs[b][s][0] = av[s]->tm_small[b][0]; c.tmAs[b][s][1] = av[s]->tm_small[b][1]; }
             for (int v = 0; v < L.n_bn; ++v) { c.tmW[v][s][0] = L.seg[s].tm_hi[v]; c.tmW[v][s][1] = L.seg[s].tm_lo[v]; }
         }
         for (int v = 0; v < L.n_bn; ++v) c.bn_v[v] = L.bn_v[v];

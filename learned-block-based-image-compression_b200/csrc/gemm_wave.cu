@@ -25,17 +25,24 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace {
 
 constexpr int WAVE_MAX_ORD = 20;
 constexpr int WAVE_MAX_RB = 32;                  // 128-row blocks per step
-constexpr int WAVE_STAGES = 4;
-constexpr int WAVE_SLOT = 2 * A_PLANE + 2 * LBIC_LAT_MAX_BN * BK * 2;   // 40 KiB: 128 activation rows + 32 weight rows, hi + lo
+// Operand ring: a slot holds one 64-wide k-block = the activation box (hi + lo planes, 16..128 rows: only the rows the
+// step has) + 32 weight rows (hi + lo).  A tile's mainloop is bound by the LATENCY of its loads (a layer's K / 64
+// k-blocks arrive one L2 round trip after they are requested; the MMAs of a k-block take 0.1 us), so the ring is as deep
+// as shared memory allows: 10 slots of 20 KiB for steps of up to 48 rows (a 768x512 image), 5 of 40 KiB for 128 rows.
+constexpr int WAVE_MAX_STAGES = 12;
+constexpr int WAVE_RING = 5 * (2 * A_PLANE + 2 * LBIC_LAT_MAX_BN * BK * 2);   // 200 KiB
+constexpr int WAVE_PAD = 16 * 1024;              // the MMA always reads 128 rows of a slot's activation planes: rows past the
+                                                 // box are never used, but the last slot's must still be shared memory
 constexpr int WAVE_THREADS = WS_THREADS + 32;    // producer | MMA issuer | 8 epilogue warps | publisher
-constexpr int WAVE_BAR_BLOCK = 256;              // full[4] empty[4] acc_full[2] acc_empty[2] tile_done[2] pub_free[2] tmem slot
-constexpr int WAVE_TAIL = WAVE_BAR_BLOCK + 2 * 1024 + ROWTAB_BYTES + STAB_BYTES + 256;
-constexpr int WAVE_SMEM = 1024 + WAVE_STAGES * WAVE_SLOT + WGDN_BYTES + WAVE_TAIL;
+constexpr int WAVE_BAR_BLOCK = 512;              // full[12] empty[12] acc_full[2] acc_empty[2] tile_done[2] pub_free[2] tmem slot
+constexpr int WAVE_TAIL = WAVE_BAR_BLOCK + ROWTAB_BYTES + STAB_BYTES + 256;
+constexpr int WAVE_SMEM = 1024 + WAVE_RING + WAVE_PAD + WAVE_TAIL;
 constexpr int WAVE_RANS_PARTS = 16;              // rANS tiles per 128-row block: 8 rows each, one warp per row
 static_assert(WAVE_SMEM <= SMEM_LIMIT, "wave kernel shared memory");
 
@@ -60,6 +67,8 @@ struct WaveParams {
     int s_begin, s_end;
     int n_img, Hb, Wb;
     int variant;
+    int stages;                  // ring depth of this launch
+    uint32_t slot_bytes, a_plane_bytes;   // slot stride; bytes of one activation plane of the launch's largest box
     const float *x_cl, *zhat_cl;
     int Cin, gather_first;       // gather tiles cover segments gather_first .. 4 (0 = x, 1..4 = the four zhat taps)
     h16 *X_hi, *X_lo; int ldX;
@@ -67,7 +76,16 @@ struct WaveParams {
     const int32_t *cdf; int cdf_stride; const int32_t *cdf_len, *offs; const float *scale_tab;
     RansStreamState *states; const uint8_t *const *lane_ptr; int lanes;
     const float *ksi; int ld_ksi; h16 *yq_hi, *yq_lo; int ld_yq; int32_t *sym_out; int M;
+    // debug (LBIC_WAVE_TRACE): %globaltimer stamps of every tile of steps [trace_s0, trace_s0 + trace_ns), 8 words each
+    unsigned long long *trace;
+    int trace_s0, trace_ns, trace_stride;
 };
+
+__device__ __forceinline__ unsigned long long wave_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ bool wave_step_desc(const WaveParams &p, int s, StepDesc &sd) {
     sd.n_img = p.n_img; sd.Hb = p.Hb; sd.Wb = p.Wb;
@@ -88,7 +106,15 @@ struct WaveTile {
     StepDesc sd;
     int R, n_rb, prev_n_rb;
     int oi, rb, nt;      // list entry, row block, tile within (entry, row block)
+    int s, j;            // step, tile index within the step (trace)
 };
+
+// trace slot `k` of the tile, or nullptr when the tile is not being traced
+__device__ __forceinline__ unsigned long long *wave_trace_slot(const WaveParams &p, const WaveTile &w, int k) {
+    if (!p.trace || w.s < p.trace_s0 || w.s >= p.trace_s0 + p.trace_ns || w.j >= p.trace_stride) return nullptr;
+    return p.trace + ((size_t)(w.s - p.trace_s0) * p.trace_stride + w.j) * 8 + k;
+}
+#define WAVE_TRACE(k) do { if (unsigned long long *tp__ = wave_trace_slot(p, w, (k))) *tp__ = wave_now(); } while (0)
 
 // Every role of a CTA walks the same sequence of tiles: tile j of a step belongs to CTA (off + j) mod gridDim.x, where
 // off is the number of tiles of all earlier steps.  gen[rb] = number of earlier steps of this launch that had row
@@ -108,6 +134,7 @@ __device__ __forceinline__ void wave_for_each_tile(const WaveParams &p, F &&f) {
         w.n_rb = (w.R + BM - 1) / BM;
         w.prev_n_rb = prev_n_rb;
         const int total = w.n_rb * p.tiles_per_rb;
+        w.s = s;
         int first = (int)blockIdx.x - off;
         if (first < 0) first += G;
 #pragma unroll 1
@@ -118,6 +145,7 @@ __device__ __forceinline__ void wave_for_each_tile(const WaveParams &p, F &&f) {
             w.oi = oi;
             w.rb = v / p.ord[oi].ntn;
             w.nt = v - w.rb * p.ord[oi].ntn;
+            w.j = j;
             f(w, gen);
         }
         off = (off + total) % G;
@@ -150,36 +178,100 @@ __device__ __forceinline__ void wave_wait_prev_step(const WaveParams &p, const W
         wave_wait(p.counters + p.recon_ord * WAVE_MAX_RB + rb, p.ord[p.recon_ord].ntn * gen[rb]);
 }
 
-// ---- GATHER tile: one K segment (x, or one of the four causal zhat taps) of the step's first-layer operands for the
-// rows of one row block; the arithmetic of gather_kernel (kernels_misc.cu), by the 8 epilogue warps.
-__device__ __forceinline__ void wave_gather_tile(const WaveParams &p, const WaveTile &w, int ew, int lane) {
-    const int seg = p.gather_first + w.nt;
-    const int m0 = w.rb * BM;
-    const int rows = (w.R - m0) < BM ? (w.R - m0) : BM;
+// ---- GATHER tile: one K segment (x, or one of the four causal zhat taps) of the step's first-layer operands for a
+// quarter (32 rows) of one row block; the arithmetic of gather_kernel (kernels_misc.cu), by the 8 epilogue warps.  The
+// rows' source / destination addresses go through the (idle) row table, then every thread converts independent
+// (row, 4-channel) items, eight loads in flight at a time.
+constexpr int WAVE_GATHER_PARTS = 4;
+
+__device__ __forceinline__ void wave_gather_tile(const WaveParams &p, const WaveTile &w, RowTab *rt, int et) {
+    const int seg = p.gather_first + w.nt / WAVE_GATHER_PARTS;
+    const int part = w.nt % WAVE_GATHER_PARTS;
+    const int m0 = w.rb * BM + part * 32;
+    int rows = w.R - m0;
+    rows = rows < 0 ? 0 : (rows > 32 ? 32 : rows);
     const int c4n = p.Cin >> 2;
-    for (int rl = ew; rl < rows; rl += 8) {
-        const int r = m0 + rl;
+    if (et < rows) {
+        const int r = m0 + et;
         int img, v, h;
         step_row_to_block(w.sd, r, img, v, h);
         const float *src = nullptr;
-        h16 *ph, *pl;
+        size_t dst;
         if (seg == 0) {
             src = p.x_cl + (((size_t)img * w.sd.Hb + v) * w.sd.Wb + h) * p.Cin;
-            ph = p.X_hi + (size_t)r * p.ldX;
-            pl = p.X_lo + (size_t)r * p.ldX;
+            dst = (size_t)r * p.ldX;
         } else {
             const int tap = seg - 1;
             const int vv = v + ((tap == 3) ? 0 : -1), hh = h + ((tap == 3) ? -1 : tap - 1);
             if (vv >= 0 && vv < w.sd.Hb && hh >= 0 && hh < w.sd.Wb)
                 src = p.zhat_cl + (((size_t)img * w.sd.Hb + vv) * w.sd.Wb + hh) * p.Cin;
-            ph = p.T_hi + (size_t)r * p.ldT + tap * p.Cin;
-            pl = p.T_lo + (size_t)r * p.ldT + tap * p.Cin;
+            dst = (size_t)r * p.ldT + (size_t)tap * p.Cin;
         }
-        for (int c4 = lane; c4 < c4n; c4 += 32) {
-            const float4 val = src ? __ldcg(reinterpret_cast<const float4 *>(src) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float f[4] = {val.x, val.y, val.z, val.w};
-            store_hilo<4>(ph + c4 * 4, pl + c4 * 4, f);
+        rt->f32[et] = reinterpret_cast<unsigned long long>(src);
+        rt->hilo[et] = (unsigned long long)dst;
+    }
+    epi_bar();
+    h16 *ph = seg == 0 ? p.X_hi : p.T_hi, *pl = seg == 0 ? p.X_lo : p.T_lo;
+    const int items = rows * c4n;
+    for (int i0 = et; i0 < items; i0 += 8 * WS_EPI_THREADS) {
+        float4 val[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * WS_EPI_THREADS;
+            val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < items) {
+                const int row = i / c4n, c4 = i - row * c4n;
+                const float4 *src = reinterpret_cast<const float4 *>(rt->f32[row]);
+                if (src) val[u] = __ldcg(src + c4);
+            }
         }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * WS_EPI_THREADS;
+            if (i < items) {
+                const int row = i / c4n, c4 = i - row * c4n;
+                const float f[4] = {val[u].x, val[u].y, val[u].z, val[u].w};
+                store_hilo<4>(ph + rt->hilo[row] + c4 * 4, pl + rt->hilo[row] + c4 * 4, f);
+            }
+        }
+    }
+}
+
+// ---- GEMM tile epilogue of the latency kernel: 128 rows x (<= 32) columns, one thread per (row, 16-column chunk).
+// The arithmetic is epi_compute -- the same function every GEMM kernel of the library runs -- but outputs go straight
+// from registers to global memory (epi_store_direct, as in the SIMT twin): with at most 48 live rows per tile there is
+// nothing to coalesce, and the staged epilogue's six CTA-wide barriers cost more than the stores.  Side inputs (GDN
+// pre-activations, entropy parameters) are requested before the accumulator is waited for.
+__device__ __forceinline__ void wave_tile_epilogue(const EpiParams &ep, int bn, int m0, int n0, const EpiCtx &cx) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ew = warp - 2, q = warp & 3, sub = ew >> 2, et = threadIdx.x - 64;
+    const int mode = ep.mode;
+    const int r = m0 + q * 32 + lane;
+    const int c = n0 + sub * 16;
+    const bool ok = r < ep.R && sub * 16 < bn && c < ep.cout;
+    const int *side = (mode == EPI_GDN || mode == EPI_IGDN) ? cx.dep_cnt : (mode == EPI_QUANT ? cx.dep2_cnt : nullptr);
+    if (side) {                                         // written by another tile of this launch
+        if (et == 0) wave_wait(side, (mode == EPI_QUANT) ? cx.dep2_target : cx.dep_target);
+        epi_bar();
+    }
+    EpiPre<16> pre;
+    if (ok) epi_prefetch<16>(ep, r, c, pre);            // L1-bypassing loads, in flight while the mainloop finishes
+    mbar_wait(cx.acc_full_bar, cx.full_phase);
+    tc_fence_after();
+    if (cx.trace_acc) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(*cx.trace_acc));
+    uint32_t acc[16];
+    tmem_ld_issue(cx.tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 16), acc);
+    tmem_ld_wait(acc);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(cx.acc_empty_bar);       // the accumulator is in registers: hand it back to the MMA issuer
+    if (ok) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
+        EpiOut<16> o;
+        epi_compute<16>(ep, ep.bias + c, v, pre, o, cx.stab);
+        epi_store_direct<16>(ep, r, c, o);
     }
 }
 
@@ -238,25 +330,26 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t ring = (raw + 1023u) & ~1023u;
-    const uint32_t stg = ring + WAVE_STAGES * WAVE_SLOT;
-    const uint32_t bars = stg + WGDN_BYTES;
+    const uint32_t bars = ring + WAVE_RING + WAVE_PAD;
     auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (4 + s); };
-    auto acc_full = [&](int a) { return bars + 8u * (8 + a); };
-    auto acc_empty = [&](int a) { return bars + 8u * (10 + a); };
-    auto tile_done = [&](int a) { return bars + 8u * (12 + a); };
-    auto pub_free = [&](int a) { return bars + 8u * (14 + a); };
-    const uint32_t tmem_slot = bars + 8u * 16;
+    auto empty_bar = [&](int s) { return bars + 8u * (WAVE_MAX_STAGES + s); };
+    auto acc_full = [&](int a) { return bars + 8u * (2 * WAVE_MAX_STAGES + a); };
+    auto acc_empty = [&](int a) { return bars + 8u * (2 * WAVE_MAX_STAGES + 2 + a); };
+    auto tile_done = [&](int a) { return bars + 8u * (2 * WAVE_MAX_STAGES + 4 + a); };
+    auto pub_free = [&](int a) { return bars + 8u * (2 * WAVE_MAX_STAGES + 6 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * WAVE_MAX_STAGES + 8);
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - raw));
-    float *sbias = reinterpret_cast<float *>(smem_raw + (bars + WAVE_BAR_BLOCK - raw));        // [2][256]
-    RowTab *rt = reinterpret_cast<RowTab *>(smem_raw + (bars + WAVE_BAR_BLOCK + 2048 - raw));
+    RowTab *rt = reinterpret_cast<RowTab *>(smem_raw + (bars + WAVE_BAR_BLOCK - raw));
     float *stab = reinterpret_cast<float *>(rt + 1);
     EpiParams *s_ep = reinterpret_cast<EpiParams *>(stab + 64);
     if (p.scale_tab && threadIdx.x < 64) stab[threadIdx.x] = p.scale_tab[threadIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stages = p.stages;
+    // slot layout: activation hi | activation lo (a_plane_bytes each) | weight hi | weight lo
+    const uint32_t off_alo = p.a_plane_bytes, off_w = 2 * p.a_plane_bytes;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < WAVE_STAGES; ++s) {
+        for (int s = 0; s < WAVE_MAX_STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
@@ -287,25 +380,36 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                 const ChainLayer &Lr = p.layers[o.layer];
                 const int bn = o.bn;
                 const int m0 = w.rb * BM, n0 = w.nt * bn;
-                const bool half = (w.R - m0) <= 64;            // at most 64 valid rows: load half the activation tile
+                const int rows = (w.R - m0) < BM ? (w.R - m0) : BM;
+                const int cls = lbic_box_class(rows);          // only the rows the step has are loaded
+                const int nseg = Lr.nseg > 1 ? 2 : 1;
+                // descriptors of this tile's operands into the descriptor cache while the inputs are still being produced
+                for (int sg = 0; sg < nseg; ++sg)
+                    for (int pl = 0; pl < 2; ++pl) {
+                        const CUtensorMap *ta = cls < 4 ? &Lr.tmAs[cls][sg][pl] : &Lr.tmA[sg][pl];
+                        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(ta)) : "memory");
+                        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&Lr.tmW[p.variant][sg][pl])) : "memory");
+                    }
                 wave_wait_deps(p, w, gen);
+                WAVE_TRACE(0);
                 asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores of other CTAs -> our TMA reads
                 const int kb0 = Lr.kb[0], nkb = kb0 + (Lr.nseg > 1 ? Lr.kb[1] : 0);
                 const uint32_t w_plane = (uint32_t)bn * (BK * 2);
-                const uint32_t stage_tx = (half ? A_PLANE : 2 * A_PLANE) + 2 * w_plane;
+                const uint32_t stage_tx = 2u * (uint32_t)lbic_box_rows(cls) * (BK * 2) + 2 * w_plane;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % WAVE_STAGES;
-                    const uint32_t ph = (it / WAVE_STAGES) & 1u;
+                    const int s = it % stages;
+                    const uint32_t ph = (it / stages) & 1u;
                     mbar_wait(empty_bar(s), ph ^ 1u);
-                    const uint32_t sa = ring + s * WAVE_SLOT;
+                    const uint32_t sa = ring + s * p.slot_bytes;
                     const int seg = kb >= kb0 ? 1 : 0;
                     const int kk = (seg ? kb - kb0 : kb) * BK;
                     mbar_expect_tx(full_bar(s), stage_tx);
-                    tma_load_2d(sa, half ? &Lr.tmA64[seg][0] : &Lr.tmA[seg][0], full_bar(s), kk, m0);
-                    tma_load_2d(sa + A_PLANE, half ? &Lr.tmA64[seg][1] : &Lr.tmA[seg][1], full_bar(s), kk, m0);
-                    tma_load_2d(sa + 2 * A_PLANE, &Lr.tmW[p.variant][seg][0], full_bar(s), kk, n0);
-                    tma_load_2d(sa + 2 * A_PLANE + w_plane, &Lr.tmW[p.variant][seg][1], full_bar(s), kk, n0);
+                    tma_load_2d(sa, cls < 4 ? &Lr.tmAs[cls][seg][0] : &Lr.tmA[seg][0], full_bar(s), kk, m0);
+                    tma_load_2d(sa + off_alo, cls < 4 ? &Lr.tmAs[cls][seg][1] : &Lr.tmA[seg][1], full_bar(s), kk, m0);
+                    tma_load_2d(sa + off_w, &Lr.tmW[p.variant][seg][0], full_bar(s), kk, n0);
+                    tma_load_2d(sa + off_w + w_plane, &Lr.tmW[p.variant][seg][1], full_bar(s), kk, n0);
                 }
+                WAVE_TRACE(1);
             });
         }
     } else if (warp == 1) {
@@ -325,15 +429,16 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                 tc_fence_after();
                 const uint32_t tmem_acc = tmem_base + a * WS_ACC_STRIDE;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % WAVE_STAGES;
-                    const uint32_t ph = (it / WAVE_STAGES) & 1u;
+                    const int s = it % stages;
+                    const uint32_t ph = (it / stages) & 1u;
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
-                    const uint32_t sa = ring + s * WAVE_SLOT;
+                    if (kb == 0) WAVE_TRACE(2);
+                    const uint32_t sa = ring + s * p.slot_bytes;
                     const uint64_t a_hi = make_smem_desc(sa);
-                    const uint64_t a_lo = make_smem_desc(sa + A_PLANE);
-                    const uint64_t w_hi = make_smem_desc(sa + 2 * A_PLANE);
-                    const uint64_t w_lo = make_smem_desc(sa + 2 * A_PLANE + w_plane);
+                    const uint64_t a_lo = make_smem_desc(sa + off_alo);
+                    const uint64_t w_hi = make_smem_desc(sa + off_w);
+                    const uint64_t w_lo = make_smem_desc(sa + off_w + w_plane);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
 #pragma unroll
@@ -343,6 +448,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                     umma_commit(empty_bar(s));
                 }
                 umma_commit(acc_full(a));
+                WAVE_TRACE(3);
                 ++gi;
             });
         }
@@ -357,6 +463,10 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                 asm volatile("fence.proxy.async;" ::: "memory");
                 asm volatile("fence.acq_rel.gpu;" ::: "memory");
                 asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.counters + w.oi * WAVE_MAX_RB + w.rb) : "memory");
+                WAVE_TRACE(6);
+                if (unsigned long long *tp = wave_trace_slot(p, w, 7))
+                    *tp = (unsigned long long)w.oi | ((unsigned long long)w.rb << 8) | ((unsigned long long)w.nt << 16) |
+                          ((unsigned long long)blockIdx.x << 32);
                 ++di;
             });
         }
@@ -372,7 +482,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                 const int bn = o.bn;
                 const int m0 = w.rb * BM, n0 = w.nt * bn;
                 // this tile's epilogue description: the layer's, with the step and its row count
-                epi_bar();     // every epilogue thread is past the previous tile (which read the old copy)
+                epi_bar();     // every epilogue thread is past the previous tile (which read the old copy / the row table)
                 {
                     constexpr int NW = (int)(sizeof(EpiParams) / 4);
                     constexpr int OFF_R = (int)(offsetof(EpiParams, R) / 4), OFF_STEP = (int)(offsetof(EpiParams, step) / 4);
@@ -389,26 +499,30 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                 epi_bar();
                 const uint32_t a = gi & 1u;
                 EpiCtx c;
-                c.stg = stg; c.acc_full_bar = acc_full(a); c.acc_empty_bar = acc_empty(a); c.full_phase = (gi >> 1) & 1u;
-                c.tmem_acc = tmem_base + a * WS_ACC_STRIDE; c.sb = sbias + a * 256; c.rt = rt; c.stab = stab; c.rank = 0;
+                c.stg = 0; c.acc_full_bar = acc_full(a); c.acc_empty_bar = acc_empty(a); c.full_phase = (gi >> 1) & 1u;
+                c.tmem_acc = tmem_base + a * WS_ACC_STRIDE; c.sb = nullptr; c.rt = rt; c.stab = stab; c.rank = 0;
                 const int dl = o.dep[0];
                 c.dep_cnt = dl >= 0 ? p.counters + dl * WAVE_MAX_RB + w.rb : nullptr;
                 c.dep_target = dl >= 0 ? p.ord[dl].ntn * (gen[w.rb] + 1) : 0;
                 const int dl2 = o.dep[1];
                 c.dep2_cnt = dl2 >= 0 ? p.counters + dl2 * WAVE_MAX_RB + w.rb : nullptr;
                 c.dep2_target = dl2 >= 0 ? p.ord[dl2].ntn * (gen[w.rb] + 1) : 0;
-                ws_tile_epilogue<false>(*s_ep, bn, m0, n0, c);
+                c.trace_acc = et == 0 ? wave_trace_slot(p, w, 4) : nullptr;
+                wave_tile_epilogue(*s_ep, bn, m0, n0, c);
                 ++gi;
             } else {
                 // non-GEMM tiles: one thread waits for the inputs, then all eight warps work
+                epi_bar();     // the previous tile is done with the row table
                 if (et == 0) {
                     if (o.kind == WK_GATHER) wave_wait_prev_step(p, w, gen);
                     else wave_wait_deps(p, w, gen);
+                    WAVE_TRACE(0);
                 }
                 epi_bar();
-                if (o.kind == WK_GATHER) wave_gather_tile(p, w, ew, lane);
+                if (o.kind == WK_GATHER) wave_gather_tile(p, w, rt, et);
                 else wave_rans_tile(p, w, ew, lane);
             }
+            if (et == 0) WAVE_TRACE(5);
             // this CTA's tile is stored: hand it to the publisher warp (which must have taken tile di - 2 off this barrier)
             __syncwarp();
             if (lane == 0) {
@@ -476,6 +590,16 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
     p.ksi = w.ksi; p.ld_ksi = w.ld_ksi; p.yq_hi = w.yq_hi; p.yq_lo = w.yq_lo; p.ld_yq = w.ld_yq; p.sym_out = w.sym_out; p.M = w.M;
     const int max_rows = w.raster ? w.n_img : w.n_img * (w.Hb < (w.Wb + 1) / 2 ? w.Hb : (w.Wb + 1) / 2);
     if (max_rows > WAVE_MAX_RB * BM) return lbic_fail(LBIC_ERR_INVALID, "wave kernel: step of %d rows exceeds %d", max_rows, WAVE_MAX_RB * BM);
+    {
+        const int box = lbic_box_rows(lbic_box_class(max_rows < BM ? max_rows : BM));   // largest activation box of this launch
+        p.a_plane_bytes = (uint32_t)box * (BK * 2);
+        p.slot_bytes = 2 * p.a_plane_bytes + 2 * (uint32_t)LBIC_LAT_MAX_BN * (BK * 2);
+        p.stages = WAVE_RING / (int)p.slot_bytes;
+        if (p.stages > WAVE_MAX_STAGES) p.stages = WAVE_MAX_STAGES;
+        static int cap = -1;   // tuning hook: LBIC_WAVE_STAGES caps the ring depth
+        if (cap < 0) { const char *e = getenv("LBIC_WAVE_STAGES"); cap = e ? atoi(e) : 0; }
+        if (cap >= 2 && p.stages > cap) p.stages = cap;
+    }
     // the step's list.  ids[0..3] = entropy net, [4..10] = encoder net (F0 G0 F1 G1 F2 G2 F3), [11..17] = decoder net.
     // The encoder net (the critical path of an encode step) comes first so that its tiles are never queued behind the
     // entropy net's in a CTA's own list; the entropy net only has to be done when F3 quantises.
@@ -496,7 +620,7 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
     }
     const int *E = w.ids, *F = w.ids + 4, *D = w.ids + 11;
     p.gather_first = w.decode ? 1 : 0;
-    const int g = add(WK_GATHER, -1, w.decode ? 4 : 5, 0, -1, -1);
+    const int g = add(WK_GATHER, -1, (w.decode ? 4 : 5) * WAVE_GATHER_PARTS, 0, -1, -1);
     int last_e, last;
     if (!w.decode) {
         // interleaved: F0 E0 G0 E1 F1 E2 G1 E3 F2 G2 F3 | D0 .. D3
@@ -527,6 +651,24 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
     p.tiles_per_rb = total;
     if ((size_t)n * WAVE_MAX_RB > w.counters_cap) return lbic_fail(LBIC_ERR_INVALID, "wave kernel: counter buffer too small");
     LBIC_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(int) * (size_t)n * WAVE_MAX_RB, st));
+    // debug: LBIC_WAVE_TRACE=<first step> [LBIC_WAVE_TRACE_STEPS=<n>] dumps per-tile time stamps of one launch to
+    // LBIC_WAVE_TRACE_FILE (default gpurun_out/wave_trace.txt); see scripts/wave_trace.py
+    static int trace_s0 = -2;
+    if (trace_s0 == -2) { const char *e = getenv("LBIC_WAVE_TRACE"); trace_s0 = e ? atoi(e) : -1; }
+    static unsigned long long *d_trace = nullptr;
+    const bool tracing = trace_s0 >= 0 && trace_s0 >= w.s_begin && trace_s0 < w.s_end;
+    size_t trace_words = 0;
+    if (tracing) {
+        const char *e = getenv("LBIC_WAVE_TRACE_STEPS");
+        p.trace_s0 = trace_s0;
+        p.trace_ns = e ? atoi(e) : 3;
+        p.trace_stride = ((max_rows + BM - 1) / BM) * total;
+        trace_words = (size_t)p.trace_ns * p.trace_stride * 8;
+        if (d_trace) cudaFree(d_trace);
+        LBIC_CUDA(cudaMalloc(&d_trace, trace_words * 8));
+        LBIC_CUDA(cudaMemsetAsync(d_trace, 0, trace_words * 8, st));
+        p.trace = d_trace;
+    }
     int n_sm = 148, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -549,5 +691,27 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
         return lbic_fail(LBIC_ERR_CUDA, "wave launch failed: %s", cudaGetErrorString(e));
     }
     count_launch(0);
+    if (tracing) {
+        std::vector<unsigned long long> h(trace_words);
+        LBIC_CUDA(cudaStreamSynchronize(st));
+        LBIC_CUDA(cudaMemcpy(h.data(), d_trace, trace_words * 8, cudaMemcpyDeviceToHost));
+        const char *fn = getenv("LBIC_WAVE_TRACE_FILE");
+        FILE *f = fopen(fn ? fn : "gpurun_out/wave_trace.txt", "w");
+        if (f) {
+            fprintf(f, "# decode=%d raster=%d n_ord=%d; per tile: step j oi kind layer rb nt cta | dep_ready tma_issued first_full mma_issued acc_full epi_done published (ns, %%globaltimer)\n",
+                    w.decode, w.raster, n);
+            for (int si = 0; si < p.trace_ns; ++si)
+                for (int j = 0; j < p.trace_stride; ++j) {
+                    const unsigned long long *r = h.data() + ((size_t)si * p.trace_stride + j) * 8;
+                    if (!r[6]) continue;
+                    const int oi = (int)(r[7] & 0xFF);
+                    fprintf(f, "%d %d %d %d %d %d %d %d | %llu %llu %llu %llu %llu %llu %llu\n", trace_s0 + si, j, oi, p.ord[oi].kind,
+                            p.ord[oi].layer, (int)((r[7] >> 8) & 0xFF), (int)((r[7] >> 16) & 0xFFFF), (int)(r[7] >> 32), r[0], r[1], r[2],
+                            r[3], r[4], r[5], r[6]);
+                }
+            fclose(f);
+        }
+        trace_s0 = -1;     // one launch only
+    }
     return 0;
 }

@@ -123,11 +123,15 @@ constexpr int LBIC_PAIR_WIDE = 8;     // CTA-pair form with tiles up to 256 wide
 constexpr int LBIC_SMALL_VARIANT = 9;  // tiles of at most 96 columns for the single-CTA dataflow launch of small steps
 constexpr int LBIC_LAT_VARIANT = 10;   // tiles of at most 32 columns for the persistent wavefront (latency) kernel, gemm_wave.cu
 constexpr int LBIC_LAT_MAX_BN = 32;
+// rows of the activation TMA box for a tile with `rows` valid rows: class 0..3 = 16 / 32 / 48 / 64, 4 = the full 128
+__host__ __device__ inline int lbic_box_class(int rows) { return rows <= 16 ? 0 : rows <= 32 ? 1 : rows <= 48 ? 2 : rows <= 64 ? 3 : 4; }
+__host__ __device__ inline int lbic_box_rows(int cls) { return cls < 4 ? 16 * (cls + 1) : 128; }
 constexpr int LBIC_PAIR_VARIANT = 7;  // same tile width as LBIC_WS_VARIANT; weight TMA box = half the tile (one half per CTA)
 __host__ __device__ inline int lbic_split(int i) { return i == 0 ? 1 : i == 1 ? 2 : i == 2 ? 3 : i == 3 ? 4 : i == 4 ? 6 : 8; }
 struct alignas(64) ChainLayer {
     CUtensorMap tmA[2][2];              // [segment][hi, lo]   box 64 x 128
-    CUtensorMap tmA64[2][2];            // same operands, box 64 x 64 rows: steps with at most 64 rows load half the bytes
+    CUtensorMap tmAs[4][2][2];          // [box class][segment][hi, lo]: boxes of 64 k x 16 / 32 / 48 / 64 rows for the latency
+                                        // kernel (a step of a single image has at most min(Hb, Wb/2) rows)
     CUtensorMap tmW[LBIC_NBN][2][2];    // [variant][segment][hi, lo]   box 64 x bn_v[variant]
     int kb[2];                          // 64-wide k-blocks per segment
     int nseg;

@@ -108,6 +108,7 @@ struct EpiCtx {
     // second side input written inside the same launch: the entropy parameters (ksi) the QUANT epilogue reads
     const int *dep2_cnt;
     int dep2_target;
+    unsigned long long *trace_acc = nullptr;   // debug: %globaltimer when the accumulator became available
 };
 
 template <bool PAIR>
@@ -204,6 +205,7 @@ __device__ __forceinline__ void ws_tile_epilogue(const EpiParams &ep, int bn, in
     }
     mbar_wait(cx.acc_full_bar, cx.full_phase);
     tc_fence_after();
+    if (cx.trace_acc) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(*cx.trace_acc));
     tmem_ld_issue(lane_base + (uint32_t)(sub * 16), accA);
     for (int g = 0; g < ngroups; ++g) {
         const int g0 = g * GC;
