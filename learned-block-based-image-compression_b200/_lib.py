@@ -33,6 +33,8 @@ LBIC_OPT_FLOW_SMALL = 13
 LBIC_OPT_HOST_BANDS = 14
 LBIC_OPT_WAVE = 15
 LBIC_OPT_ENC_BLOCK_STREAMS = 17
+LBIC_OPT_WAVE_DEC_MAX_ROWS = 18
+LBIC_OPT_WAVE_BN = 19
 LBIC_OPT_WAVE_MAX_ROWS = 16
 LBIC_OPT_PDL = 7
 

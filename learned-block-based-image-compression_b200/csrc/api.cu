@@ -131,7 +131,9 @@ struct lbic_model {
                            // layer (default: the counter hand-off costs as much as a PDL-chained launch, profiles/r1_dataflow.md)
     int flow_max_rows = 1 << 30;
     int use_wave = 1;      // persistent wavefront (latency) kernel for steps of at most wave_max_rows rows (KS[1] == 1)
-    int wave_max_rows = 2048;
+    int wave_max_rows = 1536;
+    int wave_dec_max_rows = 64;    // decode: the rANS tiles run one warp per row on 8 entropy CTAs (64 rows at a time)
+    int wave_bn = 0;               // forced tile width of the wave kernel (32 / 64 / 128), 0 = by rows per step
     float *selfinfo_cl = nullptr;   // set by lbic_validate for the duration of the call: (n,Hb,Wb,M) self-information
     cudaStream_t hs[3] = {nullptr, nullptr, nullptr};   // host-call pipeline: copies in, compute, copies out
     cudaEvent_t hev[2 * LBIC_MAX_BANDS] = {};            // band b copied in / band b ready to copy out
@@ -183,9 +185,11 @@ void free_all(std::vector<void *> &list) {
 // tile-width variants of a layer, one per split factor (lbic_split): widest first
 int bn_variants(int cout, int *out) {
     for (int i = 0; i < NBN; ++i) {
-        if (i == LBIC_WS_VARIANT || i == LBIC_PAIR_VARIANT || i == LBIC_PAIR_WIDE || i == LBIC_SMALL_VARIANT || i == LBIC_LAT_VARIANT) {
+        if (i >= LBIC_WS_VARIANT) {
             const int wmax = i == LBIC_PAIR_WIDE ? gemm_pair_max_bn()
-                             : (i == LBIC_SMALL_VARIANT ? gemm_ws_max_bn() / 2 : (i == LBIC_LAT_VARIANT ? LBIC_LAT_MAX_BN : gemm_ws_max_bn()));
+                             : i == LBIC_SMALL_VARIANT ? gemm_ws_max_bn() / 2
+                             : i == LBIC_LAT_VARIANT ? 32 : i == LBIC_LAT64_VARIANT ? 64 : i == LBIC_LAT128_VARIANT ? 128
+                             : gemm_ws_max_bn();
             const int nt = (cout + wmax - 1) / wmax;
             out[i] = ((cout + nt - 1) / nt + 15) / 16 * 16;
             continue;
@@ -774,13 +778,17 @@ struct RowHooks {
 };
 
 // The persistent wavefront kernel (gemm_wave.cu) takes over when every step of the call has at most wave_max_rows rows.
-bool wave_applies(const lbic_model *m, int n_img, int Hb, int Wb, bool raster) {
+bool wave_applies(const lbic_model *m, int n_img, int Hb, int Wb, bool raster, bool decode) {
     if (!m->use_wave || m->gemm_core != 0 || m->force_bn || m->k1 != 1 || m->profiling || m->selfinfo_cl ||
         m->recon_cl || !gemm_wave_supported())
         return false;
     const int max_nv = Hb < (Wb + 1) / 2 ? Hb : (Wb + 1) / 2;
     const long rows = raster ? n_img : (long)n_img * max_nv;
-    const int cap = m->wave_max_rows < gemm_wave_max_rows() ? m->wave_max_rows : gemm_wave_max_rows();
+    int cap = m->wave_max_rows < gemm_wave_max_rows() ? m->wave_max_rows : gemm_wave_max_rows();
+    if (decode) {
+        if (m->tables.cdf16_total <= 0) return false;      // the entropy CTAs need the compact tables
+        cap = cap < m->wave_dec_max_rows ? cap : m->wave_dec_max_rows;
+    }
     return rows <= cap;
 }
 
@@ -793,6 +801,12 @@ int run_wave(lbic_model *m, bool decode, bool raster, int s_begin, int s_end, in
     w.decode = decode ? 1 : 0; w.raster = raster ? 1 : 0;
     w.s_begin = s_begin; w.s_end = s_end; w.n_img = n_img; w.Hb = Hb; w.Wb = Wb;
     for (int i = 0; i < L_COUNT; ++i) w.ids[i] = i;
+    {
+        // tile width: 32 columns.  The MMA chain of a tile takes the same time for any width up to ~176 columns (it is
+        // bound by the latency of dependent accumulations), but the staged epilogue grows with the width (1.5 us per 32
+        // columns) and sits on the layer-to-layer critical path: profiles/r2_wave_latency.md.  64 / 128 stay selectable.
+        w.variant = m->wave_bn == 64 ? LBIC_LAT64_VARIANT : m->wave_bn == 128 ? LBIC_LAT128_VARIANT : LBIC_LAT_VARIANT;
+    }
     w.x_cl = ws.x_cl; w.zhat_cl = ws.zhat_cl; w.Cin = m->Cin;
     w.X_hi = ws.X.hi; w.X_lo = ws.X.lo; w.ldX = ws.X.ld;
     w.T_hi = ws.T.hi; w.T_lo = ws.T.lo; w.ldT = ws.T.ld;
@@ -803,6 +817,7 @@ int run_wave(lbic_model *m, bool decode, bool raster, int s_begin, int s_end, in
         w.states = ws.dec_states; w.lane_ptr = ws.lane_ptr; w.lanes = lanes_L;
         w.ksi = ws.KSI; w.ld_ksi = ws.ldKSI; w.yq_hi = ws.YQ.hi; w.yq_lo = ws.YQ.lo; w.ld_yq = ws.YQ.ld;
         w.sym_out = sym_out; w.M = m->M;
+        w.cdf16 = T.cdf16; w.cdf16_off = T.cdf16_off; w.cdf16_total = T.cdf16_total;
     }
     w.counters = ws.wave_counters; w.counters_cap = ws.wave_counters_cap;
     w.err_flag = m->err_flag;
@@ -870,6 +885,8 @@ extern "C" int lbic_create(const lbic_config *cfg, int device, lbic_model **out)
     if (const char *e = getenv("LBIC_FLOW_SMALL")) m->flow_small = atoi(e) ? 1 : 0;
     if (const char *e = getenv("LBIC_WAVE")) m->use_wave = atoi(e) ? 1 : 0;
     if (const char *e = getenv("LBIC_WAVE_MAX_ROWS")) m->wave_max_rows = atoi(e) < 1 ? 1 : atoi(e);
+    if (const char *e = getenv("LBIC_WAVE_DEC_MAX_ROWS")) m->wave_dec_max_rows = atoi(e) < 1 ? 1 : atoi(e);
+    if (const char *e = getenv("LBIC_WAVE_BN")) m->wave_bn = atoi(e);
     m->cfg = *cfg;
     m->device = device;
     m->Cin = 3 * cfg->block_size * cfg->block_size;
@@ -949,6 +966,13 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
         return 0;
     case LBIC_OPT_WAVE_MAX_ROWS:
         m->wave_max_rows = value < 1 ? 1 : (value > gemm_wave_max_rows() ? gemm_wave_max_rows() : value);
+        return 0;
+    case LBIC_OPT_WAVE_DEC_MAX_ROWS:
+        m->wave_dec_max_rows = value < 1 ? 1 : value;
+        return 0;
+    case LBIC_OPT_WAVE_BN:
+        if (value != 0 && value != 32 && value != 64 && value != 128) return lbic_fail(LBIC_ERR_INVALID, "wave tile width must be 0, 32, 64 or 128");
+        m->wave_bn = value;
         return 0;
     case LBIC_OPT_HOST_BANDS:
         m->host_bands = value < 1 ? 1 : (value > LBIC_MAX_BANDS ? LBIC_MAX_BANDS : value);
@@ -1124,7 +1148,7 @@ int encode_impl(lbic_model *m, const float *x, int n_img, int Hb, int Wb, float 
     };
     // Small steps (single images, small batches): consecutive steps are collected into ONE launch of the persistent
     // wavefront kernel, cut only where a host hook has copies or conversions to put between two steps.
-    bool wave = wave_applies(m, n_img, Hb, Wb, false);
+    bool wave = wave_applies(m, n_img, Hb, Wb, false, false);
     int pend = -1;                                   // steps [pend, t) wait to be launched
     auto flush = [&](int t_end) -> int {
         if (pend < 0) return 0;
@@ -1354,7 +1378,7 @@ int decode_impl(lbic_model *m, const uint8_t *streams, const uint32_t *stream_le
         if (!wave_step(s, n_img, Hb, Wb, sd)) return 0;
         return one_step(sd, n_img * sd.nv);
     };
-    bool wave = wave_applies(m, n_img, Hb, Wb, raster);
+    bool wave = wave_applies(m, n_img, Hb, Wb, raster, true);
     int pend = -1;
     auto flush = [&](int s_end) -> int {
         if (pend < 0) return 0;

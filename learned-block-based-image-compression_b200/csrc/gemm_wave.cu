@@ -34,16 +34,18 @@ constexpr int WAVE_MAX_RB = 32;                  // 128-row blocks per step
 // Operand ring: a slot holds one 64-wide k-block = the activation box (hi + lo planes, 16..128 rows: only the rows the
 // step has) + 32 weight rows (hi + lo).  A tile's mainloop is bound by the LATENCY of its loads (a layer's K / 64
 // k-blocks arrive one L2 round trip after they are requested; the MMAs of a k-block take 0.1 us), so the ring is as deep
-// as shared memory allows: 10 slots of 20 KiB for steps of up to 48 rows (a 768x512 image), 5 of 40 KiB for 128 rows.
+// as the staging area of the epilogue leaves room for: 152 KiB = 5 slots of 28 KiB (48 rows + 64 weight rows) for a
+// 768x512 image, 2 of 64 KiB for 128 rows x 128 columns (that case is bound by the MMA chain, not by the ring).
 constexpr int WAVE_MAX_STAGES = 12;
-constexpr int WAVE_RING = 5 * (2 * A_PLANE + 2 * LBIC_LAT_MAX_BN * BK * 2);   // 200 KiB
+constexpr int WAVE_RING = 152 * 1024;
 constexpr int WAVE_PAD = 16 * 1024;              // the MMA always reads 128 rows of a slot's activation planes: rows past the
                                                  // box are never used, but the last slot's must still be shared memory
 constexpr int WAVE_THREADS = WS_THREADS + 32;    // producer | MMA issuer | 8 epilogue warps | publisher
 constexpr int WAVE_BAR_BLOCK = 512;              // full[12] empty[12] acc_full[2] acc_empty[2] tile_done[2] pub_free[2] tmem slot
-constexpr int WAVE_TAIL = WAVE_BAR_BLOCK + ROWTAB_BYTES + STAB_BYTES + 256;
-constexpr int WAVE_SMEM = 1024 + WAVE_RING + WAVE_PAD + WAVE_TAIL;
+constexpr int WAVE_TAIL = WAVE_BAR_BLOCK + 2 * 1024 + ROWTAB_BYTES + STAB_BYTES + 256;
+constexpr int WAVE_SMEM = 1024 + WAVE_RING + WAVE_PAD + WGDN_BYTES + WAVE_TAIL;
 constexpr int WAVE_RANS_PARTS = 16;              // rANS tiles per 128-row block: 8 rows each, one warp per row
+constexpr int WAVE_ENT_CTAS = 8;                 // decode launches: CTAs that keep the CDF tables in shared memory (rANS tiles only)
 static_assert(WAVE_SMEM <= SMEM_LIMIT, "wave kernel shared memory");
 
 enum WaveKind { WK_GEMM = 0, WK_GATHER = 1, WK_RANS = 2 };
@@ -76,6 +78,10 @@ struct WaveParams {
     const int32_t *cdf; int cdf_stride; const int32_t *cdf_len, *offs; const float *scale_tab;
     RansStreamState *states; const uint8_t *const *lane_ptr; int lanes;
     const float *ksi; int ld_ksi; h16 *yq_hi, *yq_lo; int ld_yq; int32_t *sym_out; int M;
+    // decode: the last n_ent CTAs are ENTROPY CTAs: they keep the compact 16-bit CDF rows (Tables::cdf16) in shared
+    // memory (they need no operand ring) and run the rANS tiles, nothing else; every other tile goes to the other CTAs
+    int n_ent, rans_ord;
+    const uint16_t *cdf16; const int32_t *cdf16_off; int cdf16_total;
     // debug (LBIC_WAVE_TRACE): %globaltimer stamps of every tile of steps [trace_s0, trace_s0 + trace_ns), 8 words each
     unsigned long long *trace;
     int trace_s0, trace_ns, trace_stride;
@@ -124,8 +130,9 @@ __device__ __forceinline__ void wave_for_each_tile(const WaveParams &p, F &&f) {
     int gen[WAVE_MAX_RB];
 #pragma unroll 1
     for (int i = 0; i < WAVE_MAX_RB; ++i) gen[i] = 0;
-    int off = 0, prev_n_rb = 0;
-    const int G = (int)gridDim.x;
+    int off = 0, off_e = 0, prev_n_rb = 0;
+    const int NE = p.n_ent, Gw = (int)gridDim.x - NE;        // worker CTAs 0 .. Gw-1, entropy CTAs Gw .. Gw+NE-1
+    const bool is_ent = NE > 0 && (int)blockIdx.x >= Gw;
 #pragma unroll 1
     for (int s = p.s_begin; s < p.s_end; ++s) {
         WaveTile w;
@@ -133,22 +140,39 @@ __device__ __forceinline__ void wave_for_each_tile(const WaveParams &p, F &&f) {
         w.R = w.sd.n_img * w.sd.nv;
         w.n_rb = (w.R + BM - 1) / BM;
         w.prev_n_rb = prev_n_rb;
-        const int total = w.n_rb * p.tiles_per_rb;
         w.s = s;
-        int first = (int)blockIdx.x - off;
-        if (first < 0) first += G;
+        const int total = w.n_rb * p.tiles_per_rb;
+        const int cnt_r = NE > 0 ? w.n_rb * p.ord[p.rans_ord].ntn : 0;     // rANS tiles of the step, a contiguous range
+        const int start_r = NE > 0 ? w.n_rb * p.pre[p.rans_ord] : 0;
+        if (is_ent) {
+            int first = (int)blockIdx.x - Gw - off_e;
+            if (first < 0) first += NE;
 #pragma unroll 1
-        for (int j = first; j < total; j += G) {
-            int oi = 0;
-            while (j >= w.n_rb * p.pre[oi + 1]) ++oi;
-            const int v = j - w.n_rb * p.pre[oi];
-            w.oi = oi;
-            w.rb = v / p.ord[oi].ntn;
-            w.nt = v - w.rb * p.ord[oi].ntn;
-            w.j = j;
-            f(w, gen);
+            for (int k = first; k < cnt_r; k += NE) {
+                w.oi = p.rans_ord;
+                w.rb = k / p.ord[p.rans_ord].ntn;
+                w.nt = k - w.rb * p.ord[p.rans_ord].ntn;
+                w.j = start_r + k;
+                f(w, gen);
+            }
+        } else {
+            int first = (int)blockIdx.x - off;
+            if (first < 0) first += Gw;
+#pragma unroll 1
+            for (int jj = first; jj < total - cnt_r; jj += Gw) {
+                const int j = jj < start_r ? jj : jj + cnt_r;
+                int oi = 0;
+                while (j >= w.n_rb * p.pre[oi + 1]) ++oi;
+                const int v = j - w.n_rb * p.pre[oi];
+                w.oi = oi;
+                w.rb = v / p.ord[oi].ntn;
+                w.nt = v - w.rb * p.ord[oi].ntn;
+                w.j = j;
+                f(w, gen);
+            }
         }
-        off = (off + total) % G;
+        off = (off + total - cnt_r) % Gw;
+        if (NE > 0) off_e = (off_e + cnt_r) % NE;
         for (int rb = 0; rb < w.n_rb; ++rb) gen[rb]++;
         prev_n_rb = w.n_rb;
     }
@@ -184,7 +208,7 @@ __device__ __forceinline__ void wave_wait_prev_step(const WaveParams &p, const W
 // (row, 4-channel) items, eight loads in flight at a time.
 constexpr int WAVE_GATHER_PARTS = 4;
 
-__device__ __forceinline__ void wave_gather_tile(const WaveParams &p, const WaveTile &w, RowTab *rt, int et) {
+__device__ __noinline__ void wave_gather_tile(const WaveParams &p, const WaveTile w, RowTab *rt, int et) {
     const int seg = p.gather_first + w.nt / WAVE_GATHER_PARTS;
     const int part = w.nt % WAVE_GATHER_PARTS;
     const int m0 = w.rb * BM + part * 32;
@@ -237,73 +261,134 @@ __device__ __forceinline__ void wave_gather_tile(const WaveParams &p, const Wave
     }
 }
 
-// ---- GEMM tile epilogue of the latency kernel: 128 rows x (<= 32) columns, one thread per (row, 16-column chunk).
-// The arithmetic is epi_compute -- the same function every GEMM kernel of the library runs -- but outputs go straight
-// from registers to global memory (epi_store_direct, as in the SIMT twin): with at most 48 live rows per tile there is
-// nothing to coalesce, and the staged epilogue's six CTA-wide barriers cost more than the stores.  Side inputs (GDN
-// pre-activations, entropy parameters) are requested before the accumulator is waited for.
-__device__ __forceinline__ void wave_tile_epilogue(const EpiParams &ep, int bn, int m0, int n0, const EpiCtx &cx) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ew = warp - 2, q = warp & 3, sub = ew >> 2, et = threadIdx.x - 64;
-    const int mode = ep.mode;
-    const int r = m0 + q * 32 + lane;
-    const int c = n0 + sub * 16;
-    const bool ok = r < ep.R && sub * 16 < bn && c < ep.cout;
-    const int *side = (mode == EPI_GDN || mode == EPI_IGDN) ? cx.dep_cnt : (mode == EPI_QUANT ? cx.dep2_cnt : nullptr);
-    if (side) {                                         // written by another tile of this launch
-        if (et == 0) wave_wait(side, (mode == EPI_QUANT) ? cx.dep2_target : cx.dep_target);
-        epi_bar();
-    }
-    EpiPre<16> pre;
-    if (ok) epi_prefetch<16>(ep, r, c, pre);            // L1-bypassing loads, in flight while the mainloop finishes
-    mbar_wait(cx.acc_full_bar, cx.full_phase);
-    tc_fence_after();
-    if (cx.trace_acc) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(*cx.trace_acc));
-    uint32_t acc[16];
-    tmem_ld_issue(cx.tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * 16), acc);
-    tmem_ld_wait(acc);
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(cx.acc_empty_bar);       // the accumulator is in registers: hand it back to the MMA issuer
-    if (ok) {
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
-        EpiOut<16> o;
-        epi_compute<16>(ep, ep.bias + c, v, pre, o, cx.stab);
-        epi_store_direct<16>(ep, r, c, o);
-    }
+// the staged epilogue of the throughput kernels, compiled as a function of its own (register allocation separate from
+// the role loops; the context travels by value)
+__device__ __noinline__ void wave_gemm_epilogue(const EpiParams *ep, int bn, int m0, int n0, const EpiCtx cx) {
+    ws_tile_epilogue<false>(*ep, bn, m0, n0, cx);
 }
 
 // ---- RANS tile: 8 rows of a row block, one warp per row: build_indexes, decode M symbols from the row's stream,
-// dequantise -> y_qnt planes (rans_dec_step_kernel of rans.cu; ksi / the stream states were written by other CTAs of
-// this launch, hence the L1-bypassing loads).
-__device__ __forceinline__ void wave_rans_tile(const WaveParams &p, const WaveTile &w, int ew, int lane) {
+// dequantise -> y_qnt planes.  The symbol chain is serial, so nothing on it may touch global memory: the CDF rows are
+// the entropy CTA's shared-memory copy (16-bit, the final 65536 implicit), a symbol's start / frequency come out of the
+// same 32-wide window load that finds it (shuffles), and the next 64 words of the stream sit in registers.
+// Same symbols as dec_symbol_warp / dec_symbol_thread (rans_device.cuh, rans.cu): first k with cdf[k] > slot, minus 1.
+struct WaveEntTables {
+    const uint16_t *cdf16;     // shared memory
+    const int *off16, *len, *offs;
+};
+
+struct DecCursorW {
+    unsigned long long x;
+    const uint32_t *words;
+    uint32_t pos, nwords, base, w0, w1;    // lane i holds words base + i and base + 32 + i
+};
+__device__ __forceinline__ void dec_fill_w(DecCursorW &d, int lane) {
+    d.base = d.pos;
+    d.w0 = d.base + lane < d.nwords ? __ldg(d.words + d.base + lane) : 0u;
+    d.w1 = d.base + 32 + lane < d.nwords ? __ldg(d.words + d.base + 32 + lane) : 0u;
+}
+__device__ __forceinline__ uint32_t dec_word_w(DecCursorW &d, int lane) {
+    if (d.pos - d.base >= 64) dec_fill_w(d, lane);                 // warp-uniform
+    const uint32_t rel = d.pos - d.base;
+    const uint32_t v0 = __shfl_sync(0xffffffffu, d.w0, rel & 31), v1 = __shfl_sync(0xffffffffu, d.w1, rel & 31);
+    d.pos++;
+    return rel < 32 ? v0 : v1;                                      // past the end of the stream: zeros (a corrupt stream stays finite)
+}
+__device__ __forceinline__ int dec_bits_w(DecCursorW &d, int lane) {
+    const int val = (int)(d.x & MAX_BYPASS);
+    d.x >>= BYPASS;
+    if (d.x < RANS_L) d.x = (d.x << 32) | dec_word_w(d, lane);
+    return val;
+}
+__device__ __forceinline__ int dec_symbol_w(DecCursorW &d, const uint16_t *row, int len, int off, int lane) {
+    const uint32_t cf = (uint32_t)(d.x & 0xFFFFu);
+    const int max_value = len - 2;
+    int g = -off - 15;                         // 32-wide window around the distribution centre
+    g = g < 0 ? 0 : g;
+    g = g > len - 32 ? (len - 32 < 0 ? 0 : len - 32) : g;
+    const int k = g + lane;
+    const uint32_t val = k < len - 1 ? (uint32_t)row[k] : 65536u;
+    const bool gt = (k < len) && (val > cf);
+    const unsigned ball = __ballot_sync(0xffffffffu, gt);
+    int sidx;
+    uint32_t start, next;
+    if ((ball & 1u) == 0 && ball != 0) {
+        const int j = __ffs(ball) - 1;
+        sidx = g + j - 1;
+        start = __shfl_sync(0xffffffffu, val, j - 1);
+        next = __shfl_sync(0xffffffffu, val, j);
+    } else {
+        int lo = 0, hi = len - 1;              // entry len-1 (= 65536) always exceeds the slot
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((uint32_t)row[mid] > cf) hi = mid; else lo = mid + 1;
+        }
+        sidx = lo - 1;
+        start = row[sidx];
+        next = sidx + 1 < len - 1 ? (uint32_t)row[sidx + 1] : 65536u;
+    }
+    d.x = (unsigned long long)(next - start) * (d.x >> PREC) + cf - start;
+    if (d.x < RANS_L) d.x = (d.x << 32) | dec_word_w(d, lane);
+    int value = sidx;
+    if (value == max_value) {
+        int v = dec_bits_w(d, lane);
+        int nb = v;
+        while (v == MAX_BYPASS) {
+            v = dec_bits_w(d, lane);
+            nb += v;
+        }
+        int raw = 0;
+        for (int j = 0; j < nb; ++j) {
+            v = dec_bits_w(d, lane);
+            raw |= v << (j * BYPASS);
+        }
+        value = raw >> 1;
+        if (raw & 1) value = -value - 1; else value += max_value;
+    }
+    return value + off;
+}
+
+__device__ __noinline__ void wave_rans_tile(const WaveParams &p, const WaveTile w, const WaveEntTables tb, const float *stab,
+                                            int ew, int lane) {
+    // (small structs by value: a reference would leave them in the caller's local memory, one L2 round trip per use)
+    const uint16_t *const t_cdf16 = tb.cdf16;
+    const int *const t_off16 = tb.off16, *const t_len = tb.len, *const t_offs = tb.offs;
     const int r = w.rb * BM + w.nt * 8 + ew;
     if (r >= w.R) return;
     int img, v, h;
     step_row_to_block(w.sd, r, img, v, h);
     const int sidx = p.lanes > 1 ? img * p.lanes + v : img;
-    DecCursor d;
+    DecCursorW d;
     {
         const uint4 raw = __ldcg(reinterpret_cast<const uint4 *>(p.states + sidx));
         d.x = (unsigned long long)raw.x | ((unsigned long long)raw.y << 32);
         d.pos = raw.z; d.nwords = raw.w;
         d.words = reinterpret_cast<const uint32_t *>(p.lane_ptr[sidx]);
     }
+    dec_fill_w(d, lane);
     const float *krow = p.ksi + (size_t)r * p.ld_ksi;
     const int M = p.M;
-    int my_idx[8], my_sym[8];
     const int per = (M + 31) >> 5;   // M <= 256
-    for (int j = 0; j < per; ++j) {
+    int my_idx[8], my_sym[8];
+    float my_mu[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
         const int c = j * 32 + lane;
-        my_idx[j] = c < M ? scale_to_index(__ldcg(krow + c), p.scale_tab) : 0;
+        const bool in = j < per && c < M;
+        my_idx[j] = in ? scale_to_index(__ldcg(krow + c), stab) : 0;
+        my_mu[j] = in ? __ldcg(krow + M + c) : 0.0f;
         my_sym[j] = 0;
     }
-    for (int c = 0; c < M; ++c) {
-        const int ci = __shfl_sync(0xffffffffu, my_idx[c >> 5], c & 31);
-        const int sym = dec_symbol_warp(d, p.cdf + (size_t)ci * p.cdf_stride, p.cdf_len[ci], p.offs[ci], lane);
-        if (lane == (c & 31)) my_sym[c >> 5] = sym;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (j < per) {
+#pragma unroll 1
+            for (int cc = 0; cc < 32 && j * 32 + cc < M; ++cc) {
+                const int ci = __shfl_sync(0xffffffffu, my_idx[j], cc);
+                const int sym = dec_symbol_w(d, t_cdf16 + t_off16[ci], t_len[ci], t_offs[ci], lane);
+                if (lane == cc) my_sym[j] = sym;
+            }
+        }
     }
     if (lane == 0) {
         uint4 raw;
@@ -311,10 +396,11 @@ __device__ __forceinline__ void wave_rans_tile(const WaveParams &p, const WaveTi
         __stcg(reinterpret_cast<uint4 *>(p.states + sidx), raw);
     }
     const size_t o = (((size_t)img * w.sd.Hb + v) * w.sd.Wb + h) * M;
-    for (int j = 0; j < per; ++j) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
         const int c = j * 32 + lane;
-        if (c < M) {
-            const float yq = (float)my_sym[j] + __ldcg(krow + M + c);
+        if (j < per && c < M) {
+            const float yq = (float)my_sym[j] + my_mu[j];
             h16 hi, lo;
             split_h16(yq, hi, lo);
             p.yq_hi[(size_t)r * p.ld_yq + c] = hi;
@@ -330,7 +416,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t ring = (raw + 1023u) & ~1023u;
-    const uint32_t bars = ring + WAVE_RING + WAVE_PAD;
+    const uint32_t stg = ring + WAVE_RING + WAVE_PAD;      // epilogue staging (ws_tile_epilogue)
+    const uint32_t bars = stg + WGDN_BYTES;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (WAVE_MAX_STAGES + s); };
     auto acc_full = [&](int a) { return bars + 8u * (2 * WAVE_MAX_STAGES + a); };
@@ -339,12 +426,31 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
     auto pub_free = [&](int a) { return bars + 8u * (2 * WAVE_MAX_STAGES + 6 + a); };
     const uint32_t tmem_slot = bars + 8u * (2 * WAVE_MAX_STAGES + 8);
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - raw));
-    RowTab *rt = reinterpret_cast<RowTab *>(smem_raw + (bars + WAVE_BAR_BLOCK - raw));
+    float *sbias = reinterpret_cast<float *>(smem_raw + (bars + WAVE_BAR_BLOCK - raw));        // [2][256]
+    RowTab *rt = reinterpret_cast<RowTab *>(smem_raw + (bars + WAVE_BAR_BLOCK + 2048 - raw));
     float *stab = reinterpret_cast<float *>(rt + 1);
     EpiParams *s_ep = reinterpret_cast<EpiParams *>(stab + 64);
     if (p.scale_tab && threadIdx.x < 64) stab[threadIdx.x] = p.scale_tab[threadIdx.x];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stages = p.stages;
+    WaveEntTables tb;
+    tb.cdf16 = nullptr; tb.off16 = nullptr; tb.len = nullptr; tb.offs = nullptr;
+    if (p.n_ent > 0 && (int)blockIdx.x >= (int)gridDim.x - p.n_ent) {
+        // entropy CTA: compact CDF rows + per-level offsets / lengths / symbol offsets into the (unused) operand ring
+        uint8_t *base = smem_raw + (ring - raw);
+        uint4 *dst = reinterpret_cast<uint4 *>(base);
+        const int nvec = (p.cdf16_total + 7) >> 3;
+        for (int i = threadIdx.x; i < nvec; i += WAVE_THREADS) dst[i] = reinterpret_cast<const uint4 *>(p.cdf16)[i];
+        int *s_off = reinterpret_cast<int *>(dst + nvec);
+        int *s_len = s_off + 64, *s_offs = s_len + 64;
+        if (threadIdx.x < 64) {
+            s_off[threadIdx.x] = p.cdf16_off[threadIdx.x];
+            s_len[threadIdx.x] = p.cdf_len[threadIdx.x];
+            s_offs[threadIdx.x] = p.offs[threadIdx.x];
+        }
+        tb.cdf16 = reinterpret_cast<const uint16_t *>(base);
+        tb.off16 = s_off; tb.len = s_len; tb.offs = s_offs;
+    }
     // slot layout: activation hi | activation lo (a_plane_bytes each) | weight hi | weight lo
     const uint32_t off_alo = p.a_plane_bytes, off_w = 2 * p.a_plane_bytes;
 
@@ -499,8 +605,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                 epi_bar();
                 const uint32_t a = gi & 1u;
                 EpiCtx c;
-                c.stg = 0; c.acc_full_bar = acc_full(a); c.acc_empty_bar = acc_empty(a); c.full_phase = (gi >> 1) & 1u;
-                c.tmem_acc = tmem_base + a * WS_ACC_STRIDE; c.sb = nullptr; c.rt = rt; c.stab = stab; c.rank = 0;
+                c.stg = stg; c.acc_full_bar = acc_full(a); c.acc_empty_bar = acc_empty(a); c.full_phase = (gi >> 1) & 1u;
+                c.tmem_acc = tmem_base + a * WS_ACC_STRIDE; c.sb = sbias + a * 256; c.rt = rt; c.stab = stab; c.rank = 0;
                 const int dl = o.dep[0];
                 c.dep_cnt = dl >= 0 ? p.counters + dl * WAVE_MAX_RB + w.rb : nullptr;
                 c.dep_target = dl >= 0 ? p.ord[dl].ntn * (gen[w.rb] + 1) : 0;
@@ -508,7 +614,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                 c.dep2_cnt = dl2 >= 0 ? p.counters + dl2 * WAVE_MAX_RB + w.rb : nullptr;
                 c.dep2_target = dl2 >= 0 ? p.ord[dl2].ntn * (gen[w.rb] + 1) : 0;
                 c.trace_acc = et == 0 ? wave_trace_slot(p, w, 4) : nullptr;
-                wave_tile_epilogue(*s_ep, bn, m0, n0, c);
+                wave_gemm_epilogue(s_ep, bn, m0, n0, c);
                 ++gi;
             } else {
                 // non-GEMM tiles: one thread waits for the inputs, then all eight warps work
@@ -519,8 +625,9 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                     WAVE_TRACE(0);
                 }
                 epi_bar();
+                __syncwarp();  // lane 0 of warp 2 took the branch above: the warp-wide shuffles / votes below want it reconverged
                 if (o.kind == WK_GATHER) wave_gather_tile(p, w, rt, et);
-                else wave_rans_tile(p, w, ew, lane);
+                else wave_rans_tile(p, w, tb, stab, ew, lane);
             }
             if (et == 0) WAVE_TRACE(5);
             // this CTA's tile is stored: hand it to the publisher warp (which must have taken tile di - 2 off this barrier)
@@ -582,7 +689,7 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
     p.layers = w.d_layers; p.counters = w.counters;
     p.mode = w.raster ? 1 : 0; p.s_begin = w.s_begin; p.s_end = w.s_end;
     p.n_img = w.n_img; p.Hb = w.Hb; p.Wb = w.Wb;
-    p.variant = LBIC_LAT_VARIANT;
+    p.variant = w.variant;
     p.x_cl = w.x_cl; p.zhat_cl = w.zhat_cl; p.Cin = w.Cin;
     p.X_hi = w.X_hi; p.X_lo = w.X_lo; p.ldX = w.ldX; p.T_hi = w.T_hi; p.T_lo = w.T_lo; p.ldT = w.ldT;
     p.cdf = w.cdf; p.cdf_stride = w.cdf_stride; p.cdf_len = w.cdf_len; p.offs = w.offs; p.scale_tab = w.scale_tab;
@@ -590,12 +697,19 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
     p.ksi = w.ksi; p.ld_ksi = w.ld_ksi; p.yq_hi = w.yq_hi; p.yq_lo = w.yq_lo; p.ld_yq = w.ld_yq; p.sym_out = w.sym_out; p.M = w.M;
     const int max_rows = w.raster ? w.n_img : w.n_img * (w.Hb < (w.Wb + 1) / 2 ? w.Hb : (w.Wb + 1) / 2);
     if (max_rows > WAVE_MAX_RB * BM) return lbic_fail(LBIC_ERR_INVALID, "wave kernel: step of %d rows exceeds %d", max_rows, WAVE_MAX_RB * BM);
+    int bn_max = 16;
+    for (int i = 0; i < 18; ++i) {
+        const int bn = w.h_layers[w.ids[i]].bn_v[w.variant];
+        if (bn % 16 || bn < 16 || bn > LBIC_LAT_MAX_BN) return lbic_fail(LBIC_ERR_INVALID, "wave kernel: bad tile N %d", bn);
+        bn_max = bn > bn_max ? bn : bn_max;
+    }
     {
         const int box = lbic_box_rows(lbic_box_class(max_rows < BM ? max_rows : BM));   // largest activation box of this launch
         p.a_plane_bytes = (uint32_t)box * (BK * 2);
-        p.slot_bytes = 2 * p.a_plane_bytes + 2 * (uint32_t)LBIC_LAT_MAX_BN * (BK * 2);
+        p.slot_bytes = 2 * p.a_plane_bytes + 2 * (uint32_t)bn_max * (BK * 2);
         p.stages = WAVE_RING / (int)p.slot_bytes;
         if (p.stages > WAVE_MAX_STAGES) p.stages = WAVE_MAX_STAGES;
+        if (p.stages < 2) return lbic_fail(LBIC_ERR_INVALID, "wave kernel: operand slot does not fit the ring");
         static int cap = -1;   // tuning hook: LBIC_WAVE_STAGES caps the ring depth
         if (cap < 0) { const char *e = getenv("LBIC_WAVE_STAGES"); cap = e ? atoi(e) : 0; }
         if (cap >= 2 && p.stages > cap) p.stages = cap;
@@ -611,13 +725,9 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
     };
     auto gemm = [&](int id, int d0, int d1) {
         const ChainLayer &L = w.h_layers[id];
-        const int bn = L.bn_v[LBIC_LAT_VARIANT];
+        const int bn = L.bn_v[w.variant];
         return add(WK_GEMM, id, (L.cout + bn - 1) / bn, bn, d0, d1);
     };
-    for (int i = 0; i < 18; ++i) {
-        const int bn = w.h_layers[w.ids[i]].bn_v[LBIC_LAT_VARIANT];
-        if (bn % 16 || bn < 16 || bn > LBIC_LAT_MAX_BN) return lbic_fail(LBIC_ERR_INVALID, "wave kernel: bad tile N %d", bn);
-    }
     const int *E = w.ids, *F = w.ids + 4, *D = w.ids + 11;
     p.gather_first = w.decode ? 1 : 0;
     const int g = add(WK_GATHER, -1, (w.decode ? 4 : 5) * WAVE_GATHER_PARTS, 0, -1, -1);
@@ -641,6 +751,11 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
         const int e2 = gemm(E[2], e1, -1);
         last_e = gemm(E[3], e2, -1);
         last = add(WK_RANS, -1, WAVE_RANS_PARTS, 0, last_e, -1);
+        p.rans_ord = last;
+        p.n_ent = WAVE_ENT_CTAS;
+        p.cdf16 = w.cdf16; p.cdf16_off = w.cdf16_off; p.cdf16_total = w.cdf16_total;
+        if (!w.cdf16 || w.cdf16_total <= 0 || (size_t)w.cdf16_total * 2 + 16 + 3 * 64 * 4 > (size_t)WAVE_RING)
+            return lbic_fail(LBIC_ERR_INVALID, "wave kernel: entropy tables do not fit shared memory");
     }
     for (int i = 0; i < 7; ++i) last = gemm(D[i], last, -1);   // D0 IG0 D1 IG1 D2 IG2 D3: each reads the one before
     p.recon_ord = last;

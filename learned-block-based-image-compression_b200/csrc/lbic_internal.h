@@ -117,12 +117,14 @@ struct GemmCall {
 // One layer as the persistent multi-layer kernels see it (gemm_flow_kernel, gemm_wave_kernel), resident in device memory.
 // Tile-width variants per layer, indexed by "split factor" f: the layer's Cout is cut into f * ceil(Cout / (256 f))
 // equal tiles (width rounded up to 16), so a cluster of f CTAs gets the same number of tiles per CTA.
-constexpr int LBIC_NBN = 11;          // 6 split factors + the warp-specialised kernel's tiling (width <= 192) + its CTA-pair forms + small / latency tilings
+constexpr int LBIC_NBN = 13;          // 6 split factors + the warp-specialised kernel's tiling (width <= 192) + its CTA-pair forms + small / latency tilings
 constexpr int LBIC_WS_VARIANT = 6;
 constexpr int LBIC_PAIR_WIDE = 8;     // CTA-pair form with tiles up to 256 wide (2 pipeline stages instead of 3)
 constexpr int LBIC_SMALL_VARIANT = 9;  // tiles of at most 96 columns for the single-CTA dataflow launch of small steps
-constexpr int LBIC_LAT_VARIANT = 10;   // tiles of at most 32 columns for the persistent wavefront (latency) kernel, gemm_wave.cu
-constexpr int LBIC_LAT_MAX_BN = 32;
+constexpr int LBIC_LAT_VARIANT = 10;   // tilings of the persistent wavefront (latency) kernel, gemm_wave.cu: at most 32 columns,
+constexpr int LBIC_LAT64_VARIANT = 11;  // 64,
+constexpr int LBIC_LAT128_VARIANT = 12; // 128 (the time of a tile's MMA chain does not depend on its width up to ~176 columns)
+constexpr int LBIC_LAT_MAX_BN = 128;
 // rows of the activation TMA box for a tile with `rows` valid rows: class 0..3 = 16 / 32 / 48 / 64, 4 = the full 128
 __host__ __device__ inline int lbic_box_class(int rows) { return rows <= 16 ? 0 : rows <= 32 ? 1 : rows <= 48 ? 2 : rows <= 64 ? 3 : 4; }
 __host__ __device__ inline int lbic_box_rows(int cls) { return cls < 4 ? 16 * (cls + 1) : 128; }
@@ -156,6 +158,8 @@ struct WaveLaunch {
     int raster;                 // 1: steps are single blocks in raster order (reference container decode)
     int s_begin, s_end;         // wavefront: t in [s_begin, s_end); raster: block number v * Wb + h
     int n_img, Hb, Wb;
+    int variant;                // LBIC_LAT*_VARIANT: tile width
+    const uint16_t *cdf16; const int32_t *cdf16_off; int cdf16_total;   // compact CDF rows (Tables), decode only
     int ids[20];                // LayerId of E0..E3, F0..F3 (7), D0..D3 (7) in api.cu's LayerId order (18 entries)
     const float *x_cl, *zhat_cl;
     int Cin;

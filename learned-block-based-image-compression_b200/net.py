@@ -43,7 +43,7 @@ def get_lru(KS):
 
 class BlockBasedImgCompLossyNetv9:
     def __init__(self, config, device=None):
-        self.config = load_config(config) if not hasattr(config, "block_size") else load_config(vars(config))
+        self.config = load_config(config)      # JSON path, built-in name, dict / EasyDict (the reference's config object), namespace
         c = self.config
         self.B, self.N, self.M = int(c.block_size), int(c.N), int(c.M)
         self.KS = [int(k) for k in c.KS]
@@ -115,7 +115,8 @@ class BlockBasedImgCompLossyNetv9:
         """Tuning hooks: 'force_bn' (forced tile width), 'ws' (0 off / 1 auto / 2 always: persistent kernel),
         'pair' (CTA-pair form of the persistent kernel), 'pdl', 'host_bands' (bands of block rows of the host calls),
         'wave' (persistent wavefront kernel for small steps), 'wave_max_rows'."""
-        opt = {"force_bn": _lib.LBIC_OPT_FORCE_BN, "wave": _lib.LBIC_OPT_WAVE, "wave_max_rows": _lib.LBIC_OPT_WAVE_MAX_ROWS,
+        opt = {"force_bn": _lib.LBIC_OPT_FORCE_BN, "wave": _lib.LBIC_OPT_WAVE, "wave_max_rows": _lib.LBIC_OPT_WAVE_MAX_ROWS, "wave_dec_max_rows": _lib.LBIC_OPT_WAVE_DEC_MAX_ROWS,
+               "wave_bn": _lib.LBIC_OPT_WAVE_BN,
                "ws": _lib.LBIC_OPT_WS, "pdl": _lib.LBIC_OPT_PDL,
                "pair": _lib.LBIC_OPT_PAIR, "dec_thread_rows": _lib.LBIC_OPT_DEC_THREAD_ROWS,
                "enc_thread_streams": _lib.LBIC_OPT_ENC_THREAD_STREAMS, "enc_block_streams": _lib.LBIC_OPT_ENC_BLOCK_STREAMS, "flow": _lib.LBIC_OPT_FLOW,

@@ -71,3 +71,77 @@ def load():
     compressai.entropy_models = em
     _load("graphs.layers.masked_conv2d", "graphs/layers/masked_conv2d.py")
     return _load("graphs.models.BlockBasedImgCompLossy_net", "graphs/models/BlockBasedImgCompLossy_net.py")
+
+
+class EasyDict(dict):
+    """Minimal stand-in for easydict.EasyDict (attribute access on a dict), enough for utils/config.py and the agent."""
+
+    def __init__(self, d=None, **kw):
+        super().__init__()
+        for k, v in dict(d or {}, **kw).items():
+            self[k] = v
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def load_agent():
+    """Returns the reference module agents.blkbsdimgcomp_agent (class BlockBasedImgCompLossyAgent), UNMODIFIED, with
+    stand-ins for the packages it imports that are not installed here: easydict, matplotlib (display only),
+    bjontegaard, ptflops, torchsummary, and pytorch_msssim (-> lbic_b200.codec.ms_ssim, a restatement: MS-SSIM values
+    printed by a run through this loader are NOT a pin of that package)."""
+    load()
+    import torch
+
+    def stub(name, **attrs):
+        m = sys.modules.get(name) or types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    stub("easydict", EasyDict=EasyDict)
+    mpl = stub("matplotlib")
+    mpl.__path__ = []
+    mpl.pyplot = stub("matplotlib.pyplot")
+    stub("bjontegaard")
+    stub("ptflops", get_model_complexity_info=lambda *a, **k: (0, 0))
+    stub("torchsummary", summary=lambda *a, **k: None)
+    from lbic_b200 import codec as _codec
+
+    class _MS(torch.nn.Module):                       # MS_SSIM / SSIM module forms (training losses only)
+        def __init__(self, *a, data_range=1.0, **k):
+            super().__init__()
+            self.data_range = data_range
+
+        def forward(self, x, y):
+            return _codec.ms_ssim(x, y, data_range=self.data_range)
+
+    stub("pytorch_msssim", ms_ssim=lambda x, y, data_range=1.0, **k: _codec.ms_ssim(x, y, data_range=data_range),
+         MS_SSIM=_MS, SSIM=_MS, ssim=lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("ssim stub")))
+    # the reference was written against an older torch: ReduceLROnPlateau(verbose=...) no longer exists (torch >= 2.7);
+    # accept and drop the argument (an environment stand-in, the reference file itself stays untouched)
+    import inspect
+    _RLP = torch.optim.lr_scheduler.ReduceLROnPlateau
+    if "verbose" not in inspect.signature(_RLP.__init__).parameters and not getattr(_RLP, "_lbic_compat", False):
+        class ReduceLROnPlateau(_RLP):
+            _lbic_compat = True
+
+            def __init__(self, *a, verbose=False, **k):
+                super().__init__(*a, **k)
+
+        torch.optim.lr_scheduler.ReduceLROnPlateau = ReduceLROnPlateau
+    for pkg in ("agents", "dataloaders", "loggers", "graphs.losses"):
+        _ns(pkg)
+    _load("utils.image_plots", "utils/image_plots.py")
+    _load("graphs.losses.rate_dist", "graphs/losses/rate_dist.py")
+    _load("dataloaders.image_dl_ACL", "dataloaders/image_dl_ACL.py")
+    _load("loggers.rate", "loggers/rate.py")
+    _load("agents.base", "agents/base.py")
+    return _load("agents.blkbsdimgcomp_agent", "agents/blkbsdimgcomp_agent.py")

@@ -324,17 +324,22 @@ def test_wave_kernel_equals_per_layer_launches(dev, cfgname, n, Hb, Wb):
             m.set_option("wave", 0)
             ref = m.compress_batch(x, lanes=lanes, return_symbols=True)
             zref = m.decompress_batch(ref[0], x.shape, lanes=lanes)
-            l0 = m.launch_count()
             m.set_option("wave", 1)
-            got = m.compress_batch(x, lanes=lanes, return_symbols=True)
-            assert m.launch_count() - l0 < 12, "the wave path should need a handful of launches per encode"
-            assert torch.equal(got[2], ref[2]), f"symbols differ (lanes={lanes})"
-            assert torch.equal(got[3], ref[3]) and torch.equal(got[1], ref[1])
-            assert got[0] == ref[0], f"bitstreams differ (lanes={lanes})"
-            o = m.encode_device(x, lanes=lanes)
-            zdec, sdec = m.decode_device(o.streams, o.lens, n, Hb, Wb, lanes=lanes, want_symbols=True)
-            assert torch.equal(sdec, ref[2]), f"decoded symbols differ (lanes={lanes})"
-            assert torch.equal(zdec, zref) and torch.equal(zdec, got[1])
+            for bn in (0, 32, 128):                      # tile width: automatic (64 / 128 by rows), narrowest, widest
+                m.set_option("wave_bn", bn)
+                l0 = m.launch_count()
+                got = m.compress_batch(x, lanes=lanes, return_symbols=True)
+                assert m.launch_count() - l0 < 12, "the wave path should need a handful of launches per encode"
+                assert torch.equal(got[2], ref[2]), f"symbols differ (lanes={lanes}, bn={bn})"
+                assert torch.equal(got[3], ref[3]) and torch.equal(got[1], ref[1])
+                assert got[0] == ref[0], f"bitstreams differ (lanes={lanes}, bn={bn})"
+                o = m.encode_device(x, lanes=lanes)
+                l0 = m.launch_count()
+                zdec, sdec = m.decode_device(o.streams, o.lens, n, Hb, Wb, lanes=lanes, want_symbols=True)
+                assert m.launch_count() - l0 < 12, "the wave path should need a handful of launches per decode"
+                assert torch.equal(sdec, ref[2]), f"decoded symbols differ (lanes={lanes}, bn={bn})"
+                assert torch.equal(zdec, zref) and torch.equal(zdec, got[1])
+            m.set_option("wave_bn", 0)
         # host calls: the band hooks cut the wave launch; 8-bit entry points on the same images
         imgs_u8 = (img * 255).round().to(torch.uint8).numpy()
         m.set_option("wave", 0)
@@ -347,6 +352,7 @@ def test_wave_kernel_equals_per_layer_launches(dev, cfgname, n, Hb, Wb):
             assert np.array_equal(m.decompress_images_u8(got_s, Hb * B, Wb * B, lanes=0), want_rec)
     finally:
         m.set_option("wave", 1)
+        m.set_option("wave_bn", 0)
         m.set_option("host_bands", 16)
 
 
@@ -519,6 +525,41 @@ def test_full_size_image_vs_reference_closed_loop(dev, cfgname, gw, gh):
     assert abs(psnr - float(gold["psnr"])) < 0.01
     zdec = m.decompress_batch(strings, x.shape, lanes=1)
     assert torch.equal(zdec, zhat)
+
+
+def test_eval_model_matches_reference_log_line(dev):
+    """eval_model's per-image body (AGENT:578-637) on the image and weights of tests/golden/eval_model_*.json, which
+    holds what the UNMODIFIED reference agent logged for them on the CPU (make_golden_eval_model.py): ToTensor, -0.5,
+    padding, space-to-depth, compress, decompress, Enc-Dec check, bpp, MSE / PSNR.  Bars: bpp within 0.1 %, PSNR within
+    0.01 dB, Enc-Dec.Mad/Max/Min = 0; the formatted log line must agree in every field but the timings."""
+    import json, math
+    from lbic_b200.codec import pad_to_blocks, ms_ssim
+    gold = json.load(open(os.path.join(GOLDEN, "eval_model_B8_lowrate_208x176.json")))
+    g = gold["record"]
+    m = get_model(gold["config"], int(gold["weight_seed"]), False, dev)
+    B, H, W = m.B, int(gold["H"]), int(gold["W"])
+    img = weights.synth_image_u8(H, W, int(gold["image_seed"]))
+    x = (torch.from_numpy(img).float().div(255)[None] - 0.5).to(dev)                       # ToTensor on the CPU, AGENT:581
+    xp = lbic_b200.arrange_block_pixels_to_channel_dim(pad_to_blocks(x, B), B)              # AGENT:583-589
+    L = list(get_lru(m.KS))
+    bitstream, xhat_enc = m.compress(xp, L, m.M)                                            # AGENT:592
+    xhat_dec = m.decompress(bitstream, L, xp.shape, m.M, dev)                               # AGENT:598
+    dif = (xhat_enc - xhat_dec).abs()
+    bpp = len(bitstream) * 8.0 / (H * W)                                                    # AGENT:608-609
+    xhat_img = lbic_b200.arrange_channel_dim_to_block_pixels(xhat_enc, B)
+    mse = float(torch.nn.functional.mse_loss(x, xhat_img))                                  # AGENT:611
+    psnr = -10 * math.log10(mse)
+    msssim = float(ms_ssim(x + 0.5, xhat_img + 0.5, data_range=1.0))
+    assert float(dif.max()) == 0.0                                                          # Enc-Dec.Mad/Max/Min 0.00/0.00/0.00
+    assert abs(len(bitstream) - g["bytes"]) <= g["bytes"] * 1e-3, (len(bitstream), g["bytes"])
+    assert abs(psnr - (-10 * math.log10(g["mse_padded"]))) < 0.01
+    line = ('RDLoss:{:.3f} MSE/PSNR:{:.5f}/{:.2f} Rate:{:.3f} MS-SSIM/dB:{:.6f}/{:.2f} Enc-Dec.Mad/Max/Min:{:.2f}/{:.2f}/{:.2f}'
+            .format(bpp + 117.045 * mse, mse, psnr, bpp, msssim, -10 * math.log10(1.0 - msssim), float(dif.mean()) * 255,
+                    float(dif.max()) * 255, float(dif.min()) * 255))
+    import re
+    want = re.sub(r"Enc/DecTime:[\d.]+/[\d.]+ ", "", gold["log_line"].split("--> ")[1].rsplit(" (", 1)[0])
+    if len(bitstream) == g["bytes"]:
+        assert line == want, (line, want)
 
 
 def test_validation_rate_estimate(dev):
