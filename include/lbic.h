@@ -169,6 +169,22 @@ int lbic_encode_images_u8_host(lbic_model *m, const uint8_t *img, int n_img, int
 int lbic_decode_images_u8_host(lbic_model *m, const uint8_t *streams, const uint32_t *stream_len, size_t stream_cap,
                                int n_img, int H, int W, uint8_t *img_out, int lanes);
 
+/* Block-row bands: ONE large image split over several GPUs (BASELINE.json config 5).  A rank owns block rows [v0, v1)
+ * and runs every wavefront step t = h + 2 v (NET:339-357 restated) restricted to them; the only exchange is the halo:
+ * after step t the owner of row v1-1 passes zhat(v1-1, t - 2 (v1-1)) to the rank below before its step t+1 (the caller
+ * moves it, e.g. torch.distributed send / recv on views of lbic_band_zhat; lbic_b200/band.py).  KS[1] = 1 only.
+ *   lbic_band_begin  x: device (n_img, 3B^2, Hb, Wb) to encode, or NULL with `streams` = lane containers to decode
+ *   lbic_band_zhat   device pointer to the working reconstruction, channel-last (n_img, Hb, Wb, 3B^2)
+ *   lbic_band_step   step t for block rows [v0, v1)
+ *   lbic_band_end    the band's rows of the reconstruction (channel-last) and, after an encode, one rANS stream per
+ *                    owned block row (the lanes of the 'LBML' container: n_img * (v1-v0) slots of lane_cap bytes) */
+int lbic_band_begin(lbic_model *m, const float *x, int n_img, int Hb, int Wb, const uint8_t *streams,
+                    const uint32_t *stream_len, size_t stream_cap, void *stream);
+float *lbic_band_zhat(lbic_model *m);
+int lbic_band_step(lbic_model *m, int t, int v0, int v1, void *stream);
+int lbic_band_end(lbic_model *m, int v0, int v1, float *zhat_rows_out, uint8_t *lane_out, size_t lane_cap,
+                  uint32_t *lane_len, void *stream);
+
 /* Worst-case size in bytes of one image's bitstream for the given grid (8 bytes per symbol + 64 per rANS stream + the
  * lane-container header): a buffer of this size cannot overflow, whatever the symbols.  Typical streams are far smaller;
  * callers that size stream_cap from experience must check stream_len / lbic_check_errors. */

@@ -58,6 +58,10 @@ PROTOTYPES = {
     "lbic_check_errors": (_i, [_vp, _vp]),
     "lbic_encode_images_u8_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp, _i]),
     "lbic_decode_images_u8_host": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _vp, _i]),
+    "lbic_band_begin": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "lbic_band_zhat": (_vp, [_vp]),
+    "lbic_band_step": (_i, [_vp, _i, _i, _i, _vp]),
+    "lbic_band_end": (_i, [_vp, _i, _i, _vp, _vp, _sz, _vp, _vp]),
     "lbic_stream_bound": (_sz, [_vp, _i, _i, _i]),
     "lbic_space_to_depth": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "lbic_depth_to_space": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

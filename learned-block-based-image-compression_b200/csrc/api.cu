@@ -143,6 +143,8 @@ struct lbic_model {
     int host_bands = LBIC_MAX_BANDS;   // host calls: bands of block rows per batch (copy / compute overlap granularity)
     float *recon_cl = nullptr;      // set by lbic_forward: the decoder net writes here instead of the zhat feedback buffer
     int recon_no_clamp = 0;
+    // block-row-band mode (one large image over several GPUs): geometry of the call in progress
+    int band_n = 0, band_Hb = 0, band_Wb = 0, band_decode = 0;
     int64_t launches[2] = {0, 0};
     int *err_flag = nullptr;
     // the workspace is shared by all calls on this model: a call on another stream than the previous one waits for it
@@ -1638,6 +1640,97 @@ extern "C" int lbic_decode_images_u8_host(lbic_model *m, const uint8_t *streams,
     const int B = m->cfg.block_size;
     return decode_host_impl(m, 1, streams, stream_len, stream_cap, n_img, H, W, (H + B - 1) / B, (W + B - 1) / B, img_out,
                             lanes);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block-row bands: ONE large image over several GPUs (BASELINE config 5).
+//
+// Dependencies cross a horizontal cut only downwards: block (v, h) reads zhat of row v-1 at columns h-1 .. h+1
+// (KS[1] = 1), and (v-1, h+1) belongs to wavefront step t-1.  Rank g owns block rows [v0, v1) and runs every step
+// restricted to them; after step t it owes the rank below ONE block, zhat(v1-1, t - 2 (v1-1)), before that rank's step
+// t+1.  The library runs the steps and exposes the reconstruction buffer; the caller (band.py, torch.distributed
+// send / recv over NVLink) moves the halo blocks -- the only exchange on the data path.  Each band is entropy-coded as
+// the lanes of its own block rows (the lane container holds one rANS stream per block row), so the bands' payloads
+// concatenate into the same container a single GPU writes.
+// ------------------------------------------------------------------------------------------------
+extern "C" int lbic_band_begin(lbic_model *m, const float *x, int n_img, int Hb, int Wb, const uint8_t *streams,
+                               const uint32_t *stream_len, size_t stream_cap, void *stream) {
+    const bool decode = streams != nullptr;
+    LBIC_TRY(check_ready(m, decode));
+    if ((!x && !decode) || (decode && !stream_len) || n_img < 1 || Hb < 1 || Wb < 1) return lbic_fail(LBIC_ERR_INVALID, "bad arguments");
+    if (m->k1 != 1) return lbic_fail(LBIC_ERR_INVALID, "band mode supports KS[1] = 1 (one halo block per step)");
+    Active act(m);
+    cudaStream_t st = (cudaStream_t)stream;
+    LBIC_TRY(ensure_workspace(m, n_img, Hb, Wb));
+    Workspace &ws = m->ws;
+    const size_t nblk = (size_t)n_img * Hb * Wb;
+    LBIC_TRY(ws_acquire(m, st));
+    LBIC_CUDA(cudaMemsetAsync(m->err_flag, 0, sizeof(int), st));
+    LBIC_CUDA(cudaMemsetAsync(ws.zhat_cl, 0, sizeof(float) * nblk * m->Cin, st));
+    if (decode) {
+        if (stream_cap % 4) return lbic_fail(LBIC_ERR_INVALID, "stream_cap must be a multiple of 4");
+        LBIC_TRY(launch_rans_dec_init(streams, stream_len, stream_cap, n_img, Hb, 1, ws.dec_states, ws.lane_ptr, m->err_flag, st));
+    } else {
+        LBIC_TRY(launch_nchw_to_cl(x, ws.x_cl, n_img, m->Cin, Hb * Wb, st));
+    }
+    m->band_n = n_img; m->band_Hb = Hb; m->band_Wb = Wb; m->band_decode = decode ? 1 : 0;
+    return 0;
+}
+
+extern "C" float *lbic_band_zhat(lbic_model *m) { return (m && m->band_n) ? m->ws.zhat_cl : nullptr; }
+
+// wavefront step t restricted to block rows [v0, v1)
+extern "C" int lbic_band_step(lbic_model *m, int t, int v0, int v1, void *stream) {
+    if (!m || !m->band_n) return lbic_fail(LBIC_ERR_STATE, "lbic_band_begin has not been called");
+    Active act(m);
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace &ws = m->ws;
+    const int n_img = m->band_n, Hb = m->band_Hb, Wb = m->band_Wb;
+    StepDesc sd;
+    if (!wave_step(t, n_img, Hb, Wb, sd)) return 0;
+    const int lo = sd.vmin > v0 ? sd.vmin : v0;
+    const int hi = (sd.vmin + sd.nv) < v1 ? (sd.vmin + sd.nv) : v1;
+    if (hi <= lo) return 0;
+    sd.vmin = lo; sd.nv = hi - lo;
+    const int R = n_img * sd.nv;
+    if (m->band_decode) {
+        LBIC_TRY(launch_gather(nullptr, ws.zhat_cl, m->Cin, sd, R, nullptr, nullptr, 0, ws.T.hi, ws.T.lo, ws.T.ld, st));
+        LBIC_TRY(run_ent(m, sd, R, st));
+        LBIC_TRY(launch_rans_dec_step(m->tables, ws.dec_states, ws.lane_ptr, Hb, sd, R, m->M, ws.KSI, ws.ldKSI, ws.YQ.hi,
+                                      ws.YQ.lo, ws.YQ.ld, nullptr, st));
+        return run_dec(m, sd, R, st);
+    }
+    LBIC_TRY(launch_gather(ws.x_cl, ws.zhat_cl, m->Cin, sd, R, ws.X.hi, ws.X.lo, ws.X.ld, ws.T.hi, ws.T.lo, ws.T.ld, st));
+    return encode_step(m, sd, R, true, st);
+}
+
+// Ends the call for block rows [v0, v1): the band's reconstruction (channel-last rows, (n_img, v1-v0, Wb, 3B^2)) and,
+// after an encode, its lanes: lane_out holds n_img * (v1-v0) slots of lane_cap bytes, lane_len their byte counts.
+extern "C" int lbic_band_end(lbic_model *m, int v0, int v1, float *zhat_rows_out, uint8_t *lane_out, size_t lane_cap,
+                             uint32_t *lane_len, void *stream) {
+    if (!m || !m->band_n) return lbic_fail(LBIC_ERR_STATE, "lbic_band_begin has not been called");
+    Active act(m);
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace &ws = m->ws;
+    const int n_img = m->band_n, Hb = m->band_Hb, Wb = m->band_Wb, nr = v1 - v0;
+    if (v0 < 0 || v1 > Hb || nr <= 0) return lbic_fail(LBIC_ERR_INVALID, "bad band");
+    const size_t row_f = (size_t)Wb * m->Cin;
+    if (zhat_rows_out)
+        LBIC_CUDA(cudaMemcpy2DAsync(zhat_rows_out, sizeof(float) * row_f * nr, ws.zhat_cl + (size_t)v0 * row_f,
+                                    sizeof(float) * row_f * Hb, sizeof(float) * row_f * nr, n_img, cudaMemcpyDeviceToDevice, st));
+    if (lane_out && !m->band_decode) {
+        if (!lane_len || lane_cap % 4) return lbic_fail(LBIC_ERR_INVALID, "lane_cap must be a multiple of 4");
+        const int64_t n_sym = (int64_t)Wb * m->M;
+        const size_t per = lane_cap / 4;
+        LBIC_TRY(ensure_rans_scratch(m, (size_t)nr * per + 2 * (size_t)nr));
+        for (int i = 0; i < n_img; ++i) {
+            const size_t o = ((size_t)i * Hb + v0) * Wb * m->M;
+            LBIC_TRY(launch_rans_encode(m->tables, ws.sym + o, ws.idx + o, nr, n_sym, n_sym, ws.rans_scratch, per,
+                                        lane_out + (size_t)i * nr * lane_cap, lane_cap, lane_len + (size_t)i * nr, m->err_flag, st));
+        }
+    }
+    m->band_n = 0;
+    return ws_release(m, st);
 }
 
 extern "C" int lbic_space_to_depth(const float *img, float *blk, int n, int C, int Hb, int Wb, int B, void *stream) {

@@ -320,12 +320,13 @@ def test_wave_kernel_equals_per_layer_launches(dev, cfgname, n, Hb, Wb):
     img = weights.synth_images(n, Hb * B, Wb * B, seed0=131)
     x = arrange_block_pixels_to_channel_dim((img - 0.5).to(dev), B)
     try:
+        m.set_option("wave_dec_max_rows", 4096)          # (default 64: beyond that the per-layer decode is faster)
         for lanes in (0, 1):
             m.set_option("wave", 0)
             ref = m.compress_batch(x, lanes=lanes, return_symbols=True)
             zref = m.decompress_batch(ref[0], x.shape, lanes=lanes)
             m.set_option("wave", 1)
-            for bn in (0, 32, 128):                      # tile width: automatic (64 / 128 by rows), narrowest, widest
+            for bn in (0, 64, 128):                      # tile width: automatic (64 / 128 by rows), narrowest, widest
                 m.set_option("wave_bn", bn)
                 l0 = m.launch_count()
                 got = m.compress_batch(x, lanes=lanes, return_symbols=True)
@@ -353,6 +354,7 @@ def test_wave_kernel_equals_per_layer_launches(dev, cfgname, n, Hb, Wb):
     finally:
         m.set_option("wave", 1)
         m.set_option("wave_bn", 0)
+        m.set_option("wave_dec_max_rows", 64)
         m.set_option("host_bands", 16)
 
 
@@ -688,6 +690,61 @@ def test_two_devices_in_one_process(dev):
         m.set_option("enc_thread_streams", 4096)
         m.set_option("dec_thread_rows", 4096)
     assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("Hb,Wb,ranks", [(12, 17, 1), (12, 17, 3), (5, 40, 2), (9, 4, 4)])
+def test_band_steps_with_halo_exchange_equal_single_pass(dev, Hb, Wb, ranks):
+    """BASELINE config 5 (one large image in block-row bands over several GPUs, lbic_b200/band.py) on ONE GPU: `ranks`
+    model instances on the same device play the ranks, every wavefront step runs per band (lbic_band_step) and the halo
+    block of lbic_b200.band.halo_columns is copied from the upper instance's reconstruction to the lower one's -- the
+    only thing torch.distributed moves in the real thing.  Streams (lane container) and reconstruction must be
+    bit-identical to compress_batch / decompress_batch of the whole image."""
+    from lbic_b200 import band
+    from lbic_b200.layout import arrange_block_pixels_to_channel_dim
+    cfg = lbic_b200.load_config("B8_lowrate")
+    sd = weights.synth_state_dict(cfg, 1337)
+    ref_m = get_model("B8_lowrate", 1337, False, dev)
+    img = weights.synth_images(1, Hb * 8, Wb * 8, seed0=909)
+    x = arrange_block_pixels_to_channel_dim((img - 0.5).to(dev), 8)
+    want_s, want_z = ref_m.compress_batch(x, lanes=0)
+    models = []
+    for _ in range(ranks):
+        mm = BlockBasedImgCompLossyNetv9(cfg, device=dev)
+        mm.load_state_dict(sd)
+        mm.update(force=True)
+        models.append(mm)
+    bands = [band.band_rows(Hb, ranks, r) for r in range(ranks)]
+
+    def run(decode_blob=None):
+        engs = [band.LibEngine(mm) for mm in models]
+        if decode_blob is None:
+            zts = [e.begin(x, 1, Hb, Wb) for e in engs]
+        else:
+            cap = (len(decode_blob) + 3) // 4 * 4
+            host = np.zeros((1, cap), np.uint8)
+            host[0, :len(decode_blob)] = np.frombuffer(decode_blob, np.uint8)
+            st = torch.from_numpy(host).to(dev)
+            ln = torch.tensor([len(decode_blob)], dtype=torch.int32, device=dev)
+            zts = [e.begin(None, 1, Hb, Wb, st, ln) for e in engs]
+        for t in range(Wb + 2 * (Hb - 1)):
+            for r, (v0, v1) in enumerate(bands):
+                recv_h, _ = band.halo_columns(t, v0, v1, Hb, Wb)
+                if recv_h is not None and r > 0:
+                    zts[r][:, v0 - 1, recv_h] = zts[r - 1][:, v0 - 1, recv_h]
+            for r, (v0, v1) in enumerate(bands):
+                engs[r].step(t, v0, v1)
+        outs = [e.end(v0, v1, decode_blob is None) for e, (v0, v1) in zip(engs, bands)]
+        z = torch.cat([o[0][0] for o in outs], dim=0).permute(2, 0, 1).unsqueeze(0)
+        lanes = [l for o in outs for l in (o[1] or [])]
+        return z, lanes
+
+    z, lanes = run()
+    blob = band.pack_lane_container(lanes)
+    assert blob == want_s[0], "band-encoded lane container differs from the single-pass one"
+    assert torch.equal(z, want_z)
+    zd, _ = run(blob)
+    assert torch.equal(zd, want_z)
+    assert torch.equal(ref_m.decompress_batch([blob], x.shape, lanes=0), want_z)
 
 
 def test_host_calls_banded_pipeline_equals_device_calls(dev):
