@@ -169,6 +169,20 @@ int lbic_encode_images_u8_host(lbic_model *m, const uint8_t *img, int n_img, int
 int lbic_decode_images_u8_host(lbic_model *m, const uint8_t *streams, const uint32_t *stream_len, size_t stream_cap,
                                int n_img, int H, int W, uint8_t *img_out, int lanes);
 
+/* The quality figures eval_model logs (AGENT:611-619), computed on the device: per-image MSE of x vs y ((n, C, H, W)
+ * fp32 device tensors; PSNR = -10 log10(mse) for the unit-range images the agent compares) and, if msssim_out != NULL,
+ * pytorch_msssim.ms_ssim(x + offset, y + offset, data_range) per image (the agent passes offset 0.5, data_range 1.0;
+ * the smaller image side must exceed 160).  mse_out / msssim_out: HOST arrays of n doubles; the call synchronises. */
+int lbic_image_metrics(lbic_model *m, const float *x, const float *y, int n, int C, int H, int W, float offset,
+                       float data_range, double *mse_out, double *msssim_out, void *stream);
+
+/* The optional post-processing module -- BlkBasedPostProcessing (NET:455-476), `use_postpm` in the config JSON,
+ * applied by eval_model to the block tensor of the reconstruction (AGENT:604-606).
+ *   lbic_load_postpm_weights   the module's state_dict: res_net.0.{weight (4C, C, 3, 3), bias}, res_net.2.{weight (C, 4C, 1, 1), bias}, C = 3B^2
+ *   lbic_postprocess           z, out: device (n_img, 3B^2, Hb, Wb) fp32; clamp != 0 applies the caller's clamp_(-0.5, 0.5) */
+int lbic_load_postpm_weights(lbic_model *m, const lbic_tensor_desc *tensors, int n_tensors, void *stream);
+int lbic_postprocess(lbic_model *m, const float *z, int n_img, int Hb, int Wb, float *out, int clamp, void *stream);
+
 /* Block-row bands: ONE large image split over several GPUs (BASELINE.json config 5).  A rank owns block rows [v0, v1)
  * and runs every wavefront step t = h + 2 v (NET:339-357 restated) restricted to them; the only exchange is the halo:
  * after step t the owner of row v1-1 passes zhat(v1-1, t - 2 (v1-1)) to the rank below before its step t+1 (the caller

@@ -6,6 +6,6 @@ hand-written sm_100a CUDA behind the C ABI declared in include/lbic.h.  There is
 """
 from . import weights  # noqa: F401
 from .config import load_config  # noqa: F401
-from .net import BlockBasedImgCompLossyNetv9, get_lru, get_scale_table  # noqa: F401,E402
+from .net import BlkBasedPostProcessing, BlockBasedImgCompLossyNetv9, get_lru, get_scale_table  # noqa: F401,E402
 from .layout import arrange_block_pixels_to_channel_dim, arrange_channel_dim_to_block_pixels  # noqa: F401,E402
 from .codec import ImageCodec, ms_ssim, pack_container, psnr, unpack_container  # noqa: F401,E402

@@ -17,7 +17,7 @@ SO = os.path.join(HERE, "liblbic_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
-SOURCES = ["api.cu", "gemm_tc.cu", "gemm_ws.cu", "gemm_wave.cu", "gemm_simt.cu", "kernels_misc.cu", "tables.cu", "rans.cu"]
+SOURCES = ["api.cu", "gemm_tc.cu", "gemm_ws.cu", "gemm_wave.cu", "gemm_simt.cu", "kernels_misc.cu", "tables.cu", "rans.cu", "metrics.cu"]
 
 
 def _newer(a, b):

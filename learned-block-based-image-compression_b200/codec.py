@@ -166,10 +166,13 @@ class ImageCodec:
         blob = self.encode(t)
         rec = self.decode(blob)
         meta, payload = unpack_container(blob)
+        # the figures of AGENT:611-619 on the GPU (lbic_image_metrics), on the [-0.5, 0.5] images the agent compares
+        big = min(t.shape[2], t.shape[3]) > 160
+        q = self.model.image_metrics((t - 0.5).contiguous(), (rec - 0.5).contiguous(), msssim=big)
         out = dict(bytes=len(payload), container_bytes=len(blob), bpp=8.0 * len(payload) / (t.shape[2] * t.shape[3]),
-                   psnr=psnr(t, rec))
-        if min(t.shape[2], t.shape[3]) > 160:
-            m = float(ms_ssim(t, rec, data_range=1.0))
+                   mse=float(q["mse"][0]), psnr=float(q["psnr"][0]))
+        if big:
+            m = float(q["msssim"][0])
             out.update(msssim=m, msssim_db=float(-10.0 * np.log10(max(1.0 - m, 1e-12))))
         return out
 

@@ -118,6 +118,14 @@ struct lbic_model {
     int Cin = 0, N = 0, C2 = 0, C3 = 0, M = 0, E1 = 0, E2 = 0, E3 = 0, EO = 0, k1 = 1;
     PackedLayer L[L_COUNT];
     bool weights_loaded = false;
+    // optional post-processing net (BlkBasedPostProcessing, NET:455-476): 3x3 conv (all nine taps) -> lrelu -> 1x1 conv
+    PackedLayer PP[2];
+    bool postpm_loaded = false;
+    std::vector<void *> pp_allocs;       // its packed weights
+    ActBuf PPA, PPH;                     // nine-tap operand (9 * 3B^2 wide) and hidden activations (4 * 3B^2)
+    ActView vPPA, vPPH;
+    int pp_rcap = 0;
+    std::vector<void *> pp_ws_allocs;
     std::vector<void *> weight_allocs;
     Tables tables;
     Workspace ws;
@@ -138,8 +146,8 @@ struct lbic_model {
     cudaStream_t hs[3] = {nullptr, nullptr, nullptr};   // host-call pipeline: copies in, compute, copies out
     cudaEvent_t hev[2 * LBIC_MAX_BANDS] = {};            // band b copied in / band b ready to copy out
     // grow-only device temporaries of lbic_validate / lbic_forward (channel-last self-information, reconstruction)
-    float *aux[2] = {nullptr, nullptr};
-    size_t aux_bytes[2] = {0, 0};
+    float *aux[3] = {nullptr, nullptr, nullptr};     // [2]: scratch of lbic_image_metrics
+    size_t aux_bytes[3] = {0, 0, 0};
     int host_bands = LBIC_MAX_BANDS;   // host calls: bands of block rows per batch (copy / compute overlap granularity)
     float *recon_cl = nullptr;      // set by lbic_forward: the decoder net writes here instead of the zhat feedback buffer
     int recon_no_clamp = 0;
@@ -249,6 +257,7 @@ int scalar(const SdView &sd, const std::string &name, float fallback, float *out
 const int TAPS_A[8] = {0, 0, 0, 1, 0, 2, 1, 0};            // 3x3 mask 'A' live taps (kh,kw)  MC:12-17
 const int TAPS_B[10] = {0, 0, 0, 1, 0, 2, 1, 0, 1, 1};     // 3x3 mask 'B' adds the centre
 const int TAPS_1[2] = {0, 0};
+const int TAPS_9[18] = {0, 0, 0, 1, 0, 2, 1, 0, 1, 1, 1, 2, 2, 0, 2, 1, 2, 2};   // plain 3x3 conv (post-processing net)
 
 int pack_conv_seg(lbic_model *m, const SdView &sd, const std::string &prefix, int cout, int cin, int k,
                   const int *taps, int ntaps, int bn, PackedSeg &seg, float **bias_tmp, std::vector<void *> &tmp,
@@ -296,9 +305,14 @@ int finish_layer(lbic_model *m, PackedLayer &L, cudaStream_t st) {
     return 0;
 }
 
+int pack_linear_into(lbic_model *m, PackedLayer &L, const SdView &sd, const std::string &prefix, int cout, int cin, int k,
+                     const int *taps, int ntaps, std::vector<void *> &tmp, cudaStream_t st);
 int pack_linear(lbic_model *m, const SdView &sd, int id, const std::string &prefix, int cout, int cin, int k,
                 const int *taps, int ntaps, std::vector<void *> &tmp, cudaStream_t st) {
-    PackedLayer &L = m->L[id];
+    return pack_linear_into(m, m->L[id], sd, prefix, cout, cin, k, taps, ntaps, tmp, st);
+}
+int pack_linear_into(lbic_model *m, PackedLayer &L, const SdView &sd, const std::string &prefix, int cout, int cin, int k,
+                     const int *taps, int ntaps, std::vector<void *> &tmp, cudaStream_t st) {
     L.cout = cout;
     L.bn = pick_bn(cout);
     L.n_bn = bn_variants(cout, L.bn_v);
@@ -563,8 +577,13 @@ int ensure_rans_scratch(lbic_model *m, size_t words) {
 }
 
 // ---- GEMM dispatch --------------------------------------------------------------------------------
+int run_gemm_layer(lbic_model *m, const PackedLayer &L, int id, int R, const ActView *a0, const ActView *a1, EpiParams ep,
+                   cudaStream_t st);
 int run_gemm(lbic_model *m, int id, int R, const ActView *a0, const ActView *a1, EpiParams ep, cudaStream_t st) {
-    const PackedLayer &L = m->L[id];
+    return run_gemm_layer(m, m->L[id], id, R, a0, a1, ep, st);
+}
+int run_gemm_layer(lbic_model *m, const PackedLayer &L, int id, int R, const ActView *a0, const ActView *a1, EpiParams ep,
+                   cudaStream_t st) {
     GemmCall g;
     // Tile width: the widest variant that still gives about one CTA per SM; small steps (few rows) take narrower
     // tiles so that more SMs share the layer -- the result does not depend on the choice (no split-K, fixed k order).
@@ -586,7 +605,7 @@ int run_gemm(lbic_model *m, int id, int R, const ActView *a0, const ActView *a1,
             int ktot = 0;
             for (int s = 0; s < L.nseg; ++s) ktot += (L.seg[s].K + 63) / 64 * 64;
             const int md = ep.mode;   // bytes per output element: fp32 plane, hi+lo planes, (GDN) pre-activation read back
-            const int out_b = ((md == EPI_RAW || md == EPI_PREGDN || md == EPI_KSI || md == EPI_RECON || md == EPI_QUANT) ? 4 : 0) +
+            const int out_b = ((md == EPI_RAW || md == EPI_PREGDN || md == EPI_KSI || md == EPI_RECON || md == EPI_QUANT || md == EPI_RESID) ? 4 : 0) +
                               ((md == EPI_LRELU || md == EPI_PREGDN || md == EPI_GDN || md == EPI_IGDN || md == EPI_QUANT) ? 4 : 0) +
                               ((md == EPI_GDN || md == EPI_IGDN) ? 4 : 0);
             const int rt2 = (R + 255) / 256;
@@ -923,6 +942,8 @@ extern "C" void lbic_destroy(lbic_model *m) {
     cudaDeviceSynchronize();
     free_all(m->ws.allocs);
     free_all(m->weight_allocs);
+    free_all(m->pp_allocs);
+    free_all(m->pp_ws_allocs);
     tables_free(m->tables);
     if (m->tables.d_scale_table) cudaFree(m->tables.d_scale_table);
     if (m->err_flag) cudaFree(m->err_flag);
@@ -1640,6 +1661,90 @@ extern "C" int lbic_decode_images_u8_host(lbic_model *m, const uint8_t *streams,
     const int B = m->cfg.block_size;
     return decode_host_impl(m, 1, streams, stream_len, stream_cap, n_img, H, W, (H + B - 1) / B, (W + B - 1) / B, img_out,
                             lanes);
+}
+
+// ------------------------------------------------------------------------------------------------
+// eval_model's quality figures on the GPU (AGENT:611-619): per-image MSE and MS-SSIM.
+// ------------------------------------------------------------------------------------------------
+extern "C" int lbic_image_metrics(lbic_model *m, const float *x, const float *y, int n, int C, int H, int W, float offset,
+                                  float data_range, double *mse_out, double *msssim_out, void *stream) {
+    if (!m || !x || !y || !mse_out) return lbic_fail(LBIC_ERR_INVALID, "null argument");
+    Active act(m);
+    float *scratch = nullptr;
+    LBIC_TRY(ensure_aux(m, 2, metrics_scratch_bytes(n, C, H, W), &scratch));
+    return launch_image_metrics(x, y, n, C, H, W, offset, data_range, scratch, mse_out, msssim_out, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Post-processing net: BlkBasedPostProcessing, NET:455-476, applied to the block tensor of a
+// reconstruction when `use_postpm` is set (AGENT:604-606).  x + pad(conv1x1(lrelu(conv3x3_valid(x)))): two GEMMs over
+// all blocks of the batch in raster chunks (nothing is recursive here), the residual add and the caller's clamp fused
+// into the second epilogue; blocks on the image border keep their input (the residual is zero padded).
+// ------------------------------------------------------------------------------------------------
+extern "C" int lbic_load_postpm_weights(lbic_model *m, const lbic_tensor_desc *tensors, int n_tensors, void *stream) {
+    if (!m || !tensors) return lbic_fail(LBIC_ERR_INVALID, "null argument");
+    Active act(m);
+    cudaStream_t st = (cudaStream_t)stream;
+    LBIC_TRY(gemm_tc_init());
+    SdView sd;
+    for (int i = 0; i < n_tensors; ++i)
+        if (tensors[i].name && tensors[i].data) sd.by_name[tensors[i].name] = &tensors[i];
+    LBIC_CUDA(cudaDeviceSynchronize());
+    free_all(m->pp_allocs);
+    m->postpm_loaded = false;
+    std::vector<void *> tmp;
+    std::swap(m->weight_allocs, m->pp_allocs);          // the packers allocate into weight_allocs
+    int rc = pack_linear_into(m, m->PP[0], sd, "res_net.0", 4 * m->Cin, m->Cin, 3, TAPS_9, 9, tmp, st);
+    if (rc == 0) rc = pack_linear_into(m, m->PP[1], sd, "res_net.2", m->Cin, 4 * m->Cin, 1, TAPS_1, 1, tmp, st);
+    std::swap(m->weight_allocs, m->pp_allocs);
+    cudaError_t e = cudaStreamSynchronize(st);
+    free_all(tmp);
+    if (rc) return rc;
+    if (e != cudaSuccess) return lbic_fail(LBIC_ERR_CUDA, "weight packing failed: %s", cudaGetErrorString(e));
+    m->postpm_loaded = true;
+    return 0;
+}
+
+extern "C" int lbic_postprocess(lbic_model *m, const float *z, int n_img, int Hb, int Wb, float *out, int clamp, void *stream) {
+    if (!m || !z || !out || n_img < 1 || Hb < 1 || Wb < 1) return lbic_fail(LBIC_ERR_INVALID, "bad arguments");
+    if (!m->postpm_loaded) return lbic_fail(LBIC_ERR_STATE, "post-processing weights not loaded: call lbic_load_postpm_weights first");
+    Active act(m);
+    cudaStream_t st = (cudaStream_t)stream;
+    LBIC_TRY(ensure_workspace(m, n_img, Hb, Wb));
+    Workspace &ws = m->ws;
+    if (m->pp_rcap != ws.R_cap) {                       // operand buffers of the two layers, sized like the workspace's
+        LBIC_CUDA(cudaDeviceSynchronize());
+        free_all(m->pp_ws_allocs);
+        m->PPA.ld = 9 * m->Cin; m->PPH.ld = 4 * m->Cin;
+        for (ActBuf *b : {&m->PPA, &m->PPH}) {
+            LBIC_TRY(dev_alloc(m->pp_ws_allocs, (void **)&b->hi, sizeof(h16) * (size_t)ws.R_cap * b->ld, true));
+            LBIC_TRY(dev_alloc(m->pp_ws_allocs, (void **)&b->lo, sizeof(h16) * (size_t)ws.R_cap * b->ld, true));
+        }
+        LBIC_TRY(make_view(ws, m->vPPA, m->PPA, 9 * m->Cin));
+        LBIC_TRY(make_view(ws, m->vPPH, m->PPH, 4 * m->Cin));
+        m->pp_rcap = ws.R_cap;
+    }
+    const int HW = Hb * Wb;
+    const long nblk = (long)n_img * HW;
+    float *out_cl = nullptr;
+    LBIC_TRY(ws_acquire(m, st));
+    LBIC_TRY(ensure_aux(m, 1, sizeof(float) * (size_t)nblk * m->Cin, &out_cl));
+    LBIC_TRY(launch_nchw_to_cl(z, ws.zhat_cl, n_img, m->Cin, HW, st));
+    const int chunk = ws.R_cap;
+    for (long r0 = 0; r0 < nblk; r0 += chunk) {
+        const int R = (int)(nblk - r0 < chunk ? nblk - r0 : chunk);
+        const StepDesc sd{n_img, 0, 0, (int)r0, Hb, Wb};                       // raster chunk: row r = block r0 + r
+        LBIC_TRY(launch_gather9(ws.zhat_cl, m->Cin, sd, R, m->PPA.hi, m->PPA.lo, m->PPA.ld, st));
+        LBIC_TRY(run_gemm_layer(m, m->PP[0], -1, R, &m->vPPA, nullptr, epi_hilo(EPI_LRELU, sd, m->PPH), st));
+        EpiParams e = epi(EPI_RESID, sd);
+        e.out_f32 = out_cl + (size_t)r0 * m->Cin; e.ld_f32 = m->Cin;
+        e.aux = ws.zhat_cl + (size_t)r0 * m->Cin; e.ld_aux = m->Cin;
+        e.no_clamp = clamp ? 0 : 1;
+        LBIC_TRY(run_gemm_layer(m, m->PP[1], -1, R, &m->vPPH, nullptr, e, st));
+    }
+    LBIC_TRY(launch_restore_border(ws.zhat_cl, out_cl, m->Cin, n_img, Hb, Wb, st));
+    LBIC_TRY(launch_cl_to_nchw(out_cl, out, n_img, m->Cin, HW, st));
+    return ws_release(m, st);
 }
 
 // ------------------------------------------------------------------------------------------------

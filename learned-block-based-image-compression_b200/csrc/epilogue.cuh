@@ -118,6 +118,8 @@ template <int NV>
 __device__ __forceinline__ void epi_prefetch(const EpiParams &p, int r, int c, EpiPre<NV> &pre) {
     if (p.mode == EPI_GDN || p.mode == EPI_IGDN) {
         load_f32_cg<NV>(p.aux + (size_t)r * p.ld_aux + c, pre.a);
+    } else if (p.mode == EPI_RESID) {
+        load_f32_cg<NV>(p.aux + (size_t)r * p.ld_aux + c, pre.a);            // the block the residual is added to
     } else if (p.mode == EPI_QUANT) {
         load_f32_cg<NV>(p.aux + (size_t)r * p.ld_aux + c, pre.a);            // scales = ksi[:, :M]   (NET:369)
         load_f32_cg<NV>(p.aux + (size_t)r * p.ld_aux + p.M + c, pre.a2);     // means  = ksi[:, M:]
@@ -136,7 +138,7 @@ struct EpiOut {
 };
 
 __host__ __device__ __forceinline__ bool epi_has_f32(int mode) {
-    return mode == EPI_RAW || mode == EPI_PREGDN || mode == EPI_KSI || mode == EPI_RECON || mode == EPI_QUANT;
+    return mode == EPI_RAW || mode == EPI_PREGDN || mode == EPI_KSI || mode == EPI_RECON || mode == EPI_QUANT || mode == EPI_RESID;
 }
 __host__ __device__ __forceinline__ bool epi_has_hilo(int mode) {
     return mode == EPI_LRELU || mode == EPI_PREGDN || mode == EPI_GDN || mode == EPI_IGDN || mode == EPI_QUANT;
@@ -203,6 +205,14 @@ __device__ __forceinline__ void epi_compute(const EpiParams &p, const float *__r
 #pragma unroll
         for (int i = 0; i < NV; ++i) o.f[i] = v[i];
     } break;
+    case EPI_RESID: {
+        // x + res_net(x) (NET:475-476), then the caller's clamp_(-0.5, 0.5) (AGENT:606) unless no_clamp
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const float s = pre.a[i] + v[i];
+            o.f[i] = p.no_clamp ? s : fminf(fmaxf(s, -0.5f), 0.5f);
+        }
+    } break;
     case EPI_QUANT: {
         const float *tab = stab ? stab : p.scale_tab;
         const ScaleHint hint = scale_hint(tab);
@@ -256,7 +266,7 @@ __device__ __forceinline__ EpiRowDst epi_row_dst(const EpiParams &p, int r) {
 // f32-plane destination pointer of (row, column c); nullptr if the mode has none / it is not requested
 __device__ __forceinline__ float *epi_f32_ptr(const EpiParams &p, const EpiRowDst &d, int c) {
     switch (p.mode) {
-    case EPI_RAW: case EPI_PREGDN: case EPI_KSI: return p.out_f32 + d.f32 + c;
+    case EPI_RAW: case EPI_PREGDN: case EPI_KSI: case EPI_RESID: return p.out_f32 + d.f32 + c;
     case EPI_RECON: return p.zhat + d.blk * p.cout + c;
     case EPI_QUANT: return p.sym ? reinterpret_cast<float *>(p.sym) + d.blk * p.M + c : nullptr;
     default: return nullptr;

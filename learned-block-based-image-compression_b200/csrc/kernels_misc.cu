@@ -213,6 +213,42 @@ __global__ void gather5_kernel(const h16 *__restrict__ g_hi, const h16 *__restri
     }
 }
 
+// Post-processing net (NET:462-463: nn.Conv2d(C1, 4 C1, 3, padding=0), no mask): out[r, tap*Cin + c] = z(v+dv, h+dh)[c]
+// for all nine taps (dv, dh) in raster order of the kernel, zero outside the image (only interior blocks keep the
+// result, NET:476 pads the residual back with zeros).
+__global__ void gather9_kernel(const float *__restrict__ z_cl, int Cin, StepDesc s, int R, h16 *__restrict__ o_hi,
+                               h16 *__restrict__ o_lo, int ld) {
+    const int r = blockIdx.x;
+    if (r >= R) return;
+    int img, v, h;
+    step_row_to_block(s, r, img, v, h);
+    const int c4n = Cin >> 2;
+    for (int e = threadIdx.x; e < 9 * c4n; e += blockDim.x) {
+        const int tap = e / c4n, c = (e - tap * c4n) << 2;
+        const int vv = v + tap / 3 - 1, hh = h + tap % 3 - 1;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vv >= 0 && vv < s.Hb && hh >= 0 && hh < s.Wb)
+            val = *reinterpret_cast<const float4 *>(z_cl + (((size_t)img * s.Hb + vv) * s.Wb + hh) * Cin + c);
+        const float f[4] = {val.x, val.y, val.z, val.w};
+        store_hilo<4>(o_hi + (size_t)r * ld + (size_t)tap * Cin + c, o_lo + (size_t)r * ld + (size_t)tap * Cin + c, f);
+    }
+}
+
+// blocks on the image border: the zero-padded residual leaves them unchanged (NET:476)
+__global__ void restore_border_kernel(const float *__restrict__ z_cl, float *__restrict__ out_cl, int Cin, int n_img, int Hb,
+                                      int Wb) {
+    const int per = 2 * Wb + 2 * (Hb > 2 ? Hb - 2 : 0);        // border blocks of one image (Hb, Wb >= 1)
+    const int b = blockIdx.x;
+    const int img = b / per, q = b - img * per;
+    int v, h;
+    if (q < Wb) { v = 0; h = q; }
+    else if (q < 2 * Wb) { v = Hb - 1; h = q - Wb; }
+    else { const int k = q - 2 * Wb; v = 1 + (k >> 1); h = (k & 1) ? Wb - 1 : 0; }
+    if (v >= Hb) return;
+    const size_t o = (((size_t)img * Hb + v) * Wb + h) * Cin;
+    for (int c = threadIdx.x; c < Cin; c += blockDim.x) out_cl[o + c] = z_cl[o + c];
+}
+
 // KS[1] == 3: row v = -1 of the hidden map sees only zero padding, so g0(-1, h) = lrelu(0 + b_e0) for every h --
 // bit-identical to what the E0 GEMM epilogue produces from an all-zero accumulator.
 __global__ void fill_g0_top_kernel(const float *__restrict__ bias, int E1, int n_img, int Hb, int Wb,
@@ -233,7 +269,7 @@ __global__ void fill_g0_top_kernel(const float *__restrict__ bias, int E1, int n
 // ---- weight packing -------------------------------------------------------------------------------
 struct TapList {
     int n;
-    int kh[8], kw[8];
+    int kh[9], kw[9];      // up to a full 3x3 kernel (post-processing net); the masked convs use 1, 4 or 5
 };
 
 // weff[co][t*cin + ci] = w[co][ci][kh_t][kw_t] * mask[co][ci][kh_t][kw_t]      (NET:381 weight * mask)
@@ -394,6 +430,22 @@ int launch_gather5(const h16 *g0_hi, const h16 *g0_lo, int E1, const StepDesc &s
     return 0;
 }
 
+int launch_gather9(const float *z_cl, int Cin, const StepDesc &s, int R, h16 *out_hi, h16 *out_lo, int ld, cudaStream_t st) {
+    if (R <= 0) return 0;
+    gather9_kernel<<<R, 256, 0, st>>>(z_cl, Cin, s, R, out_hi, out_lo, ld);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_restore_border(const float *z_cl, float *out_cl, int Cin, int n_img, int Hb, int Wb, cudaStream_t st) {
+    const int per = 2 * Wb + 2 * (Hb > 2 ? Hb - 2 : 0);
+    restore_border_kernel<<<n_img * per, 128, 0, st>>>(z_cl, out_cl, Cin, n_img, Hb, Wb);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_fill_g0_top(const float *bias, int E1, int n_img, int Hb, int Wb, h16 *g_hi, h16 *g_lo, cudaStream_t st) {
     fill_g0_top_kernel<<<n_img * (Wb + 2), 256, 0, st>>>(bias, E1, n_img, Hb, Wb, g_hi, g_lo);
     count_launch(1);
@@ -403,6 +455,7 @@ int launch_fill_g0_top(const float *bias, int E1, int n_img, int Hb, int Wb, h16
 
 int launch_pack_conv(const float *w, const float *mask, int cout, int cin, int kh, int kw, const int *taps_host,
                      int ntaps, float *weff, int ld, cudaStream_t st) {
+    if (ntaps < 1 || ntaps > 9) return lbic_fail(LBIC_ERR_INVALID, "pack_conv: %d taps", ntaps);
     TapList tl;
     tl.n = ntaps;
     for (int i = 0; i < ntaps; ++i) {

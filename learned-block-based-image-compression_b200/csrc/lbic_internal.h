@@ -74,7 +74,8 @@ enum EpiMode {
     EPI_KSI = 4,     // acc+b                                 -> f32 (scales | means, NET:369)
     EPI_QUANT = 5,   // y=acc+b; sym=rint(y-mean); idx; yq    -> hi/lo, sym, idx (NET:371-374)
     EPI_RECON = 6,   // clamp(acc+b, -.5, .5)                 -> zhat (NET:357)
-    EPI_RAW = 7      // acc                                   -> f32 (debug gemm)
+    EPI_RAW = 7,     // acc                                   -> f32 (debug gemm)
+    EPI_RESID = 8    // aux + acc + b (optionally clamped)     -> f32 (post-processing net, NET:475-476)
 };
 
 struct EpiParams {
@@ -214,6 +215,10 @@ int launch_pack_gdn(const float *gamma, const float *beta, int C, float gbound, 
 int launch_absmax(const float *v, int64_t n, float *out_dev, cudaStream_t st);   // *out_dev = max(*out_dev, max|v|)
 int launch_split_scaled(const float *src, h16 *hi, h16 *lo, int64_t n, float scale, cudaStream_t st);
 // KS[1]==3: A operand of get_meanscale[2] = the five mask-'B' taps of g0 around each block of the step
+// post-processing net (NET:455-476): A operand of its 3x3 conv = all nine taps of the reconstruction around each block
+// of a raster chunk, zero outside the image; and the final fix-up: blocks on the image border keep their input
+int launch_gather9(const float *z_cl, int Cin, const StepDesc &s, int R, h16 *out_hi, h16 *out_lo, int ld, cudaStream_t st);
+int launch_restore_border(const float *z_cl, float *out_cl, int Cin, int n_img, int Hb, int Wb, cudaStream_t st);
 int launch_gather5(const h16 *g0_hi, const h16 *g0_lo, int E1, const StepDesc &s, int R, h16 *out_hi, h16 *out_lo,
                    int ld, cudaStream_t st);
 int launch_fill_g0_top(const float *bias, int E1, int n_img, int Hb, int Wb, h16 *g_hi, h16 *g_lo, cudaStream_t st);
@@ -270,6 +275,11 @@ int launch_selfinfo_step(const StepDesc &s, int R, int M, const float *ksi, int 
                          cudaStream_t st);
 int launch_rans_decode_full(const Tables &T, const uint8_t *streams, const uint32_t *stream_len, size_t stream_stride,
                             const uint8_t *idx, int n_streams, int64_t n_sym, int32_t *sym_out, cudaStream_t st);
+
+// image metrics (metrics.cu)
+size_t metrics_scratch_bytes(int n, int C, int H, int W);
+int launch_image_metrics(const float *x, const float *y, int n, int C, int H, int W, float offset, float range, void *scratch,
+                         double *mse_out, double *msssim_out, cudaStream_t st);
 
 // launch bookkeeping
 void count_launch(int family);   // 0 = gemm, 1 = other

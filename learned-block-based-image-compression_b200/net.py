@@ -407,6 +407,23 @@ class BlockBasedImgCompLossyNetv9:
         self._check_call(LRU, chlat)
         return self.decompress_batch([bitstream], xshape, lanes=1, device=devc)
 
+    # ---- quality figures of eval_model, on the GPU (AGENT:611-619) -------------------------------------------------
+    def image_metrics(self, x, y, msssim: bool = True, offset: float = 0.5, data_range: float = 1.0):
+        """x, y: (n, C, H, W) CUDA fp32 images (eval_model passes the [-0.5, 0.5] original and reconstruction).
+        -> dict(mse=[n], psnr=[n], msssim=[n] or None): mse = F.mse_loss per image, psnr = -10 log10(mse),
+        msssim = pytorch_msssim.ms_ssim(x + offset, y + offset, data_range) per image."""
+        if not (x.is_cuda and y.is_cuda and x.shape == y.shape and x.dim() == 4 and x.dtype == torch.float32 == y.dtype):
+            raise ValueError("x and y must be CUDA fp32 tensors of the same (n, C, H, W) shape")
+        x, y = x.contiguous(), y.contiguous()
+        n, C, H, W = x.shape
+        mse = np.zeros(n, dtype=np.float64)
+        ms = np.zeros(n, dtype=np.float64) if msssim else None
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().lbic_image_metrics(self._need(), x.data_ptr(), y.data_ptr(), n, C, H, W, float(offset),
+                                                     float(data_range), mse.ctypes.data, ms.ctypes.data if msssim else None,
+                                                     self._stream()))
+        return dict(mse=mse, psnr=-10.0 * np.log10(mse), msssim=ms)
+
     # ---- instrumentation ----------------------------------------------------------------------------
     def launch_count(self) -> int:
         return int(_lib.lib().lbic_launch_count(self._need()))
@@ -440,3 +457,66 @@ class BlockBasedImgCompLossyNetv9:
             _lib.check(_lib.lib().lbic_debug_gemm(self._need(), A.data_ptr(), W.data_ptr(), D.data_ptr(), A.shape[0],
                                                   A.shape[1], W.shape[0], self._stream()))
         return D
+
+
+class BlkBasedPostProcessing:
+    """Mirror of the reference's optional post-processing module (graphs/models/BlockBasedImgCompLossy_net.py:455-476,
+    `use_postpm`): `out = x + pad(conv1x1(lrelu(conv3x3_valid(x))))` on the (n, 3B^2, Hb, Wb) block tensor of a
+    reconstruction, as eval_model applies it (AGENT:604-606).  Runs in liblbic_b200 on the device of the codec model it
+    is bound to (it shares that model's workspace); `state_dict` keys are the reference module's: res_net.0.weight
+    (4C, C, 3, 3), res_net.0.bias, res_net.2.weight (C, 4C, 1, 1), res_net.2.bias with C = 3B^2."""
+
+    KEYS = ("res_net.0.weight", "res_net.0.bias", "res_net.2.weight", "res_net.2.bias")
+
+    def __init__(self, model: BlockBasedImgCompLossyNetv9):
+        self.model = model
+        self._sd = None
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        return self
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        missing = [k for k in self.KEYS if k not in state_dict]
+        if missing:
+            raise RuntimeError(f"Missing key(s) in state_dict: {missing}")
+        C = self.model.Cin
+        want = {"res_net.0.weight": (4 * C, C, 3, 3), "res_net.0.bias": (4 * C,), "res_net.2.weight": (C, 4 * C, 1, 1),
+                "res_net.2.bias": (C,)}
+        keep, descs = [], []
+        for k in self.KEYS:
+            t = state_dict[k].detach().to(torch.float32).contiguous()
+            if tuple(t.shape) != want[k]:
+                raise RuntimeError(f"size mismatch for {k}: {tuple(t.shape)} vs {want[k]}")
+            keep.append(t)
+            d = _lib.LbicTensorDesc()
+            d.name, d.data, d.ndim = k.encode(), t.data_ptr(), t.dim()
+            for i, n in enumerate(t.shape):
+                d.shape[i] = n
+            descs.append(d)
+        arr = (_lib.LbicTensorDesc * len(descs))(*descs)
+        m = self.model
+        with torch.cuda.device(m._device):
+            _lib.check(_lib.lib().lbic_load_postpm_weights(m._need(), arr, len(descs), m._stream()))
+        self._sd = OrderedDict((k, state_dict[k].detach().clone()) for k in self.KEYS)
+        return SimpleNamespace(missing_keys=[], unexpected_keys=[])
+
+    def state_dict(self):
+        return OrderedDict(self._sd or {})
+
+    def forward(self, x, clamp: bool = False):
+        """x: (n, 3B^2, Hb, Wb) CUDA fp32 -> same shape; clamp=True folds in the caller's clamp_(-0.5, 0.5) (AGENT:606)."""
+        m = self.model
+        if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == m.Cin):
+            raise ValueError(f"x must be a CUDA fp32 tensor of shape (n, {m.Cin}, Hb, Wb)")
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        n, _, Hb, Wb = x.shape
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().lbic_postprocess(m._need(), x.data_ptr(), n, Hb, Wb, out.data_ptr(), 1 if clamp else 0,
+                                                   m._stream()))
+        return out
+
+    __call__ = forward

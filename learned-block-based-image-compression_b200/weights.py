@@ -141,6 +141,20 @@ def synth_state_dict(cfg, seed: int = 1337, conditioned: bool = True, harsh: boo
     return sd
 
 
+def synth_postpm_state_dict(cfg, seed: int = 4321, gain: float = 8.0):
+    """Deterministic weights for the optional post-processing module (BlkBasedPostProcessing, NET:455-476), with the
+    reference module's key set: res_net.0 = Conv2d(C, 4C, 3), res_net.2 = Conv2d(4C, C, 1), C = 3B^2.  PyTorch's default
+    Conv2d scale, the last layer times `gain` so that the residual is visible (default init gives ~1e-3)."""
+    C = 3 * int(cfg.block_size) ** 2
+    sd = OrderedDict()
+    for name, cout, cin, k, g_ in (("res_net.0", 4 * C, C, 3, 1.0), ("res_net.2", C, 4 * C, 1, gain)):
+        bound = 1.0 / math.sqrt(cin * k * k)
+        g = _gen(seed, "postpm." + name)
+        sd[name + ".weight"] = (torch.rand(cout, cin, k, k, generator=g) * 2 - 1) * bound * g_
+        sd[name + ".bias"] = (torch.rand(cout, generator=g) * 2 - 1) * bound
+    return sd
+
+
 def synth_images(n: int, H: int, W: int, seed0: int = 1000, kind: str = "smooth") -> torch.Tensor:
     """Synthetic test images in [0,1], (n,3,H,W) fp32: low-resolution
     noise bicubic-upsampled plus 0.05*randn ("smooth"), or white noise ("noise").  Image i uses

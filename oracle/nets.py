@@ -348,3 +348,16 @@ def arrange_channel_dim_to_block_pixels(y, B):
             i = (v * B + h) * C
             x[:, :, v::B, h::B] = y[:, i:i + C]
     return x
+
+
+# ----------------------------------------------------------------------------------------------
+# optional post-processing module (NET:455-476, applied by eval_model at AGENT:604-606)
+# ----------------------------------------------------------------------------------------------
+@torch.no_grad()
+def postprocess(sd, x, clamp=False):
+    """BlkBasedPostProcessing.forward: x + F.pad(conv1x1(leaky_relu(conv3x3(x, padding=0))), (1, 1, 1, 1)).
+    sd: the module's state_dict (res_net.0.weight/bias, res_net.2.weight/bias); x: (n, 3B^2, Hb, Wb)."""
+    res = F.conv2d(F.leaky_relu(F.conv2d(x, sd["res_net.0.weight"], sd["res_net.0.bias"])),
+                   sd["res_net.2.weight"], sd["res_net.2.bias"])
+    out = x + F.pad(res, (1, 1, 1, 1), "constant", 0) if min(x.shape[2], x.shape[3]) >= 3 else x.clone()
+    return out.clamp(-0.5, 0.5) if clamp else out
