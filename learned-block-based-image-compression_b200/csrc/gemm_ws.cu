@@ -638,7 +638,9 @@ int gemm_flow_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int
     // the occupancy query of gemm_flow_supported() alone cannot see what else is running.  A refused launch is
     // reported as LBIC_FLOW_REFUSED and the caller runs one launch per layer instead.
     // (no programmatic dependent launch here: the counters are zeroed by a memset node right before the kernel)
-    static int use_coop = 1;   // 0 after a driver that rejects cooperative + cluster launches outright
+    static int use_coop = -1;  // 0 after a driver that rejects cooperative + cluster launches outright; LBIC_FLOW_COOP=0 turns
+                               // the attribute off (Nsight Compute cannot replay a cooperative cluster launch)
+    if (use_coop < 0) { const char *e = getenv("LBIC_FLOW_COOP"); use_coop = (e && atoi(e) == 0) ? 0 : 1; }
     for (int attempt = 0; attempt < 2; ++attempt) {
         int n_attr = na;
         if (use_coop) {
