@@ -975,6 +975,9 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
     case LBIC_OPT_ENC_THREAD_STREAMS:
         rans_set_enc_thread_min_streams(value);
         return 0;
+    case LBIC_OPT_DEC_SMEM_WARP:
+        rans_set_dec_smem_warp(value);
+        return 0;
     case LBIC_OPT_ENC_BLOCK_STREAMS:
         rans_set_enc_block_max_streams(value);
         return 0;

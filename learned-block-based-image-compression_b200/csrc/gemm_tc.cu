@@ -87,33 +87,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-                mbar_wait(empty_bar(s), ph ^ 1u);
+        // all 32 lanes walk the loop, one elected lane issues (tc_common.cuh: elect_one)
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % p.stages;
+            const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            const uint32_t sa = ring + s * stage_bytes;
+            const bool seg1 = kb >= p.kb[0];
+            const int kk = (seg1 ? kb - p.kb[0] : kb) * BK;
+            if (elect_one()) {
                 mbar_expect_tx(full_bar(s), stage_bytes);
-                const uint32_t sa = ring + s * stage_bytes;
-                const bool seg1 = kb >= p.kb[0];
-                const int kk = (seg1 ? kb - p.kb[0] : kb) * BK;
                 tma_load_2d(sa, seg1 ? &tmA1h : &tmA0h, full_bar(s), kk, m0);
                 tma_load_2d(sa + A_PLANE, seg1 ? &tmA1l : &tmA0l, full_bar(s), kk, m0);
                 tma_load_2d(sa + 2 * A_PLANE, seg1 ? &tmW1h : &tmW0h, full_bar(s), kk, n0);
                 tma_load_2d(sa + 2 * A_PLANE + w_plane, seg1 ? &tmW1l : &tmW0l, full_bar(s), kk, n0);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-                mbar_wait(full_bar(s), ph);
-                tc_fence_after();
-                const uint32_t sa = ring + s * stage_bytes;
-                const uint64_t a_hi = make_smem_desc(sa);
-                const uint64_t a_lo = make_smem_desc(sa + A_PLANE);
-                const uint64_t w_hi = make_smem_desc(sa + 2 * A_PLANE);
-                const uint64_t w_lo = make_smem_desc(sa + 2 * A_PLANE + w_plane);
+        // all 32 lanes walk the loop, one elected lane issues (tc_common.cuh: elect_one)
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % p.stages;
+            const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t sa = ring + s * stage_bytes;
+            const uint64_t a_hi = make_smem_desc(sa);
+            const uint64_t a_lo = make_smem_desc(sa + A_PLANE);
+            const uint64_t w_hi = make_smem_desc(sa + 2 * A_PLANE);
+            const uint64_t w_lo = make_smem_desc(sa + 2 * A_PLANE + w_plane);
+            if (elect_one()) {
                 // each k16 step advances the start address by 32 B (= 2 in 16-B units)
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k)
@@ -123,8 +126,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, p.idesc, 1u);
                 umma_commit(empty_bar(s));   // frees the stage once these MMAs have read it
+                if (kb == nkb - 1) umma_commit(tmem_full_bar);      // accumulator complete
             }
-            umma_commit(tmem_full_bar);      // accumulator complete
+            __syncwarp();
         }
     }
     __syncwarp();

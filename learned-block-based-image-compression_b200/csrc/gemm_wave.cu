@@ -268,91 +268,14 @@ __device__ __noinline__ void wave_gemm_epilogue(const EpiParams *ep, int bn, int
 }
 
 // ---- RANS tile: 8 rows of a row block, one warp per row: build_indexes, decode M symbols from the row's stream,
-// dequantise -> y_qnt planes.  The symbol chain is serial, so nothing on it may touch global memory: the CDF rows are
-// the entropy CTA's shared-memory copy (16-bit, the final 65536 implicit), a symbol's start / frequency come out of the
-// same 32-wide window load that finds it (shuffles), and the next 64 words of the stream sit in registers.
-// Same symbols as dec_symbol_warp / dec_symbol_thread (rans_device.cuh, rans.cu): first k with cdf[k] > slot, minus 1.
+// dequantise -> y_qnt planes.  The symbol chain is serial and sits on the critical path of every decode step, so it
+// runs the lean shared-memory decoder of rans_device.cuh on the entropy CTA's copy of the compact CDF rows.
 struct WaveEntTables {
-    const uint16_t *cdf16;     // shared memory
-    const int *off16, *len, *offs;
+    uint32_t cdf16, meta, scratch;     // shared addresses: 16-bit rows | int[3][64] | 8 warps x RANS_ROW_SCRATCH(M)
 };
-
-struct DecCursorW {
-    unsigned long long x;
-    const uint32_t *words;
-    uint32_t pos, nwords, base, w0, w1;    // lane i holds words base + i and base + 32 + i
-};
-__device__ __forceinline__ void dec_fill_w(DecCursorW &d, int lane) {
-    d.base = d.pos;
-    d.w0 = d.base + lane < d.nwords ? __ldg(d.words + d.base + lane) : 0u;
-    d.w1 = d.base + 32 + lane < d.nwords ? __ldg(d.words + d.base + 32 + lane) : 0u;
-}
-__device__ __forceinline__ uint32_t dec_word_w(DecCursorW &d, int lane) {
-    if (d.pos - d.base >= 64) dec_fill_w(d, lane);                 // warp-uniform
-    const uint32_t rel = d.pos - d.base;
-    const uint32_t v0 = __shfl_sync(0xffffffffu, d.w0, rel & 31), v1 = __shfl_sync(0xffffffffu, d.w1, rel & 31);
-    d.pos++;
-    return rel < 32 ? v0 : v1;                                      // past the end of the stream: zeros (a corrupt stream stays finite)
-}
-__device__ __forceinline__ int dec_bits_w(DecCursorW &d, int lane) {
-    const int val = (int)(d.x & MAX_BYPASS);
-    d.x >>= BYPASS;
-    if (d.x < RANS_L) d.x = (d.x << 32) | dec_word_w(d, lane);
-    return val;
-}
-__device__ __forceinline__ int dec_symbol_w(DecCursorW &d, const uint16_t *row, int len, int off, int lane) {
-    const uint32_t cf = (uint32_t)(d.x & 0xFFFFu);
-    const int max_value = len - 2;
-    int g = -off - 15;                         // 32-wide window around the distribution centre
-    g = g < 0 ? 0 : g;
-    g = g > len - 32 ? (len - 32 < 0 ? 0 : len - 32) : g;
-    const int k = g + lane;
-    const uint32_t val = k < len - 1 ? (uint32_t)row[k] : 65536u;
-    const bool gt = (k < len) && (val > cf);
-    const unsigned ball = __ballot_sync(0xffffffffu, gt);
-    int sidx;
-    uint32_t start, next;
-    if ((ball & 1u) == 0 && ball != 0) {
-        const int j = __ffs(ball) - 1;
-        sidx = g + j - 1;
-        start = __shfl_sync(0xffffffffu, val, j - 1);
-        next = __shfl_sync(0xffffffffu, val, j);
-    } else {
-        int lo = 0, hi = len - 1;              // entry len-1 (= 65536) always exceeds the slot
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if ((uint32_t)row[mid] > cf) hi = mid; else lo = mid + 1;
-        }
-        sidx = lo - 1;
-        start = row[sidx];
-        next = sidx + 1 < len - 1 ? (uint32_t)row[sidx + 1] : 65536u;
-    }
-    d.x = (unsigned long long)(next - start) * (d.x >> PREC) + cf - start;
-    if (d.x < RANS_L) d.x = (d.x << 32) | dec_word_w(d, lane);
-    int value = sidx;
-    if (value == max_value) {
-        int v = dec_bits_w(d, lane);
-        int nb = v;
-        while (v == MAX_BYPASS) {
-            v = dec_bits_w(d, lane);
-            nb += v;
-        }
-        int raw = 0;
-        for (int j = 0; j < nb; ++j) {
-            v = dec_bits_w(d, lane);
-            raw |= v << (j * BYPASS);
-        }
-        value = raw >> 1;
-        if (raw & 1) value = -value - 1; else value += max_value;
-    }
-    return value + off;
-}
 
 __device__ __noinline__ void wave_rans_tile(const WaveParams &p, const WaveTile w, const WaveEntTables tb, const float *stab,
                                             int ew, int lane) {
-    // (small structs by value: a reference would leave them in the caller's local memory, one L2 round trip per use)
-    const uint16_t *const t_cdf16 = tb.cdf16;
-    const int *const t_off16 = tb.off16, *const t_len = tb.len, *const t_offs = tb.offs;
     const int r = w.rb * BM + w.nt * 8 + ew;
     if (r >= w.R) return;
     int img, v, h;
@@ -368,45 +291,22 @@ __device__ __noinline__ void wave_rans_tile(const WaveParams &p, const WaveTile 
     dec_fill_w(d, lane);
     const float *krow = p.ksi + (size_t)r * p.ld_ksi;
     const int M = p.M;
-    const int per = (M + 31) >> 5;   // M <= 256
-    int my_idx[8], my_sym[8];
-    float my_mu[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = j * 32 + lane;
-        const bool in = j < per && c < M;
-        my_idx[j] = in ? scale_to_index(__ldcg(krow + c), stab) : 0;
-        my_mu[j] = in ? __ldcg(krow + M + c) : 0.0f;
-        my_sym[j] = 0;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        if (j < per) {
-#pragma unroll 1
-            for (int cc = 0; cc < 32 && j * 32 + cc < M; ++cc) {
-                const int ci = __shfl_sync(0xffffffffu, my_idx[j], cc);
-                const int sym = dec_symbol_w(d, t_cdf16 + t_off16[ci], t_len[ci], t_offs[ci], lane);
-                if (lane == cc) my_sym[j] = sym;
-            }
-        }
-    }
+    const uint32_t scr = tb.scratch + (uint32_t)ew * RANS_ROW_SCRATCH(M);
+    rans_decode_row_warp(d, tb.cdf16, tb.meta, scr, krow, stab, M, lane);
     if (lane == 0) {
         uint4 raw;
         raw.x = (uint32_t)d.x; raw.y = (uint32_t)(d.x >> 32); raw.z = d.pos; raw.w = d.nwords;
         __stcg(reinterpret_cast<uint4 *>(p.states + sidx), raw);
     }
     const size_t o = (((size_t)img * w.sd.Hb + v) * w.sd.Wb + h) * M;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = j * 32 + lane;
-        if (j < per && c < M) {
-            const float yq = (float)my_sym[j] + my_mu[j];
-            h16 hi, lo;
-            split_h16(yq, hi, lo);
-            p.yq_hi[(size_t)r * p.ld_yq + c] = hi;
-            p.yq_lo[(size_t)r * p.ld_yq + c] = lo;
-            if (p.sym_out) p.sym_out[o + c] = my_sym[j];
-        }
+    for (int c = lane; c < M; c += 32) {
+        const int sym = lds_s32(scr + 8u * M + 4u * c);
+        const float yq = (float)sym + __ldcg(krow + M + c);
+        h16 hi, lo;
+        split_h16(yq, hi, lo);
+        p.yq_hi[(size_t)r * p.ld_yq + c] = hi;
+        p.yq_lo[(size_t)r * p.ld_yq + c] = lo;
+        if (p.sym_out) p.sym_out[o + c] = sym;
     }
 }
 
@@ -434,22 +334,22 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int stages = p.stages;
     WaveEntTables tb;
-    tb.cdf16 = nullptr; tb.off16 = nullptr; tb.len = nullptr; tb.offs = nullptr;
+    tb.cdf16 = 0; tb.meta = 0; tb.scratch = 0;
     if (p.n_ent > 0 && (int)blockIdx.x >= (int)gridDim.x - p.n_ent) {
-        // entropy CTA: compact CDF rows + per-level offsets / lengths / symbol offsets into the (unused) operand ring
+        // entropy CTA: compact CDF rows | row offsets, lengths, symbol offsets | per-warp scratch, in the (unused) operand ring
         uint8_t *base = smem_raw + (ring - raw);
         uint4 *dst = reinterpret_cast<uint4 *>(base);
         const int nvec = (p.cdf16_total + 7) >> 3;
         for (int i = threadIdx.x; i < nvec; i += WAVE_THREADS) dst[i] = reinterpret_cast<const uint4 *>(p.cdf16)[i];
-        int *s_off = reinterpret_cast<int *>(dst + nvec);
-        int *s_len = s_off + 64, *s_offs = s_len + 64;
+        int *s_meta = reinterpret_cast<int *>(dst + nvec);
         if (threadIdx.x < 64) {
-            s_off[threadIdx.x] = p.cdf16_off[threadIdx.x];
-            s_len[threadIdx.x] = p.cdf_len[threadIdx.x];
-            s_offs[threadIdx.x] = p.offs[threadIdx.x];
+            s_meta[threadIdx.x] = p.cdf16_off[threadIdx.x];
+            s_meta[64 + threadIdx.x] = p.cdf_len[threadIdx.x];
+            s_meta[128 + threadIdx.x] = p.offs[threadIdx.x];
         }
-        tb.cdf16 = reinterpret_cast<const uint16_t *>(base);
-        tb.off16 = s_off; tb.len = s_len; tb.offs = s_offs;
+        tb.cdf16 = ring;
+        tb.meta = ring + 16u * (uint32_t)nvec;
+        tb.scratch = tb.meta + 768u;
     }
     // slot layout: activation hi | activation lo (a_plane_bytes each) | weight hi | weight lo
     const uint32_t off_alo = p.a_plane_bytes, off_w = 2 * p.a_plane_bytes;
@@ -477,8 +377,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
-        // ---- TMA producer -------------------------------------------------------------------------------
-        if (lane == 0) {
+        // ---- TMA producer: all 32 lanes walk the loop, one elected lane issues (tc_common.cuh: elect_one) ----
+        {
             uint32_t it = 0;
             wave_for_each_tile(p, [&](const WaveTile &w, const int *gen) {
                 const WaveOrd &o = p.ord[w.oi];
@@ -490,14 +390,17 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                 const int cls = lbic_box_class(rows);          // only the rows the step has are loaded
                 const int nseg = Lr.nseg > 1 ? 2 : 1;
                 // descriptors of this tile's operands into the descriptor cache while the inputs are still being produced
-                for (int sg = 0; sg < nseg; ++sg)
-                    for (int pl = 0; pl < 2; ++pl) {
-                        const CUtensorMap *ta = cls < 4 ? &Lr.tmAs[cls][sg][pl] : &Lr.tmA[sg][pl];
-                        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(ta)) : "memory");
-                        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&Lr.tmW[p.variant][sg][pl])) : "memory");
-                    }
-                wave_wait_deps(p, w, gen);
-                WAVE_TRACE(0);
+                if (lane == 0) {
+                    for (int sg = 0; sg < nseg; ++sg)
+                        for (int pl = 0; pl < 2; ++pl) {
+                            const CUtensorMap *ta = cls < 4 ? &Lr.tmAs[cls][sg][pl] : &Lr.tmA[sg][pl];
+                            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(ta)) : "memory");
+                            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&Lr.tmW[p.variant][sg][pl])) : "memory");
+                        }
+                    wave_wait_deps(p, w, gen);
+                    WAVE_TRACE(0);
+                }
+                __syncwarp();
                 asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores of other CTAs -> our TMA reads
                 const int kb0 = Lr.kb[0], nkb = kb0 + (Lr.nseg > 1 ? Lr.kb[1] : 0);
                 const uint32_t w_plane = (uint32_t)bn * (BK * 2);
@@ -509,18 +412,21 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                     const uint32_t sa = ring + s * p.slot_bytes;
                     const int seg = kb >= kb0 ? 1 : 0;
                     const int kk = (seg ? kb - kb0 : kb) * BK;
-                    mbar_expect_tx(full_bar(s), stage_tx);
-                    tma_load_2d(sa, cls < 4 ? &Lr.tmAs[cls][seg][0] : &Lr.tmA[seg][0], full_bar(s), kk, m0);
-                    tma_load_2d(sa + off_alo, cls < 4 ? &Lr.tmAs[cls][seg][1] : &Lr.tmA[seg][1], full_bar(s), kk, m0);
-                    tma_load_2d(sa + off_w, &Lr.tmW[p.variant][seg][0], full_bar(s), kk, n0);
-                    tma_load_2d(sa + off_w + w_plane, &Lr.tmW[p.variant][seg][1], full_bar(s), kk, n0);
+                    if (elect_one()) {
+                        mbar_expect_tx(full_bar(s), stage_tx);
+                        tma_load_2d(sa, cls < 4 ? &Lr.tmAs[cls][seg][0] : &Lr.tmA[seg][0], full_bar(s), kk, m0);
+                        tma_load_2d(sa + off_alo, cls < 4 ? &Lr.tmAs[cls][seg][1] : &Lr.tmA[seg][1], full_bar(s), kk, m0);
+                        tma_load_2d(sa + off_w, &Lr.tmW[p.variant][seg][0], full_bar(s), kk, n0);
+                        tma_load_2d(sa + off_w + w_plane, &Lr.tmW[p.variant][seg][1], full_bar(s), kk, n0);
+                    }
+                    __syncwarp();
                 }
-                WAVE_TRACE(1);
+                if (lane == 0) WAVE_TRACE(1);
             });
         }
     } else if (warp == 1) {
         // ---- tcgen05.mma issuer ---------------------------------------------------------------------------
-        if (lane == 0) {
+        {   // all 32 lanes walk the loop, one elected lane issues (tc_common.cuh: elect_one)
             uint32_t it = 0, gi = 0;
             wave_for_each_tile(p, [&](const WaveTile &w, const int *) {
                 const WaveOrd &o = p.ord[w.oi];
@@ -539,22 +445,25 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                     const uint32_t ph = (it / stages) & 1u;
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
-                    if (kb == 0) WAVE_TRACE(2);
+                    if (kb == 0 && lane == 0) WAVE_TRACE(2);
                     const uint32_t sa = ring + s * p.slot_bytes;
                     const uint64_t a_hi = make_smem_desc(sa);
                     const uint64_t a_lo = make_smem_desc(sa + off_alo);
                     const uint64_t w_hi = make_smem_desc(sa + off_w);
                     const uint64_t w_lo = make_smem_desc(sa + off_w + w_plane);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
+                        for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
-                    umma_commit(empty_bar(s));
+                        for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
+                        umma_commit(empty_bar(s));
+                        if (kb == nkb - 1) umma_commit(acc_full(a));
+                    }
+                    __syncwarp();
                 }
-                umma_commit(acc_full(a));
-                WAVE_TRACE(3);
+                if (lane == 0) WAVE_TRACE(3);
                 ++gi;
             });
         }
@@ -754,7 +663,8 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
         p.rans_ord = last;
         p.n_ent = WAVE_ENT_CTAS;
         p.cdf16 = w.cdf16; p.cdf16_off = w.cdf16_off; p.cdf16_total = w.cdf16_total;
-        if (!w.cdf16 || w.cdf16_total <= 0 || (size_t)w.cdf16_total * 2 + 16 + 3 * 64 * 4 > (size_t)WAVE_RING)
+        if (!w.cdf16 || w.cdf16_total <= 0 ||
+            (size_t)w.cdf16_total * 2 + 16 + 3 * 64 * 4 + 8 * (size_t)RANS_ROW_SCRATCH(w.M) > (size_t)WAVE_RING)
             return lbic_fail(LBIC_ERR_INVALID, "wave kernel: entropy tables do not fit shared memory");
     }
     for (int i = 0; i < 7; ++i) last = gemm(D[i], last, -1);   // D0 IG0 D1 IG1 D2 IG2 D3: each reads the one before

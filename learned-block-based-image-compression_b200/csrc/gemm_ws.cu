@@ -96,7 +96,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // all 32 lanes walk the loop, one elected lane issues (tc_common.cuh: elect_one)
             uint32_t it = 0;
             for (int t = tile_first; t < p.total_tiles; t += tile_stride) {
                 const int m0 = (t / p.ntiles_n) * tile_rows + (int)rank * BM;
@@ -108,25 +108,28 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
                     const uint32_t sa = ring + s * p.slot_bytes;
                     const bool seg1 = kb >= p.kb[0];
                     const int kk = (seg1 ? kb - p.kb[0] : kb) * BK;
-                    if (PAIR) {
-                        if (rank == 0) mbar_expect_tx(full_bar(s), stage_tx);
-                        else mbar_arrive_remote(full_bar(s), 0);
-                        tma_load_2d_pair(sa, seg1 ? &tmA1h : &tmA0h, full_bar(s), kk, m0);
-                        tma_load_2d_pair(sa + A_PLANE, seg1 ? &tmA1l : &tmA0l, full_bar(s), kk, m0);
-                        tma_load_2d_pair(sa + 2 * A_PLANE, seg1 ? &tmW1h : &tmW0h, full_bar(s), kk, n0);
-                        tma_load_2d_pair(sa + 2 * A_PLANE + w_plane, seg1 ? &tmW1l : &tmW0l, full_bar(s), kk, n0);
-                    } else {
-                        mbar_expect_tx(full_bar(s), stage_tx);
-                        tma_load_2d(sa, seg1 ? &tmA1h : &tmA0h, full_bar(s), kk, m0);
-                        tma_load_2d(sa + A_PLANE, seg1 ? &tmA1l : &tmA0l, full_bar(s), kk, m0);
-                        tma_load_2d(sa + 2 * A_PLANE, seg1 ? &tmW1h : &tmW0h, full_bar(s), kk, n0);
-                        tma_load_2d(sa + 2 * A_PLANE + w_plane, seg1 ? &tmW1l : &tmW0l, full_bar(s), kk, n0);
+                    if (elect_one()) {
+                        if (PAIR) {
+                            if (rank == 0) mbar_expect_tx(full_bar(s), stage_tx);
+                            else mbar_arrive_remote(full_bar(s), 0);
+                            tma_load_2d_pair(sa, seg1 ? &tmA1h : &tmA0h, full_bar(s), kk, m0);
+                            tma_load_2d_pair(sa + A_PLANE, seg1 ? &tmA1l : &tmA0l, full_bar(s), kk, m0);
+                            tma_load_2d_pair(sa + 2 * A_PLANE, seg1 ? &tmW1h : &tmW0h, full_bar(s), kk, n0);
+                            tma_load_2d_pair(sa + 2 * A_PLANE + w_plane, seg1 ? &tmW1l : &tmW0l, full_bar(s), kk, n0);
+                        } else {
+                            mbar_expect_tx(full_bar(s), stage_tx);
+                            tma_load_2d(sa, seg1 ? &tmA1h : &tmA0h, full_bar(s), kk, m0);
+                            tma_load_2d(sa + A_PLANE, seg1 ? &tmA1l : &tmA0l, full_bar(s), kk, m0);
+                            tma_load_2d(sa + 2 * A_PLANE, seg1 ? &tmW1h : &tmW0h, full_bar(s), kk, n0);
+                            tma_load_2d(sa + 2 * A_PLANE + w_plane, seg1 ? &tmW1l : &tmW0l, full_bar(s), kk, n0);
+                        }
                     }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {       // all 32 lanes walk the loop, one elected lane issues (tc_common.cuh: elect_one)
             uint32_t it = 0, ti = 0;
             for (int t = tile_first; t < p.total_tiles; t += tile_stride, ++ti) {
                 const uint32_t a = ti & 1u;
@@ -147,15 +150,18 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
                         if (PAIR) umma_f16_pair(tmem_acc, ad, wd, p.idesc, acc);
                         else umma_f16(tmem_acc, ad, wd, p.idesc, acc);
                     };
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) mma(a_hi + 2 * k, w_hi + 2 * k, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; ++k) mma(a_hi + 2 * k, w_hi + 2 * k, (kb | k) != 0 ? 1u : 0u);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) mma(a_hi + 2 * k, w_lo + 2 * k, 1u);
+                        for (int k = 0; k < BK / 16; ++k) mma(a_hi + 2 * k, w_lo + 2 * k, 1u);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) mma(a_lo + 2 * k, w_hi + 2 * k, 1u);
-                    if (PAIR) umma_commit_pair(empty_bar(s)); else umma_commit(empty_bar(s));
+                        for (int k = 0; k < BK / 16; ++k) mma(a_lo + 2 * k, w_hi + 2 * k, 1u);
+                        if (PAIR) umma_commit_pair(empty_bar(s)); else umma_commit(empty_bar(s));
+                        if (kb == nkb - 1) { if (PAIR) umma_commit_pair(acc_full(a)); else umma_commit(acc_full(a)); }
+                    }
+                    __syncwarp();
                 }
-                if (PAIR) umma_commit_pair(acc_full(a)); else umma_commit(acc_full(a));
             }
         }
     } else {
@@ -287,7 +293,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowPa
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
-        if (lane == 0) {
+        {   // all 32 lanes walk the loop, one elected lane issues (tc_common.cuh: elect_one)
             uint32_t it = 0;
             for (int t = tile_first; t < p.total_tiles; t += tile_stride) {
                 int li, rb, nt;
@@ -302,11 +308,14 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowPa
                     if (dl < 0) continue;
                     const int *cnt = p.counters + (size_t)dl * p.n_rb + rb;
                     const int target = CTAS * p.ntn[dl];
-                    uint32_t spins = 0;
-                    while (ld_acquire_gpu(cnt) < target) {
-                        __nanosleep(64);
-                        if (++spins > (1u << 24)) __trap();     // a broken dependency must fail the launch, not hang
+                    if (lane == 0) {
+                        uint32_t spins = 0;
+                        while (ld_acquire_gpu(cnt) < target) {
+                            __nanosleep(64);
+                            if (++spins > (1u << 24)) __trap();     // a broken dependency must fail the launch, not hang
+                        }
                     }
+                    __syncwarp();
                 }
                 asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores of other CTAs -> our TMA reads
                 const int kb0 = Lr.kb[0], nkb = kb0 + (Lr.nseg > 1 ? Lr.kb[1] : 0);
@@ -319,25 +328,28 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowPa
                     const uint32_t sa = ring + s * FLOW_SLOT;
                     const int seg = kb >= kb0 ? 1 : 0;
                     const int kk = (seg ? kb - kb0 : kb) * BK;
-                    if (PAIR) {
-                        if (rank == 0) mbar_expect_tx(full_bar(s), stage_tx);
-                        else mbar_arrive_remote(full_bar(s), 0);
-                        tma_load_2d_pair(sa, &Lr.tmA[seg][0], full_bar(s), kk, m0);
-                        tma_load_2d_pair(sa + A_PLANE, &Lr.tmA[seg][1], full_bar(s), kk, m0);
-                        tma_load_2d_pair(sa + 2 * A_PLANE, &Lr.tmW[p.variant][seg][0], full_bar(s), kk, n0);
-                        tma_load_2d_pair(sa + 2 * A_PLANE + w_plane, &Lr.tmW[p.variant][seg][1], full_bar(s), kk, n0);
-                    } else {
-                        mbar_expect_tx(full_bar(s), stage_tx);
-                        tma_load_2d(sa, &Lr.tmA[seg][0], full_bar(s), kk, m0);
-                        tma_load_2d(sa + A_PLANE, &Lr.tmA[seg][1], full_bar(s), kk, m0);
-                        tma_load_2d(sa + 2 * A_PLANE, &Lr.tmW[p.variant][seg][0], full_bar(s), kk, n0);
-                        tma_load_2d(sa + 2 * A_PLANE + w_plane, &Lr.tmW[p.variant][seg][1], full_bar(s), kk, n0);
+                    if (elect_one()) {
+                        if (PAIR) {
+                            if (rank == 0) mbar_expect_tx(full_bar(s), stage_tx);
+                            else mbar_arrive_remote(full_bar(s), 0);
+                            tma_load_2d_pair(sa, &Lr.tmA[seg][0], full_bar(s), kk, m0);
+                            tma_load_2d_pair(sa + A_PLANE, &Lr.tmA[seg][1], full_bar(s), kk, m0);
+                            tma_load_2d_pair(sa + 2 * A_PLANE, &Lr.tmW[p.variant][seg][0], full_bar(s), kk, n0);
+                            tma_load_2d_pair(sa + 2 * A_PLANE + w_plane, &Lr.tmW[p.variant][seg][1], full_bar(s), kk, n0);
+                        } else {
+                            mbar_expect_tx(full_bar(s), stage_tx);
+                            tma_load_2d(sa, &Lr.tmA[seg][0], full_bar(s), kk, m0);
+                            tma_load_2d(sa + A_PLANE, &Lr.tmA[seg][1], full_bar(s), kk, m0);
+                            tma_load_2d(sa + 2 * A_PLANE, &Lr.tmW[p.variant][seg][0], full_bar(s), kk, n0);
+                            tma_load_2d(sa + 2 * A_PLANE + w_plane, &Lr.tmW[p.variant][seg][1], full_bar(s), kk, n0);
+                        }
                     }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {       // all 32 lanes walk the loop, one elected lane issues (tc_common.cuh: elect_one)
             uint32_t it = 0, ti = 0;
             for (int t = tile_first; t < p.total_tiles; t += tile_stride, ++ti) {
                 int li, rb, nt;
@@ -365,15 +377,18 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowPa
                         if (PAIR) umma_f16_pair(tmem_acc, ad, wd, idesc, acc);
                         else umma_f16(tmem_acc, ad, wd, idesc, acc);
                     };
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) mma(a_hi + 2 * k, w_hi + 2 * k, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; ++k) mma(a_hi + 2 * k, w_hi + 2 * k, (kb | k) != 0 ? 1u : 0u);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) mma(a_hi + 2 * k, w_lo + 2 * k, 1u);
+                        for (int k = 0; k < BK / 16; ++k) mma(a_hi + 2 * k, w_lo + 2 * k, 1u);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) mma(a_lo + 2 * k, w_hi + 2 * k, 1u);
-                    if (PAIR) umma_commit_pair(empty_bar(s)); else umma_commit(empty_bar(s));
+                        for (int k = 0; k < BK / 16; ++k) mma(a_lo + 2 * k, w_hi + 2 * k, 1u);
+                        if (PAIR) umma_commit_pair(empty_bar(s)); else umma_commit(empty_bar(s));
+                        if (kb == nkb - 1) { if (PAIR) umma_commit_pair(acc_full(a)); else umma_commit(acc_full(a)); }
+                    }
+                    __syncwarp();
                 }
-                if (PAIR) umma_commit_pair(acc_full(a)); else umma_commit(acc_full(a));
             }
         }
     } else if (warp == 10) {

@@ -53,6 +53,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm,
         : "memory");
 }
 
+// One lane of a CONVERGED warp.  The single-thread instructions (tcgen05.mma, tcgen05.commit) are issued under this
+// predicate by a warp whose 32 lanes all walk the role loop: control flow and operands are then warp-uniform, ptxas keeps
+// the descriptors in uniform registers and emits the UTCHMMAs of a k-block back to back.  Under `if (lane == 0)` (a
+// divergent region) it wraps EVERY UTCHMMA in an ELECT / R2UR / BRA.U.ANY sequence that costs ~150 cycles per MMA --
+// more than a 256 x 192 x 16 MMA takes (96) -- scripts/mma_chain_bench.cu, profiles/r2_mma_issue.md.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 

@@ -269,7 +269,11 @@ def test_thread_per_stream_decode_equals_warp_per_stream(dev, cfgname):
             for lanes in (0, 1):
                 strings, zhat, sym, _ = m.compress_batch(x, lanes=lanes, return_symbols=True)
                 out = {}
-                for rows in (1 << 30, 1):          # never / always the thread-per-stream kernels (decoder and encoder)
+                # never / always the thread-per-stream kernels (decoder and encoder); the warp-per-row decode step on the
+                # int32 tables in global memory (key 2) and on shared-memory copies of the compact rows (the default)
+                for rows in (1 << 30, 1, 2):
+                    m.set_option("dec_smem_warp", 0 if rows == 2 else 1)
+                    rows = (1 << 30) if rows == 2 else rows
                     m.set_option("dec_thread_rows", rows)
                     m.set_option("enc_thread_streams", rows)
                     enc_dev = m.encode_device(x, lanes=lanes)
@@ -277,6 +281,9 @@ def test_thread_per_stream_decode_equals_warp_per_stream(dev, cfgname):
                     assert got == strings, "bitstreams differ between the two encoder kernels"
                     z, s = m.decode_device(enc_dev.streams, enc_dev.lens, x.shape[0], x.shape[2], x.shape[3], lanes=lanes,
                                            want_symbols=True)
+                    if rows == (1 << 30) and (1 << 30) in out:
+                        assert torch.equal(out[rows][1], s) and torch.equal(out[rows][0], z), \
+                            "warp-per-row decode differs between shared-memory and global-memory tables"
                     out[rows] = (z, s)
                 assert torch.equal(out[1][1], out[1 << 30][1]), "symbols differ between the two decode kernels"
                 assert torch.equal(out[1][0], out[1 << 30][0])
@@ -284,6 +291,7 @@ def test_thread_per_stream_decode_equals_warp_per_stream(dev, cfgname):
         finally:
             m.set_option("dec_thread_rows", 4096)
             m.set_option("enc_thread_streams", 4096)
+            m.set_option("dec_smem_warp", 1)
             m.set_option("wave", 1)
 
 
