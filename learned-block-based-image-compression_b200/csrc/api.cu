@@ -135,6 +135,7 @@ struct lbic_model {
     int use_pair = 1;      // CTA-pair (cta_group::2) form of the persistent kernel
     int use_flow = 1;      // dataflow launch of a whole layer range per step (1 = steps with >= flow_min_rows rows, 2 = always)
     int flow_min_rows = 4096;
+    int flow_quad = 0;     // large steps: dataflow launch on clusters of four (activation operand shared by TMA multicast)
     int flow_small = 0;    // steps below flow_min_rows: 1 = single-CTA dataflow launch with 96-wide tiles, 0 = one launch per
                            // layer (default: the counter hand-off costs as much as a PDL-chained launch, profiles/r1_dataflow.md)
     int flow_max_rows = 1 << 30;
@@ -195,6 +196,12 @@ void free_all(std::vector<void *> &list) {
 // tile-width variants of a layer, one per split factor (lbic_split): widest first
 int bn_variants(int cout, int *out) {
     for (int i = 0; i < NBN; ++i) {
+        if (i == LBIC_QUAD_VARIANT) {
+            int nt = (cout + gemm_ws_max_bn() - 1) / gemm_ws_max_bn();
+            nt += nt & 1;
+            out[i] = ((cout + nt - 1) / nt + 15) / 16 * 16;
+            continue;
+        }
         if (i >= LBIC_WS_VARIANT) {
             const int wmax = i == LBIC_PAIR_WIDE ? gemm_pair_max_bn()
                              : i == LBIC_SMALL_VARIANT ? gemm_ws_max_bn() / 2
@@ -276,7 +283,7 @@ int pack_conv_seg(lbic_model *m, const SdView &sd, const std::string &prefix, in
     const int nb = bn_variants(cout, bnv);
     (void)bn;
     for (int i = 0; i < nb; ++i) {
-        const int box = (i == LBIC_PAIR_VARIANT || i == LBIC_PAIR_WIDE) ? bnv[i] / 2 : bnv[i];   // a CTA pair loads half the tile per CTA
+        const int box = (i == LBIC_PAIR_VARIANT || i == LBIC_PAIR_WIDE || i == LBIC_QUAD_VARIANT) ? bnv[i] / 2 : bnv[i];   // a CTA pair loads half the tile per CTA
         LBIC_TRY(make_tmap_2d(&seg.tm_hi[i], seg.hi, seg.K, cout, seg.K, 64, box));
         LBIC_TRY(make_tmap_2d(&seg.tm_lo[i], seg.lo, seg.K, cout, seg.K, 64, box));
     }
@@ -365,7 +372,7 @@ int pack_gdn(lbic_model *m, const SdView &sd, int id, const std::string &prefix,
     LBIC_TRY(dev_alloc(tmp, (void **)&seg.weff, sizeof(float) * (size_t)C * C));
     LBIC_TRY(launch_pack_gdn(g, b, C, gbound, gped, bbound, bped, seg.weff, C, L.bias, st));
     for (int i = 0; i < L.n_bn; ++i) {
-        const int box = (i == LBIC_PAIR_VARIANT || i == LBIC_PAIR_WIDE) ? L.bn_v[i] / 2 : L.bn_v[i];
+        const int box = (i == LBIC_PAIR_VARIANT || i == LBIC_PAIR_WIDE || i == LBIC_QUAD_VARIANT) ? L.bn_v[i] / 2 : L.bn_v[i];
         LBIC_TRY(make_tmap_2d(&seg.tm_hi[i], seg.hi, C, C, C, 64, box));
         LBIC_TRY(make_tmap_2d(&seg.tm_lo[i], seg.lo, C, C, C, 64, box));
     }
@@ -558,8 +565,15 @@ int run_flow(lbic_model *m, int l0, int l1, const StepDesc &sd, int R, cudaStrea
         rec.layer = -1;
         cudaEventRecord(rec.a, st);
     }
-    const int rc = gemm_flow_launch(ws.d_chain, ws.h_chain.data(), l0, l1, FLOW_DEP, R, sd, ws.flow_counters,
-                                    ws.flow_counters_cap, st, flow_applies(m, R) == 1);
+    const int mode = flow_applies(m, R) == 1 ? 1 : 0;
+    int rc = LBIC_FLOW_REFUSED;
+    if (mode == 1 && m->flow_quad) {
+        rc = gemm_flow_launch(ws.d_chain, ws.h_chain.data(), l0, l1, FLOW_DEP, R, sd, ws.flow_counters, ws.flow_counters_cap, st, 2);
+        if (rc == LBIC_FLOW_REFUSED) m->flow_quad = 0;       // no clusters of four on this device: CTA pairs from now on
+    }
+    if (rc == LBIC_FLOW_REFUSED)
+        rc = gemm_flow_launch(ws.d_chain, ws.h_chain.data(), l0, l1, FLOW_DEP, R, sd, ws.flow_counters, ws.flow_counters_cap, st,
+                              mode);
     if (m->profiling) {
         cudaEventRecord(rec.b, st);
         m->prof.push_back(rec);
@@ -904,6 +918,7 @@ extern "C" int lbic_create(const lbic_config *cfg, int device, lbic_model **out)
     if (const char *e = getenv("LBIC_FLOW_MIN_ROWS")) m->flow_min_rows = atoi(e) < 1 ? 1 : atoi(e);
     if (const char *e = getenv("LBIC_FLOW_MAX_ROWS")) m->flow_max_rows = atoi(e) < 1 ? 1 : atoi(e);
     if (const char *e = getenv("LBIC_FLOW_SMALL")) m->flow_small = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("LBIC_FLOW_QUAD")) m->flow_quad = atoi(e) ? 1 : 0;
     if (const char *e = getenv("LBIC_WAVE")) m->use_wave = atoi(e) ? 1 : 0;
     if (const char *e = getenv("LBIC_WAVE_MAX_ROWS")) m->wave_max_rows = atoi(e) < 1 ? 1 : atoi(e);
     if (const char *e = getenv("LBIC_WAVE_DEC_MAX_ROWS")) m->wave_dec_max_rows = atoi(e) < 1 ? 1 : atoi(e);
@@ -1005,6 +1020,9 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
         return 0;
     case LBIC_OPT_FLOW_SMALL:
         m->flow_small = value ? 1 : 0;
+        return 0;
+    case LBIC_OPT_FLOW_QUAD:
+        m->flow_quad = value ? 1 : 0;
         return 0;
     case LBIC_OPT_PAIR:
         m->use_pair = value < 0 ? 0 : (value > 3 ? 3 : value);   // 2 = narrow (<= 192) tiles only, 3 = wide (<= 256) in the microbench

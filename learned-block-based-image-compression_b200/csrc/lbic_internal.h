@@ -118,7 +118,7 @@ struct GemmCall {
 // One layer as the persistent multi-layer kernels see it (gemm_flow_kernel, gemm_wave_kernel), resident in device memory.
 // Tile-width variants per layer, indexed by "split factor" f: the layer's Cout is cut into f * ceil(Cout / (256 f))
 // equal tiles (width rounded up to 16), so a cluster of f CTAs gets the same number of tiles per CTA.
-constexpr int LBIC_NBN = 13;          // 6 split factors + the warp-specialised kernel's tiling (width <= 192) + its CTA-pair forms + small / latency tilings
+constexpr int LBIC_NBN = 14;          // 6 split factors + the warp-specialised kernel's tiling (width <= 192) + its CTA-pair forms + small / latency tilings
 constexpr int LBIC_WS_VARIANT = 6;
 constexpr int LBIC_PAIR_WIDE = 8;     // CTA-pair form with tiles up to 256 wide (2 pipeline stages instead of 3)
 constexpr int LBIC_SMALL_VARIANT = 9;  // tiles of at most 96 columns for the single-CTA dataflow launch of small steps
@@ -129,6 +129,8 @@ constexpr int LBIC_LAT_MAX_BN = 128;
 // rows of the activation TMA box for a tile with `rows` valid rows: class 0..3 = 16 / 32 / 48 / 64, 4 = the full 128
 __host__ __device__ inline int lbic_box_class(int rows) { return rows <= 16 ? 0 : rows <= 32 ? 1 : rows <= 48 ? 2 : rows <= 64 ? 3 : 4; }
 __host__ __device__ inline int lbic_box_rows(int cls) { return cls < 4 ? 16 * (cls + 1) : 128; }
+constexpr int LBIC_QUAD_VARIANT = 13;   // quad form of the dataflow launch: width <= 192 with an EVEN number of column tiles (two pairs
+                                        // of a cluster take adjacent tiles); weight TMA box = half the tile
 constexpr int LBIC_PAIR_VARIANT = 7;  // same tile width as LBIC_WS_VARIANT; weight TMA box = half the tile (one half per CTA)
 __host__ __device__ inline int lbic_split(int i) { return i == 0 ? 1 : i == 1 ? 2 : i == 2 ? 3 : i == 3 ? 4 : i == 4 ? 6 : 8; }
 struct alignas(64) ChainLayer {
@@ -149,6 +151,7 @@ int gemm_flow_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int
                      const StepDesc &step, int *d_counters, size_t counters_cap, cudaStream_t st, int pair = 1);
 constexpr int LBIC_FLOW_REFUSED = 1000;   // gemm_flow_launch: the (cooperative) launch was refused; use the per-layer path
 int gemm_flow_supported();   // 1 if all CTA pairs of the dataflow launch can be co-resident on this device
+int gemm_flow_quad_clusters();   // clusters of four of the quad form resident at once (0 = not available)
 struct RansStreamState;
 // The latency path (gemm_wave.cu): a range of wavefront steps (or raster blocks) of ONE encode / decode in a single
 // persistent cooperative launch; gather, GEMM layers and (decode) the rANS step are tiles of one in-kernel work list.

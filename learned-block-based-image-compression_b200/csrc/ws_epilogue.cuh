@@ -78,11 +78,21 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, u
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// completion of all prior MMAs of the pair -> arrive on the barrier at this offset in both CTAs
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+// completion of all prior MMAs of the pair -> arrive on the barrier at this offset in the CTAs of `mask` (cluster ranks;
+// 3 = both CTAs of a cluster of two)
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask = 3) {
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(bar), "h"((uint16_t)3) : "memory");
+        ::"r"(bar), "h"(mask) : "memory");
+}
+// TMA load whose box lands at the same shared-memory offset in every CTA of `mask` (cluster ranks); each destination's
+// bytes are credited to the barrier at this offset in the leader of ITS pair (peer bit cleared, as in tma_load_2d_pair).
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1,
+                                                    uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
 }
 
 __device__ __forceinline__ int ld_acquire_gpu(const int *p) {
@@ -100,7 +110,8 @@ struct EpiCtx {
     float *sb;                // this tile's bias slice buffer
     RowTab *rt;
     const float *stab;
-    uint32_t rank;
+    uint32_t rank;            // CTA within its pair (0 = leader)
+    uint32_t leader = 0;      // cluster rank of the pair's leader CTA (2 for the second pair of a cluster of four)
     // dataflow launch only: the epilogue's own side input (GDN pre-activations) is written by another layer of the same
     // launch; it may be fetched once *dep_cnt >= dep_target (the epilogue warps run ahead of the TMA producer)
     const int *dep_cnt;
@@ -239,7 +250,7 @@ __device__ __forceinline__ void ws_tile_epilogue(const EpiParams &ep, int bn, in
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    if (PAIR) mbar_arrive_remote(cx.acc_empty_bar, 0);
+                    if (PAIR) mbar_arrive_remote(cx.acc_empty_bar, cx.leader);
                     else mbar_arrive(cx.acc_empty_bar);
                 }
             }
@@ -262,27 +273,36 @@ __device__ __forceinline__ void ws_tile_epilogue(const EpiParams &ep, int bn, in
         auto store_hl = [&]() {
             const int c8 = lane & 3;                 // 16-byte chunk within the 64-byte plane row
             const bool is_lo = (lane >> 2) & 1;
+            // all shared-memory reads of the four rows first (any row of the staging area / row table may be read; only
+            // the stores are predicated), then the stores: four independent load -> store chains instead of one
             if (c8 * 8 < nvalid) {
                 h16 *base = (is_lo ? ep.out_lo : ep.out_hi) + g0 + c8 * 8;
                 const uint32_t src = stg + (is_lo ? WHL_LO : 0) + c8 * 16;
+                uint4 v[4];
+                unsigned long long off[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int row = ew * 16 + j * 4 + rsub;
-                    if (row < rows_valid) {
-                        const uint4 v = lds128(src + row * hl_stride);
-                        *reinterpret_cast<uint4 *>(base + cx.rt->hilo[row]) = v;
-                    }
+                    v[j] = lds128(src + row * hl_stride);
+                    off[j] = cx.rt->hilo[row];
                 }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (ew * 16 + j * 4 + rsub < rows_valid) *reinterpret_cast<uint4 *>(base + off[j]) = v[j];
             }
             if (mode == EPI_QUANT && ep.idx && c16 < 2 && c16 * 16 < nvalid) {      // 2 x 16 B per row
+                uint4 v[4];
+                unsigned long long dst[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int row = ew * 16 + j * 4 + rsub;
-                    if (row < rows_valid) {
-                        const uint4 v = lds128(stg + row * WHL_STRIDE + WHL_IDX + c16 * 16);
-                        *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(cx.rt->idx[row]) + g0 + c16 * 16) = v;
-                    }
+                    v[j] = lds128(stg + row * WHL_STRIDE + WHL_IDX + c16 * 16);
+                    dst[j] = cx.rt->idx[row];
                 }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (ew * 16 + j * 4 + rsub < rows_valid)
+                        *reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(dst[j]) + g0 + c16 * 16) = v[j];
             }
         };
         if (has_f32) {
@@ -296,15 +316,18 @@ __device__ __forceinline__ void ws_tile_epilogue(const EpiParams &ep, int bn, in
             }
             epi_bar();
             if (c16 * 4 < nvalid) {
+                uint4 v[4];
+                unsigned long long dst[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int row = ew * 16 + j * 4 + rsub;
-                    if (row < rows_valid) {
-                        const uint4 v = lds128(stg + row * WF_STRIDE + c16 * 16);
-                        float *dst = reinterpret_cast<float *>(cx.rt->f32[row]) + g0 + c16 * 4;
-                        *reinterpret_cast<uint4 *>(dst) = v;
-                    }
+                    v[j] = lds128(stg + row * WF_STRIDE + c16 * 16);
+                    dst[j] = cx.rt->f32[row];
                 }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (ew * 16 + j * 4 + rsub < rows_valid)
+                        *reinterpret_cast<uint4 *>(reinterpret_cast<float *>(dst[j]) + g0 + c16 * 4) = v[j];
             }
             if (has_hilo) {
                 epi_bar();               // the fp32 stores have read the staging area

@@ -415,6 +415,15 @@ def test_dataflow_launch_equals_per_layer_launches(dev, cfgname):
         assert torch.equal(zdec, zref) and torch.equal(zdec, got[1])
         zv, iv = m.validate_recu_reco(x)
         assert torch.equal(zv, got[1])
+        # the quad form: clusters of four CTAs, two pairs on adjacent column tiles sharing the activation operand by
+        # TMA multicast (layers with an odd number of column tiles give the second pair a dummy tile)
+        m.set_option("flow_quad", 1)
+        l0 = m.launch_count()
+        quad = m.compress_batch(x, lanes=0, return_symbols=True)
+        assert quad[0] == ref[0], "bitstreams differ (quad form)"
+        assert torch.equal(quad[1], ref[1]) and torch.equal(quad[2], ref[2]) and torch.equal(quad[3], ref[3])
+        assert torch.equal(m.decompress_batch(quad[0], x.shape, lanes=0), zref)
+        m.set_option("flow_quad", 0)
         # the single-CTA form for small steps (128 x 96 tiles, off by default)
         m.set_option("flow", 1)
         m.set_option("flow_small", 1)
@@ -424,6 +433,7 @@ def test_dataflow_launch_equals_per_layer_launches(dev, cfgname):
     finally:
         m.set_option("flow", 1)
         m.set_option("flow_small", 0)
+        m.set_option("flow_quad", 0)
         m.set_option("wave", 1)
 
 
