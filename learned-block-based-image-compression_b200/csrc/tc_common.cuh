@@ -1,5 +1,5 @@
-// Device-side building blocks shared by the tcgen05 kernels (gemm_tc.cu: one layer per launch;
-// gemm_chain.cu: a persistent chain of layers per launch): mbarrier / TMA / UMMA / TMEM wrappers and the
+// Device-side building blocks shared by the tcgen05 kernels (gemm_tc.cu: one tile per CTA; gemm_ws.cu: persistent
+// per-layer and dataflow kernels; gemm_wave.cu: the latency kernel): mbarrier / TMA / UMMA / TMEM wrappers and the
 // shared-memory staged epilogue.
 #pragma once
 #include "epilogue.cuh"
