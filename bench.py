@@ -204,6 +204,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-reference-container", action="store_true")
+    ap.add_argument("--refc-images", type=int, default=2048,
+                    help="second, larger batch for the reference-container round trip (0 = skip)")
     args = ap.parse_args()
 
     import lbic_b200
@@ -315,8 +317,10 @@ def main():
                     gemm_share_of_encode=prof["gemm_ms"] / (ms_enc / args.steps),
                     algorithmic_flop_per_pixel=dict(encode=2 * macs["encode"] / (B * B), decode=2 * macs["decode"] / (B * B)),
                     **measured_traffic(args),
-                    binding_resource="L2 -> SM bandwidth (~43 B/clk/SM chip-wide): launch time tracks the operand + output "
-                                     "bytes through L2, see profiles/r1_l2_bound.md; the tensor peak is the contract's denominator",
+                    binding_resource="the epilogue warps' instruction issue (two per scheduler, ~8 cycles between instructions): a "
+                                     "256 x 192 tile costs 26-27 k cycles whatever its K while its MMAs need 10-21 k; ncu: tensor "
+                                     "pipe 57-62 %, L2 34 %, DRAM 36 % of peak (profiles/r2_flow_epilogue.md); the tensor peak is "
+                                     "the contract's denominator",
                     layers_tflops_per_layer_launches={k: round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)
                                                       for k, v in layers.items() if v["ms"] > 0})
 
@@ -368,6 +372,29 @@ def main():
                    parity=bool(torch.equal(oh.to(dev), want)), ratio_to_device_value=None)
         e2e["ratio_to_device_value"] = e2e["value"] / value
         del ih, oh, sh, want
+
+    # The reference container's decode is Hb * Wb strictly serial steps whose time does not depend on the number of
+    # images (profiles/r2_wave_latency.md), so its throughput grows with the batch: the same round trip at a larger one.
+    if refc is not None and args.refc_images > n and args.lanes != 1:
+        n2 = args.refc_images
+        free_b, _ = torch.cuda.mem_get_info()
+        need = 30e6 * n2 * (H * W) / (512 * 768)           # ~27 MB of workspace + I/O per 768x512 image (B8 N768)
+        ok = torch.tensor([1 if free_b + torch.cuda.memory_reserved() > need * 1.3 else 0], device=dev)
+        if dist is not None:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # every rank takes the same branch (the timing has barriers)
+        if int(ok.item()):
+            x2 = x.repeat((n2 + n - 1) // n, 1, 1, 1)[:n2].contiguous()
+            o2 = m.encode_device(x2, lanes=1)
+            torch.cuda.synchronize()
+            ms_e2 = timed(lambda: m.encode_device(x2, lanes=1, out=o2), 1)
+            ms_d2 = timed(lambda: m.decode_device(o2.streams, o2.lens, n2, Hb, Wb, lanes=1), 1)
+            z2 = m.decode_device(o2.streams, o2.lens, n2, Hb, Wb, lanes=1)
+            px2 = world * n2 * H * W
+            refc["larger_batch"] = dict(images_per_gpu=n2, value=px2 / ((ms_e2 + ms_d2) * 1e-3) / 1e6,
+                                        encode_mpix_s=px2 / (ms_e2 * 1e-3) / 1e6, decode_mpix_s=px2 / (ms_d2 * 1e-3) / 1e6,
+                                        enc_dec_identical=bool(torch.equal(z2, o2.zhat)))
+            del x2, o2, z2
+            torch.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:   # reported at N=1 only (host cores are shared by the ranks)
