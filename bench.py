@@ -317,10 +317,11 @@ def main():
                     gemm_share_of_encode=prof["gemm_ms"] / (ms_enc / args.steps),
                     algorithmic_flop_per_pixel=dict(encode=2 * macs["encode"] / (B * B), decode=2 * macs["decode"] / (B * B)),
                     **measured_traffic(args),
-                    binding_resource="the epilogue warps' instruction issue (two per scheduler, ~8 cycles between instructions): a "
-                                     "256 x 192 tile costs 26-27 k cycles whatever its K while its MMAs need 10-21 k; ncu: tensor "
-                                     "pipe 57-62 %, L2 34 %, DRAM 36 % of peak (profiles/r2_flow_epilogue.md); the tensor peak is "
-                                     "the contract's denominator",
+                    binding_resource="data movement under the board's power cap: a 256 x 192 tile costs 26-27 k cycles whatever its K "
+                                     "(its MMAs need 10-21 k); ablation: of a layer's time the mainloop is ~60 %, the epilogue's "
+                                     "global stores 13-26 %, its arithmetic 3-12 %; not DRAM bound, not instruction bound (TMA "
+                                     "stores change nothing); ncu: tensor pipe 57-62 %, L2 34 %, DRAM 36 % of peak "
+                                     "(profiles/r2_flow_epilogue.md); the tensor peak is the contract's denominator",
                     layers_tflops_per_layer_launches={k: round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)
                                                       for k, v in layers.items() if v["ms"] > 0})
 

@@ -493,6 +493,24 @@ int build_chain(lbic_model *m) {
         for (int v = 0; v < L.n_bn; ++v) c.bn_v[v] = L.bn_v[v];
         ep.cout = L.cout; ep.bias = L.bias; ep.scale_tab = m->tables.d_scale_table; ep.acc_scale = L.acc_scale;
         c.ep = ep;
+        // output descriptors for the TMA-store epilogue: layers whose output rows are the step's compact rows
+        const bool row_indexed = (ep.mode == EPI_LRELU && !ep.out_pos && !(id == L_E0 && m->k1 == 3)) || ep.mode == EPI_PREGDN || ep.mode == EPI_GDN ||
+                                 ep.mode == EPI_IGDN || ep.mode == EPI_KSI;
+        c.tma_out = 0;
+        if (row_indexed) {
+            bool ok = true;
+            const bool has_hilo = ep.mode != EPI_KSI, has_f32 = ep.mode == EPI_PREGDN || ep.mode == EPI_KSI;
+            if (has_hilo)
+                ok = make_tmap_2d_ex(&c.tmO[0], ep.out_hi, 2, L.cout, ws.R_cap, ep.ld_out, 16, 128, 32) == 0 &&
+                     make_tmap_2d_ex(&c.tmO[1], ep.out_lo, 2, L.cout, ws.R_cap, ep.ld_out, 16, 128, 32) == 0;
+            if (ok && has_hilo)
+                ok = make_tmap_2d_ex(&c.tmO[3], ep.out_hi, 2, L.cout, ws.R_cap, ep.ld_out, 64, 128, 128) == 0 &&
+                     make_tmap_2d_ex(&c.tmO[4], ep.out_lo, 2, L.cout, ws.R_cap, ep.ld_out, 64, 128, 128) == 0;
+            if (ok && has_f32)
+                ok = make_tmap_2d_ex(&c.tmO[2], ep.out_f32, 4, L.cout, ws.R_cap, ep.ld_f32, 16, 128, 64) == 0 &&
+                     make_tmap_2d_ex(&c.tmO[5], ep.out_f32, 4, L.cout, ws.R_cap, ep.ld_f32, 32, 128, 128) == 0;
+            c.tma_out = ok ? 1 : 0;
+        }
     };
     auto pre = [&]() { return epi_pregdn(m, none); };
     auto gdn = [&](bool inv) {
@@ -1023,6 +1041,9 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
         return 0;
     case LBIC_OPT_FLOW_QUAD:
         m->flow_quad = value ? 1 : 0;
+        return 0;
+    case LBIC_OPT_TMA_STORE:
+        gemm_set_tma_store(value);
         return 0;
     case LBIC_OPT_PAIR:
         m->use_pair = value < 0 ? 0 : (value > 3 ? 3 : value);   // 2 = narrow (<= 192) tiles only, 3 = wide (<= 256) in the microbench

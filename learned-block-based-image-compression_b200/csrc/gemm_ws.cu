@@ -174,6 +174,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tmA0h, const __grid_constant_
             c.stg = stg; c.acc_full_bar = acc_full(a); c.acc_empty_bar = acc_empty(a); c.full_phase = (ti >> 1) & 1u;
             c.tmem_acc = tmem_base + a * WS_ACC_STRIDE; c.sb = sbias + a * 256; c.rt = rt; c.stab = stab; c.rank = rank;
             c.dep_cnt = nullptr; c.dep_target = 0; c.dep2_cnt = nullptr; c.dep2_target = 0;
+            c.hack = p.hack;
             ws_tile_epilogue<PAIR>(p.ep, p.bn, m0, n0, c);
         }
     }
@@ -210,6 +211,8 @@ struct FlowParams {
     const ChainLayer *layers;     // device table indexed by absolute layer id
     int *counters;                // [n_layers][n_rb], zero at launch
     int l0, n_layers, n_rb, R, variant, total_tiles;
+    int tma_store;                // 1: row-indexed layers store through the TMA engine (ws_tile_epilogue)
+    int hack;                     // LBIC_EPI_HACK (timing experiments)
     StepDesc step;
     int chunk_rb;                 // row blocks per chunk: tiles are ordered chunk by chunk, layer by layer inside a chunk,
     int tiles_per_chunk;          // so that a chunk's activations are still in L2 when the next layer reads them
@@ -463,6 +466,8 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) gemm_flow_kernel(const FlowPa
             c.stg = stg; c.acc_full_bar = acc_full(a); c.acc_empty_bar = acc_empty(a); c.full_phase = (ti >> 1) & 1u;
             c.tmem_acc = tmem_base + a * WS_ACC_STRIDE; c.sb = sbias + a * 256; c.rt = rt; c.stab = stab; c.rank = rank;
             c.leader = leader;
+            c.tmo = (p.tma_store && Lr.tma_out) ? Lr.tmO : nullptr;
+            c.hack = p.hack;
             const int dl = p.dep[li][0];
             c.dep_cnt = dl >= 0 ? p.counters + (size_t)dl * p.n_rb + rb : nullptr;
             c.dep_target = dl >= 0 ? CTAS * p.ntn[dl] : 0;
@@ -527,6 +532,7 @@ int gemm_ws_launch(const GemmCall &g, cudaStream_t st, int pair) {
     p.ring_bytes = (uint32_t)stages * p.slot_bytes;
     p.idesc = (1u << 4) | ((uint32_t)(g.bn >> 3) << 17) | ((uint32_t)(tile_rows >> 4) << 24);
     p.ep = g.ep;
+    { static int hack = -1; if (hack < 0) { const char *e = getenv("LBIC_EPI_HACK"); hack = e ? atoi(e) : 0; } p.hack = hack; }
     int n_sm = 148;
     {
         int dev = 0;
@@ -669,6 +675,8 @@ int gemm_flow_launch(const ChainLayer *d_layers, const ChainLayer *h_layers, int
     memset(&p, 0, sizeof(p));
     p.layers = d_layers; p.counters = d_counters; p.l0 = l0; p.n_layers = nl; p.R = R; p.step = step;
     p.variant = variant;
+    p.tma_store = gemm_get_tma_store();
+    { static int hack = -1; if (hack < 0) { const char *e = getenv("LBIC_EPI_HACK"); hack = e ? atoi(e) : 0; } p.hack = hack; }
     p.n_rb = (R + tile_rows - 1) / tile_rows;
     if ((size_t)nl * p.n_rb > counters_cap) return lbic_fail(LBIC_ERR_INVALID, "flow kernel: counter buffer too small");
     int total = 0;

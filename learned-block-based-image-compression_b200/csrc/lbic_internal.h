@@ -144,6 +144,11 @@ struct alignas(64) ChainLayer {
     int bn_v[LBIC_NBN];
     int n_bn;
     EpiParams ep;                       // R and step are filled in per launch
+    // TMA-store epilogue (ws_tile_epilogue): descriptors of the layer's row-indexed OUTPUT planes, boxes of 16 columns x
+    // 128 rows: [0] hi, [1] lo (fp16, SWIZZLE_32B), [2] fp32 plane (SWIZZLE_64B).  tma_out = 0: the layer scatters its
+    // rows (QUANT symbols / indexes, RECON, the position-indexed g0 store) and keeps the staged copy loops.
+    CUtensorMap tmO[6];                 // [3] hi, [4] lo as 64-column boxes (SWIZZLE_128B), [5] fp32 as a 32-column box (SWIZZLE_128B)
+    int tma_out;
 };
 
 int gemm_ws_launch(const GemmCall &g, cudaStream_t st, int pair = 0);   // persistent warp-specialised kernel (gemm_ws.cu)
@@ -183,9 +188,14 @@ int gemm_ws_max_bn();
 int gemm_pair_max_bn();
 void gemm_set_pdl(int on);   // programmatic dependent launch between consecutive GEMM kernels (default on)
 int gemm_get_pdl();
+void gemm_set_tma_store(int on);   // dataflow launch: row-indexed layers store their outputs through the TMA engine (default on)
+int gemm_get_tma_store();
 int gemm_simt_launch(const GemmCall &g, cudaStream_t st);
 int gemm_tc_launch(const GemmCall &g, cudaStream_t st);
 int gemm_tc_init();   // resolves cuTensorMapEncodeTiled, sets smem attributes
+// general form: element size 2 (fp16) or 4 (fp32), swizzle 32 / 64 / 128 bytes
+int make_tmap_2d_ex(CUtensorMap *tm, const void *base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                    uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
 int make_tmap_2d(CUtensorMap *tm, const void *base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                  uint32_t box_inner, uint32_t box_outer);
 

@@ -408,11 +408,13 @@ def test_dataflow_launch_equals_per_layer_launches(dev, cfgname):
         ref = m.compress_batch(x, lanes=0, return_symbols=True)
         zref = m.decompress_batch(ref[0], x.shape, lanes=0)
         m.set_option("flow", 2)
-        got = m.compress_batch(x, lanes=0, return_symbols=True)
-        assert got[0] == ref[0], "bitstreams differ"
-        assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2]) and torch.equal(got[3], ref[3])
-        zdec = m.decompress_batch(got[0], x.shape, lanes=0)
-        assert torch.equal(zdec, zref) and torch.equal(zdec, got[1])
+        for tma_store in (1, 0):     # TMA stores from swizzled staging planes / staged copy loops (the default)
+            m.set_option("tma_store", tma_store)
+            got = m.compress_batch(x, lanes=0, return_symbols=True)
+            assert got[0] == ref[0], f"bitstreams differ (tma_store={tma_store})"
+            assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2]) and torch.equal(got[3], ref[3])
+            zdec = m.decompress_batch(got[0], x.shape, lanes=0)
+            assert torch.equal(zdec, zref) and torch.equal(zdec, got[1])
         zv, iv = m.validate_recu_reco(x)
         assert torch.equal(zv, got[1])
         # the quad form: clusters of four CTAs, two pairs on adjacent column tiles sharing the activation operand by
@@ -434,6 +436,7 @@ def test_dataflow_launch_equals_per_layer_launches(dev, cfgname):
         m.set_option("flow", 1)
         m.set_option("flow_small", 0)
         m.set_option("flow_quad", 0)
+        m.set_option("tma_store", 0)
         m.set_option("wave", 1)
 
 
