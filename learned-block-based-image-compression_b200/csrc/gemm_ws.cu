@@ -517,7 +517,7 @@ int gemm_ws_launch(const GemmCall &g, cudaStream_t st, int pair) {
     p.ntiles_n = (g.cout + g.bn - 1) / g.bn;
     p.total_tiles = ((g.R + tile_rows - 1) / tile_rows) * p.ntiles_n;
     p.slot_bytes = 2 * A_PLANE + 2 * (uint32_t)w_rows * BK * 2;
-    const bool gdn_mode = g.ep.mode == EPI_GDN || g.ep.mode == EPI_IGDN;
+    const bool gdn_mode = g.ep.mode == EPI_GDN || g.ep.mode == EPI_IGDN || g.ep.mode == EPI_QUANT;   // modes with side-input buffers
     p.stg_bytes = (uint32_t)(gdn_mode ? WGDN_BYTES : WSTG_BYTES);
     const int avail = SMEM_LIMIT - 1024 - (int)p.stg_bytes - 128 - WS_TAIL;
     int stages = avail / (int)p.slot_bytes;

@@ -203,6 +203,28 @@ __device__ __forceinline__ void ws_tile_epilogue(const EpiParams &ep, int bn, in
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // QUANT: the predicted scales (ksi[:, :M]) and means (ksi[:, M:]) of a 32-column group, same coalesced cp.async form,
+    // scales into buffer 0 and means into buffer 1.  A row-per-thread read of the two 64-byte pieces costs 32 sectors per
+    // warp instruction and made this epilogue 3.4x as long as the GDN one (profiles/r2_epilogue_ablation.log).  Single
+    // buffered: the first 4 KiB of buffer 0 are also the tail of the hi / lo staging rows of this mode, which are only
+    // written after every thread has read its side inputs (the barrier of pass F lies between).
+    const bool quant = (mode == EPI_QUANT);
+    auto aux_issue_q = [&](int g) {
+        const int nv = group_valid(g);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const uint32_t buf = aux_base + (uint32_t)half * WAUX_BUF;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int row = ew * 16 + j * 4 + rsub;
+                const bool valid = row < rows_valid && c16 * 4 < nv && !(cx.hack & 4);
+                const float *src = valid ? ep.aux + (size_t)(m0 + row) * ep.ld_aux + half * ep.M + n0 + g * GC + c16 * 4 : ep.aux;
+                const uint32_t dst = buf + row * 128 + ((uint32_t)(c16 ^ (row & 7)) << 4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     uint32_t accA[16], accB[16];
     if (gdn) {                                       // overlaps the wait for the accumulator
         if (cx.dep_cnt) {
@@ -254,6 +276,11 @@ __device__ __forceinline__ void ws_tile_epilogue(const EpiParams &ep, int bn, in
         const bool even = (g & 1) == 0;
         const bool ok = chunk_ok(g);
         EpiOut<16> o;
+        if (quant) {                     // (the staging rows are free: barrier at the end of the previous group / tile setup)
+            aux_issue_q(g);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            epi_bar();
+        }
         // phase A: this warp's 16-column chunk of the group
         {
             const int c = n0 + g0 + sub * 16;
@@ -266,6 +293,17 @@ __device__ __forceinline__ void ws_tile_epilogue(const EpiParams &ep, int bn, in
                         const uint4 v = lds128(src + ((uint32_t)((sub * 4 + i) ^ (rl & 7)) << 4));
                         pre.a[4 * i] = __uint_as_float(v.x); pre.a[4 * i + 1] = __uint_as_float(v.y);
                         pre.a[4 * i + 2] = __uint_as_float(v.z); pre.a[4 * i + 3] = __uint_as_float(v.w);
+                    }
+                } else if (quant) {
+                    const uint32_t src = aux_base + rl * 128;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t off = (uint32_t)((sub * 4 + i) ^ (rl & 7)) << 4;
+                        const uint4 va = lds128(src + off), vb = lds128(src + WAUX_BUF + off);
+                        pre.a[4 * i] = __uint_as_float(va.x); pre.a[4 * i + 1] = __uint_as_float(va.y);
+                        pre.a[4 * i + 2] = __uint_as_float(va.z); pre.a[4 * i + 3] = __uint_as_float(va.w);
+                        pre.a2[4 * i] = __uint_as_float(vb.x); pre.a2[4 * i + 1] = __uint_as_float(vb.y);
+                        pre.a2[4 * i + 2] = __uint_as_float(vb.z); pre.a2[4 * i + 3] = __uint_as_float(vb.w);
                     }
                 } else {
                     epi_prefetch<16>(ep, r, c, pre);
