@@ -37,6 +37,7 @@ LBIC_OPT_WAVE_DEC_MAX_ROWS = 18
 LBIC_OPT_WAVE_BN = 19
 LBIC_OPT_DEC_SMEM_WARP = 20
 LBIC_OPT_FLOW_QUAD = 21
+LBIC_OPT_FLOW_PAIR_MIN_ROWS = 25
 LBIC_OPT_TMA_STORE = 24
 LBIC_OPT_WAVE_MAX_ROWS = 16
 LBIC_OPT_PDL = 7

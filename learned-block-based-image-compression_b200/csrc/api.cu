@@ -134,7 +134,8 @@ struct lbic_model {
     int use_ws = 1;        // warp-specialised persistent kernel for large steps
     int use_pair = 1;      // CTA-pair (cta_group::2) form of the persistent kernel
     int use_flow = 1;      // dataflow launch of a whole layer range per step (1 = steps with >= flow_min_rows rows, 2 = always)
-    int flow_min_rows = 4096;
+    int flow_min_rows = 2560;       // (profiles/r2_midsize.log: 2048 gains 4-8 % at 128-256 images and loses 2 % at 48)
+    int flow_pair_min_rows = 8192;   // dataflow steps below this many rows run on single CTAs (128 x 96 tiles), from it on CTA pairs
     int flow_quad = 0;     // large steps: dataflow launch on clusters of four (activation operand shared by TMA multicast)
     int flow_small = 0;    // steps below flow_min_rows: 1 = single-CTA dataflow launch with 96-wide tiles, 0 = one launch per
                            // layer (default: the counter hand-off costs as much as a PDL-chained launch, profiles/r1_dataflow.md)
@@ -567,7 +568,16 @@ const int FLOW_DEP[L_COUNT][2] = {
 // 0: one launch per layer; 1: dataflow launch on CTA pairs (large steps); 2: dataflow launch on single CTAs (small steps)
 int flow_applies(const lbic_model *m, int R) {
     if (m->gemm_core != 0 || !m->use_pair || !m->use_flow || m->force_bn || !gemm_flow_supported()) return 0;
-    if (m->use_flow == 2 || (R >= m->flow_min_rows && R <= m->flow_max_rows)) return 1;
+    if (m->use_flow == 2) return 1;
+    // mid-size steps: the single-CTA form has twice the tiles per worker (128 x 96 on 148 CTAs against 256 x 192 on 74
+    // pairs), which is what a step of 4-8 k rows needs to keep the workers busy across layer boundaries; from ~8 k rows
+    // the pair form's smaller operand traffic wins (profiles/r2_midsize.log)
+    // (the threshold is quoted for 768-wide layers and scales with the tiles per row block, i.e. inversely with N).
+    // KS[1] = 3 topologies (five-tap second entropy layer, K = 5 E1) measure no gain from the single-CTA window
+    // (B8_highrate at 64 / 128 / 256 images: 110 / 153 / 187 against 112 / 152 / 189 Mpixel/s): pairs from 4096 rows as before.
+    if (m->k1 == 3) return (R >= (m->flow_min_rows > 4096 ? m->flow_min_rows : 4096) && R <= m->flow_max_rows) ? 1 : ((m->flow_small && R < m->flow_min_rows) ? 2 : 0);
+    if (R >= m->flow_min_rows && R <= m->flow_max_rows)
+        return (long)R * (m->N > 0 ? m->N : 768) >= (long)m->flow_pair_min_rows * 768 ? 1 : 2;
     return (m->flow_small && R < m->flow_min_rows) ? 2 : 0;
 }
 
@@ -936,6 +946,7 @@ extern "C" int lbic_create(const lbic_config *cfg, int device, lbic_model **out)
     if (const char *e = getenv("LBIC_FLOW_MIN_ROWS")) m->flow_min_rows = atoi(e) < 1 ? 1 : atoi(e);
     if (const char *e = getenv("LBIC_FLOW_MAX_ROWS")) m->flow_max_rows = atoi(e) < 1 ? 1 : atoi(e);
     if (const char *e = getenv("LBIC_FLOW_SMALL")) m->flow_small = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("LBIC_FLOW_PAIR_MIN_ROWS")) m->flow_pair_min_rows = atoi(e) < 1 ? 1 : atoi(e);
     if (const char *e = getenv("LBIC_FLOW_QUAD")) m->flow_quad = atoi(e) ? 1 : 0;
     if (const char *e = getenv("LBIC_WAVE")) m->use_wave = atoi(e) ? 1 : 0;
     if (const char *e = getenv("LBIC_WAVE_MAX_ROWS")) m->wave_max_rows = atoi(e) < 1 ? 1 : atoi(e);
@@ -1041,6 +1052,9 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
         return 0;
     case LBIC_OPT_FLOW_QUAD:
         m->flow_quad = value ? 1 : 0;
+        return 0;
+    case LBIC_OPT_FLOW_PAIR_MIN_ROWS:
+        m->flow_pair_min_rows = value < 1 ? 1 : value;
         return 0;
     case LBIC_OPT_TMA_STORE:
         gemm_set_tma_store(value);

@@ -1,0 +1,17 @@
+#!/bin/bash
+# lower row threshold of the dataflow launch (single-CTA form below 8192 rows): LBIC_FLOW_MIN_ROWS
+mkdir -p gpurun_out
+L=gpurun_out/r2_midsize3.log
+: > $L
+run() {
+  echo "== flow_min_rows=$1 images=$2" >> $L
+  LBIC_FLOW_MIN_ROWS=$1 timeout 600 python bench.py --images $2 --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-reference-container 2>> $L | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('value %.1f enc %.1f dec %.1f sm_mhz %s identical %s' % (d['value'], d['encode_mpix_s'], d['decode_mpix_s'], d['clocks']['sm_mhz'], d['enc_dec_identical']))" >> $L
+}
+for n in 48 64 128 256 1024; do
+  for t in 4096 2048 1024 512; do
+    run $t $n
+  done
+done
+cat $L
