@@ -70,6 +70,8 @@ struct WaveParams {
     int n_img, Hb, Wb;
     int variant;
     int stages;                  // ring depth of this launch
+    int kb_group;                // k-blocks the MMA issuer takes per barrier round trip (1..4)
+    int m64;                     // every step of the launch has at most 64 rows: M = 64 MMAs (40 instead of 52 cycles each)
     uint32_t slot_bytes, a_plane_bytes;   // slot stride; bytes of one activation plane of the launch's largest box
     const float *x_cl, *zhat_cl;
     int Cin, gather_first;       // gather tiles cover segments gather_first .. 4 (0 = x, 1..4 = the four zhat taps)
@@ -435,33 +437,54 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                 const int bn = o.bn;
                 const int nkb = Lr.kb[0] + (Lr.nseg > 1 ? Lr.kb[1] : 0);
                 const uint32_t w_plane = (uint32_t)bn * (BK * 2);
-                const uint32_t idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                const uint32_t idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)((p.m64 ? 64 : BM) >> 4) << 24);
                 const uint32_t a = gi & 1u;
                 mbar_wait(acc_empty(a), ((gi >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t tmem_acc = tmem_base + a * WS_ACC_STRIDE;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % stages;
-                    const uint32_t ph = (it / stages) & 1u;
-                    mbar_wait(full_bar(s), ph);
+                // up to four k-blocks per barrier round trip: the issue of an MMA blocks until the tensor core takes it, so the
+                // wait / fence / elect sequence between k-blocks is not hidden behind the MMAs (profiles/r2_wave_latency.md)
+                const int nb_max = p.kb_group < stages ? p.kb_group : stages;
+                uint32_t slot = it % stages, phase = (it / stages) & 1u;        // ring position of the next k-block
+                for (int kb = 0; kb < nkb;) {
+                    const int nb = nkb - kb < nb_max ? nkb - kb : nb_max;
+                    {
+                        uint32_t s2 = slot, p2 = phase;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (u < nb) {
+                                mbar_wait(full_bar(s2), p2);
+                                if (++s2 == (uint32_t)stages) { s2 = 0; p2 ^= 1u; }
+                            }
+                    }
                     tc_fence_after();
                     if (kb == 0 && lane == 0) WAVE_TRACE(2);
-                    const uint32_t sa = ring + s * p.slot_bytes;
-                    const uint64_t a_hi = make_smem_desc(sa);
-                    const uint64_t a_lo = make_smem_desc(sa + off_alo);
-                    const uint64_t w_hi = make_smem_desc(sa + off_w);
-                    const uint64_t w_lo = make_smem_desc(sa + off_w + w_plane);
                     if (elect_one()) {
+                        uint32_t s2 = slot;
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int u = 0; u < 4; ++u)
+                            if (u < nb) {
+                                const uint32_t sa = ring + s2 * p.slot_bytes;
+                                const uint64_t a_hi = make_smem_desc(sa);
+                                const uint64_t a_lo = make_smem_desc(sa + off_alo);
+                                const uint64_t w_hi = make_smem_desc(sa + off_w);
+                                const uint64_t w_lo = make_smem_desc(sa + off_w + w_plane);
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
+                                for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_hi + 2 * k, w_hi + 2 * k, idesc, ((kb + u) | k) != 0 ? 1u : 0u);
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
-                        umma_commit(empty_bar(s));
-                        if (kb == nkb - 1) umma_commit(acc_full(a));
+                                for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_hi + 2 * k, w_lo + 2 * k, idesc, 1u);
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k) umma_f16(tmem_acc, a_lo + 2 * k, w_hi + 2 * k, idesc, 1u);
+                                umma_commit(empty_bar(s2));
+                                if (++s2 == (uint32_t)stages) s2 = 0;
+                            }
+                        if (kb + nb == nkb) umma_commit(acc_full(a));
                     }
                     __syncwarp();
+                    for (int u = 0; u < nb; ++u)
+                        if (++slot == (uint32_t)stages) { slot = 0; phase ^= 1u; }
+                    kb += nb;
+                    it += nb;
                 }
                 if (lane == 0) WAVE_TRACE(3);
                 ++gi;
@@ -523,6 +546,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                 c.dep2_cnt = dl2 >= 0 ? p.counters + dl2 * WAVE_MAX_RB + w.rb : nullptr;
                 c.dep2_target = dl2 >= 0 ? p.ord[dl2].ntn * (gen[w.rb] + 1) : 0;
                 c.trace_acc = et == 0 ? wave_trace_slot(p, w, 4) : nullptr;
+                c.m64 = p.m64;
                 wave_gemm_epilogue(s_ep, bn, m0, n0, c);
                 ++gi;
             } else {
@@ -606,6 +630,14 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
     p.ksi = w.ksi; p.ld_ksi = w.ld_ksi; p.yq_hi = w.yq_hi; p.yq_lo = w.yq_lo; p.ld_yq = w.ld_yq; p.sym_out = w.sym_out; p.M = w.M;
     const int max_rows = w.raster ? w.n_img : w.n_img * (w.Hb < (w.Wb + 1) / 2 ? w.Hb : (w.Wb + 1) / 2);
     if (max_rows > WAVE_MAX_RB * BM) return lbic_fail(LBIC_ERR_INVALID, "wave kernel: step of %d rows exceeds %d", max_rows, WAVE_MAX_RB * BM);
+    {
+        static int m64 = -1;     // LBIC_WAVE_M64=0 keeps M = 128 (tests, measurements)
+        if (m64 < 0) { const char *e = getenv("LBIC_WAVE_M64"); m64 = (e && atoi(e) == 0) ? 0 : 1; }
+        p.m64 = (m64 && max_rows <= 64) ? 1 : 0;
+        static int kbg = -1;     // LBIC_WAVE_KB_GROUP: tuning hook
+        if (kbg < 0) { const char *e = getenv("LBIC_WAVE_KB_GROUP"); kbg = e ? atoi(e) : 4; kbg = kbg < 1 ? 1 : (kbg > 4 ? 4 : kbg); }
+        p.kb_group = kbg;
+    }
     int bn_max = 16;
     for (int i = 0; i < 18; ++i) {
         const int bn = w.h_layers[w.ids[i]].bn_v[w.variant];

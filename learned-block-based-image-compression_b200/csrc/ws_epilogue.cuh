@@ -136,6 +136,9 @@ struct EpiCtx {
     // arithmetic, 4 = no GDN side-input fetch, 8 = skip the whole group loop (release the accumulator and return),
     // 16 = staging kept, only the global stores dropped
     int hack = 0;
+    // the accumulator was produced by M = 64 MMAs (latency kernel, steps of at most 64 rows): row r sits in TMEM lane
+    // 32 (r / 16) + r % 16, i.e. each warp's lanes 0-15 hold rows 16 q .. 16 q + 15 (scripts/mma_m64_layout.cu)
+    int m64 = 0;
 };
 constexpr uint32_t WTMA_LO = 8192, WTMA_F32 = 16384;   // narrow staging: hi 2 x 4 KiB | lo 2 x 4 KiB | fp32 2 x 8 KiB
 constexpr uint32_t WTMA_LO_W = 16384, WTMA_F32_W = 32768;   // wide staging: hi 16 KiB | lo 16 KiB | fp32 16 KiB
@@ -147,12 +150,12 @@ __device__ __forceinline__ void ws_tile_epilogue(const EpiParams &ep, int bn, in
     const int q = warp & 3;                  // TMEM lane quarter (warp id % 4)
     const int sub = ew >> 2;                 // which 16-column chunk of a 32-column group
     const int et = threadIdx.x - 64;         // 0..255
-    const int rl = q * 32 + lane;
+    const int rl = cx.m64 ? q * 16 + (lane & 15) : q * 32 + lane;
     const int mode = ep.mode;
     const bool gdn = (mode == EPI_GDN || mode == EPI_IGDN);
     const uint32_t stg = cx.stg;
     const int r = m0 + rl;
-    const bool row_ok = r < ep.R;
+    const bool row_ok = r < ep.R && !(cx.m64 && lane >= 16);
     const int rows_valid = (ep.R - m0) < BM ? (ep.R - m0) : BM;
     float *sb = cx.sb;
     // per-tile setup (overlaps the mainloop of this tile): bias slice, row table
