@@ -446,6 +446,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                 // wait / fence / elect sequence between k-blocks is not hidden behind the MMAs (profiles/r2_wave_latency.md)
                 const int nb_max = p.kb_group < stages ? p.kb_group : stages;
                 uint32_t slot = it % stages, phase = (it / stages) & 1u;        // ring position of the next k-block
+                // (starting with a single k-block so that the first MMAs go out as soon as it has landed -- groups of 1, 2, 4, 4 --
+                // measured the same: 33.4 / 32.1 against 33.3 / 31.9 ms)
                 for (int kb = 0; kb < nkb;) {
                     const int nb = nkb - kb < nb_max ? nkb - kb : nb_max;
                     {

@@ -259,6 +259,7 @@ __device__ __forceinline__ void ws_tile_epilogue(const EpiParams &ep, int bn, in
         }
         epi_bar();
     }
+    if (quant) aux_issue_q(0);     // the first group's scales / means travel while the mainloop is still running
     mbar_wait(cx.acc_full_bar, cx.full_phase);
     tc_fence_after();
     if (cx.trace_acc) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(*cx.trace_acc));
@@ -280,7 +281,7 @@ __device__ __forceinline__ void ws_tile_epilogue(const EpiParams &ep, int bn, in
         const bool ok = chunk_ok(g);
         EpiOut<16> o;
         if (quant) {                     // (the staging rows are free: barrier at the end of the previous group / tile setup)
-            aux_issue_q(g);
+            if (g > 0) aux_issue_q(g);
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             epi_bar();
         }
