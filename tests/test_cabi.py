@@ -28,6 +28,15 @@ def test_exports_every_declared_symbol():
     assert sorted(_lib.PROTOTYPES) == names
 
 
+def test_option_constants_match_the_header():
+    """Every LBIC_OPT_* of include/lbic.h has the same value in the python binding and a name in set_option()."""
+    src = open(os.path.join(ROOT, "include", "lbic.h")).read()
+    opts = {k: int(v) for k, v in re.findall(r"#define\s+(LBIC_OPT_[A-Z0-9_]+)\s+(\d+)", src)}
+    assert len(opts) >= 20 and len(set(opts.values())) == len(opts), "duplicate option numbers"
+    for k, v in opts.items():
+        assert getattr(_lib, k, None) == v, f"{k}: header says {v}, _lib.py says {getattr(_lib, k, None)}"
+
+
 def test_blackwell_instructions_in_sass():
     """The shipped kernels are tcgen05/TMA code, not a legacy mma.sync path."""
     import shutil
