@@ -181,7 +181,9 @@ def workload_config(args, cfg):
                 images_per_gpu=args.images, height=args.height, width=args.width,
                 container="reference (1 rANS stream per image)" if args.lanes == 1 else "lane (1 rANS stream per block row)",
                 l2="inputs larger than L2 (batch of input blocks > 126 MB)" if args.images * args.height * args.width * 12 > 126e6
-                else "inputs smaller than L2; L2 flushed between steps")
+                else "inputs smaller than L2; L2 flushed between steps",
+                **({} if (args.latent_gain == 60.0 and args.scale_span == 5.2) else
+                   {"synthetic_rate": f"latent_gain {args.latent_gain}, scale_span {args.scale_span} (see bpp)"}))
 
 
 def main():
@@ -203,6 +205,9 @@ def main():
     ap.add_argument("--core", default="tcgen05", choices=["tcgen05", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--latent-gain", type=float, default=60.0,
+                    help="rate of the synthetic model (weights.synth_state_dict): 60 / 5.2 = ~11 bpp (default), 2.5 / 2.0 = ~1 bpp")
+    ap.add_argument("--scale-span", type=float, default=5.2)
     ap.add_argument("--no-reference-container", action="store_true")
     ap.add_argument("--refc-images", type=int, default=2048,
                     help="second, larger batch for the reference-container round trip (0 = skip)")
@@ -239,7 +244,7 @@ def main():
     B, H, W, n = int(cfg.block_size), args.height, args.width, args.images
     Hb, Wb = H // B, W // B
     m = BlockBasedImgCompLossyNetv9(cfg, device=dev)
-    m.load_state_dict(weights.synth_state_dict(cfg, 1337))
+    m.load_state_dict(weights.synth_state_dict(cfg, 1337, latent_gain=args.latent_gain, scale_span=args.scale_span))
     m.update(force=True)
     m.set_gemm_core(args.core)
     img_u8 = synth_batch_gpu(n, H, W, 1000 + rank, dev)

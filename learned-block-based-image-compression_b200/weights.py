@@ -83,7 +83,8 @@ def reparam_init(x: torch.Tensor) -> torch.Tensor:
     return torch.sqrt(torch.max(x + ped, ped))
 
 
-def synth_state_dict(cfg, seed: int = 1337, conditioned: bool = True, harsh: bool = False):
+def synth_state_dict(cfg, seed: int = 1337, conditioned: bool = True, harsh: bool = False, latent_gain: float = 60.0,
+                     scale_span: float = 5.2):
     """Synthetic state_dict with the reference's exact key set, order, shapes and dtypes.
 
     conv weight/bias ~ U(-1/sqrt(fan_in), 1/sqrt(fan_in)) (PyTorch's default Conv2d scale); masked
@@ -91,6 +92,9 @@ def synth_state_dict(cfg, seed: int = 1337, conditioned: bool = True, harsh: boo
     NET:381).  conditioned=True applies the SURVEY.md section 8(d) recipe plus a dense non-negative
     GDN gamma so that the six gamma-matmuls are exercised (default-init gamma is exactly diagonal).
     harsh=True keeps prtr_inverse1 at full scale (clamp active on about half the samples).
+    latent_gain / scale_span set the rate of the synthetic model: the last encoder layer is scaled by latent_gain and the
+    predicted scales are spread over exp(U(0, scale_span) - 2.2); the defaults (60, 5.2) give ~11 bpp on noise-like
+    images (every golden fixture uses them), (2.5, 2.0) about 1 bpp, the range of the reference's released models.
     """
     w = widths(cfg)
     M = w["M"]
@@ -123,13 +127,13 @@ def synth_state_dict(cfg, seed: int = 1337, conditioned: bool = True, harsh: boo
             sd[prefix + ".gamma_reparam.lower_bound.bound"] = torch.tensor(
                 [(0.0 + PEDESTAL) ** 0.5], dtype=torch.float32)
     if conditioned:
-        sd["prtr_forward3.5.weight"] *= 60.0
-        sd["prtr_forward3.5.bias"] *= 60.0
+        sd["prtr_forward3.5.weight"] *= latent_gain
+        sd["prtr_forward3.5.bias"] *= latent_gain
         if not harsh:
             sd["prtr_inverse1.weight"] *= 0.3
         sd["get_meanscale.6.weight"] *= 20.0
         g = _gen(seed, "scale_bias")
-        sd["get_meanscale.6.bias"][:M] = torch.exp(torch.rand(M, generator=g) * 5.2 - 2.2)
+        sd["get_meanscale.6.bias"][:M] = torch.exp(torch.rand(M, generator=g) * scale_span - 2.2)
     # entropy-model buffers: empty until update(), exactly as in released checkpoints (AGENT:570)
     sd["conditional_gaussian_model._offset"] = torch.IntTensor()
     sd["conditional_gaussian_model._quantized_cdf"] = torch.IntTensor()
