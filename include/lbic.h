@@ -67,6 +67,7 @@ typedef struct {
 #define LBIC_OPT_FLOW 11         /* 1 (default) = run each large wavefront step's layers as ONE dataflow launch (row-block dependencies instead of kernel boundaries): on single CTAs below LBIC_OPT_FLOW_PAIR_MIN_ROWS block rows, on CTA pairs from there; 2 = always (pairs); 0 = one launch per layer */
 #define LBIC_OPT_FLOW_QUAD 21     /* dataflow launch on clusters of FOUR CTAs: two CTA pairs take adjacent column tiles of one 256-row block and share its activation operand by TMA multicast (each CTA fetches one plane); 0 = CTA pairs only */
 #define LBIC_OPT_TMA_STORE 24     /* 1: in the dataflow launch the layers whose output rows are the step's compact rows store through the TMA engine from swizzled staging tiles (full 128-byte lines where the tile allows); 0 (default): staged copy loops; bit-identical, measured equal (process-wide) */
+#define LBIC_OPT_CHECK_SATURATION 26 /* 1: count the elements of the fp16 operand planes clipped at +-65504 (lbic_saturation_count); debug, per-layer launches */
 #define LBIC_OPT_FLOW_MIN_ROWS 12 /* steps with at least this many block rows take the dataflow launch (default 2560) */
 #define LBIC_OPT_FLOW_PAIR_MIN_ROWS 25 /* dataflow steps with fewer block rows than this (default 8192) run on single CTAs with 128 x 96 tiles, larger ones on CTA pairs with 256 x 192 tiles */
 #define LBIC_OPT_FLOW_SMALL 13    /* 1 = steps below LBIC_OPT_FLOW_MIN_ROWS also run as one dataflow launch, on single CTAs with 128 x 96 tiles; 0 (default) = one launch per layer there */
@@ -233,6 +234,12 @@ int lbic_debug_gemm(lbic_model *m, const float *A, const float *W, float *D, int
 int lbic_debug_gemm_bench(lbic_model *m, int R, int K, int cout, int with_epilogue, int iters, double *ms_per_launch);
 
 /* Number of kernels this library has launched on behalf of `m` since creation. */
+/* Debug aid for the fp16 operand planes: every activation is stored as hi + lo fp16 planes, which CLIP at +-65504
+ * instead of overflowing (the squares of the GDN layers clip for |x| > 255.9).  With LBIC_OPT_CHECK_SATURATION set, every
+ * GEMM layer's hi plane is scanned after the layer (one launch per layer; the dataflow and wave kernels are bypassed,
+ * results unchanged) and the clipped elements are counted; this call synchronises `stream` and returns the total since
+ * the last reset.  A non-zero count means rate / distortion may deviate from the reference for these weights. */
+int lbic_saturation_count(lbic_model *m, void *stream, int64_t *count, int reset);
 int64_t lbic_launch_count(const lbic_model *m);
 /* Per-kernel-family launch counts and (if timing is enabled) accumulated device milliseconds for
  * the GEMM family; used by bench.py for the roofline line. */

@@ -37,6 +37,7 @@ LBIC_OPT_WAVE_DEC_MAX_ROWS = 18
 LBIC_OPT_WAVE_BN = 19
 LBIC_OPT_DEC_SMEM_WARP = 20
 LBIC_OPT_FLOW_QUAD = 21
+LBIC_OPT_CHECK_SATURATION = 26
 LBIC_OPT_FLOW_PAIR_MIN_ROWS = 25
 LBIC_OPT_TMA_STORE = 24
 LBIC_OPT_WAVE_MAX_ROWS = 16
@@ -76,6 +77,7 @@ PROTOTYPES = {
     "lbic_rans_decode": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _i64, _vp, _vp]),
     "lbic_debug_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "lbic_debug_gemm_bench": (_i, [_vp, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_double)]),
+    "lbic_saturation_count": (_i, [_vp, _vp, ctypes.POINTER(ctypes.c_int64), _i]),
     "lbic_launch_count": (_i64, [_vp]),
     "lbic_set_profiling": (_i, [_vp, _i]),
     "lbic_get_profile": (_i, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(ctypes.c_double),

@@ -157,6 +157,10 @@ struct lbic_model {
     int band_n = 0, band_Hb = 0, band_Wb = 0, band_decode = 0;
     int64_t launches[2] = {0, 0};
     int *err_flag = nullptr;
+    // debug: count the elements of every fp16 operand plane a GEMM layer writes that were clipped at +-65504
+    // (LBIC_OPT_CHECK_SATURATION: per-layer launches only, one scan per layer; lbic_saturation_count reads the total)
+    int check_sat = 0;
+    unsigned long long *d_sat = nullptr;
     // the workspace is shared by all calls on this model: a call on another stream than the previous one waits for it
     cudaEvent_t ws_event = nullptr;
     cudaStream_t ws_stream = nullptr;
@@ -567,6 +571,7 @@ const int FLOW_DEP[L_COUNT][2] = {
 
 // 0: one launch per layer; 1: dataflow launch on CTA pairs (large steps); 2: dataflow launch on single CTAs (small steps)
 int flow_applies(const lbic_model *m, int R) {
+    if (m->check_sat) return 0;
     if (m->gemm_core != 0 || !m->use_pair || !m->use_flow || m->force_bn || !gemm_flow_supported()) return 0;
     if (m->use_flow == 2) return 1;
     // mid-size steps: the single-CTA form has twice the tiles per worker (128 x 96 on 148 CTAs against 256 x 192 on 74
@@ -692,6 +697,9 @@ int run_gemm_layer(lbic_model *m, const PackedLayer &L, int id, int R, const Act
         cudaEventRecord(rec.b, st);
         m->prof.push_back(rec);
     }
+    if (rc == 0 && m->check_sat && m->d_sat && !ep.out_pos &&
+        (ep.mode == EPI_LRELU || ep.mode == EPI_PREGDN || ep.mode == EPI_GDN || ep.mode == EPI_IGDN || ep.mode == EPI_QUANT))
+        return launch_sat_scan(ep.out_hi, R, L.cout, ep.ld_out, m->d_sat, st);
     return rc;
 }
 
@@ -842,7 +850,7 @@ struct RowHooks {
 
 // The persistent wavefront kernel (gemm_wave.cu) takes over when every step of the call has at most wave_max_rows rows.
 bool wave_applies(const lbic_model *m, int n_img, int Hb, int Wb, bool raster, bool decode) {
-    if (!m->use_wave || m->gemm_core != 0 || m->force_bn || m->k1 != 1 || m->profiling || m->selfinfo_cl ||
+    if (!m->use_wave || m->gemm_core != 0 || m->force_bn || m->k1 != 1 || m->profiling || m->check_sat || m->selfinfo_cl ||
         m->recon_cl || !gemm_wave_supported())
         return false;
     const int max_nv = Hb < (Wb + 1) / 2 ? Hb : (Wb + 1) / 2;
@@ -969,6 +977,7 @@ extern "C" int lbic_create(const lbic_config *cfg, int device, lbic_model **out)
         return lbic_fail(LBIC_ERR_NOMEM, "cudaMalloc failed");
     }
     cudaMemset(m->err_flag, 0, sizeof(int));
+    if (cudaMalloc(&m->d_sat, sizeof(unsigned long long)) == cudaSuccess) cudaMemset(m->d_sat, 0, sizeof(unsigned long long));
     if (cudaEventCreateWithFlags(&m->ws_event, cudaEventDisableTiming) != cudaSuccess) {
         cudaFree(m->err_flag);
         delete m;
@@ -991,6 +1000,7 @@ extern "C" void lbic_destroy(lbic_model *m) {
     tables_free(m->tables);
     if (m->tables.d_scale_table) cudaFree(m->tables.d_scale_table);
     if (m->err_flag) cudaFree(m->err_flag);
+    if (m->d_sat) cudaFree(m->d_sat);
     if (m->ws_event) cudaEventDestroy(m->ws_event);
     if (m->io_dev) cudaFree(m->io_dev);
     for (auto &a : m->aux) if (a) cudaFree(a);
@@ -1052,6 +1062,9 @@ extern "C" int lbic_set_option(lbic_model *m, int option, int value) {
         return 0;
     case LBIC_OPT_FLOW_QUAD:
         m->flow_quad = value ? 1 : 0;
+        return 0;
+    case LBIC_OPT_CHECK_SATURATION:
+        m->check_sat = value ? 1 : 0;
         return 0;
     case LBIC_OPT_FLOW_PAIR_MIN_ROWS:
         m->flow_pair_min_rows = value < 1 ? 1 : value;
@@ -2071,6 +2084,19 @@ extern "C" int lbic_get_layer_profile(lbic_model *m, int max_layers, int64_t *la
         launches[r.layer] += 1; ms[r.layer] += t; flops[r.layer] += r.flops;
     }
     return n;
+}
+
+extern "C" int lbic_saturation_count(lbic_model *m, void *stream, int64_t *count, int reset) {
+    if (!m || !count) return lbic_fail(LBIC_ERR_INVALID, "null argument");
+    Active act(m);
+    *count = 0;
+    if (!m->d_sat) return 0;
+    LBIC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    unsigned long long v = 0;
+    LBIC_CUDA(cudaMemcpy(&v, m->d_sat, sizeof(v), cudaMemcpyDeviceToHost));
+    if (reset) LBIC_CUDA(cudaMemset(m->d_sat, 0, sizeof(v)));
+    *count = (int64_t)v;
+    return 0;
 }
 
 extern "C" int64_t lbic_launch_count(const lbic_model *m) { return m ? m->launches[0] + m->launches[1] : 0; }

@@ -478,6 +478,31 @@ int launch_pack_gdn(const float *gamma, const float *beta, int C, float gbound, 
     return 0;
 }
 
+// Saturation check of an fp16 operand plane (debug option LBIC_OPT_CHECK_SATURATION): the hi planes clip at +-65504
+// instead of overflowing (epilogue.cuh: pack_hilo), silently; this counts the clipped elements of rows [0, R) x columns
+// [0, C) of a plane with row stride ld.
+__global__ void sat_scan_kernel(const h16 *__restrict__ hi, int R, int C, int ld, unsigned long long *__restrict__ count) {
+    const long long n = (long long)R * C;
+    unsigned int local = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / C), c = (int)(i - (long long)r * C);
+        const unsigned short bits = __half_as_ushort(hi[(size_t)r * ld + c]);
+        local += ((bits & 0x7FFFu) >= 0x7BFFu) ? 1u : 0u;           // |x| = 65504 (the clip value), inf or nan
+    }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, (unsigned long long)local);
+}
+
+int launch_sat_scan(const h16 *hi, int R, int C, int ld, unsigned long long *count, cudaStream_t st) {
+    if (R <= 0 || C <= 0) return 0;
+    const long long n = (long long)R * C;
+    const int blocks = (int)((n + 1023) / 1024 < 1184 ? (n + 1023) / 1024 : 1184);
+    sat_scan_kernel<<<blocks, 256, 0, st>>>(hi, R, C, ld, count);
+    count_launch(1);
+    LBIC_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_absmax(const float *v, int64_t n, float *out_dev, cudaStream_t st) {
     absmax_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(v, (size_t)n, out_dev);
     count_launch(1);

@@ -225,6 +225,7 @@ int launch_pack_conv(const float *w, const float *mask, int cout, int cin, int k
                      const int *taps_host, int ntaps, float *weff, int ld, cudaStream_t st);
 int launch_pack_gdn(const float *gamma, const float *beta, int C, float gbound, float gped, float bbound,
                     float bped, float *weff, int ld, float *beta_out, cudaStream_t st);
+int launch_sat_scan(const h16 *hi, int R, int C, int ld, unsigned long long *count, cudaStream_t st);   // *count += clipped elements
 int launch_absmax(const float *v, int64_t n, float *out_dev, cudaStream_t st);   // *out_dev = max(*out_dev, max|v|)
 int launch_split_scaled(const float *src, h16 *hi, h16 *lo, int64_t n, float scale, cudaStream_t st);
 // KS[1]==3: A operand of get_meanscale[2] = the five mask-'B' taps of g0 around each block of the step

@@ -116,7 +116,7 @@ class BlockBasedImgCompLossyNetv9:
         'pair' (CTA-pair form of the persistent kernel), 'pdl', 'host_bands' (bands of block rows of the host calls),
         'wave' (persistent wavefront kernel for small steps), 'wave_max_rows'."""
         opt = {"force_bn": _lib.LBIC_OPT_FORCE_BN, "wave": _lib.LBIC_OPT_WAVE, "wave_max_rows": _lib.LBIC_OPT_WAVE_MAX_ROWS, "wave_dec_max_rows": _lib.LBIC_OPT_WAVE_DEC_MAX_ROWS,
-               "wave_bn": _lib.LBIC_OPT_WAVE_BN, "dec_smem_warp": _lib.LBIC_OPT_DEC_SMEM_WARP, "flow_quad": _lib.LBIC_OPT_FLOW_QUAD, "flow_pair_min_rows": _lib.LBIC_OPT_FLOW_PAIR_MIN_ROWS, "tma_store": _lib.LBIC_OPT_TMA_STORE,
+               "wave_bn": _lib.LBIC_OPT_WAVE_BN, "dec_smem_warp": _lib.LBIC_OPT_DEC_SMEM_WARP, "flow_quad": _lib.LBIC_OPT_FLOW_QUAD, "check_saturation": _lib.LBIC_OPT_CHECK_SATURATION, "flow_pair_min_rows": _lib.LBIC_OPT_FLOW_PAIR_MIN_ROWS, "tma_store": _lib.LBIC_OPT_TMA_STORE,
                "ws": _lib.LBIC_OPT_WS, "pdl": _lib.LBIC_OPT_PDL,
                "pair": _lib.LBIC_OPT_PAIR, "dec_thread_rows": _lib.LBIC_OPT_DEC_THREAD_ROWS,
                "enc_thread_streams": _lib.LBIC_OPT_ENC_THREAD_STREAMS, "enc_block_streams": _lib.LBIC_OPT_ENC_BLOCK_STREAMS, "flow": _lib.LBIC_OPT_FLOW,
@@ -425,6 +425,14 @@ class BlockBasedImgCompLossyNetv9:
         return dict(mse=mse, psnr=-10.0 * np.log10(mse), msssim=ms)
 
     # ---- instrumentation ----------------------------------------------------------------------------
+    def saturation_count(self, reset: bool = True) -> int:
+        """Elements of the fp16 operand planes clipped at +-65504 since the last reset (needs set_option("check_saturation", 1));
+        synchronises the current stream."""
+        n = ctypes.c_int64()
+        with torch.cuda.device(self._device):
+            _lib.check(_lib.lib().lbic_saturation_count(self._need(), self._stream(), ctypes.byref(n), 1 if reset else 0))
+        return int(n.value)
+
     def launch_count(self) -> int:
         return int(_lib.lib().lbic_launch_count(self._need()))
 

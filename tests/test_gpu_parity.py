@@ -911,6 +911,34 @@ def test_layout_kernels_match_reference_definition(dev):
         assert torch.equal(back.cpu(), img)
 
 
+def test_saturation_counter(dev):
+    """The fp16 operand planes clip at +-65504 silently; with check_saturation set every layer's hi plane is scanned and
+    the clipped elements are counted: none for the conditioned synthetic weights, many when the last encoder layer is
+    scaled far out of range; results do not depend on the option."""
+    from lbic_b200.layout import arrange_block_pixels_to_channel_dim
+    cfg = lbic_b200.load_config("B8_lowrate")
+    img = weights.synth_images(3, 5 * 8, 7 * 8, seed0=9)
+    x = arrange_block_pixels_to_channel_dim((img - 0.5).to(dev), 8)
+    m = get_model("B8_lowrate", 1337, False, dev)
+    ref = m.compress_batch(x, lanes=0, return_symbols=True)
+    try:
+        m.set_option("check_saturation", 1)
+        m.saturation_count(reset=True)
+        got = m.compress_batch(x, lanes=0, return_symbols=True)
+        assert m.saturation_count() == 0
+        assert got[0] == ref[0] and torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2])
+    finally:
+        m.set_option("check_saturation", 0)
+    big = BlockBasedImgCompLossyNetv9(cfg, device=dev)
+    big.load_state_dict(weights.synth_state_dict(cfg, 1337, latent_gain=3e6))
+    big.update(force=True)
+    big.set_option("check_saturation", 1)
+    o = big.encode_device(x, lanes=0, stream_cap=1 << 20)
+    n = big.saturation_count()
+    assert n > 0, "y_qnt of ~1e5 must clip its fp16 hi plane"
+    assert big.saturation_count() == 0      # reset by the previous call
+
+
 def test_error_behaviour(dev):
     cfg = lbic_b200.load_config("B8_lowrate")
     m = BlockBasedImgCompLossyNetv9(cfg, device=dev)
