@@ -524,7 +524,11 @@ int build_chain(lbic_model *m) {
         return e;
     };
     if (m->k1 == 3) {
-        set(L_E0, &ws.vText, nullptr, epi_hilo(EPI_LRELU, none, ws.G0));   // not run through the chain (ring rows)
+        {
+            EpiParams e0 = epi_hilo(EPI_LRELU, none, ws.G0);                // rows of the EXTENDED step, scattered into the g0
+            e0.out_pos = 1;                                                 // store (wave kernel; the dataflow launch starts at E1)
+            set(L_E0, &ws.vText, nullptr, e0);
+        }
         set(L_E1, &ws.vH1x5, nullptr, epi_hilo(EPI_LRELU, none, ws.H2));
     } else {
         set(L_E0, &ws.vT, nullptr, epi_hilo(EPI_LRELU, none, ws.H1));
@@ -850,10 +854,18 @@ struct RowHooks {
 
 // The persistent wavefront kernel (gemm_wave.cu) takes over when every step of the call has at most wave_max_rows rows.
 bool wave_applies(const lbic_model *m, int n_img, int Hb, int Wb, bool raster, bool decode) {
-    if (!m->use_wave || m->gemm_core != 0 || m->force_bn || m->k1 != 1 || m->profiling || m->check_sat || m->selfinfo_cl ||
+    if (!m->use_wave || m->gemm_core != 0 || m->force_bn || m->profiling || m->check_sat || m->selfinfo_cl ||
         m->recon_cl || !gemm_wave_supported())
         return false;
     const int max_nv = Hb < (Wb + 1) / 2 ? Hb : (Wb + 1) / 2;
+    if (m->k1 == 3) {
+        // five-tap topologies: wavefront calls whose EXTENDED steps (two ring positions more per image) fit one row block
+        const int nv_ext = Hb < (Wb + 3) / 2 + 1 ? Hb : (Wb + 3) / 2 + 1;
+        // (a one-column image has steps with ring positions but no block of the image: those stay on the per-layer path)
+        if (raster || Wb < 2 || (long)n_img * nv_ext > 128) return false;
+        if (decode && (m->tables.cdf16_total <= 0 || (long)n_img * nv_ext > m->wave_dec_max_rows)) return false;
+        return true;
+    }
     const long rows = raster ? n_img : (long)n_img * max_nv;
     int cap = m->wave_max_rows < gemm_wave_max_rows() ? m->wave_max_rows : gemm_wave_max_rows();
     if (decode) {
@@ -882,6 +894,12 @@ int run_wave(lbic_model *m, bool decode, bool raster, int s_begin, int s_end, in
     w.X_hi = ws.X.hi; w.X_lo = ws.X.lo; w.ldX = ws.X.ld;
     w.T_hi = ws.T.hi; w.T_lo = ws.T.lo; w.ldT = ws.T.ld;
     w.scale_tab = m->tables.d_scale_table;
+    if (m->k1 == 3) {
+        w.k3 = 1; w.E1 = m->E1;
+        w.Text_hi = ws.Text.hi; w.Text_lo = ws.Text.lo; w.ldText = ws.Text.ld;
+        w.G0_hi = ws.G0.hi; w.G0_lo = ws.G0.lo;
+        w.H5_hi = ws.H1x5.hi; w.H5_lo = ws.H1x5.lo; w.ldH5 = ws.H1x5.ld;
+    }
     if (decode) {
         const Tables &T = m->tables;
         w.cdf = T.cdf; w.cdf_stride = T.stride; w.cdf_len = T.cdf_length; w.offs = T.offset;
@@ -1264,7 +1282,8 @@ int encode_impl(lbic_model *m, const float *x, int n_img, int Hb, int Wb, float 
             }
         }
         if (wave) {
-            if (has && pend < 0) pend = t;
+            if (!has) LBIC_TRY(launch_step(t));      // KS[1] = 3: step -1 has ring positions only (one small GEMM, per-layer path)
+            else if (pend < 0) pend = t;
         } else {
             LBIC_TRY(launch_step(t));
         }
@@ -1487,7 +1506,8 @@ int decode_impl(lbic_model *m, const uint8_t *streams, const uint32_t *stream_le
     const int s_last = raster ? Hb * Wb : Wb + 2 * (Hb - 1);
     for (int s = s_first; s < s_last; ++s) {
         if (wave) {
-            if (pend < 0 && s >= 0) pend = s;
+            if (s < 0) LBIC_TRY(launch_step(s));     // KS[1] = 3: step -1 has ring positions only
+            else if (pend < 0) pend = s;
         } else {
             LBIC_TRY(launch_step(s));
         }

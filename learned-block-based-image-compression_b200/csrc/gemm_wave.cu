@@ -29,7 +29,7 @@
 
 namespace {
 
-constexpr int WAVE_MAX_ORD = 20;
+constexpr int WAVE_MAX_ORD = 24;
 constexpr int WAVE_MAX_RB = 32;                  // 128-row blocks per step
 // Operand ring: a slot holds one 64-wide k-block = the activation box (hi + lo planes, 16..128 rows: only the rows the
 // step has) + 32 weight rows (hi + lo).  A tile's mainloop is bound by the LATENCY of its loads (a layer's K / 64
@@ -48,10 +48,15 @@ constexpr int WAVE_RANS_PARTS = 16;              // rANS tiles per 128-row block
 constexpr int WAVE_ENT_CTAS = 8;                 // decode launches: CTAs that keep the CDF tables in shared memory (rANS tiles only)
 static_assert(WAVE_SMEM <= SMEM_LIMIT, "wave kernel shared memory");
 
-enum WaveKind { WK_GEMM = 0, WK_GATHER = 1, WK_RANS = 2 };
+// KS[1] = 3 (five-tap second entropy layer): the hidden map g0 = lrelu(E0 T) lives in a position-indexed store that
+// includes a one-block ring outside the image (api.cu: run_g0).  A step then also has WK_GATHER_EXT tiles (the four
+// zhat taps of the EXTENDED step's rows -- the step's blocks plus the ring positions that become computable), the E0
+// layer on those rows (epilogue scatters into the store) and WK_GATHER5 tiles (the five taps of g0 -> operand of E1).
+enum WaveKind { WK_GEMM = 0, WK_GATHER = 1, WK_RANS = 2, WK_GATHER_EXT = 3, WK_GATHER5 = 4 };
 
 struct WaveOrd {
     int kind;
+    int ext;        // 1: the entry's rows are those of the extended step (KS[1] = 3: WK_GATHER_EXT and the E0 layer)
     int layer;      // ChainLayer index (WK_GEMM)
     int ntn;        // tiles per 128-row block
     int bn;         // tile width (WK_GEMM)
@@ -77,6 +82,11 @@ struct WaveParams {
     int Cin, gather_first;       // gather tiles cover segments gather_first .. 4 (0 = x, 1..4 = the four zhat taps)
     h16 *X_hi, *X_lo; int ldX;
     h16 *T_hi, *T_lo; int ldT;
+    // KS[1] = 3
+    int k3, E1;
+    h16 *Text_hi, *Text_lo; int ldText;          // zhat taps of the extended step's rows (operand of E0)
+    const h16 *G0_hi, *G0_lo;                    // ring-extended hidden-map store, rows g0_pos_index(), E1 columns
+    h16 *H5_hi, *H5_lo; int ldH5;                // five-tap operand of E1
     const int32_t *cdf; int cdf_stride; const int32_t *cdf_len, *offs; const float *scale_tab;
     RansStreamState *states; const uint8_t *const *lane_ptr; int lanes;
     const float *ksi; int ld_ksi; h16 *yq_hi, *yq_lo; int ld_yq; int32_t *sym_out; int M;
@@ -110,8 +120,24 @@ __device__ __forceinline__ bool wave_step_desc(const WaveParams &p, int s, StepD
     return true;
 }
 
+// extended step of KS[1] = 3 (api.cu: wave_step_ext): the positions (v, h = t - 2 v) with h in [-1, Wb]
+__device__ __forceinline__ bool wave_step_desc_ext(const WaveParams &p, int t, StepDesc &sd) {
+    sd.n_img = p.n_img; sd.Hb = p.Hb; sd.Wb = p.Wb;
+    const int a = t - p.Wb + 1;
+    int vmin = a >= 0 ? a / 2 : -((-a + 1) / 2);          // floor(a / 2)
+    if (vmin < 0) vmin = 0;
+    const int b = t + 1;
+    int vmax = b >= 0 ? b / 2 : -((-b + 1) / 2);
+    if (vmax > p.Hb - 1) vmax = p.Hb - 1;
+    if (vmax < vmin) return false;
+    sd.nv = vmax - vmin + 1; sd.vmin = vmin; sd.t = t;
+    return true;
+}
+
 struct WaveTile {
     StepDesc sd;
+    StepDesc sd_ext;     // KS[1] = 3
+    int R_ext;
     int R, n_rb, prev_n_rb;
     int oi, rb, nt;      // list entry, row block, tile within (entry, row block)
     int s, j;            // step, tile index within the step (trace)
@@ -140,6 +166,10 @@ __device__ __forceinline__ void wave_for_each_tile(const WaveParams &p, F &&f) {
         WaveTile w;
         if (!wave_step_desc(p, s, w.sd)) continue;
         w.R = w.sd.n_img * w.sd.nv;
+        w.R_ext = 0;
+        if (p.k3) {              // (one row block per step in this mode: the launch is refused otherwise)
+            if (wave_step_desc_ext(p, s, w.sd_ext)) w.R_ext = w.sd_ext.n_img * w.sd_ext.nv;
+        }
         w.n_rb = (w.R + BM - 1) / BM;
         w.prev_n_rb = prev_n_rb;
         w.s = s;
@@ -210,8 +240,11 @@ __device__ __forceinline__ void wave_wait_prev_step(const WaveParams &p, const W
 // (row, 4-channel) items, eight loads in flight at a time.
 constexpr int WAVE_GATHER_PARTS = 4;
 
-__device__ __noinline__ void wave_gather_tile(const WaveParams &p, const WaveTile w, RowTab *rt, int et) {
-    const int seg = p.gather_first + w.nt / WAVE_GATHER_PARTS;
+__device__ __noinline__ void wave_gather_tile(const WaveParams &p, const WaveTile w0, RowTab *rt, int et, int ext) {
+    // ext: the four zhat taps of the EXTENDED step's rows -> the operand of E0 (KS[1] = 3); same arithmetic
+    WaveTile w = w0;
+    if (ext) { w.sd = w0.sd_ext; w.R = w0.R_ext; }
+    const int seg = (ext ? 1 : p.gather_first) + w.nt / WAVE_GATHER_PARTS;
     const int part = w.nt % WAVE_GATHER_PARTS;
     const int m0 = w.rb * BM + part * 32;
     int rows = w.R - m0;
@@ -231,13 +264,13 @@ __device__ __noinline__ void wave_gather_tile(const WaveParams &p, const WaveTil
             const int vv = v + ((tap == 3) ? 0 : -1), hh = h + ((tap == 3) ? -1 : tap - 1);
             if (vv >= 0 && vv < w.sd.Hb && hh >= 0 && hh < w.sd.Wb)
                 src = p.zhat_cl + (((size_t)img * w.sd.Hb + vv) * w.sd.Wb + hh) * p.Cin;
-            dst = (size_t)r * p.ldT + (size_t)tap * p.Cin;
+            dst = (size_t)r * (ext ? p.ldText : p.ldT) + (size_t)tap * p.Cin;
         }
         rt->f32[et] = reinterpret_cast<unsigned long long>(src);
         rt->hilo[et] = (unsigned long long)dst;
     }
     epi_bar();
-    h16 *ph = seg == 0 ? p.X_hi : p.T_hi, *pl = seg == 0 ? p.X_lo : p.T_lo;
+    h16 *ph = seg == 0 ? p.X_hi : (ext ? p.Text_hi : p.T_hi), *pl = seg == 0 ? p.X_lo : (ext ? p.Text_lo : p.T_lo);
     const int items = rows * c4n;
     for (int i0 = et; i0 < items; i0 += 8 * WS_EPI_THREADS) {
         float4 val[8];
@@ -258,6 +291,51 @@ __device__ __noinline__ void wave_gather_tile(const WaveParams &p, const WaveTil
                 const int row = i / c4n, c4 = i - row * c4n;
                 const float f[4] = {val[u].x, val[u].y, val[u].z, val[u].w};
                 store_hilo<4>(ph + rt->hilo[row] + c4 * 4, pl + rt->hilo[row] + c4 * 4, f);
+            }
+        }
+    }
+}
+
+// ---- GATHER5 tile (KS[1] = 3): one of the five live taps of the 3x3 mask-'B' kernel for a quarter (32 rows) of the row
+// block: H5[r, tap * E1 + c] = g0(v + dv, h + dh)[c], both planes, from the ring-extended store (gather5_kernel).
+__device__ __noinline__ void wave_gather5_tile(const WaveParams &p, const WaveTile w, RowTab *rt, int et) {
+    const int tap = w.nt / WAVE_GATHER_PARTS, part = w.nt % WAVE_GATHER_PARTS;
+    const int m0 = w.rb * BM + part * 32;
+    int rows = w.R - m0;
+    rows = rows < 0 ? 0 : (rows > 32 ? 32 : rows);
+    if (et < rows) {
+        const int r = m0 + et;
+        int img, v, h;
+        step_row_to_block(w.sd, r, img, v, h);
+        const int dv = (tap >= 3) ? 0 : -1;
+        const int dh = (tap >= 3) ? tap - 4 : tap - 1;
+        rt->f32[et] = (unsigned long long)(g0_pos_index(img, v + dv, h + dh, w.sd.Hb, w.sd.Wb) * (size_t)p.E1);
+        rt->hilo[et] = (unsigned long long)((size_t)r * p.ldH5 + (size_t)tap * p.E1);
+    }
+    epi_bar();
+    const int c8n = p.E1 >> 3;                   // 16-byte chunks per plane row
+    const int items = rows * c8n * 2;            // (row, chunk, plane)
+    for (int i0 = et; i0 < items; i0 += 8 * WS_EPI_THREADS) {
+        uint4 val[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * WS_EPI_THREADS;
+            val[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < items) {
+                const int pl = i & 1, j = i >> 1;
+                const int row = j / c8n, c8 = j - row * c8n;
+                const h16 *src = (pl ? p.G0_lo : p.G0_hi) + rt->f32[row] + c8 * 8;
+                val[u] = __ldcg(reinterpret_cast<const uint4 *>(src));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * WS_EPI_THREADS;
+            if (i < items) {
+                const int pl = i & 1, j = i >> 1;
+                const int row = j / c8n, c8 = j - row * c8n;
+                h16 *dst = (pl ? p.H5_lo : p.H5_hi) + rt->hilo[row] + c8 * 8;
+                *reinterpret_cast<uint4 *>(dst) = val[u];
             }
         }
     }
@@ -388,7 +466,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                 const ChainLayer &Lr = p.layers[o.layer];
                 const int bn = o.bn;
                 const int m0 = w.rb * BM, n0 = w.nt * bn;
-                const int rows = (w.R - m0) < BM ? (w.R - m0) : BM;
+                const int R_use = o.ext ? w.R_ext : w.R;
+                const int rows = (R_use - m0) < BM ? (R_use - m0) : BM;
                 const int cls = lbic_box_class(rows);          // only the rows the step has are loaded
                 const int nseg = Lr.nseg > 1 ? 2 : 1;
                 // descriptors of this tile's operands into the descriptor cache while the inputs are still being produced
@@ -528,10 +607,10 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                     constexpr int OFF_R = (int)(offsetof(EpiParams, R) / 4), OFF_STEP = (int)(offsetof(EpiParams, step) / 4);
                     constexpr int NSTEP = (int)(sizeof(StepDesc) / 4);
                     const uint32_t *g = reinterpret_cast<const uint32_t *>(&Lr.ep);
-                    const uint32_t *sw = reinterpret_cast<const uint32_t *>(&w.sd);
+                    const uint32_t *sw = reinterpret_cast<const uint32_t *>(o.ext ? &w.sd_ext : &w.sd);
                     if (et < NW) {
                         uint32_t wd = g[et];
-                        if (et == OFF_R) wd = (uint32_t)w.R;
+                        if (et == OFF_R) wd = (uint32_t)(o.ext ? w.R_ext : w.R);
                         else if (et >= OFF_STEP && et < OFF_STEP + NSTEP) wd = sw[et - OFF_STEP];
                         reinterpret_cast<uint32_t *>(s_ep)[et] = wd;
                     }
@@ -555,13 +634,15 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                 // non-GEMM tiles: one thread waits for the inputs, then all eight warps work
                 epi_bar();     // the previous tile is done with the row table
                 if (et == 0) {
-                    if (o.kind == WK_GATHER) wave_wait_prev_step(p, w, gen);
+                    if (o.kind == WK_GATHER || o.kind == WK_GATHER_EXT) wave_wait_prev_step(p, w, gen);
                     else wave_wait_deps(p, w, gen);
                     WAVE_TRACE(0);
                 }
                 epi_bar();
                 __syncwarp();  // lane 0 of warp 2 took the branch above: the warp-wide shuffles / votes below want it reconverged
-                if (o.kind == WK_GATHER) wave_gather_tile(p, w, rt, et);
+                if (o.kind == WK_GATHER) wave_gather_tile(p, w, rt, et, 0);
+                else if (o.kind == WK_GATHER_EXT) wave_gather_tile(p, w, rt, et, 1);
+                else if (o.kind == WK_GATHER5) wave_gather5_tile(p, w, rt, et);
                 else wave_rans_tile(p, w, tb, stab, ew, lane);
             }
             if (et == 0) WAVE_TRACE(5);
@@ -630,7 +711,19 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
     p.cdf = w.cdf; p.cdf_stride = w.cdf_stride; p.cdf_len = w.cdf_len; p.offs = w.offs; p.scale_tab = w.scale_tab;
     p.states = w.states; p.lane_ptr = w.lane_ptr; p.lanes = w.lanes;
     p.ksi = w.ksi; p.ld_ksi = w.ld_ksi; p.yq_hi = w.yq_hi; p.yq_lo = w.yq_lo; p.ld_yq = w.ld_yq; p.sym_out = w.sym_out; p.M = w.M;
-    const int max_rows = w.raster ? w.n_img : w.n_img * (w.Hb < (w.Wb + 1) / 2 ? w.Hb : (w.Wb + 1) / 2);
+    int max_rows = w.raster ? w.n_img : w.n_img * (w.Hb < (w.Wb + 1) / 2 ? w.Hb : (w.Wb + 1) / 2);
+    p.k3 = w.k3 ? 1 : 0;
+    if (p.k3) {
+        // KS[1] = 3: the extended step has up to two more positions per image (the ring columns); one 128-row block only
+        if (w.raster) return lbic_fail(LBIC_ERR_INVALID, "wave kernel: KS[1] = 3 has no raster mode");
+        const int nv_ext = (w.Hb < (w.Wb + 3) / 2 + 1 ? w.Hb : (w.Wb + 3) / 2 + 1);
+        max_rows = w.n_img * nv_ext;
+        if (max_rows > BM) return lbic_fail(LBIC_ERR_INVALID, "wave kernel: KS[1] = 3 steps must fit one row block (%d rows)", max_rows);
+        p.E1 = w.E1;
+        p.Text_hi = w.Text_hi; p.Text_lo = w.Text_lo; p.ldText = w.ldText;
+        p.G0_hi = w.G0_hi; p.G0_lo = w.G0_lo;
+        p.H5_hi = w.H5_hi; p.H5_lo = w.H5_lo; p.ldH5 = w.ldH5;
+    }
     if (max_rows > WAVE_MAX_RB * BM) return lbic_fail(LBIC_ERR_INVALID, "wave kernel: step of %d rows exceeds %d", max_rows, WAVE_MAX_RB * BM);
     {
         static int m64 = -1;     // LBIC_WAVE_M64=0 keeps M = 128 (tests, measurements)
@@ -662,7 +755,7 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
     // entropy net's in a CTA's own list; the entropy net only has to be done when F3 quantises.
     int n = 0;
     auto add = [&](int kind, int layer, int ntn, int bn, int d0, int d1) {
-        p.ord[n].kind = kind; p.ord[n].layer = layer; p.ord[n].ntn = ntn; p.ord[n].bn = bn;
+        p.ord[n].kind = kind; p.ord[n].ext = 0; p.ord[n].layer = layer; p.ord[n].ntn = ntn; p.ord[n].bn = bn;
         p.ord[n].dep[0] = d0; p.ord[n].dep[1] = d1;
         return n++;
     };
@@ -675,7 +768,37 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
     p.gather_first = w.decode ? 1 : 0;
     const int g = add(WK_GATHER, -1, (w.decode ? 4 : 5) * WAVE_GATHER_PARTS, 0, -1, -1);
     int last_e, last;
-    if (!w.decode) {
+    // KS[1] = 3: the entropy net's first layer runs on the extended step's rows and scatters into the g0 store; the
+    // second layer reads its five taps from there
+    auto ent_k3 = [&]() {
+        const int gx = add(WK_GATHER_EXT, -1, 4 * WAVE_GATHER_PARTS, 0, -1, -1);
+        const int e0 = gemm(E[0], gx, -1);
+        p.ord[gx].ext = 1; p.ord[e0].ext = 1;
+        const int g5 = add(WK_GATHER5, -1, 5 * WAVE_GATHER_PARTS, 0, e0, -1);
+        const int e1 = gemm(E[1], g5, -1);
+        const int e2 = gemm(E[2], e1, -1);
+        return gemm(E[3], e2, -1);
+    };
+    if (p.k3 && !w.decode) {
+        // the entropy net is the longer chain here (E1 has K = 5 E1): its tiles first
+        const int f0 = gemm(F[0], g, -1);
+        last_e = ent_k3();
+        const int g0 = gemm(F[1], f0, -1);
+        const int f1 = gemm(F[2], g0, -1);
+        const int g1 = gemm(F[3], f1, -1);
+        const int f2 = gemm(F[4], g1, -1);
+        const int g2 = gemm(F[5], f2, -1);
+        last = gemm(F[6], g2, last_e);
+    } else if (p.k3) {
+        last_e = ent_k3();
+        last = add(WK_RANS, -1, WAVE_RANS_PARTS, 0, last_e, -1);
+        p.rans_ord = last;
+        p.n_ent = WAVE_ENT_CTAS;
+        p.cdf16 = w.cdf16; p.cdf16_off = w.cdf16_off; p.cdf16_total = w.cdf16_total;
+        if (!w.cdf16 || w.cdf16_total <= 0 ||
+            (size_t)w.cdf16_total * 2 + 16 + 3 * 64 * 4 + 8 * (size_t)RANS_ROW_SCRATCH(w.M) > (size_t)WAVE_RING)
+            return lbic_fail(LBIC_ERR_INVALID, "wave kernel: entropy tables do not fit shared memory");
+    } else if (!w.decode) {
         // interleaved: F0 E0 G0 E1 F1 E2 G1 E3 F2 G2 F3 | D0 .. D3
         const int f0 = gemm(F[0], g, -1);
         const int e0 = gemm(E[0], g, -1);

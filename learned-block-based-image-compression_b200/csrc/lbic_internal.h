@@ -174,6 +174,11 @@ struct WaveLaunch {
     int Cin;
     h16 *X_hi, *X_lo; int ldX;
     h16 *T_hi, *T_lo; int ldT;
+    // KS[1] = 3: taps of the extended step (operand of E0), the ring-extended g0 store, the five-tap operand of E1
+    int k3, E1;
+    h16 *Text_hi, *Text_lo; int ldText;
+    const h16 *G0_hi, *G0_lo;
+    h16 *H5_hi, *H5_lo; int ldH5;
     // decode only
     const int32_t *cdf; int cdf_stride; const int32_t *cdf_len, *offs; const float *scale_tab;
     RansStreamState *states; const uint8_t *const *lane_ptr; int lanes;
