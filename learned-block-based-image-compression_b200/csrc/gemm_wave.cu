@@ -793,7 +793,7 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
         last_e = ent_k3();
         last = add(WK_RANS, -1, WAVE_RANS_PARTS, 0, last_e, -1);
         p.rans_ord = last;
-        p.n_ent = WAVE_ENT_CTAS;
+        p.n_ent = max_rows > 8 * WAVE_ENT_CTAS ? 2 * WAVE_ENT_CTAS : WAVE_ENT_CTAS;   // one warp per row: 64 or 128 rows per round
         p.cdf16 = w.cdf16; p.cdf16_off = w.cdf16_off; p.cdf16_total = w.cdf16_total;
         if (!w.cdf16 || w.cdf16_total <= 0 ||
             (size_t)w.cdf16_total * 2 + 16 + 3 * 64 * 4 + 8 * (size_t)RANS_ROW_SCRATCH(w.M) > (size_t)WAVE_RING)
@@ -818,7 +818,7 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
         last_e = gemm(E[3], e2, -1);
         last = add(WK_RANS, -1, WAVE_RANS_PARTS, 0, last_e, -1);
         p.rans_ord = last;
-        p.n_ent = WAVE_ENT_CTAS;
+        p.n_ent = max_rows > 8 * WAVE_ENT_CTAS ? 2 * WAVE_ENT_CTAS : WAVE_ENT_CTAS;   // one warp per row: 64 or 128 rows per round
         p.cdf16 = w.cdf16; p.cdf16_off = w.cdf16_off; p.cdf16_total = w.cdf16_total;
         if (!w.cdf16 || w.cdf16_total <= 0 ||
             (size_t)w.cdf16_total * 2 + 16 + 3 * 64 * 4 + 8 * (size_t)RANS_ROW_SCRATCH(w.M) > (size_t)WAVE_RING)
