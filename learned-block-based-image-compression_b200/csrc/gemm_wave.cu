@@ -61,6 +61,10 @@ struct WaveOrd {
     int ntn;        // tiles per 128-row block
     int bn;         // tile width (WK_GEMM)
     int dep[2];     // list entries this one reads from, -1 = none
+    // WK_GEMM: a dependency that only the k-blocks from kb_late on have (KS[1] = 3: the last of E1's five taps is the only
+    // one this step's E0 produces; the chain of the other four -- 4/5 of the layer's K -- starts at the top of the step)
+    int dep_late, kb_late;
+    int tap0;       // WK_GATHER5: first tap of this entry (its ntn / WAVE_GATHER_PARTS taps)
 };
 
 struct WaveParams {
@@ -76,6 +80,8 @@ struct WaveParams {
     int variant;
     int stages;                  // ring depth of this launch
     int kb_group;                // k-blocks the MMA issuer takes per barrier round trip (1..4)
+    int kb_adapt;                // 1: only as many of them as have landed when the first one has
+    int w_first;                 // a tile's first w_first weight boxes are requested before its dependency wait
     int m64;                     // every step of the launch has at most 64 rows: M = 64 MMAs (40 instead of 52 cycles each)
     uint32_t slot_bytes, a_plane_bytes;   // slot stride; bytes of one activation plane of the launch's largest box
     const float *x_cl, *zhat_cl;
@@ -93,6 +99,7 @@ struct WaveParams {
     // decode: the last n_ent CTAs are ENTROPY CTAs: they keep the compact 16-bit CDF rows (Tables::cdf16) in shared
     // memory (they need no operand ring) and run the rANS tiles, nothing else; every other tile goes to the other CTAs
     int n_ent, rans_ord;
+    int n_xg, xg_e0, xg_e1;      // side-chain CTAs and their list entries [xg_e0, xg_e1) (0 CTAs = no such group)
     const uint16_t *cdf16; const int32_t *cdf16_off; int cdf16_total;
     // debug (LBIC_WAVE_TRACE): %globaltimer stamps of every tile of steps [trace_s0, trace_s0 + trace_ns), 8 words each
     unsigned long long *trace;
@@ -158,9 +165,13 @@ __device__ __forceinline__ void wave_for_each_tile(const WaveParams &p, F &&f) {
     int gen[WAVE_MAX_RB];
 #pragma unroll 1
     for (int i = 0; i < WAVE_MAX_RB; ++i) gen[i] = 0;
-    int off = 0, off_e = 0, prev_n_rb = 0;
-    const int NE = p.n_ent, Gw = (int)gridDim.x - NE;        // worker CTAs 0 .. Gw-1, entropy CTAs Gw .. Gw+NE-1
-    const bool is_ent = NE > 0 && (int)blockIdx.x >= Gw;
+    int off = 0, off_e = 0, off_x = 0, prev_n_rb = 0;
+    // CTA groups: workers 0 .. Gw-1 | NX CTAs of the side chain (KS[1] = 3: the entropy net, whose E1 tiles are five times
+    // as long as any other and must not sit in front of an encoder-net tile in a CTA's queue) | NE entropy CTAs (rANS
+    // tiles).  Each group walks its own tiles of the list round-robin; the list positions of a group are contiguous.
+    const int NE = p.n_ent, NX = p.n_xg, Gw = (int)gridDim.x - NE - NX;
+    const bool is_ent = NE > 0 && (int)blockIdx.x >= Gw + NX;
+    const bool is_x = NX > 0 && !is_ent && (int)blockIdx.x >= Gw;
 #pragma unroll 1
     for (int s = p.s_begin; s < p.s_end; ++s) {
         WaveTile w;
@@ -176,34 +187,35 @@ __device__ __forceinline__ void wave_for_each_tile(const WaveParams &p, F &&f) {
         const int total = w.n_rb * p.tiles_per_rb;
         const int cnt_r = NE > 0 ? w.n_rb * p.ord[p.rans_ord].ntn : 0;     // rANS tiles of the step, a contiguous range
         const int start_r = NE > 0 ? w.n_rb * p.pre[p.rans_ord] : 0;
-        if (is_ent) {
-            int first = (int)blockIdx.x - Gw - off_e;
-            if (first < 0) first += NE;
+        const int cnt_x = NX > 0 ? w.n_rb * (p.pre[p.xg_e1] - p.pre[p.xg_e0]) : 0;   // side-chain tiles, contiguous, before the rANS tiles
+        const int start_x = NX > 0 ? w.n_rb * p.pre[p.xg_e0] : 0;
+        auto locate = [&](int j) {               // list position -> (entry, row block, tile)
+            int oi = 0;
+            while (j >= w.n_rb * p.pre[oi + 1]) ++oi;
+            const int v = j - w.n_rb * p.pre[oi];
+            w.oi = oi;
+            w.rb = v / p.ord[oi].ntn;
+            w.nt = v - w.rb * p.ord[oi].ntn;
+            w.j = j;
+        };
+        // one loop (one copy of every role's code) for the three groups: tile k of the group's share of the step
+        int cnt, stride, first, base;
+        if (is_ent) { cnt = cnt_r; stride = NE; first = (int)blockIdx.x - Gw - NX - off_e; base = start_r; }
+        else if (is_x) { cnt = cnt_x; stride = NX; first = (int)blockIdx.x - Gw - off_x; base = start_x; }
+        else { cnt = total - cnt_r - cnt_x; stride = Gw; first = (int)blockIdx.x - off; base = 0; }
+        if (first < 0) first += stride;
 #pragma unroll 1
-            for (int k = first; k < cnt_r; k += NE) {
-                w.oi = p.rans_ord;
-                w.rb = k / p.ord[p.rans_ord].ntn;
-                w.nt = k - w.rb * p.ord[p.rans_ord].ntn;
-                w.j = start_r + k;
-                f(w, gen);
+        for (int k = first; k < cnt; k += stride) {
+            int j = base + k;
+            if (!is_ent && !is_x) {          // the workers' share is the list without the other groups' ranges
+                if (cnt_x > 0 && j >= start_x) j += cnt_x;
+                if (cnt_r > 0 && j >= start_r) j += cnt_r;
             }
-        } else {
-            int first = (int)blockIdx.x - off;
-            if (first < 0) first += Gw;
-#pragma unroll 1
-            for (int jj = first; jj < total - cnt_r; jj += Gw) {
-                const int j = jj < start_r ? jj : jj + cnt_r;
-                int oi = 0;
-                while (j >= w.n_rb * p.pre[oi + 1]) ++oi;
-                const int v = j - w.n_rb * p.pre[oi];
-                w.oi = oi;
-                w.rb = v / p.ord[oi].ntn;
-                w.nt = v - w.rb * p.ord[oi].ntn;
-                w.j = j;
-                f(w, gen);
-            }
+            locate(j);
+            f(w, gen);
         }
-        off = (off + total - cnt_r) % Gw;
+        if (NX > 0) off_x = (off_x + cnt_x) % NX;
+        off = (off + total - cnt_r - cnt_x) % Gw;
         if (NE > 0) off_e = (off_e + cnt_r) % NE;
         for (int rb = 0; rb < w.n_rb; ++rb) gen[rb]++;
         prev_n_rb = w.n_rb;
@@ -298,11 +310,13 @@ __device__ __noinline__ void wave_gather_tile(const WaveParams &p, const WaveTil
 
 // ---- GATHER5 tile (KS[1] = 3): one of the five live taps of the 3x3 mask-'B' kernel for a quarter (32 rows) of the row
 // block: H5[r, tap * E1 + c] = g0(v + dv, h + dh)[c], both planes, from the ring-extended store (gather5_kernel).
+constexpr int WAVE_G5_PARTS = 16;          // 8 rows of one tap per tile (2 x 18 KiB for E1 = 1152): a tile takes ~1 us per row
+
 __device__ __noinline__ void wave_gather5_tile(const WaveParams &p, const WaveTile w, RowTab *rt, int et) {
-    const int tap = w.nt / WAVE_GATHER_PARTS, part = w.nt % WAVE_GATHER_PARTS;
-    const int m0 = w.rb * BM + part * 32;
+    const int tap = p.ord[w.oi].tap0 + w.nt / WAVE_G5_PARTS, part = w.nt % WAVE_G5_PARTS;
+    const int m0 = w.rb * BM + part * (BM / WAVE_G5_PARTS);
     int rows = w.R - m0;
-    rows = rows < 0 ? 0 : (rows > 32 ? 32 : rows);
+    rows = rows < 0 ? 0 : (rows > BM / WAVE_G5_PARTS ? BM / WAVE_G5_PARTS : rows);
     if (et < rows) {
         const int r = m0 + et;
         int img, v, h;
@@ -478,27 +492,54 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(ta)) : "memory");
                             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&Lr.tmW[p.variant][sg][pl])) : "memory");
                         }
+                }
+                const int kb0 = Lr.kb[0], nkb = kb0 + (Lr.nseg > 1 ? Lr.kb[1] : 0);
+                const uint32_t w_plane = (uint32_t)bn * (BK * 2);
+                const uint32_t stage_tx = 2u * (uint32_t)lbic_box_rows(cls) * (BK * 2) + 2 * w_plane;
+                // the weights do not depend on the previous layer: the ring's worth of weight boxes goes out BEFORE the
+                // dependency wait (the slot's barrier is armed for the whole stage; the activation boxes follow below), so
+                // that a tile's first MMAs wait for one L2 round trip of its activations only
+                const int npre0 = p.w_first < stages ? p.w_first : stages, npre = nkb < npre0 ? nkb : npre0;
+                for (int j = 0; j < npre; ++j) {
+                    const uint32_t itj = it + (uint32_t)j;
+                    const int s = itj % stages;
+                    mbar_wait(empty_bar(s), ((itj / stages) & 1u) ^ 1u);
+                    const uint32_t sa = ring + s * p.slot_bytes;
+                    const int seg = j >= kb0 ? 1 : 0;
+                    const int kk = (seg ? j - kb0 : j) * BK;
+                    if (elect_one()) {
+                        mbar_expect_tx(full_bar(s), stage_tx);
+                        tma_load_2d(sa + off_w, &Lr.tmW[p.variant][seg][0], full_bar(s), kk, n0);
+                        tma_load_2d(sa + off_w + w_plane, &Lr.tmW[p.variant][seg][1], full_bar(s), kk, n0);
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) {
                     wave_wait_deps(p, w, gen);
                     WAVE_TRACE(0);
                 }
                 __syncwarp();
                 asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores of other CTAs -> our TMA reads
-                const int kb0 = Lr.kb[0], nkb = kb0 + (Lr.nseg > 1 ? Lr.kb[1] : 0);
-                const uint32_t w_plane = (uint32_t)bn * (BK * 2);
-                const uint32_t stage_tx = 2u * (uint32_t)lbic_box_rows(cls) * (BK * 2) + 2 * w_plane;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    if (o.dep_late >= 0 && kb == o.kb_late) {
+                        if (lane == 0) wave_wait(p.counters + o.dep_late * WAVE_MAX_RB + w.rb, p.ord[o.dep_late].ntn * (gen[w.rb] + 1));
+                        __syncwarp();
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                    }
                     const int s = it % stages;
                     const uint32_t ph = (it / stages) & 1u;
-                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    if (kb >= npre) mbar_wait(empty_bar(s), ph ^ 1u);
                     const uint32_t sa = ring + s * p.slot_bytes;
                     const int seg = kb >= kb0 ? 1 : 0;
                     const int kk = (seg ? kb - kb0 : kb) * BK;
                     if (elect_one()) {
-                        mbar_expect_tx(full_bar(s), stage_tx);
+                        if (kb >= npre) mbar_expect_tx(full_bar(s), stage_tx);
                         tma_load_2d(sa, cls < 4 ? &Lr.tmAs[cls][seg][0] : &Lr.tmA[seg][0], full_bar(s), kk, m0);
                         tma_load_2d(sa + off_alo, cls < 4 ? &Lr.tmAs[cls][seg][1] : &Lr.tmA[seg][1], full_bar(s), kk, m0);
-                        tma_load_2d(sa + off_w, &Lr.tmW[p.variant][seg][0], full_bar(s), kk, n0);
-                        tma_load_2d(sa + off_w + w_plane, &Lr.tmW[p.variant][seg][1], full_bar(s), kk, n0);
+                        if (kb >= npre) {
+                            tma_load_2d(sa + off_w, &Lr.tmW[p.variant][seg][0], full_bar(s), kk, n0);
+                            tma_load_2d(sa + off_w + w_plane, &Lr.tmW[p.variant][seg][1], full_bar(s), kk, n0);
+                        }
                     }
                     __syncwarp();
                 }
@@ -528,8 +569,23 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                 // (starting with a single k-block so that the first MMAs go out as soon as it has landed -- groups of 1, 2, 4, 4 --
                 // measured the same: 33.4 / 32.1 against 33.3 / 31.9 ms)
                 for (int kb = 0; kb < nkb;) {
-                    const int nb = nkb - kb < nb_max ? nkb - kb : nb_max;
-                    {
+                    int nb = nkb - kb < nb_max ? nkb - kb : nb_max;
+                    if (p.kb_adapt) {
+                        // the next k-block, and as many of the following ones as have already landed: a ring that is only a
+                        // little deeper than the group (six slots for KS3311's 64-row boxes) otherwise stalls a whole load
+                        // latency per group when the weights come from DRAM
+                        const int lim = nb;
+                        uint32_t s2 = slot, p2 = phase;
+                        mbar_wait(full_bar(s2), p2);
+                        nb = 1;
+#pragma unroll
+                        for (int u = 1; u < 4; ++u) {
+                            if (u >= lim) break;
+                            if (++s2 == (uint32_t)stages) { s2 = 0; p2 ^= 1u; }
+                            if (!__all_sync(0xffffffffu, mbar_test_wait(full_bar(s2), p2))) break;
+                            nb = u + 1;
+                        }
+                    } else {
                         uint32_t s2 = slot, p2 = phase;
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
@@ -634,7 +690,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gemm_wave_kernel(const __grid
                 // non-GEMM tiles: one thread waits for the inputs, then all eight warps work
                 epi_bar();     // the previous tile is done with the row table
                 if (et == 0) {
-                    if (o.kind == WK_GATHER || o.kind == WK_GATHER_EXT) wave_wait_prev_step(p, w, gen);
+                    if (o.kind == WK_GATHER || o.kind == WK_GATHER_EXT || (o.kind == WK_GATHER5 && o.dep[0] < 0))
+                        wave_wait_prev_step(p, w, gen);          // (reconstruction of step t-1 done => its E0 and E1 are too)
                     else wave_wait_deps(p, w, gen);
                     WAVE_TRACE(0);
                 }
@@ -732,6 +789,12 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
         static int kbg = -1;     // LBIC_WAVE_KB_GROUP: tuning hook
         if (kbg < 0) { const char *e = getenv("LBIC_WAVE_KB_GROUP"); kbg = e ? atoi(e) : 4; kbg = kbg < 1 ? 1 : (kbg > 4 ? 4 : kbg); }
         p.kb_group = kbg;
+        static int kba = -1;     // LBIC_WAVE_KB_ADAPT: tuning hook
+        if (kba < 0) { const char *e = getenv("LBIC_WAVE_KB_ADAPT"); kba = e ? atoi(e) : 1; }
+        p.kb_adapt = kba ? 1 : 0;
+        static int wf = -1;      // LBIC_WAVE_WFIRST: tuning hook
+        if (wf < 0) { const char *e = getenv("LBIC_WAVE_WFIRST"); wf = e ? atoi(e) : 0; }
+        p.w_first = wf < 0 ? 0 : wf;
     }
     int bn_max = 16;
     for (int i = 0; i < 18; ++i) {
@@ -743,7 +806,10 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
         const int box = lbic_box_rows(lbic_box_class(max_rows < BM ? max_rows : BM));   // largest activation box of this launch
         p.a_plane_bytes = (uint32_t)box * (BK * 2);
         p.slot_bytes = 2 * p.a_plane_bytes + 2 * (uint32_t)bn_max * (BK * 2);
-        p.stages = WAVE_RING / (int)p.slot_bytes;
+        // the MMA reads 128 (64) rows of a slot's activation planes whatever the box: only the last slot's over-read needs
+        // the pad behind the ring, the rest of it is ring
+        const int over = ((p.m64 ? 64 : BM) - box) * (BK * 2);
+        p.stages = (WAVE_RING + WAVE_PAD - over) / (int)p.slot_bytes;
         if (p.stages > WAVE_MAX_STAGES) p.stages = WAVE_MAX_STAGES;
         if (p.stages < 2) return lbic_fail(LBIC_ERR_INVALID, "wave kernel: operand slot does not fit the ring");
         static int cap = -1;   // tuning hook: LBIC_WAVE_STAGES caps the ring depth
@@ -756,7 +822,7 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
     int n = 0;
     auto add = [&](int kind, int layer, int ntn, int bn, int d0, int d1) {
         p.ord[n].kind = kind; p.ord[n].ext = 0; p.ord[n].layer = layer; p.ord[n].ntn = ntn; p.ord[n].bn = bn;
-        p.ord[n].dep[0] = d0; p.ord[n].dep[1] = d1;
+        p.ord[n].dep[0] = d0; p.ord[n].dep[1] = d1; p.ord[n].dep_late = -1; p.ord[n].kb_late = 0; p.ord[n].tap0 = 0;
         return n++;
     };
     auto gemm = [&](int id, int d0, int d1) {
@@ -771,13 +837,27 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
     // KS[1] = 3: the entropy net's first layer runs on the extended step's rows and scatters into the g0 store; the
     // second layer reads its five taps from there
     auto ent_k3 = [&]() {
+        // taps 0..3 of g0 were produced by earlier steps (gathered first: nothing of this step is needed), tap 4 = (v, h)
+        // by this step's E0
+        const int g5a = add(WK_GATHER5, -1, 4 * WAVE_G5_PARTS, 0, -1, -1);
         const int gx = add(WK_GATHER_EXT, -1, 4 * WAVE_GATHER_PARTS, 0, -1, -1);
         const int e0 = gemm(E[0], gx, -1);
         p.ord[gx].ext = 1; p.ord[e0].ext = 1;
-        const int g5 = add(WK_GATHER5, -1, 5 * WAVE_GATHER_PARTS, 0, e0, -1);
-        const int e1 = gemm(E[1], g5, -1);
+        const int g5b = add(WK_GATHER5, -1, 1 * WAVE_G5_PARTS, 0, e0, -1);
+        p.ord[g5b].tap0 = 4;
+        const int e1 = gemm(E[1], g5a, -1);
+        p.ord[e1].dep_late = g5b;
+        p.ord[e1].kb_late = (4 * w.E1) / BK;          // the k-block that holds the first column of tap 4
         const int e2 = gemm(E[2], e1, -1);
-        return gemm(E[3], e2, -1);
+        const int e3 = gemm(E[3], e2, -1);
+        // its own CTAs for this chain: as many as its widest entry has tiles, at most 64
+        int widest = 0;
+        for (int i = g5a; i <= e3; ++i) widest = p.ord[i].ntn > widest ? p.ord[i].ntn : widest;
+        static int xg = -1;      // LBIC_WAVE_XG: tuning hook (0 = no side-chain group)
+        if (xg < 0) { const char *e = getenv("LBIC_WAVE_XG"); xg = e ? atoi(e) : 64; }
+        p.n_xg = widest < xg ? widest : xg;
+        p.xg_e0 = g5a; p.xg_e1 = e3 + 1;
+        return e3;
     };
     if (p.k3 && !w.decode) {
         // the entropy net is the longer chain here (E1 has K = 5 E1): its tiles first

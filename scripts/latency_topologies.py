@@ -12,13 +12,16 @@ def timed(fn, reps=3):
         torch.cuda.synchronize(); a.record(); out = fn(); b.record(); torch.cuda.synchronize()
         best = min(best, a.elapsed_time(b))
     return best, out
-for cfgname in ("B8_lowrate", "B8_highrate", "B4_highrate", "B16_lowrate"):
+# LBIC_LAT_CONFIGS=a,b restricts the topologies, LBIC_LAT_LANE_ONLY=1 skips the (raster-serial) reference container
+CONFIGS = os.environ.get("LBIC_LAT_CONFIGS", "B8_lowrate,B8_highrate,B4_highrate,B16_lowrate").split(",")
+LANES = (0,) if os.environ.get("LBIC_LAT_LANE_ONLY") == "1" else (0, 1)
+for cfgname in CONFIGS:
     cfg = lbic_b200.load_config(cfgname)
     m = BlockBasedImgCompLossyNetv9(cfg, device=dev)
     m.load_state_dict(weights.synth_state_dict(cfg, 1337)); m.update(force=True)
     B = int(cfg.block_size)
     x = arrange_block_pixels_to_channel_dim(torch.rand(1, 3, 512, 768, device=dev) - 0.5, B)
-    for lanes in (0, 1):
+    for lanes in LANES:
         out = m.encode_device(x, lanes=lanes)
         l0 = m.launch_count()
         te, out = timed(lambda: m.encode_device(x, lanes=lanes, out=out))

@@ -8,7 +8,7 @@ from lbic_b200 import weights
 from lbic_b200.layout import arrange_block_pixels_to_channel_dim
 from lbic_b200.net import BlockBasedImgCompLossyNetv9
 dev = torch.device("cuda:0")
-cfg = lbic_b200.load_config("B8_lowrate")
+cfg = lbic_b200.load_config(os.environ.get("LBIC_TRACE_CONFIG", "B8_lowrate"))
 m = BlockBasedImgCompLossyNetv9(cfg, device=dev)
 m.load_state_dict(weights.synth_state_dict(cfg, 1337)); m.update(force=True)
 x = arrange_block_pixels_to_channel_dim(torch.rand(1, 3, 512, 768, device=dev) - 0.5, 8)

@@ -11,7 +11,7 @@ import statistics
 import sys
 from collections import defaultdict
 
-NAMES = {0: "GEMM", 1: "GATHER", 2: "RANS"}
+NAMES = {0: "GEMM", 1: "GATHER", 2: "RANS", 3: "GATHER_EXT", 4: "GATHER5"}
 LAYERS = ("E0", "E1", "E2", "E3", "F0", "G0", "F1", "G1", "F2", "G2", "F3", "D0", "IG0", "D1", "IG1", "D2", "IG2", "D3")
 
 
