@@ -65,6 +65,7 @@ struct WaveOrd {
     // one this step's E0 produces; the chain of the other four -- 4/5 of the layer's K -- starts at the top of the step)
     int dep_late, kb_late;
     int tap0;       // WK_GATHER5: first tap of this entry (its ntn / WAVE_GATHER_PARTS taps)
+    int xbase;      // side-chain group: tile nt of this entry belongs to the group's CTA (xbase + nt) mod n_xg
 };
 
 struct WaveParams {
@@ -165,7 +166,7 @@ __device__ __forceinline__ void wave_for_each_tile(const WaveParams &p, F &&f) {
     int gen[WAVE_MAX_RB];
 #pragma unroll 1
     for (int i = 0; i < WAVE_MAX_RB; ++i) gen[i] = 0;
-    int off = 0, off_e = 0, off_x = 0, prev_n_rb = 0;
+    int off = 0, off_e = 0, prev_n_rb = 0;
     // CTA groups: workers 0 .. Gw-1 | NX CTAs of the side chain (KS[1] = 3: the entropy net, whose E1 tiles are five times
     // as long as any other and must not sit in front of an encoder-net tile in a CTA's queue) | NE entropy CTAs (rANS
     // tiles).  Each group walks its own tiles of the list round-robin; the list positions of a group are contiguous.
@@ -201,20 +202,28 @@ __device__ __forceinline__ void wave_for_each_tile(const WaveParams &p, F &&f) {
         // one loop (one copy of every role's code) for the three groups: tile k of the group's share of the step
         int cnt, stride, first, base;
         if (is_ent) { cnt = cnt_r; stride = NE; first = (int)blockIdx.x - Gw - NX - off_e; base = start_r; }
-        else if (is_x) { cnt = cnt_x; stride = NX; first = (int)blockIdx.x - Gw - off_x; base = start_x; }
+        else if (is_x) { cnt = p.xg_e1 - p.xg_e0; stride = 1; first = 0; base = 0; }     // k = entry: at most one tile of each
         else { cnt = total - cnt_r - cnt_x; stride = Gw; first = (int)blockIdx.x - off; base = 0; }
         if (first < 0) first += stride;
 #pragma unroll 1
         for (int k = first; k < cnt; k += stride) {
-            int j = base + k;
-            if (!is_ent && !is_x) {          // the workers' share is the list without the other groups' ranges
-                if (cnt_x > 0 && j >= start_x) j += cnt_x;
-                if (cnt_r > 0 && j >= start_r) j += cnt_r;
+            if (is_x) {
+                // fixed assignment (one row block per step in this mode): the long E1 tiles sit on CTAs that have no E0 tile
+                const int oi = p.xg_e0 + k;
+                int nt = (int)blockIdx.x - Gw - p.ord[oi].xbase;
+                if (nt < 0) nt += NX;
+                if (nt >= p.ord[oi].ntn) continue;
+                w.oi = oi; w.rb = 0; w.nt = nt; w.j = w.n_rb * p.pre[oi] + nt;
+            } else {
+                int j = base + k;
+                if (!is_ent) {                   // the workers' share is the list without the other groups' ranges
+                    if (cnt_x > 0 && j >= start_x) j += cnt_x;
+                    if (cnt_r > 0 && j >= start_r) j += cnt_r;
+                }
+                locate(j);
             }
-            locate(j);
             f(w, gen);
         }
-        if (NX > 0) off_x = (off_x + cnt_x) % NX;
         off = (off + total - cnt_r - cnt_x) % Gw;
         if (NE > 0) off_e = (off_e + cnt_r) % NE;
         for (int rb = 0; rb < w.n_rb; ++rb) gen[rb]++;
@@ -822,7 +831,7 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
     int n = 0;
     auto add = [&](int kind, int layer, int ntn, int bn, int d0, int d1) {
         p.ord[n].kind = kind; p.ord[n].ext = 0; p.ord[n].layer = layer; p.ord[n].ntn = ntn; p.ord[n].bn = bn;
-        p.ord[n].dep[0] = d0; p.ord[n].dep[1] = d1; p.ord[n].dep_late = -1; p.ord[n].kb_late = 0; p.ord[n].tap0 = 0;
+        p.ord[n].dep[0] = d0; p.ord[n].dep[1] = d1; p.ord[n].dep_late = -1; p.ord[n].kb_late = 0; p.ord[n].tap0 = 0; p.ord[n].xbase = 0;
         return n++;
     };
     auto gemm = [&](int id, int d0, int d1) {
@@ -831,6 +840,18 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
         return add(WK_GEMM, id, (L.cout + bn - 1) / bn, bn, d0, d1);
     };
     const int *E = w.ids, *F = w.ids + 4, *D = w.ids + 11;
+    int n_sm = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    // KS[1] = 3: CTAs the other groups need -- one per tile of the widest encoder / decoder-net layer, the rANS CTAs of a decode
+    int main_need = WAVE_GATHER_PARTS * 5;
+    for (int i = 4; i < 18; ++i) {
+        if (w.decode && i < 11) continue;
+        const ChainLayer &L = w.h_layers[w.ids[i]];
+        const int bn = L.bn_v[w.variant], nt = (L.cout + bn - 1) / bn;
+        main_need = nt > main_need ? nt : main_need;
+    }
+    const int n_ent_k3 = w.decode ? (max_rows > 8 * WAVE_ENT_CTAS ? 2 * WAVE_ENT_CTAS : WAVE_ENT_CTAS) : 0;
     p.gather_first = w.decode ? 1 : 0;
     const int g = add(WK_GATHER, -1, (w.decode ? 4 : 5) * WAVE_GATHER_PARTS, 0, -1, -1);
     int last_e, last;
@@ -850,13 +871,26 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
         p.ord[e1].kb_late = (4 * w.E1) / BK;          // the k-block that holds the first column of tap 4
         const int e2 = gemm(E[2], e1, -1);
         const int e3 = gemm(E[3], e2, -1);
-        // its own CTAs for this chain: as many as its widest entry has tiles, at most 64
-        int widest = 0;
+        // its own CTAs for this chain, each with at most one tile of every entry: E1 (and g5a, E2, E3) from the group's CTA 0,
+        // the E0 sub-chain (gx, E0, g5b) behind E1's CTAs where the grid has room -- an E1 tile then starts as soon as the
+        // first four taps are gathered instead of queueing behind an E0 tile of its CTA
+        int widest = 0, sub = 0;
         for (int i = g5a; i <= e3; ++i) widest = p.ord[i].ntn > widest ? p.ord[i].ntn : widest;
-        static int xg = -1;      // LBIC_WAVE_XG: tuning hook (0 = no side-chain group)
-        if (xg < 0) { const char *e = getenv("LBIC_WAVE_XG"); xg = e ? atoi(e) : 64; }
-        p.n_xg = widest < xg ? widest : xg;
+        for (int i = gx; i <= g5b; ++i) sub = p.ord[i].ntn > sub ? p.ord[i].ntn : sub;
+        static int xg = -1;      // LBIC_WAVE_XG: tuning hook (cap of the group; 0 = no side-chain group)
+        if (xg < 0) { const char *e = getenv("LBIC_WAVE_XG"); xg = e ? atoi(e) : 1 << 20; }
+        int cap = n_sm - main_need - n_ent_k3;
+        cap = cap < xg ? cap : xg;
+        int nx = p.ord[e1].ntn + sub;
+        nx = nx < widest ? widest : nx;
+        nx = nx > cap ? cap : nx;
+        if (nx < widest) nx = 0;                      // no room for one tile per CTA: the workers take the chain
+        p.n_xg = nx;
         p.xg_e0 = g5a; p.xg_e1 = e3 + 1;
+        if (nx > 0) {
+            const int b = nx - sub < p.ord[e1].ntn ? nx - sub : p.ord[e1].ntn;
+            for (int i = gx; i <= g5b; ++i) p.ord[i].xbase = b;
+        }
         return e3;
     };
     if (p.k3 && !w.decode) {
@@ -931,9 +965,6 @@ int gemm_wave_launch(const WaveLaunch &w, cudaStream_t st) {
         LBIC_CUDA(cudaMemsetAsync(d_trace, 0, trace_words * 8, st));
         p.trace = d_trace;
     }
-    int n_sm = 148, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(n_sm, 1, 1);
