@@ -209,6 +209,7 @@ def main():
                     help="rate of the synthetic model (weights.synth_state_dict): 60 / 5.2 = ~11 bpp (default), 2.5 / 2.0 = ~1 bpp")
     ap.add_argument("--scale-span", type=float, default=5.2)
     ap.add_argument("--no-reference-container", action="store_true")
+    ap.add_argument("--no-single-image", action="store_true", help="skip the one-image latency leg")
     ap.add_argument("--refc-images", type=int, default=2048,
                     help="second, larger batch for the reference-container round trip (0 = skip)")
     args = ap.parse_args()
@@ -403,6 +404,24 @@ def main():
             del x2, o2, z2
             torch.cuda.empty_cache()
 
+    # The reference's own call pattern is ONE image per compress / decompress call (eval_model, AGENT:578-599): a chain of
+    # Hb + 2 Wb dependent wavefront steps, i.e. latency, not throughput (the persistent wavefront kernel, gemm_wave.cu).
+    single = None
+    if not args.no_single_image:
+        x1 = x[:1].contiguous()
+        o1 = m.encode_device(x1, lanes=args.lanes)
+        z1 = m.decode_device(o1.streams, o1.lens, 1, Hb, Wb, lanes=args.lanes)
+        torch.cuda.synchronize()
+        l1 = m.launch_count()
+        ms_e = min(timed(lambda: m.encode_device(x1, lanes=args.lanes, out=o1), 1) for _ in range(3))
+        le = (m.launch_count() - l1) // 3
+        ms_d = min(timed(lambda: m.decode_device(o1.streams, o1.lens, 1, Hb, Wb, lanes=args.lanes), 1) for _ in range(3))
+        z1 = m.decode_device(o1.streams, o1.lens, 1, Hb, Wb, lanes=args.lanes)
+        single = dict(images=1, size=f"{W}x{H}", encode_ms=ms_e, decode_ms=ms_d, launches_per_encode=int(le),
+                      container="reference" if args.lanes == 1 else "lane", timing="device-resident, CUDA events, best of 3",
+                      enc_dec_identical=bool(torch.equal(z1, o1.zhat)))
+        del x1, o1, z1
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:   # reported at N=1 only (host cores are shared by the ranks)
         threads = os.cpu_count() or 1
@@ -424,7 +443,7 @@ def main():
                     decode_mpix_s=pixels_step * args.steps / (ms_dec * 1e-3) / 1e6,
                     bpp=8.0 * bytes_total / (n * H * W), enc_dec_identical=parity_ok,
                     gpu_launches=int(launches), clocks=clocks, roofline=roofline, e2e=e2e, cpu_baseline=cpu,
-                    reference_container=refc,
+                    reference_container=refc, single_image=single,
                     gemm_core=args.core)
         print(json.dumps(line), flush=True)
     if dist is not None:
