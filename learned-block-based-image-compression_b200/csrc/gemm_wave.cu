@@ -8,7 +8,8 @@
 //
 // Here the 148 CTAs stay resident for the whole image.  Every step's work is one list of TILES in a fixed order,
 //     GATHER (operand build) | GEMM tiles of every layer, 128 rows x <= 32 columns | RANS (decode only),
-// tile j of the list goes to CTA (offset + j) mod 148, and a tile may start once the tiles it reads from have been
+// tile j of the list goes to CTA (offset + j) mod 148 (decode launches set 8 CTAs aside for the RANS tiles, KS[1] = 3
+// launches a group with a fixed assignment for the entropy chain: wave_for_each_tile), and a tile may start once the tiles it reads from have been
 // published through a monotonic counter per (list entry, 128-row block) -- release by a publisher warp after the
 // tile's stores, acquire by whoever consumes (the TMA producer before its first load, the epilogue warps before a
 // gather / rANS tile or a GDN side input).  Narrow tiles spread a layer over 20-40 SMs so that the tensor time of a
